@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE config 2.
+
+    metric   leapfrog-steps x chains / sec   (plain HMC, D-dim isotropic Gaussian)
+    workload config 2: D=1024 isotropic N(0,I), 256 chains per GPU, L=10, eps=0.05, S=1000 iterations, burn=0
+    step     one pass of the hot path over one batch: ONE persistent-kernel launch advancing all chains of the rank
+             through all S iterations (gibbs -> H -> L leapfrog steps -> H -> MH -> sample write), = C*S*L chain-steps
+
+    python bench.py --gpus N --steps K --warmup W            (under torchrun for N > 1: one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's algorithm on the host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, C_PER_GPU, S, L, EPS = 1024, 256, 1000, 10, 0.05
+METRIC = 'leapfrog-steps x chains / sec'
+UNIT = 'chain-steps/s'
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port: same Python loop + autograd as hamiltorch.sample) on host cores
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_chain(args):
+    seed, n_iter = args
+    import torch as _t
+    _t.set_num_threads(1)
+    from hamiltorch_b200 import targets as T
+    from oracle import hmc_oracle as O
+    tgt = T.GaussianIso(D)
+    _t.manual_seed(seed)
+    init = 0.1 * _t.randn(D)
+    t0 = time.perf_counter()
+    O.sample_hmc(tgt, init, num_samples=n_iter, num_steps_per_sample=L, step_size=EPS)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(n_iter, procs):
+    """`procs` independent chains (one process per host core, 1 torch thread each -- intra-op threads do not help at
+    D=1024), each running n_iter iterations of config 2.  Returns chain-steps/s and wall."""
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_chain, [(1000 + i, n_iter) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    return procs * n_iter * L / wall, wall
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_iter = args.cpu_iters
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_rate(max(2, n_iter // 10), cores)
+    t_tot, steps_tot = 0.0, 0
+    for _ in range(args.steps):
+        rate, wall = cpu_reference_rate(n_iter, cores)
+        t_tot += wall
+        steps_tot += cores * n_iter * L
+    value = steps_tot / t_tot
+    sample = '%d chains (1 per core) x %d iterations x L=%d of config 2 per step' % (cores, n_iter, L)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE config 2: D=1024 isotropic Gaussian, plain HMC, L=10, eps=0.05',
+                   'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import hamiltorch_b200 as hb
+    from hamiltorch_b200 import engine, targets as T, _native as N
+
+    N.require_cuda()
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        # fork the CPU workers BEFORE this process touches CUDA or spins up torch's intra-op pool
+        cores = os.cpu_count() or 1
+        rate, wall = cpu_reference_rate(args.cpu_iters, cores)
+        cpu_base = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                    'sample': '%d chains (1 per core) x %d iterations x L=%d of config 2, %.1f s wall'
+                              % (cores, args.cpu_iters, L, wall)}
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
+
+    C = C_PER_GPU                                   # weak scaling: every rank owns 256 chains
+    chain_offset = rank * C
+    tgt = engine.NativeTarget(T.GaussianIso(D), dev)
+    ld = N.padded_ld(D)
+    g = torch.Generator().manual_seed(1234 + rank)
+    q0_host = (0.1 * torch.randn(C, D, generator=g)).pin_memory()
+    q0 = q0_host.to(dev)
+    out = torch.empty((C, S, ld), dtype=torch.float32, device=dev)           # 1 GiB: 8x the 126 MB L2
+    host_out = torch.empty((C, S, ld), dtype=torch.float32).pin_memory()
+    stats = torch.empty((world, C, 2), dtype=torch.float32, device=dev)
+
+    def step(seed):
+        return engine.hmc_run(tgt, q0, S, L, EPS, seed=seed, chain_offset=chain_offset, out=out, device=dev)
+
+    def gather_stats(res):
+        mine = torch.stack([res.num_rejected.float(), res.step_size], 1)
+        if world > 1:
+            dist.all_gather_into_tensor(stats.view(-1), mine.view(-1))        # the run's single (tiny) collective
+        else:
+            stats[0].copy_(mine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for w in range(args.warmup):
+        gather_stats(step(w))
+    barrier()
+
+    # ---- device-timed region: EXACTLY K steps, inputs resident in HBM ----
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    ev[0].record()
+    for k in range(args.steps):
+        ev[1 + 2 * k].record()
+        res = step(100 + k)
+        ev[2 + 2 * k].record()
+        gather_stats(res)
+    ev[-1].record()
+    barrier()
+    t_total_ms = ev[0].elapsed_time(ev[-1])
+    t_kernel_ms = sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(args.steps)) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    rejected = stats[..., 0].sum().item()
+
+    # ---- e2e: public API, HOST buffers, H2D of the inputs and D2H of the result inside the timed region ----
+    def e2e_step(seed):
+        r = hb.sample_chains(T.GaussianIso(D), q0_host, num_samples=S, num_steps_per_sample=L, step_size=EPS,
+                             rng='philox', seed=seed, chain_offset=chain_offset, out=out)
+        host_out.copy_(r.samples_padded, non_blocking=True)
+        return r
+
+    e2e_step(7)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(1, min(args.steps, 3))
+    e0.record()
+    for k in range(n_e2e):
+        e2e_step(200 + k)
+    e1.record()
+    barrier()
+    t_e2e_ms = e0.elapsed_time(e1) / n_e2e
+
+    # ---- optional: cost of collecting every rank's samples with one NCCL all-gather (reported, not in `value`) ----
+    allgather_ms = None
+    if world > 1 and args.gather_samples:
+        big = torch.empty((world, C, S, ld), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(big.view(-1), out.view(-1))
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        dist.all_gather_into_tensor(big.view(-1), out.view(-1))
+        a1.record()
+        barrier()
+        allgather_ms = a0.elapsed_time(a1)
+        del big
+
+    # ---- streaming leapfrog kernel (the HBM-roofline form of samplers.leapfrog): state >> L2, L=1 ----
+    Cs = 32768                                           # 32768 x 1024 fp32 = 128 MiB per array, 4 arrays
+    qs = torch.randn(Cs, D, device=dev)
+    ps = torch.randn(Cs, D, device=dev)
+    for _ in range(3):
+        engine.leapfrog(tgt, qs, ps, 1, EPS)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_s = 10
+    eps_vec = torch.full((Cs,), EPS, device=dev)
+    s0.record()
+    for _ in range(n_s):
+        engine.leapfrog(tgt, qs, ps, 1, eps_vec)
+    s1.record()
+    torch.cuda.synchronize()
+    t_stream_ms = s0.elapsed_time(s1) / n_s
+    del qs, ps
+
+    # max over ranks of every timing
+    t = torch.tensor([t_total_ms, t_kernel_ms, t_e2e_ms, t_stream_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_total_ms, t_kernel_ms, t_e2e_ms, t_stream_ms = t.tolist()
+
+    if rank == 0:
+        units_per_step = world * C * S * L
+        ms_per_step = t_total_ms / args.steps
+        value = units_per_step / (ms_per_step * 1e-3)
+        peak, peak_src = measured_peak_hbm()
+        algo_bytes = C * S * D * 4 + C * D * 4          # per launch: every retained sample written once + init read once
+        achieved = algo_bytes / (t_kernel_ms * 1e-3) / 1e9
+        stream_bytes = Cs * D * 16                       # B_step = 16*D B per leapfrog-step x chain
+        stream_gbs = stream_bytes / (t_stream_ms * 1e-3) / 1e9
+        h2d, d2h = C * D * 4, C * S * ld * 4
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE config 2: D=1024 isotropic Gaussian, plain HMC, 256 chains/GPU, L=10, '
+                                   'eps=0.05, S=1000 iterations per step, in-kernel Philox RNG',
+                       'chains_per_gpu': C, 'dim': D, 'L': L, 'iterations_per_step': S,
+                       'l2_policy': 'each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
+                       'parallelism': 'chains sharded over %d GPU(s), no data-path collective' % world},
+            'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,1>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': t_kernel_ms,
+                         'note': 'fused trajectory kernel: L=10 steps per 4*D bytes written, fp32-issue bound by design; '
+                                 'see roofline_streaming for the HBM-bound form'},
+            'roofline_streaming': {'bound': 'hbm', 'kernel': 'leapfrog_kernel<ISO,NONE> L=1, 32768x1024 state',
+                                   'achieved': stream_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': stream_gbs / peak,
+                                   'algorithmic_bytes_per_launch': stream_bytes, 'kernel_ms': t_stream_ms,
+                                   'chain_steps_per_s': Cs / (t_stream_ms * 1e-3)},
+            'e2e': {'value': units_per_step / (t_e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': t_e2e_ms},
+            'gpu_launches': args.steps,
+            'accept_rate': 1.0 - rejected / (world * C * S),
+            'clocks': clk,
+        }
+        if allgather_ms is not None:
+            line['allgather_samples_ms'] = allgather_ms
+        if cpu_base is not None:
+            line['cpu_baseline'] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-iters', type=int, default=2000, help='iterations per chain of the bounded CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gather-samples', action='store_true', help='also time one NCCL all-gather of all samples')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit('launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus))
+    run_b200_arm(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

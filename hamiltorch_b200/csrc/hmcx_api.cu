@@ -1,0 +1,69 @@
+// hmcx_api.cu -- the extern "C" surface declared in include/hmcx.h; validates and dispatches on target kind.
+#include "hmcx_common.cuh"
+
+namespace hmcx {
+int elem_leapfrog(const hmcx_target_t*, const hmcx_mass_t*, const float*, const float*, const float*, int, int, int,
+                  float*, float*, float*, float*, cudaStream_t);
+int elem_hamiltonian(const hmcx_target_t*, const hmcx_mass_t*, const float*, const float*, int, int, float*,
+                     uint8_t*, cudaStream_t);
+int elem_gibbs(const hmcx_mass_t*, const hmcx_rng_t*, int, int, int, int64_t, float*, cudaStream_t);
+int elem_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*,
+                 float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
+                 int, cudaStream_t);
+}  // namespace hmcx
+
+static inline bool is_elem(const hmcx_target_t* t) {
+    return t && (t->kind == HMCX_TARGET_GAUSS_ISO || t->kind == HMCX_TARGET_GAUSS_DIAG);
+}
+
+extern "C" {
+
+int hmcx_abi_version(void) { return HMCX_ABI_VERSION; }
+
+const char* hmcx_status_string(int status) {
+    switch (status) {
+        case HMCX_OK: return "ok";
+        case HMCX_ERR_INVALID_ARG: return "invalid argument";
+        case HMCX_ERR_UNSUPPORTED: return "unsupported target / mass / dimension combination";
+        case HMCX_ERR_CUDA: return "CUDA launch error";
+        default: return "unknown status";
+    }
+}
+
+int hmcx_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass, const float* q_in, const float* p_in,
+                  const float* eps, int32_t C, int32_t ld, int32_t L, float* q_out, float* p_out, float* q_traj,
+                  float* p_traj, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (is_elem(target))
+        return hmcx::elem_leapfrog(target, mass, q_in, p_in, eps, C, ld, L, q_out, p_out, q_traj, p_traj,
+                                   (cudaStream_t)stream);
+    return HMCX_ERR_UNSUPPORTED;
+}
+
+int hmcx_hamiltonian(const hmcx_target_t* target, const hmcx_mass_t* mass, const float* q, const float* p,
+                     int32_t C, int32_t ld, float* H_out, uint8_t* flags_out, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (is_elem(target))
+        return hmcx::elem_hamiltonian(target, mass, q, p, C, ld, H_out, flags_out, (cudaStream_t)stream);
+    return HMCX_ERR_UNSUPPORTED;
+}
+
+int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_t C, int32_t ld, int64_t iter,
+               float* p_out, void* stream) {
+    return hmcx::elem_gibbs(mass, rng, D, C, ld, iter, p_out, (cudaStream_t)stream);
+}
+
+int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                 const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int32_t C, int32_t ld,
+                 int32_t L, int32_t num_samples, int32_t burn, int32_t iter_begin, int32_t iter_end,
+                 float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                 int32_t* num_rejected, int32_t tuning, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (is_elem(target))
+        return hmcx::elem_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
+                                  iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
+                                  num_rejected, tuning, (cudaStream_t)stream);
+    return HMCX_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

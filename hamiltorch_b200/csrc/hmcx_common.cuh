@@ -1,0 +1,114 @@
+// hmcx_common.cuh -- device helpers shared by the sm_100a HMC kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/hmcx.h"
+
+#define HMCX_CHECK_ARG(cond) do { if (!(cond)) return HMCX_ERR_INVALID_ARG; } while (0)
+
+namespace hmcx {
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 arithmetic in the reference's operation order: every product and sum is rounded separately
+// (__fmul_rn/__fadd_rn are never contracted into FMA), because the reference evaluates e.g.
+// ``params + step_size * momentum`` (samplers.py:284) as two ATen kernels.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= 3.402823466e+38f; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (Salmon et al. 2011).  Counter = (element-vector index, iteration lo, iteration hi
+// | stream<<24, chain lo), key = seed ^ (chain hi).  One call yields the 4 normals of one float4 vector.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0; k.y += W1;
+    }
+    return c;
+}
+
+enum { STREAM_MOMENTUM = 0, STREAM_ACCEPT = 1, STREAM_JITTER = 2, STREAM_PERM = 3 };
+
+__device__ __forceinline__ uint4 philox_draw(uint64_t seed, uint64_t chain, uint64_t iter, uint32_t vec,
+                                             uint32_t stream) {
+    uint4 c = make_uint4(vec, (uint32_t)iter, (uint32_t)(iter >> 32) | (stream << 24), (uint32_t)chain);
+    uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(chain >> 32));
+    return philox4x32_10(c, k);
+}
+
+// uniform in (0,1]: never 0, so log() is finite
+__device__ __forceinline__ float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// Box-Muller: two uniforms -> two independent N(0,1)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float r = sqrtf(-2.0f * __logf(u01(a)));
+    float s, c;
+    __sincosf(6.283185307179586f * (u01(b) - 0.5f), &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t chain, uint64_t iter, uint32_t vec,
+                                               float z[4]) {
+    const uint4 r = philox_draw(seed, chain, iter, vec, STREAM_MOMENTUM);
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+}
+
+__device__ __forceinline__ float philox_log_uniform(uint64_t seed, uint64_t chain, uint64_t iter) {
+    const uint4 r = philox_draw(seed, chain, iter, 0xFFFFFFFFu, STREAM_ACCEPT);
+    return logf(u01(r.x));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reductions.  xor-butterflies: every lane ends with the same bits (fp add is commutative and each level pairs
+// identical operands), so all threads of a CTA take identical decisions without a broadcast.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = add(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum N values over the CTA.  `sbuf` holds 32*N floats; callers alternate between two buffers on consecutive
+// calls so that a single __syncthreads() per call suffices.
+template <int N>
+__device__ __forceinline__ void block_sum(float (&v)[N], float* sbuf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    if (nwarp == 1) return;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) sbuf[warp * N + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(lane < nwarp ? sbuf[lane * N + i] : 0.0f);
+}
+
+// 16-byte vector access helpers
+__device__ __forceinline__ void ld4(const float* p, float v[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4_stream(const float* p, float v[4]) {   // read-once data: don't keep in L1
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4_stream(float* p, const float v[4]) {   // write-once data: evict first
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+}  // namespace hmcx

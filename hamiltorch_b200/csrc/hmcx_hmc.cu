@@ -1,0 +1,522 @@
+// hmcx_hmc.cu -- plain-HMC hot path for element-wise targets (isotropic / diagonal Gaussians) on sm_100a.
+//
+// Replaces, for a batch of C independent chains, the reference's per-chain Python loop
+//   samplers.py:965-1067  (sample: gibbs -> hamiltonian -> leapfrog -> hamiltonian -> MH -> bookkeeping -> adaptation)
+//   samplers.py:269-304   (leapfrog, plain HMC branch)      samplers.py:779-815 (hamiltonian, HMC branch)
+//   samplers.py:185-202   (gibbs)                           samplers.py:629-674 (adaptation)
+//
+// Kernels
+//   hmc_run_kernel<TK,MK,K>  persistent: one CTA owns one chain for ALL iterations of the launch.  The chain's
+//       position, proposal and momentum live in registers (K float4 vectors per thread, D <= 4*K*blockDim), the
+//       whole L-step trajectory is thread-private for these targets, the only cross-thread traffic per iteration
+//       is ONE fused block reduction of (p0.M^-1.p0, U(q_L) terms, p_L.M^-1.p_L), and HBM sees one coalesced
+//       float4 store of the retained sample (+ one read of injected normals in parity mode).
+//   leapfrog_kernel<TK,MK>   streaming form of samplers.leapfrog for (C, ld) state arrays in HBM (grid-stride
+//       float4; 16 B/element moved once, all L steps in registers).  This is the HBM-roofline kernel.
+//   hamiltonian_kernel<TK,MK>, gibbs_kernel<MK>   the remaining stand-alone pieces of the reference surface.
+#include "hmcx_common.cuh"
+
+namespace hmcx {
+
+struct ElemTarget {           // element-wise target + mass description, passed by value
+    int tk, mk;
+    int D, ld, C;
+    const float* mean;
+    const float* ivar;
+    const float* im;          // inv_mass [D]
+    const float* sd;          // sqrt(mass) [D]
+    float log_norm;
+};
+
+// per-vector constants kept in registers (dead members are eliminated for ISO / MASS_NONE)
+struct VecConst { float mean[4], ivar[4], im[4], sd[4]; };
+
+template <int TK, int MK>
+__device__ __forceinline__ void load_consts(const ElemTarget& t, int e0, VecConst& c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool ok = (e0 + j) < t.D;
+        if (TK == HMCX_TARGET_GAUSS_DIAG) {
+            c.mean[j] = (ok && t.mean) ? t.mean[e0 + j] : 0.0f;
+            c.ivar[j] = ok ? t.ivar[e0 + j] : 0.0f;
+        }
+        if (MK == HMCX_MASS_DIAG) {
+            c.im[j] = ok ? t.im[e0 + j] : 0.0f;
+            c.sd[j] = ok ? t.sd[e0 + j] : 0.0f;
+        }
+    }
+}
+
+// g = d log p / dq_i in the op order autograd produces for targets.py (GaussianIso: -x; GaussianDiag: -(iv*(x-m)))
+template <int TK>
+__device__ __forceinline__ float grad1(float q, float mean, float ivar) {
+    if (TK == HMCX_TARGET_GAUSS_ISO) return -q;
+    return -mul(ivar, sub(q, mean));
+}
+// summand of -2*(log p - log_norm)
+template <int TK>
+__device__ __forceinline__ float uterm1(float q, float mean, float ivar) {
+    if (TK == HMCX_TARGET_GAUSS_ISO) return mul(q, q);
+    const float y = sub(q, mean);
+    return mul(mul(y, y), ivar);
+}
+// samplers.py:284 / :296
+template <int MK>
+__device__ __forceinline__ float drift1(float q, float eps, float im, float p) {
+    if (MK == HMCX_MASS_NONE) return add(q, mul(eps, p));
+    return add(q, mul(mul(eps, im), p));
+}
+// summand of 2*kinetic, samplers.py:801 / :814
+template <int MK>
+__device__ __forceinline__ float kterm1(float p, float im) {
+    if (MK == HMCX_MASS_NONE) return mul(p, p);
+    return mul(p, mul(im, p));
+}
+
+// log p from the reduced sum, targets.py op order: -0.5*sum (+ log_norm)
+__device__ __forceinline__ float log_prob_from_sum(float s, float log_norm) { return add(mul(-0.5f, s), log_norm); }
+
+// One float4 vector through a whole trajectory (samplers.py:281-302).  Optionally records the L clones.
+template <int TK, int MK, bool TRAJ>
+__device__ __forceinline__ void trajectory4(float q[4], float p[4], const VecConst& c, float eps, float half,
+                                            int L, float* q_traj, float* p_traj, size_t traj_stride) {
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        g[j] = grad1<TK>(q[j], c.mean[j], c.ivar[j]);
+        p[j] = add(p[j], mul(half, g[j]));                                   // :281
+    }
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            q[j] = drift1<MK>(q[j], eps, c.im[j], p[j]);                     // :284 / :296
+            g[j] = grad1<TK>(q[j], c.mean[j], c.ivar[j]);                    // :297
+            p[j] = add(p[j], mul(eps, g[j]));                                // :298
+        }
+        if (TRAJ) {
+            if (l + 1 < L) {                                                 // :299-300
+                st4_stream(q_traj + (size_t)l * traj_stride, q);
+                st4_stream(p_traj + (size_t)l * traj_stride, p);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = sub(p[j], mul(half, g[j]));           // :302
+    if (TRAJ) {
+        st4_stream(q_traj + (size_t)(L - 1) * traj_stride, q);
+        st4_stream(p_traj + (size_t)(L - 1) * traj_stride, p);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// persistent sample() kernel
+// ---------------------------------------------------------------------------------------------------------
+struct RunArgs {
+    ElemTarget t;
+    // rng
+    int rng_mode;
+    uint64_t seed, chain_offset;
+    const float* normals;
+    const float* logu;
+    // nuts
+    int nuts;
+    double delta, mu;
+    const double* table;
+    double* h_bar;
+    double* eps_bar;
+    // state / outputs
+    const float* q_init;
+    float* q_cur;
+    float* eps;
+    int L, S, burn, it0, it1;
+    float* samples;
+    uint8_t* accept;
+    uint8_t* diverged;
+    float* ham;
+    int32_t* num_rejected;
+};
+
+template <int TK, int MK, int K>
+__global__ void __launch_bounds__(K == 1 ? 1024 : (K == 2 ? 512 : 256))
+hmc_run_kernel(const RunArgs a) {
+    __shared__ float s_red[2][32 * 3];
+    __shared__ float s_eps[2];
+
+    const int c = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
+    const ElemTarget& t = a.t;
+    const int ld = t.ld, D = t.D;
+    const size_t row = (size_t)c * ld;
+    const uint64_t chain_id = a.chain_offset + (uint64_t)c;
+
+    VecConst vc[K];
+    float qc[K][4], q[K][4], p[K][4];
+    bool live[K];                 // vector lies inside the padded row
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int e0 = 4 * (tid + k * G);
+        live[k] = e0 < ld;
+        load_consts<TK, MK>(t, e0, vc[k]);
+        if (live[k]) ld4(a.q_cur + row + e0, qc[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (!live[k] || e0 + j >= D) qc[k][j] = 0.0f;
+    }
+
+    // U(q_cur) once; afterwards it is carried (the reference recomputes the identical value, :971)
+    float lp_cur;
+    {
+        float r[1] = {0.0f};
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[0] = add(r[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
+        block_sum<1>(r, s_red[1]);
+        lp_cur = log_prob_from_sum(r[0], t.log_norm);
+        __syncthreads();
+    }
+
+    float eps = a.eps[c];
+    double h_bar = 0.0, eps_bar = 1.0;
+    if (a.nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
+    int rejected = 0;
+    const int keep = a.S - a.burn;                 // slots per chain in samples_out
+    float* const my_samples = a.samples ? a.samples + (size_t)c * keep * ld : nullptr;
+
+    if (a.it0 == 0 && my_samples) {                // ret_params = [params_init] (:959)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (live[k]) st4_stream(my_samples + 4 * (tid + k * G), qc[k]);
+    }
+
+    for (int n = a.it0; n < a.it1; ++n) {
+        const float half = mul(0.5f, eps);
+        // ---- gibbs (:969): p = z (*sqrt(mass)) ----
+        float kin0 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int v = tid + k * G, e0 = 4 * v;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (live[k]) {
+                if (a.rng_mode == HMCX_RNG_INJECTED)
+                    ld4_stream(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, z);
+                else
+                    philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)v, z);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (e0 + j >= D) z[j] = 0.0f;
+                p[k][j] = (MK == HMCX_MASS_DIAG) ? mul(z[j], vc[k].sd[j]) : z[j];
+                kin0 = add(kin0, kterm1<MK>(p[k][j], vc[k].im[j]));
+                q[k][j] = qc[k][j];
+            }
+        }
+        // ---- leapfrog (:973) : thread-private ----
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            trajectory4<TK, MK, false>(q[k], p[k], vc[k], eps, half, a.L, nullptr, nullptr, 0);
+        // ---- both Hamiltonians with one fused reduction (:971, :995) ----
+        float r[3] = {kin0, 0.0f, 0.0f};
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r[1] = add(r[1], uterm1<TK>(q[k][j], vc[k].mean[j], vc[k].ivar[j]));
+                r[2] = add(r[2], kterm1<MK>(p[k][j], vc[k].im[j]));
+            }
+        block_sum<3>(r, s_red[n & 1]);
+        const float lp_new = log_prob_from_sum(r[1], t.log_norm);
+        const float h_old = add(-lp_cur, mul(0.5f, r[0]));                   // potential + kinetic (:815)
+        const float h_new = add(-lp_new, mul(0.5f, r[2]));
+        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);            // LogProbError (:783-785)
+        // ---- MH (:1000-1004) ----
+        const float x = add(-h_new, h_old);                                  // acceptance(), :626
+        const float rho = (x < 0.0f) ? x : 0.0f;                             // Python min(0., x): nan -> 0.
+        const float logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * t.C + c]
+                                                             : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        const bool acc = !bad && (rho >= logu);
+        if (acc) {
+            lp_cur = lp_new;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) qc[k][j] = q[k][j];
+        } else {
+            ++rejected;
+            if (n == a.burn + 1) {
+                // reference quirk (:1018): the first stored iteration restores ret_params[-1] == params_init,
+                // not the pre-trajectory state.  Rare path: re-read params_init and recompute its log p.
+                float s[1] = {0.0f};
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int e0 = 4 * (tid + k * G);
+                    if (live[k]) ld4(a.q_init + row + e0, qc[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (!live[k] || e0 + j >= D) qc[k][j] = 0.0f;
+                        s[0] = add(s[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
+                    }
+                }
+                block_sum<1>(s, s_red[(n & 1) ^ 1]);
+                lp_cur = log_prob_from_sum(s[0], t.log_norm);
+                __syncthreads();          // the next iteration reduces through the same buffer
+            }
+        }
+        // ---- bookkeeping (:1007-1026): store only for n > burn ----
+        if (n > a.burn && my_samples) {
+            float* dst = my_samples + (size_t)(n - a.burn) * ld;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (live[k]) st4_stream(dst + 4 * (tid + k * G), qc[k]);
+        }
+        if (tid == 0) {
+            const size_t o = (size_t)c * a.S + n;
+            if (a.accept) a.accept[o] = acc ? 1 : 0;
+            if (a.diverged) a.diverged[o] = bad ? 1 : 0;
+            if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
+        }
+        // ---- dual averaging (:1030-1035, exception path :1060-1067) ----
+        if (a.nuts && n <= a.burn) {
+            if (tid == 0) {
+                float e = eps;
+                if (n < a.burn || bad) {
+                    const double* T = a.table + 5 * (size_t)n;               // t = n+1
+                    const double alpha = bad ? 0.0 : (double)expf(rho);      // min(1, exp(rho)), rho <= 0
+                    h_bar = __dadd_rn(__dmul_rn(T[0], h_bar), __dmul_rn(T[1], a.delta - alpha));
+                    const double x_new = a.mu - __dmul_rn(T[2], h_bar);
+                    e = expf((float)x_new);
+                    const float xb = add((float)__dmul_rn(T[3], x_new), mul((float)T[4], logf((float)eps_bar)));
+                    eps_bar = (double)expf(xb);
+                }
+                if (n == a.burn) e = (float)eps_bar;                          // freeze (:1033-1034)
+                s_eps[n & 1] = e;
+            }
+            __syncthreads();
+            eps = s_eps[n & 1];
+        }
+    }
+
+    // final state for resumption
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (live[k]) st4(a.q_cur + row + 4 * (tid + k * G), qc[k]);
+    if (tid == 0) {
+        a.eps[c] = eps;
+        if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
+        if (a.num_rejected) a.num_rejected[c] += rejected;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// streaming kernels
+// ---------------------------------------------------------------------------------------------------------
+template <int TK, int MK, bool TRAJ>
+__global__ void __launch_bounds__(256)
+leapfrog_kernel(const ElemTarget t, const float* __restrict__ q_in, const float* __restrict__ p_in,
+                const float* __restrict__ eps_c, int L, float* __restrict__ q_out, float* __restrict__ p_out,
+                float* q_traj, float* p_traj) {
+    const int vpr = t.ld >> 2;                                  // float4 vectors per row
+    const size_t nvec = (size_t)t.C * vpr;
+    const size_t traj_stride = (size_t)t.C * t.ld;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(v / vpr), e0 = 4 * (int)(v - (size_t)c * vpr);
+        VecConst vc;
+        load_consts<TK, MK>(t, e0, vc);
+        float q[4], p[4];
+        ld4_stream(q_in + 4 * v, q);
+        ld4_stream(p_in + 4 * v, p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (e0 + j >= t.D) { q[j] = 0.0f; p[j] = 0.0f; }
+        const float eps = eps_c[c];
+        trajectory4<TK, MK, TRAJ>(q, p, vc, eps, mul(0.5f, eps), L, TRAJ ? q_traj + 4 * v : nullptr,
+                                  TRAJ ? p_traj + 4 * v : nullptr, traj_stride);
+        st4_stream(q_out + 4 * v, q);
+        st4_stream(p_out + 4 * v, p);
+    }
+}
+
+template <int TK, int MK>
+__global__ void __launch_bounds__(256)
+hamiltonian_kernel(const ElemTarget t, const float* __restrict__ q, const float* __restrict__ p,
+                   float* __restrict__ H, uint8_t* __restrict__ flags) {
+    __shared__ float s_red[32 * 2];
+    const int c = blockIdx.x;
+    const size_t row = (size_t)c * t.ld;
+    float r[2] = {0.0f, 0.0f};
+    for (int e0 = 4 * threadIdx.x; e0 < t.ld; e0 += 4 * blockDim.x) {
+        VecConst vc;
+        load_consts<TK, MK>(t, e0, vc);
+        float qv[4], pv[4];
+        ld4_stream(q + row + e0, qv);
+        ld4_stream(p + row + e0, pv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (e0 + j < t.D) {
+                r[0] = add(r[0], uterm1<TK>(qv[j], vc.mean[j], vc.ivar[j]));
+                r[1] = add(r[1], kterm1<MK>(pv[j], vc.im[j]));
+            }
+        }
+    }
+    block_sum<2>(r, s_red);
+    if (threadIdx.x == 0) {
+        const float lp = log_prob_from_sum(r[0], t.log_norm);
+        H[c] = add(-lp, mul(0.5f, r[1]));
+        if (flags) flags[c] = finite_f(lp) ? 0 : 1;
+    }
+}
+
+template <int MK>
+__global__ void __launch_bounds__(256)
+gibbs_kernel(const ElemTarget t, uint64_t seed, uint64_t chain_offset, uint64_t iter, float* __restrict__ p_out) {
+    const int vpr = t.ld >> 2;
+    const size_t nvec = (size_t)t.C * vpr;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(v / vpr), vi = (int)(v - (size_t)c * vpr), e0 = 4 * vi;
+        float z[4];
+        philox_normal4(seed, chain_offset + (uint64_t)c, iter, (uint32_t)vi, z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (e0 + j >= t.D) z[j] = 0.0f;
+            else if (MK == HMCX_MASS_DIAG) z[j] = mul(z[j], t.sd[e0 + j]);
+        }
+        st4(p_out + 4 * v, z);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------------------
+static int fill_elem_target(const hmcx_target_t* target, const hmcx_mass_t* mass, int C, int ld, ElemTarget& t) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (target->kind != HMCX_TARGET_GAUSS_ISO && target->kind != HMCX_TARGET_GAUSS_DIAG) return HMCX_ERR_UNSUPPORTED;
+    const int mk = mass ? mass->kind : HMCX_MASS_NONE;
+    if (mk != HMCX_MASS_NONE && mk != HMCX_MASS_DIAG) return HMCX_ERR_UNSUPPORTED;
+    if (target->dim < 1 || C < 1 || ld < target->dim || (ld & 3)) return HMCX_ERR_INVALID_ARG;
+    if (target->kind == HMCX_TARGET_GAUSS_DIAG && !target->inv_var) return HMCX_ERR_INVALID_ARG;
+    if (mk == HMCX_MASS_DIAG && (!mass->inv_mass || !mass->mass_factor)) return HMCX_ERR_INVALID_ARG;
+    t.tk = target->kind; t.mk = mk; t.D = target->dim; t.ld = ld; t.C = C;
+    t.mean = target->mean; t.ivar = target->inv_var; t.log_norm = target->log_norm;
+    t.im = mass ? mass->inv_mass : nullptr; t.sd = mass ? mass->mass_factor : nullptr;
+    return HMCX_OK;
+}
+
+static inline int cuda_status() { return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA; }
+
+static int stream_grid(size_t nvec, int block) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t want = (nvec + block - 1) / block;
+    const size_t cap = (size_t)sms * 8;                        // 8 resident CTAs of 256 threads per SM
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+#define DISPATCH_TK_MK(t, CALL)                                                                         \
+    do {                                                                                                \
+        if ((t).tk == HMCX_TARGET_GAUSS_ISO) {                                                          \
+            if ((t).mk == HMCX_MASS_NONE) { CALL(HMCX_TARGET_GAUSS_ISO, HMCX_MASS_NONE); }              \
+            else { CALL(HMCX_TARGET_GAUSS_ISO, HMCX_MASS_DIAG); }                                       \
+        } else {                                                                                        \
+            if ((t).mk == HMCX_MASS_NONE) { CALL(HMCX_TARGET_GAUSS_DIAG, HMCX_MASS_NONE); }             \
+            else { CALL(HMCX_TARGET_GAUSS_DIAG, HMCX_MASS_DIAG); }                                      \
+        }                                                                                               \
+    } while (0)
+
+int elem_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass, const float* q_in, const float* p_in,
+                  const float* eps, int C, int ld, int L, float* q_out, float* p_out, float* q_traj,
+                  float* p_traj, cudaStream_t st) {
+    ElemTarget t;
+    const int rc = fill_elem_target(target, mass, C, ld, t);
+    if (rc != HMCX_OK) return rc;
+    if (!q_in || !p_in || !eps || !q_out || !p_out || L < 1 || ((q_traj == nullptr) != (p_traj == nullptr)))
+        return HMCX_ERR_INVALID_ARG;
+    const int grid = stream_grid((size_t)C * (ld >> 2), 256);
+#define CALL(TK, MK)                                                                                    \
+    if (q_traj) leapfrog_kernel<TK, MK, true><<<grid, 256, 0, st>>>(t, q_in, p_in, eps, L, q_out, p_out, q_traj, p_traj); \
+    else leapfrog_kernel<TK, MK, false><<<grid, 256, 0, st>>>(t, q_in, p_in, eps, L, q_out, p_out, nullptr, nullptr)
+    DISPATCH_TK_MK(t, CALL);
+#undef CALL
+    return cuda_status();
+}
+
+int elem_hamiltonian(const hmcx_target_t* target, const hmcx_mass_t* mass, const float* q, const float* p, int C,
+                     int ld, float* H, uint8_t* flags, cudaStream_t st) {
+    ElemTarget t;
+    const int rc = fill_elem_target(target, mass, C, ld, t);
+    if (rc != HMCX_OK) return rc;
+    if (!q || !p || !H) return HMCX_ERR_INVALID_ARG;
+    int block = ((ld >> 2) + 31) / 32 * 32;
+    if (block > 256) block = 256;
+#define CALL(TK, MK) hamiltonian_kernel<TK, MK><<<C, block, 0, st>>>(t, q, p, H, flags)
+    DISPATCH_TK_MK(t, CALL);
+#undef CALL
+    return cuda_status();
+}
+
+int elem_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int D, int C, int ld, int64_t iter, float* p_out,
+               cudaStream_t st) {
+    if (!rng || rng->mode != HMCX_RNG_PHILOX || !p_out || iter < 0) return HMCX_ERR_INVALID_ARG;
+    hmcx_target_t dummy = {};
+    dummy.kind = HMCX_TARGET_GAUSS_ISO; dummy.dim = D;
+    ElemTarget t;
+    const int rc = fill_elem_target(&dummy, mass, C, ld, t);
+    if (rc != HMCX_OK) return rc;
+    const int grid = stream_grid((size_t)C * (ld >> 2), 256);
+    if (t.mk == HMCX_MASS_NONE) gibbs_kernel<HMCX_MASS_NONE><<<grid, 256, 0, st>>>(t, rng->seed, rng->chain_offset, (uint64_t)iter, p_out);
+    else gibbs_kernel<HMCX_MASS_DIAG><<<grid, 256, 0, st>>>(t, rng->seed, rng->chain_offset, (uint64_t)iter, p_out);
+    return cuda_status();
+}
+
+// Register-resident geometry: K float4 vectors per thread, G threads per chain (one CTA per chain).
+//   K=1: G<=1024 (<=64 regs/thread)   K=2: G<=512   K=4: G<=256      =>  D <= 4096 in every case.
+// Prefer the widest CTA (most warps per chain => most latency hiding; BASELINE configs under-fill the GPU).
+static bool pick_geometry(int ld, int& K, int& G) {
+    const int nvec = ld >> 2;
+    if (nvec > 1024) return false;
+    K = 1;
+    G = (nvec + 31) / 32 * 32;
+    return true;
+}
+
+int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                 const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int C, int ld, int L,
+                 int S, int burn, int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged,
+                 float* ham, int32_t* num_rejected, int force_k, cudaStream_t st) {
+    RunArgs a = {};
+    const int rc = fill_elem_target(target, mass, C, ld, a.t);
+    if (rc != HMCX_OK) return rc;
+    if (!rng || !q_init || !q_cur || !eps || L < 1 || S < 1 || burn < 0 || burn >= S || it0 < 0 || it1 > S || it0 > it1)
+        return HMCX_ERR_INVALID_ARG;
+    if (rng->mode == HMCX_RNG_INJECTED) {
+        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+    } else if (rng->mode != HMCX_RNG_PHILOX) {
+        return HMCX_ERR_INVALID_ARG;
+    }
+    a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_offset = rng->chain_offset;
+    a.normals = rng->normals; a.logu = rng->log_uniforms;
+    a.nuts = (nuts && nuts->enabled) ? 1 : 0;
+    if (a.nuts) {
+        if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
+        a.delta = nuts->desired_accept_rate; a.mu = nuts->mu; a.table = nuts->table;
+        a.h_bar = nuts->h_bar; a.eps_bar = nuts->eps_bar;
+    }
+    a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
+    a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
+
+    int K, G;
+    if (!pick_geometry(ld, K, G)) return HMCX_ERR_UNSUPPORTED;
+    if (force_k == 2 || force_k == 4) {          // test / tuning hook: fewer, fatter threads
+        K = force_k;
+        G = ((ld >> 2) + K - 1) / K;
+        G = (G + 31) / 32 * 32;
+    }
+#define CALL(TK, MK)                                                                                    \
+    if (K == 1) hmc_run_kernel<TK, MK, 1><<<C, G, 0, st>>>(a);                                          \
+    else if (K == 2) hmc_run_kernel<TK, MK, 2><<<C, G, 0, st>>>(a);                                     \
+    else hmc_run_kernel<TK, MK, 4><<<C, G, 0, st>>>(a)
+    DISPATCH_TK_MK(a.t, CALL);
+#undef CALL
+    return cuda_status();
+}
+
+}  // namespace hmcx

@@ -1,0 +1,275 @@
+"""Host-side driver of the sm_100a kernels: turns descriptors + torch tensors into C-ABI calls (include/hmcx.h).
+
+Everything here is plumbing -- device buffers, padding to the (C, ld) layout, the step-size adaptation table,
+the random-stream modes.  The arithmetic of the hot path lives in csrc/*.cu.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _native as N
+from . import targets as T
+
+
+# ----------------------------------------------------------------------------------------------------------
+# descriptors -> native structs (tensors are kept alive on the wrapper object)
+# ----------------------------------------------------------------------------------------------------------
+class NativeTarget:
+    def __init__(self, target, device):
+        if not T.is_target(target):
+            raise TypeError('not a hamiltorch_b200 target descriptor: %r' % (target,))
+        self.target = target
+        self.device = torch.device(device)
+        self.dim = target.dim
+        self._keep = {}
+        s = N.TargetStruct()
+        s.kind, s.dim = target.kind, target.dim
+        s.log_norm = float(getattr(target, 'log_norm', 0.0))
+        for field, attr in (('mean', 'mean'), ('inv_var', 'inv_var'), ('prec', 'prec')):
+            t = getattr(target, attr, None)
+            if t is not None:
+                t = t.detach().to(self.device, torch.float32).contiguous()
+                self._keep[field] = t
+                setattr(s, field, t.data_ptr())
+        s.funnel_inv_var_v = float(getattr(target, 'inv_var_v', 0.0))
+        self.struct = s
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+class NativeMass:
+    """inv_mass as the reference accepts it (None | (D,) | (D,D)); the mass used by gibbs is inverted ONCE with
+    the same torch ops as samplers.py:942-952 so that sqrt(mass) is bit-identical."""
+
+    def __init__(self, inv_mass, dim, device):
+        self.device = torch.device(device)
+        s = N.MassStruct()
+        self._keep = {}
+        if inv_mass is None:
+            s.kind = N.MASS_NONE
+        elif isinstance(inv_mass, list):
+            raise NotImplementedError('block-list inv_mass (samplers.py:287-292) is not supported by the B200 engine')
+        elif inv_mass.dim() == 1:
+            if inv_mass.numel() != dim:
+                raise RuntimeError('inv_mass must have %d entries' % dim)
+            im = inv_mass.detach().to(torch.float32)
+            sd = (1 / im) ** 0.5                       # mass = 1/inv_mass (:952); Normal(0, mass**0.5) (:201)
+            s.kind = N.MASS_DIAG
+            self._keep['im'] = im.to(self.device).contiguous()
+            self._keep['sd'] = sd.to(self.device).contiguous()
+            s.inv_mass = self._keep['im'].data_ptr()
+            s.mass_factor = self._keep['sd'].data_ptr()
+        elif inv_mass.dim() == 2:
+            if tuple(inv_mass.shape) != (dim, dim):
+                raise RuntimeError('inv_mass must be (%d, %d)' % (dim, dim))
+            im = inv_mass.detach().to(torch.float32)
+            mass = torch.inverse(im)                   # :950
+            tril = torch.linalg.cholesky(mass)         # MultivariateNormal(0, mass).scale_tril (:199)
+            s.kind = N.MASS_FULL
+            self._keep['im'] = im.to(self.device).contiguous()
+            self._keep['tril'] = tril.to(self.device).contiguous()
+            s.inv_mass = self._keep['im'].data_ptr()
+            s.mass_factor = self._keep['tril'].data_ptr()
+        else:
+            raise RuntimeError('inv_mass must be None, 1-D or 2-D')
+        self.struct = s
+
+    @property
+    def kind(self):
+        return self.struct.kind
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def nuts_table(burn):
+    """The five Python-double constants of samplers.py:659-671 for t = 1..burn+1 (gamma=.05, t0=10, kappa=.75)."""
+    rows = []
+    for n in range(burn + 1):
+        t = n + 1
+        w = (1 / (t + 10))
+        rows.append([1 - w, w, (t ** 0.5) / 0.05, t ** -0.75, 1 - t ** -0.75])
+    return torch.tensor(rows, dtype=torch.float64)
+
+
+def nuts_mu(step_size_init):
+    """samplers.py:664 -- fp32 log of fp32(10*eps0), returned as a Python float."""
+    return float(torch.log(10 * torch.FloatTensor([step_size_init])))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# kernel entry points on torch tensors
+# ----------------------------------------------------------------------------------------------------------
+def _as_rows(x, ld, device):
+    x = x.detach().to(device=device, dtype=torch.float32)
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    return N.pad_rows(x.contiguous(), ld)
+
+
+def _eps_vector(step_size, C, device):
+    if torch.is_tensor(step_size):
+        e = step_size.detach().to(device=device, dtype=torch.float32).reshape(-1)
+        if e.numel() == 1:
+            e = e.expand(C)
+        return e.contiguous().clone()
+    return torch.full((C,), float(step_size), dtype=torch.float32, device=device)
+
+
+def leapfrog(target, q, p, steps, step_size, inv_mass=None, return_trajectory=False, device=None):
+    """Batched samplers.leapfrog (plain HMC branch).  q, p: (C, D) or (D,).  Returns (q_L, p_L) as (C, D), or
+    the (L, C, D) trajectories when ``return_trajectory``."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    nm = NativeMass(inv_mass, D, device)
+    qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
+    Cn = qd.shape[0]
+    eps = _eps_vector(step_size, Cn, device)
+    q_out, p_out = torch.empty_like(qd), torch.empty_like(pd)
+    q_traj = p_traj = None
+    if return_trajectory:
+        q_traj = torch.empty((steps, Cn, ld), dtype=torch.float32, device=device)
+        p_traj = torch.empty_like(q_traj)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_leapfrog(nt.ref(), nm.ref(), N.ptr(qd), N.ptr(pd), N.ptr(eps), Cn, ld, int(steps),
+                               N.ptr(q_out), N.ptr(p_out), N.ptr(q_traj), N.ptr(p_traj), N.stream_ptr(device))
+    N.check(rc, 'hmcx_leapfrog')
+    if return_trajectory:
+        return q_traj[..., :D], p_traj[..., :D]
+    return q_out[:, :D], p_out[:, :D]
+
+
+def hamiltonian(target, q, p, inv_mass=None, device=None):
+    """Batched samplers.hamiltonian (sampler=HMC).  Returns (H (C,), nonfinite_flags (C,) uint8)."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    nm = NativeMass(inv_mass, D, device)
+    qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
+    Cn = qd.shape[0]
+    H = torch.empty(Cn, dtype=torch.float32, device=device)
+    flags = torch.empty(Cn, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_hamiltonian(nt.ref(), nm.ref(), N.ptr(qd), N.ptr(pd), Cn, ld, N.ptr(H), N.ptr(flags),
+                                  N.stream_ptr(device))
+    N.check(rc, 'hmcx_hamiltonian')
+    return H, flags
+
+
+def gibbs(dim, num_chains, seed, iteration=0, inv_mass=None, chain_offset=0, device='cuda'):
+    """Batched samplers.gibbs (sampler=HMC) from the in-kernel Philox stream."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device)
+    ld = N.padded_ld(dim)
+    nm = NativeMass(inv_mass, dim, device)
+    rng = N.RngStruct()
+    rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
+    p = torch.empty((num_chains, ld), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_gibbs(nm.ref(), C.byref(rng), dim, num_chains, ld, int(iteration), N.ptr(p),
+                            N.stream_ptr(device))
+    N.check(rc, 'hmcx_gibbs')
+    return p[:, :dim]
+
+
+class HMCResult:
+    """Device-resident result of a batched run."""
+
+    def __init__(self, samples, accepted, diverged, ham, step_size, num_rejected, dim, num_samples):
+        self.samples_padded = samples            # (C, S-burn, ld)
+        self.dim = dim
+        self.accepted = accepted                 # (C, S) uint8
+        self.diverged = diverged                 # (C, S) uint8
+        self.ham = ham                           # (C, S, 2) or None
+        self.step_size = step_size               # (C,) final per-chain eps
+        self.num_rejected = num_rejected         # (C,) int32
+        self.num_samples = num_samples
+
+    @property
+    def samples(self):
+        return self.samples_padded[..., :self.dim]
+
+    @property
+    def accept_rate(self):
+        return 1.0 - self.num_rejected.double() / self.num_samples
+
+
+def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, inv_mass=None,
+            nuts=False, desired_accept_rate=0.8, seed=0, chain_offset=0, normals=None, log_uniforms=None,
+            record_ham=False, out=None, device=None, tuning=0):
+    """The reference's sample() loop for sampler in {HMC, HMC_NUTS} as one persistent kernel over C chains.
+
+    params_init (C, D) | (D,).  Randomness: in-kernel Philox keyed by (seed, chain_offset+c, iteration), or -- when
+    ``normals`` (S, C, D) and ``log_uniforms`` (S, C) are given -- the injected stream (parity mode).
+    ``out``: optional pre-allocated (C, S-burn, ld) fp32 device tensor for the samples.
+    """
+    N.require_cuda()
+    lib = N.load_library()
+    if device is None:
+        device = params_init.device if params_init.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    device = torch.device(device)
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    nm = inv_mass if isinstance(inv_mass, NativeMass) else NativeMass(inv_mass, D, device)
+    S, L, burn = int(num_samples), int(num_steps_per_sample), int(burn)
+    q_init = _as_rows(params_init, ld, device)
+    if q_init.shape[1] != ld or params_init.shape[-1] != D:
+        raise RuntimeError('params_init last dimension must be %d' % D)
+    Cn = q_init.shape[0]
+    q_cur = q_init.clone()
+    eps = _eps_vector(step_size, Cn, device)
+    keep = S - burn
+    if out is None:
+        samples = torch.empty((Cn, keep, ld), dtype=torch.float32, device=device)
+    else:
+        samples = out
+        if tuple(samples.shape) != (Cn, keep, ld) or samples.dtype != torch.float32 or not samples.is_contiguous():
+            raise RuntimeError('out must be a contiguous fp32 (C, S-burn, ld) tensor')
+    accepted = torch.empty((Cn, S), dtype=torch.uint8, device=device)
+    diverged = torch.empty((Cn, S), dtype=torch.uint8, device=device)
+    ham = torch.empty((Cn, S, 2), dtype=torch.float32, device=device) if record_ham else None
+    num_rejected = torch.zeros(Cn, dtype=torch.int32, device=device)
+
+    rng = N.RngStruct()
+    keep_alive = []
+    if normals is not None:
+        z = normals.detach().to(device=device, dtype=torch.float32)
+        if z.dim() == 2:
+            z = z.unsqueeze(1)
+        if tuple(z.shape[:2]) != (S, Cn) or z.shape[2] != D:
+            raise RuntimeError('normals must be (S, C, D)')
+        z = N.pad_rows(z.contiguous(), ld)
+        lu = log_uniforms.detach().to(device=device, dtype=torch.float32).reshape(S, Cn).contiguous()
+        rng.mode = N.RNG_INJECTED
+        rng.normals, rng.log_uniforms = z.data_ptr(), lu.data_ptr()
+        keep_alive += [z, lu]
+    else:
+        rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
+
+    nuts_s = N.NutsStruct()
+    if nuts:
+        table = nuts_table(burn).to(device)
+        h_bar = torch.zeros(Cn, dtype=torch.float64, device=device)
+        eps_bar = torch.ones(Cn, dtype=torch.float64, device=device)
+        nuts_s.enabled = 1
+        nuts_s.desired_accept_rate = float(desired_accept_rate)
+        nuts_s.mu = nuts_mu(step_size if not torch.is_tensor(step_size) else float(step_size.reshape(-1)[0]))
+        nuts_s.table, nuts_s.h_bar, nuts_s.eps_bar = table.data_ptr(), h_bar.data_ptr(), eps_bar.data_ptr()
+        keep_alive += [table, h_bar, eps_bar]
+
+    with torch.cuda.device(device):
+        rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
+                              N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),
+                              N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.stream_ptr(device))
+    N.check(rc, 'hmcx_hmc_run')
+    res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
+    res._keep_alive = keep_alive          # buffers the asynchronous kernel still reads
+    return res

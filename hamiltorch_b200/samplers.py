@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's sampler surface (hamiltorch/samplers.py) on top of the sm_100a kernels.
+
+Same names, argument order, defaults and error behaviour as the reference for the hot path:
+``sample`` (samplers.py:850), ``leapfrog`` (:205), ``hamiltonian`` (:738), ``gibbs`` (:152), ``acceptance``
+(:609), ``adaptation`` (:629) and the ``Sampler`` / ``Integrator`` / ``Metric`` enums (:11-31).
+
+What differs by design
+  * ``log_prob_func`` must be a target descriptor from ``hamiltorch_b200.targets`` (or the list of split
+    descriptors ``define_split_model_log_prob`` builds): an opaque Python callable cannot enter a CUDA kernel
+    and there is no CPU fallback -> ``TypeError``.
+  * the work runs on the current CUDA device whatever ``params_init.device`` is; results are returned on
+    ``params_init.device`` so CPU-tensor user code keeps working.
+  * extra keyword-only arguments (``rng``, ``seed``) select the random stream; ``sample_chains`` is the batched
+    many-chains entry (the engine's native shape), ``sample`` is the one-chain drop-in.
+"""
+from enum import Enum
+
+import torch
+
+from . import engine
+from . import targets as T
+from . import util
+
+
+class Sampler(Enum):          # samplers.py:11-14
+    HMC = 1
+    RMHMC = 2
+    HMC_NUTS = 3
+
+
+class Integrator(Enum):       # samplers.py:19-25
+    EXPLICIT = 1
+    IMPLICIT = 2
+    S3 = 3
+    SPLITTING = 4
+    SPLITTING_RAND = 5
+    SPLITTING_KMID = 6
+
+
+class Metric(Enum):           # samplers.py:28-31
+    HESSIAN = 1
+    SOFTABS = 2
+    JACOBIAN_DIAG = 3
+
+
+_SPLIT_INTEGRATORS = (Integrator.SPLITTING, Integrator.SPLITTING_RAND, Integrator.SPLITTING_KMID)
+
+
+def _require_target(log_prob_func):
+    if isinstance(log_prob_func, list):
+        if not all(T.is_target(f) for f in log_prob_func):
+            raise TypeError('every element of a split log_prob_func list must be a hamiltorch_b200 target')
+        return
+    if not T.is_target(log_prob_func):
+        raise TypeError(
+            'hamiltorch_b200 runs the leapfrog loop inside a CUDA kernel and cannot call an opaque Python '
+            'log_prob_func.  Pass a descriptor from hamiltorch_b200.targets (GaussianIso, GaussianDiag, '
+            'GaussianFull, Funnel) or use sample_model / sample_split_model for Bayesian NNs.  '
+            'There is no CPU fallback.')
+
+
+# ----------------------------------------------------------------------------------------------------------
+# small pieces of the reference surface
+# ----------------------------------------------------------------------------------------------------------
+def acceptance(h_old, h_new):
+    """samplers.py:609-626: log acceptance ratio as a Python float."""
+    return float(-h_new + h_old)
+
+
+def adaptation(rho, t, step_size_init, H_t, eps_bar, desired_accept_rate=0.8):
+    """samplers.py:629-674, host restatement used only for API completeness (the in-kernel version is what the
+    sampler runs).  Same mixed double / fp32 arithmetic."""
+    t = t + 1
+    if util.has_nan_or_inf(torch.tensor([rho])):
+        alpha = 0
+    else:
+        alpha = min(1., float(torch.exp(torch.FloatTensor([rho]))))
+    mu = float(torch.log(10 * torch.FloatTensor([step_size_init])))
+    w = 1 / (t + 10)
+    H_t = (1 - w) * H_t + w * (desired_accept_rate - alpha)
+    x_new = mu - (t ** 0.5) / 0.05 * H_t
+    step_size = float(torch.exp(torch.FloatTensor([x_new])))
+    x_new_bar = t ** -0.75 * x_new + (1 - t ** -0.75) * torch.log(torch.FloatTensor([eps_bar]))
+    eps_bar = float(torch.exp(x_new_bar))
+    return step_size, eps_bar, H_t
+
+
+def gibbs(params, sampler=Sampler.HMC, log_prob_func=None, jitter=None, normalizing_const=1., softabs_const=None,
+          mass=None, metric=Metric.HESSIAN):
+    """samplers.py:152-202 -- momentum refresh.  Drawn from torch's generator in the reference's way (this is a
+    host-side convenience; inside ``sample`` the draw happens in the kernel or is pre-drawn in bulk)."""
+    if sampler == Sampler.RMHMC:
+        raise NotImplementedError('RMHMC momentum refresh happens inside the RMHMC kernel')
+    if mass is None:
+        return torch.randn(params.shape, dtype=params.dtype, device=params.device)
+    if isinstance(mass, list):
+        raise NotImplementedError('block-list mass is not supported by the B200 engine')
+    if mass.dim() == 2:
+        return torch.distributions.MultivariateNormal(torch.zeros_like(params), mass).sample()
+    return torch.normal(torch.zeros_like(params), mass ** 0.5)
+
+
+def leapfrog(params, momentum, log_prob_func, steps=10, step_size=0.1, jitter=0.01, normalizing_const=1.,
+             softabs_const=1e6, explicit_binding_const=100, fixed_point_threshold=1e-20,
+             fixed_point_max_iterations=6, jitter_max_tries=10, inv_mass=None, ham_func=None, sampler=Sampler.HMC,
+             integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, store_on_GPU=True, debug=False, pass_grad=None):
+    """samplers.py:205-606.  Plain HMC branch on the GPU; returns ``(ret_params, ret_momenta)``: two lists of
+    ``steps`` tensors, the last momentum carrying the half-step correction (:302).  ``params`` may be (D,) as in
+    the reference or (C, D) for C chains at once."""
+    _require_target(log_prob_func)
+    if sampler == Sampler.HMC and integrator not in _SPLIT_INTEGRATORS:
+        if pass_grad is not None:
+            raise NotImplementedError('pass_grad: gradients are analytic inside the kernel')
+        q_traj, p_traj = engine.leapfrog(log_prob_func, params, momentum, steps, step_size, inv_mass=inv_mass,
+                                         return_trajectory=True)
+        if params.dim() == 1:
+            q_traj, p_traj = q_traj[:, 0], p_traj[:, 0]
+        dev = params.device
+        return [t.to(dev) for t in q_traj.unbind(0)], [t.to(dev) for t in p_traj.unbind(0)]
+    if sampler == Sampler.HMC:
+        if type(log_prob_func) is not list:
+            raise RuntimeError('For splitting log_prob_func must be list of functions')       # :466-467
+        if pass_grad is not None:
+            raise RuntimeError('Passing user-determined gradients not implemented for splitting')
+        raise NotImplementedError('stand-alone split leapfrog: use sample_split_model')
+    if sampler == Sampler.RMHMC:
+        if pass_grad is not None:
+            raise RuntimeError('Passing user-determined gradients not implemented for RMHMC')  # :310, :390-391
+        raise NotImplementedError('stand-alone RMHMC leapfrog: use sample(sampler=Sampler.RMHMC)')
+    raise NotImplementedError()
+
+
+def hamiltonian(params, momentum, log_prob_func, jitter=0.01, normalizing_const=1., softabs_const=1e6,
+                explicit_binding_const=100, inv_mass=None, ham_func=None, sampler=Sampler.HMC,
+                integrator=Integrator.EXPLICIT, metric=Metric.HESSIAN):
+    """samplers.py:738-846, sampler=HMC branch.  Raises util.LogProbError on a non-finite log-prob like the
+    reference (:783-785).  (D,) -> tensor of shape (); (C, D) -> (C,)."""
+    _require_target(log_prob_func)
+    if sampler != Sampler.HMC or isinstance(log_prob_func, list):
+        raise NotImplementedError()
+    H, flags = engine.hamiltonian(log_prob_func, params, momentum, inv_mass=inv_mass)
+    if int(flags.sum()) > 0:
+        raise util.LogProbError()
+    H = H.to(params.device)
+    return H[0] if params.dim() == 1 else H
+
+
+# ----------------------------------------------------------------------------------------------------------
+# sample()
+# ----------------------------------------------------------------------------------------------------------
+def _check_sample_args(params_init_dim_ok, num_samples, burn, sampler):
+    if not params_init_dim_ok:
+        raise RuntimeError('params_init must be a 1d tensor.')                  # :925-926
+    if burn >= num_samples:
+        raise RuntimeError('burn must be less than num_samples.')               # :928-929
+    if sampler == Sampler.HMC_NUTS and burn == 0:
+        raise RuntimeError('burn must be greater than 0 for NUTS.')             # :933-934
+
+
+def _draw_reference_stream(dim, num_samples, device):
+    """Pre-draw one chain's randoms from torch's GLOBAL generators in exactly the order the reference consumes
+    them: per iteration the momentum normals -- ``Normal(zeros_like(params),
+    ones_like(params)).sample()`` (:186, :202), i.e. the generator of params' device -- then ``torch.rand(1)`` on
+    the CPU generator (:1004).  Valid while no LogProbError occurs (that skips the iteration's rand(1))."""
+    z = torch.empty((num_samples, dim), dtype=torch.float32, device=device)
+    logu = torch.empty(num_samples, dtype=torch.float32)
+    for n in range(num_samples):
+        z[n] = torch.randn(dim, dtype=torch.float32, device=device)
+        logu[n] = torch.log(torch.rand(1))[0]
+    return z, logu
+
+
+def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, step_size=0.1, burn=0, jitter=None,
+           inv_mass=None, normalizing_const=1., softabs_const=None, explicit_binding_const=100,
+           fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, jitter_max_tries=10, sampler=Sampler.HMC,
+           integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, debug=False, desired_accept_rate=0.8,
+           store_on_GPU=True, pass_grad=None, verbose=True, *, rng='reference', seed=None):
+    """Drop-in for ``hamiltorch.sample`` (samplers.py:850-1091): ONE chain, same arguments, same return value --
+    a list of ``num_samples - burn`` detached (D,) tensors whose element 0 is ``params_init`` (:959), plus the
+    adapted step size (NUTS) or the acceptance rate when ``debug == 2`` (:1086-1089).
+
+    rng='reference' (default): the chain consumes torch's global random stream exactly like the reference, so
+        after ``set_random_seed(s)`` the returned samples equal the reference's (to fp32 summation order in the
+        Hamiltonian).  rng='philox': in-kernel counter RNG keyed by ``seed`` (default: drawn from torch's RNG).
+    """
+    _check_sample_args(params_init.dim() == 1, num_samples, burn, sampler)
+    _require_target(log_prob_func)
+    if pass_grad is not None:
+        if sampler == Sampler.RMHMC:
+            raise RuntimeError('Passing user-determined gradients not implemented for RMHMC')     # :310
+        if integrator in _SPLIT_INTEGRATORS:
+            raise RuntimeError('Passing user-determined gradients not implemented for splitting')  # :468-469
+        raise NotImplementedError('pass_grad: gradients are analytic inside the kernel')
+    res = _run_chains(log_prob_func, params_init.unsqueeze(0), num_samples, num_steps_per_sample, step_size, burn,
+                      jitter, inv_mass, softabs_const, explicit_binding_const, fixed_point_threshold,
+                      fixed_point_max_iterations, jitter_max_tries, sampler, integrator, metric,
+                      desired_accept_rate, rng=rng, seed=seed, record_ham=(debug == 1))
+    nuts = sampler == Sampler.HMC_NUTS
+    out_dev = params_init.device if store_on_GPU else torch.device('cpu')
+    samples = res.samples[0].to(out_dev)
+    ret = list(samples.unbind(0))
+    num_rejected = int(res.num_rejected[0])
+    final_eps = float(res.step_size[0])
+    if debug == 1:
+        ham = res.ham[0].cpu()
+        acc = res.accepted[0].cpu()
+        for n in range(num_samples):
+            print('Step: {}, Current Hamiltoninian: {}, Proposed Hamiltoninian: {}'.format(n, ham[n, 0], ham[n, 1]))
+            print('Accept rho: {}'.format(min(0., float(ham[n, 0] - ham[n, 1]))) if acc[n] else 'REJECT')
+    if nuts:
+        print('Final Adapted Step Size: ', final_eps)                                              # :1035
+    if verbose:
+        print('Acceptance Rate {:.2f}'.format(1 - num_rejected / num_samples))                     # :1085
+    if nuts and debug == 2:
+        return ret, final_eps
+    elif debug == 2:
+        return ret, 1 - num_rejected / num_samples
+    return ret
+
+
+def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, step_size=0.1, burn=0,
+                  jitter=None, inv_mass=None, softabs_const=None, explicit_binding_const=100,
+                  fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, jitter_max_tries=10,
+                  sampler=Sampler.HMC, integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN,
+                  desired_accept_rate=0.8, rng='philox', seed=0, chain_offset=0, normals=None, log_uniforms=None,
+                  record_ham=False, out=None):
+    """The engine's native entry: C independent chains at once.  ``params_init`` is (C, D); every chain gets the
+    reference's ``sample`` semantics.  Returns an ``engine.HMCResult`` whose ``.samples`` is (C, S-burn, D) on the
+    GPU (row c = what ``sample`` would have returned for chain c, stacked).
+
+    rng='philox'  in-kernel Philox4x32-10 keyed by (seed, chain_offset + c, iteration) -- results do not depend on
+                  how chains are sharded over GPUs.
+    rng='injected'  consume ``normals`` (S, C, D) / ``log_uniforms`` (S, C) (parity mode).
+    """
+    if params_init.dim() != 2:
+        raise RuntimeError('sample_chains: params_init must be (num_chains, D)')
+    _check_sample_args(True, num_samples, burn, sampler)
+    _require_target(log_prob_func)
+    return _run_chains(log_prob_func, params_init, num_samples, num_steps_per_sample, step_size, burn, jitter,
+                       inv_mass, softabs_const, explicit_binding_const, fixed_point_threshold,
+                       fixed_point_max_iterations, jitter_max_tries, sampler, integrator, metric,
+                       desired_accept_rate, rng=rng, seed=seed, chain_offset=chain_offset, normals=normals,
+                       log_uniforms=log_uniforms, record_ham=record_ham, out=out)
+
+
+def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_mass, softabs_const,
+                explicit_binding_const, fixed_point_threshold, fixed_point_max_iterations, jitter_max_tries,
+                sampler, integrator, metric, desired_accept_rate, rng='philox', seed=None, chain_offset=0,
+                normals=None, log_uniforms=None, record_ham=False, out=None):
+    nuts = sampler == Sampler.HMC_NUTS
+    if nuts:
+        sampler = Sampler.HMC                                                     # :932-936
+    if sampler == Sampler.HMC and integrator not in _SPLIT_INTEGRATORS:
+        if isinstance(log_prob_func, list):
+            raise NotImplementedError('a list log_prob_func needs a SPLITTING integrator')
+        D = log_prob_func.dim
+        if q0.shape[1] != D:
+            raise RuntimeError('params_init has %d entries, the target has %d' % (q0.shape[1], D))
+        if rng == 'reference':
+            if q0.shape[0] != 1:
+                raise RuntimeError("rng='reference' replays torch's global stream and is defined for one chain")
+            z, logu = _draw_reference_stream(D, num_samples, q0.device)
+            normals, log_uniforms = z.unsqueeze(1), logu.unsqueeze(1)
+        elif rng == 'injected':
+            if normals is None or log_uniforms is None:
+                raise RuntimeError("rng='injected' needs normals and log_uniforms")
+        elif rng == 'philox':
+            normals = log_uniforms = None
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)))
+        else:
+            raise ValueError('unknown rng mode %r' % (rng,))
+        return engine.hmc_run(log_prob_func, q0, num_samples, L, step_size, burn=burn, inv_mass=inv_mass, nuts=nuts,
+                              desired_accept_rate=desired_accept_rate, seed=seed or 0, chain_offset=chain_offset,
+                              normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out)
+    if sampler == Sampler.HMC:
+        if type(log_prob_func) is not list:
+            raise RuntimeError('For splitting log_prob_func must be list of functions')            # :466-467
+        raise NotImplementedError('split HMC kernel: not built yet')
+    if sampler == Sampler.RMHMC and integrator in (Integrator.EXPLICIT, Integrator.IMPLICIT):
+        raise NotImplementedError('RMHMC kernel: not built yet')
+    raise NotImplementedError()                                                                     # :606, :844

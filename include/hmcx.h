@@ -1,0 +1,146 @@
+/*
+ * hmcx.h -- C ABI of libhmcx.so, the B200 (sm_100a) batched-chain Hamiltonian Monte Carlo engine.
+ *
+ * Drop-in boundary for the hot path of AdamCobb/hamiltorch (reference, pure Python): the reference has no
+ * FFI of its own, its boundary is the Python function surface.  Each entry point below
+ * names the reference function (hamiltorch/samplers.py, file:line) whose arithmetic it replaces for a whole
+ * batch of C independent chains; hamiltorch_b200/_native.py binds them with ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only: raw DEVICE pointers + sizes + an opaque cudaStream_t (void*); the library never
+ *     allocates, never synchronises, keeps no global state; calls are re-entrant given distinct buffers.
+ *   - state arrays are fp32 row-major (C, ld): row c = chain c, ld >= D, ld % 4 == 0, 16-byte aligned,
+ *     pad elements are ignored on input and written as 0.
+ *   - return value: HMCX_OK or a negative HMCX_ERR_* code (hmcx_status_string()).  Numerical divergence is
+ *     NOT an error: like the reference's LogProbError -> reject (samplers.py:1045) it is reported per chain
+ *     and iteration in `diverged_out`.
+ *   - fp32 arithmetic follows the reference's operation order with fused multiply-add contraction disabled,
+ *     so that elementwise state is bit-identical to the reference's PyTorch-CPU path; reductions (the
+ *     Hamiltonian sums) differ from torch.dot only in summation order.
+ */
+#ifndef HMCX_H
+#define HMCX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMCX_ABI_VERSION 1
+
+/* status codes */
+#define HMCX_OK                0
+#define HMCX_ERR_INVALID_ARG  -1
+#define HMCX_ERR_UNSUPPORTED  -2
+#define HMCX_ERR_CUDA         -3
+
+/* hmcx_target_t.kind -- the log-densities the kernels can differentiate (hamiltorch_b200/targets.py) */
+#define HMCX_TARGET_GAUSS_ISO   0   /* log p = -0.5*sum(x*x) + log_norm                               */
+#define HMCX_TARGET_GAUSS_DIAG  1   /* log p = -0.5*sum((x-mean)^2*inv_var) + log_norm                 */
+#define HMCX_TARGET_GAUSS_FULL  2   /* log p = -0.5*(x-mean).P(x-mean) + log_norm                      */
+#define HMCX_TARGET_FUNNEL      3   /* Neal's funnel, notebooks/hamiltorch_log_prob_examples.ipynb c22 */
+#define HMCX_TARGET_MLP         4   /* define_model_log_prob, samplers.py:1093-1201 (regression, MLP)   */
+
+/* hmcx_mass_t.kind -- the inv_mass argument of sample()/leapfrog() (samplers.py:283-296) */
+#define HMCX_MASS_NONE  0
+#define HMCX_MASS_DIAG  1           /* inv_mass 1-D, samplers.py:296, :814, gibbs :201                 */
+#define HMCX_MASS_FULL  2           /* inv_mass 2-D, samplers.py:294, :812, gibbs :199                 */
+
+/* hmcx_rng_t.mode */
+#define HMCX_RNG_INJECTED 0         /* host supplies the reference's own random stream (parity mode)   */
+#define HMCX_RNG_PHILOX   1         /* in-kernel Philox4x32-10 keyed by (seed, chain, iteration)       */
+
+typedef struct hmcx_target {
+    int32_t kind;
+    int32_t dim;                    /* D                                                               */
+    const float* mean;              /* [D] device, GAUSS_DIAG / GAUSS_FULL (NULL = zeros)              */
+    const float* inv_var;           /* [D] device, GAUSS_DIAG                                          */
+    const float* prec;              /* [D,D] device row-major symmetric, GAUSS_FULL                    */
+    float log_norm;                 /* additive constant of log p                                      */
+    float funnel_inv_var_v;         /* FUNNEL: 1/sigma_v^2                                             */
+} hmcx_target_t;
+
+typedef struct hmcx_mass {
+    int32_t kind;
+    const float* inv_mass;          /* DIAG: [D]; FULL: [D,D] row-major                                */
+    const float* mass_factor;       /* DIAG: sqrt(1/inv_mass) [D] (gibbs :201);
+                                       FULL: lower Cholesky factor of inverse(inv_mass) [D,D] (:199)   */
+} hmcx_mass_t;
+
+typedef struct hmcx_rng {
+    int32_t mode;
+    uint64_t seed;                  /* PHILOX key                                                      */
+    uint64_t chain_offset;          /* PHILOX: global id of local chain 0 (multi-GPU sharding)         */
+    const float* normals;           /* INJECTED: standard normals [iter_end-iter_begin, C, ld]         */
+    const float* log_uniforms;      /* INJECTED: log(U) of the MH test [iter_end-iter_begin, C]        */
+} hmcx_rng_t;
+
+/* Dual-averaging step-size adaptation ("HMC_NUTS"), samplers.py:629-674, per chain.
+ * `table` holds, for t = 1..burn+1, the five Python-double constants the reference evaluates each call:
+ *   {1-1/(t+10), 1/(t+10), sqrt(t)/0.05, t^-0.75, 1-t^-0.75}            (row-major [burn+1][5], device) */
+typedef struct hmcx_nuts {
+    int32_t enabled;
+    double  desired_accept_rate;
+    double  mu;                     /* float(log(10*eps0)) evaluated in fp32 as samplers.py:664        */
+    const double* table;
+    double* h_bar;                  /* [C] in/out, running H_t (starts at 0, samplers.py:938)          */
+    double* eps_bar;                /* [C] in/out, running eps_bar (starts at 1, samplers.py:939)      */
+} hmcx_nuts_t;
+
+int         hmcx_abi_version(void);
+const char* hmcx_status_string(int status);
+
+/*
+ * hmcx_leapfrog == samplers.leapfrog, plain-HMC branch (samplers.py:269-304) for C chains at once.
+ *   q_in, p_in   [C, ld]   start state (not modified)
+ *   eps          [C]       per-chain step size
+ *   q_out, p_out [C, ld]   state after L steps, p_out with the half-step correction of :302 applied
+ *   q_traj, p_traj          optional (NULL to skip) [L, C, ld]: the L intermediate clones the reference returns
+ *                           (ret_params / ret_momenta, :299-300; p_traj[L-1] is the corrected one)
+ */
+int hmcx_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass,
+                  const float* q_in, const float* p_in, const float* eps,
+                  int32_t C, int32_t ld, int32_t L,
+                  float* q_out, float* p_out, float* q_traj, float* p_traj, void* stream);
+
+/*
+ * hmcx_hamiltonian == samplers.hamiltonian, sampler=HMC (samplers.py:779-815).
+ *   H_out [C]; flags_out [C] (optional) = 1 where log p is non-finite (the reference raises LogProbError, :783-785)
+ */
+int hmcx_hamiltonian(const hmcx_target_t* target, const hmcx_mass_t* mass,
+                     const float* q, const float* p, int32_t C, int32_t ld,
+                     float* H_out, uint8_t* flags_out, void* stream);
+
+/*
+ * hmcx_gibbs == samplers.gibbs, sampler=HMC (samplers.py:185-202), PHILOX mode only: p ~ N(0, M) for C chains
+ * and iteration index `iter` (the same stream hmcx_hmc_run consumes for that iteration).
+ */
+int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_t C, int32_t ld,
+               int64_t iter, float* p_out, void* stream);
+
+/*
+ * hmcx_hmc_run == the sample() loop (samplers.py:954-1067) for sampler in {HMC, HMC_NUTS}: per iteration
+ * gibbs -> hamiltonian -> leapfrog -> hamiltonian -> acceptance/MH -> bookkeeping (-> adaptation), as ONE
+ * persistent kernel launch that advances iterations [iter_begin, iter_end) of C chains.
+ *   q_init      [C, ld]  params_init (read only; needed again for the reference's first-post-burn-reject quirk)
+ *   q_cur       [C, ld]  in/out: current `params`; must equal q_init when iter_begin == 0
+ *   eps         [C]      in/out: per-chain step size (changes only when nuts->enabled)
+ *   samples_out [C, num_samples-burn, ld]  slot 0 = params_init (:959), slot n-burn = iteration n > burn
+ *   accept_out / diverged_out  optional [C, num_samples] (uint8); ham_out optional [C, num_samples, 2] = (H_old, H_new)
+ *   num_rejected optional [C] int32 in/out counter (:961, :1016, :1046)
+ *   tuning       0 = automatic geometry; 2 / 4 = force that many float4 vectors per thread (tests, tuning)
+ */
+int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                 const hmcx_nuts_t* nuts,
+                 const float* q_init, float* q_cur, float* eps,
+                 int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
+                 int32_t iter_begin, int32_t iter_end,
+                 float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                 int32_t* num_rejected, int32_t tuning, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMCX_H */

@@ -1,0 +1,57 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Shared definitions of the golden-fixture cases.
+
+Each case = (target descriptor, sampler arguments, per-chain seeds).  oracle/gen_golden.py runs the UNMODIFIED
+reference on them (build container only) and stores results under tests/golden/; the tests rebuild the same
+case objects from here and compare the oracle and the CUDA path with the stored results.
+"""
+import torch
+
+from hamiltorch_b200 import targets as T
+
+
+def _rand_var(dim, seed):
+    g = torch.Generator().manual_seed(seed)
+    return 0.25 + 1.5 * torch.rand(dim, generator=g)
+
+
+def plain_cases():
+    """name -> dict(target, kwargs for sample(), seeds, init)."""
+    cases = {}
+    # BASELINE config 1: notebooks/hamiltorch_log_prob_examples.ipynb cells 6, 9 (diag Gaussian, sigma=.5,1,2)
+    cases['cfg1_gauss3'] = dict(
+        target=T.GaussianDiag(torch.zeros(3), torch.tensor([.5, 1., 2.]) ** 2),
+        kw=dict(num_samples=400, num_steps_per_sample=5, step_size=0.3, burn=0),
+        seeds=[123], init='zeros')
+    # small twin of BASELINE config 2 (D=1024 in the live GPU tests; D=256 keeps the fixture small)
+    cases['iso256'] = dict(
+        target=T.GaussianIso(256),
+        kw=dict(num_samples=30, num_steps_per_sample=10, step_size=0.05, burn=0),
+        seeds=[0, 1, 2], init='randn0.1')
+    # diagonal inv_mass + burn: exercises gibbs :201, drift :296, kinetic :814 and the burn bookkeeping
+    var = _rand_var(48, 7)
+    cases['diag48_mass'] = dict(
+        target=T.GaussianDiag(torch.linspace(-1, 1, 48), var),
+        kw=dict(num_samples=60, num_steps_per_sample=8, step_size=0.35, burn=10, inv_mass=var.clone()),
+        seeds=[11, 12], init='randn0.1')
+    # low acceptance: large step so that rejections (incl. the first-post-burn quirk) are exercised
+    cases['diag16_rejects'] = dict(
+        target=T.GaussianDiag(torch.zeros(16), _rand_var(16, 3)),
+        kw=dict(num_samples=80, num_steps_per_sample=3, step_size=0.9, burn=5),
+        seeds=[5, 6, 7], init='randn0.1')
+    # small twin of BASELINE config 5: HMC_NUTS step-size adaptation
+    cases['nuts_iso128'] = dict(
+        target=T.GaussianIso(128),
+        kw=dict(num_samples=60, num_steps_per_sample=10, step_size=0.1, burn=40, nuts=True,
+                desired_accept_rate=0.8),
+        seeds=[21, 22], init='randn0.1')
+    return cases
+
+
+def make_init(kind, dim, seed):
+    """multi_chain convention (util.py:386-389): manual_seed(seed) then the prior draw, then sample()."""
+    torch.manual_seed(seed)
+    if kind == 'zeros':
+        return torch.zeros(dim)
+    if kind == 'randn0.1':
+        return 0.1 * torch.randn(dim)
+    raise ValueError(kind)

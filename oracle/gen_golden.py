@@ -1,0 +1,119 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden
+
+For every case in oracle/cases.py and every chain seed it
+  1. runs ``hamiltorch.sample`` (the reference) with torch seeded as util.setup_chain does (util.py:386-389),
+  2. replays the same seed through the oracle and ASSERTS the oracle's chain is bit-identical to the
+     reference's (this is what pins the oracle),
+  3. stores: the reference samples, the pre-drawn random stream the reference consumed (standard normals and
+     log-uniforms), and the per-iteration accept flags / Hamiltonians / step sizes, which the
+     reference computes but does not return (taken from the bit-identical oracle replay).
+It also stores the reference's own hot-path unit test (tests/test_util.py:97-110) as a trajectory fixture.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import cases, hmc_oracle as O          # noqa: E402
+from oracle.ref_import import import_reference     # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def run_plain_case(ref, name, case):
+    tgt, kw, dim = case['target'], dict(case['kw']), case['target'].dim
+    nuts = kw.pop('nuts', False)
+    S = kw['num_samples']
+    out = {}
+    for ci, seed in enumerate(case['seeds']):
+        init = cases.make_init(case['init'], dim, seed)
+        ref_kw = dict(kw)
+        if nuts:
+            ref_kw['sampler'] = ref.Sampler.HMC_NUTS
+        samples, extra = ref.sample(log_prob_func=tgt, params_init=init, debug=2, verbose=False, **ref_kw)
+        samples = torch.stack(samples)
+        # oracle replay from the same RNG state
+        init2 = cases.make_init(case['init'], dim, seed)
+        assert torch.equal(init, init2)
+        okw = dict(kw)
+        res = O.sample_hmc(tgt, init2, nuts=nuts, **okw)
+        osamples = torch.stack(res['samples'])
+        assert osamples.shape == samples.shape, (name, osamples.shape, samples.shape)
+        assert torch.equal(osamples, samples), '%s seed %d: oracle != reference (max abs %g)' % (
+            name, seed, (osamples - samples).abs().max())
+        if nuts:
+            assert extra == res['step_size'], (extra, res['step_size'])
+        else:
+            assert abs(extra - (1 - res['num_rejected'] / S)) < 1e-12
+        # the stream the reference consumed
+        torch.manual_seed(seed)
+        cases.make_init(case['init'], dim, seed)
+        z = torch.empty(S, dim)
+        logu = torch.empty(S)
+        for n in range(S):
+            z[n] = torch.randn(dim)
+            logu[n] = torch.log(torch.rand(1))[0]
+        assert not any(res['diverged'])
+        # and check that the oracle driven by the injected stream is again identical
+        res2 = O.sample_hmc(tgt, init2, nuts=nuts, normals=z, log_uniforms=logu, **okw)
+        assert torch.equal(torch.stack(res2['samples']), samples)
+        out['init_%d' % ci] = init.numpy()
+        out['samples_%d' % ci] = samples.numpy()
+        out['z_%d' % ci] = z.numpy()
+        out['logu_%d' % ci] = logu.numpy()
+        out['accepted_%d' % ci] = np.array(res['accepted'], dtype=np.uint8)
+        out['ham_old_%d' % ci] = np.array(res['ham_old'], dtype=np.float64)
+        out['ham_new_%d' % ci] = np.array(res['ham_new'], dtype=np.float64)
+        out['step_sizes_%d' % ci] = np.array(res['step_sizes'], dtype=np.float64)
+        out['final_step_size_%d' % ci] = np.float64(res['step_size'])
+    out['seeds'] = np.array(case['seeds'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, {k: v.shape for k, v in out.items() if k.startswith('samples')})
+
+
+def run_reversibility(ref):
+    """tests/test_util.py:97-110 -- the only hot-path test the reference owns."""
+    from hamiltorch_b200 import targets as T
+    var = torch.tensor([.10, .10])
+    tgt = T.GaussianDiag(torch.zeros(2), var)
+
+    def ref_log_prob(omega):     # the reference test's own closure
+        return torch.distributions.MultivariateNormal(torch.zeros(2), torch.diag(var)).log_prob(omega).sum()
+
+    q0 = torch.tensor([1., 1.])
+    p0 = torch.tensor([1., 1.])
+    inv_mass = torch.tensor([1., 1.])
+    kw = dict(steps=100, step_size=0.1, inv_mass=inv_mass, sampler=ref.Sampler.HMC,
+              integrator=ref.Integrator.EXPLICIT)
+    out = {}
+    for tag, lp in (('desc', tgt), ('mvn', ref_log_prob)):
+        qf, pf = ref.samplers.leapfrog(q0, p0, lp, **kw)
+        qb, pb = ref.samplers.leapfrog(qf[-1], -pf[-1].clone(), lp, **kw)
+        out['fwd_q_' + tag] = torch.stack(qf).numpy()
+        out['fwd_p_' + tag] = torch.stack(pf).numpy()
+        out['bwd_q_' + tag] = torch.stack(qb).numpy()
+        out['bwd_p_' + tag] = torch.stack(pb).numpy()
+        print('reversibility[%s]: returns to start bitwise = %s' % (tag, bool(torch.all(qb[-1] == q0))))
+    # oracle restatement agrees with the reference on the descriptor target
+    oq, op = O.leapfrog_hmc(tgt, q0, p0, 100, 0.1, inv_mass)
+    assert np.array_equal(torch.stack(oq).numpy(), out['fwd_q_desc'])
+    assert np.array_equal(torch.stack(op).numpy(), out['fwd_p_desc'])
+    np.savez_compressed(os.path.join(OUT, 'ref_reversibility.npz'), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    ref = import_reference()
+    run_reversibility(ref)
+    for name, case in cases.plain_cases().items():
+        run_plain_case(ref, name, case)
+
+
+if __name__ == '__main__':
+    main()

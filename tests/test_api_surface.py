@@ -1,0 +1,89 @@
+"""CPU: the host-side mirror keeps the reference's names, signatures, defaults and error behaviour
+(SURVEY.md section 8b); and refuses -- loudly -- what cannot run in a kernel."""
+import inspect
+
+import pytest
+import torch
+
+import hamiltorch_b200 as hb
+from hamiltorch_b200 import targets as T
+from oracle.ref_import import reference_available, import_reference
+
+
+def test_exports():
+    for name in ('sample', 'Sampler', 'Integrator', 'Metric', 'set_random_seed'):
+        assert hasattr(hb, name)
+    for name in ('flatten', 'unflatten', 'update_model_params_in_place', 'setup_chain', 'multi_chain',
+                 'LogProbError', 'has_nan_or_inf'):
+        assert hasattr(hb.util, name)
+    assert [e.name for e in hb.Sampler] == ['HMC', 'RMHMC', 'HMC_NUTS']
+    assert [(e.name, e.value) for e in hb.Integrator] == [('EXPLICIT', 1), ('IMPLICIT', 2), ('S3', 3),
+                                                          ('SPLITTING', 4), ('SPLITTING_RAND', 5),
+                                                          ('SPLITTING_KMID', 6)]
+    assert [e.name for e in hb.Metric] == ['HESSIAN', 'SOFTABS', 'JACOBIAN_DIAG']
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference only exists in the build container')
+def test_signatures_match_reference():
+    ref = import_reference()
+    for fn in ('sample', 'leapfrog', 'hamiltonian', 'gibbs', 'acceptance', 'adaptation'):
+        rp = inspect.signature(getattr(ref.samplers, fn)).parameters
+        op = inspect.signature(getattr(hb.samplers, fn)).parameters
+        pos = [p for p in op.values() if p.kind != inspect.Parameter.KEYWORD_ONLY]
+        assert [p.name for p in pos] == list(rp), fn
+        for p in pos:
+            d, rd = p.default, rp[p.name].default
+            if isinstance(rd, type(ref.Sampler.HMC)) or hasattr(rd, 'name'):
+                assert d.name == rd.name, (fn, p.name)
+            else:
+                assert d == rd, (fn, p.name)
+
+
+def test_sample_argument_errors_match_reference():
+    tgt = T.GaussianIso(4)
+    with pytest.raises(RuntimeError, match='params_init must be a 1d tensor'):
+        hb.sample(tgt, torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match='burn must be less than num_samples'):
+        hb.sample(tgt, torch.zeros(4), num_samples=5, burn=5)
+    with pytest.raises(RuntimeError, match='burn must be greater than 0 for NUTS'):
+        hb.sample(tgt, torch.zeros(4), sampler=hb.Sampler.HMC_NUTS)
+    with pytest.raises(RuntimeError, match='must be list'):
+        hb.sample(tgt, torch.zeros(4), integrator=hb.Integrator.SPLITTING, rng='philox')
+    with pytest.raises(RuntimeError, match='not implemented for RMHMC'):
+        hb.sample(tgt, torch.zeros(4), sampler=hb.Sampler.RMHMC, pass_grad=torch.zeros(4))
+
+
+def test_opaque_callable_is_refused():
+    with pytest.raises(TypeError, match='no CPU fallback'):
+        hb.sample(lambda x: -(x * x).sum(), torch.zeros(4))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_gpu_fails_loudly():
+    from hamiltorch_b200._native import NativeError
+    with pytest.raises(NativeError, match='no CPU fallback'):
+        hb.sample(T.GaussianIso(4), torch.zeros(4), verbose=False)
+
+
+def test_flatten_unflatten_roundtrip():
+    """The reference's tests/test_util.py:12-24 on our util."""
+    import torch.nn as nn
+    model = nn.Linear(4, 4)
+    flat = hb.util.flatten(model)
+    new_model = nn.Linear(4, 4)
+    hb.util.update_model_params_in_place(new_model, hb.util.unflatten(new_model, flat))
+    assert torch.all(torch.eq(flat, hb.util.flatten(new_model)))
+    assert flat.shape == (20,)
+    assert torch.equal(flat[:16].view(4, 4), model.weight)       # weight (o,i) row-major then bias
+
+
+def test_nuts_table_matches_python_doubles():
+    from hamiltorch_b200 import engine
+    tab = engine.nuts_table(3)
+    for n in range(4):
+        t = n + 1
+        assert tab[n, 0].item() == 1 - (1 / (t + 10))
+        assert tab[n, 1].item() == (1 / (t + 10))
+        assert tab[n, 2].item() == (t ** 0.5) / 0.05
+        assert tab[n, 3].item() == t ** -0.75
+        assert tab[n, 4].item() == 1 - t ** -0.75

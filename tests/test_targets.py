@@ -1,0 +1,73 @@
+"""CPU: every descriptor is a valid reference log_prob_func and its analytic gradient (the op order the CUDA
+kernels use) equals autograd's BIT FOR BIT -- the premise of trajectory-level parity."""
+import torch
+
+from hamiltorch_b200 import targets as T
+
+
+def _autograd(tgt, x):
+    x = x.detach().requires_grad_()
+    return torch.autograd.grad(tgt(x), x)[0]
+
+
+def test_gaussian_iso_grad_bitexact():
+    torch.manual_seed(0)
+    for D in (3, 17, 1024):
+        for normalized in (False, True):
+            tgt = T.GaussianIso(D, normalized=normalized)
+            x = torch.randn(D) * 3
+            assert tgt(x).dim() == 0
+            assert torch.equal(_autograd(tgt, x), tgt.grad(x))
+
+
+def test_gaussian_diag_grad_bitexact():
+    torch.manual_seed(1)
+    for D in (2, 3, 48, 1000):
+        mean = torch.randn(D)
+        var = 0.1 + 3 * torch.rand(D)
+        tgt = T.GaussianDiag(mean, var)
+        for _ in range(3):
+            x = torch.randn(D) * 2
+            assert torch.equal(_autograd(tgt, x), tgt.grad(x))
+
+
+def test_gaussian_diag_matches_torch_distribution():
+    mean = torch.tensor([0.3, -1.0, 2.0])
+    std = torch.tensor([.5, 1., 2.])
+    tgt = T.GaussianDiag(mean, std ** 2)
+    x = torch.tensor([0.1, 0.2, -0.7])
+    ref = torch.distributions.MultivariateNormal(mean, torch.diag(std ** 2)).log_prob(x)
+    assert abs(float(tgt(x)) - float(ref)) < 1e-5
+
+
+def test_gaussian_full_grad():
+    torch.manual_seed(2)
+    D = 6
+    A = torch.randn(D, D, dtype=torch.float64)
+    cov = A @ A.t() + D * torch.eye(D, dtype=torch.float64)
+    mean = torch.randn(D)
+    tgt = T.GaussianFull(mean, cov=cov)
+    x = torch.randn(D)
+    torch.testing.assert_close(_autograd(tgt, x), tgt.grad(x), rtol=1e-5, atol=1e-6)
+    ref = torch.distributions.MultivariateNormal(mean.double(), cov).log_prob(x.double())
+    assert abs(float(tgt(x)) - float(ref)) < 1e-4
+
+
+def test_funnel_matches_notebook_definition():
+    """notebooks/hamiltorch_log_prob_examples.ipynb cell 22 (with validation off)."""
+    torch.distributions.Distribution.set_default_validate_args(False)
+    D = 10
+
+    def funnel_ll(w):
+        v_dist = torch.distributions.Normal(0, 3)
+        ll = v_dist.log_prob(w[0])
+        x_dist = torch.distributions.Normal(0, torch.exp(-w[0]) ** 0.5)
+        ll += x_dist.log_prob(w[1:]).sum()
+        return ll
+
+    tgt = T.Funnel(D + 1)
+    torch.manual_seed(3)
+    for _ in range(5):
+        w = torch.randn(D + 1)
+        assert abs(float(tgt(w)) - float(funnel_ll(w))) < 1e-4 * (1 + abs(float(tgt(w))))
+        torch.testing.assert_close(_autograd(tgt, w), tgt.grad(w), rtol=1e-5, atol=1e-5)
