@@ -38,7 +38,8 @@ class RngStruct(C.Structure):
 
 class NutsStruct(C.Structure):
     _fields_ = [('enabled', C.c_int32), ('desired_accept_rate', C.c_double), ('mu', C.c_double),
-                ('table', C.c_void_p), ('h_bar', C.c_void_p), ('eps_bar', C.c_void_p)]
+                ('table', C.c_void_p), ('h_bar', C.c_void_p), ('eps_bar', C.c_void_p),
+                ('eps_schedule', C.c_void_p), ('eps_trace', C.c_void_p)]
 
 
 _PROTOS = {

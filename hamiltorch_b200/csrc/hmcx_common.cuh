@@ -78,8 +78,53 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Sum N values over the CTA.  `sbuf` holds 32*N floats; callers alternate between two buffers on consecutive
-// calls so that a single __syncthreads() per call suffices.
+// Three sums over a warp with a packed butterfly: 9 shuffles instead of 15.  After the xor-16 / xor-8 exchange
+// lanes [0,8) own a, [8,16) own b, [16,24) own c; three more levels finish each, then the totals are broadcast, so
+// every lane returns the same bits.
+__device__ __forceinline__ void warp_sum3(float& a, float& b, float& c, bool broadcast) {
+    const int lane = threadIdx.x & 31;
+    const bool h16 = lane & 16, h8 = lane & 8;
+    float k0 = h16 ? c : a, k1 = h16 ? 0.0f : b;
+    const float s0 = h16 ? a : c, s1 = h16 ? b : 0.0f;
+    k0 = add(k0, __shfl_xor_sync(0xffffffffu, s0, 16));
+    k1 = add(k1, __shfl_xor_sync(0xffffffffu, s1, 16));
+    float k = h8 ? k1 : k0;
+    const float s = h8 ? k0 : k1;
+    k = add(k, __shfl_xor_sync(0xffffffffu, s, 8));
+    k = add(k, __shfl_xor_sync(0xffffffffu, k, 4));
+    k = add(k, __shfl_xor_sync(0xffffffffu, k, 2));
+    k = add(k, __shfl_xor_sync(0xffffffffu, k, 1));
+    if (broadcast) {
+        a = __shfl_sync(0xffffffffu, k, 0);
+        b = __shfl_sync(0xffffffffu, k, 8);
+        c = __shfl_sync(0xffffffffu, k, 16);
+    } else {
+        a = k;          // valid in lane 0 (a), lane 8 (b), lane 16 (c)
+    }
+}
+
+// Sum 3 values over the CTA and hand every thread one extra scalar produced by thread 0 (`extra`, e.g. the
+// iteration's log-uniform) through the same shared buffer and the same single barrier.
+// `sbuf` holds 3*32+1 floats; callers alternate between two buffers on consecutive calls.
+__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float& extra, float* sbuf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    if (nwarp == 1) {
+        warp_sum3(a, b, c, true);
+        extra = __shfl_sync(0xffffffffu, extra, 0);
+        return;
+    }
+    warp_sum3(a, b, c, false);
+    if ((lane & 7) == 0 && lane < 24) sbuf[(lane >> 3) * 32 + warp] = a;
+    if (threadIdx.x == 0) sbuf[96] = extra;
+    __syncthreads();
+    a = lane < nwarp ? sbuf[lane] : 0.0f;
+    b = lane < nwarp ? sbuf[32 + lane] : 0.0f;
+    c = lane < nwarp ? sbuf[64 + lane] : 0.0f;
+    extra = sbuf[96];
+    warp_sum3(a, b, c, true);
+}
+
+// Sum N values over the CTA (generic, used off the hot loop).  `sbuf` holds 32*N floats.
 template <int N>
 __device__ __forceinline__ void block_sum(float (&v)[N], float* sbuf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;

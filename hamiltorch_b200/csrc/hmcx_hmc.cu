@@ -86,7 +86,7 @@ __device__ __forceinline__ void trajectory4(float q[4], float p[4], const VecCon
         g[j] = grad1<TK>(q[j], c.mean[j], c.ivar[j]);
         p[j] = add(p[j], mul(half, g[j]));                                   // :281
     }
-    for (int l = 0; l < L; ++l) {
+    auto one_step = [&](int l) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             q[j] = drift1<MK>(q[j], eps, c.im[j], p[j]);                     // :284 / :296
@@ -99,7 +99,10 @@ __device__ __forceinline__ void trajectory4(float q[4], float p[4], const VecCon
                 st4_stream(p_traj + (size_t)l * traj_stride, p);
             }
         }
-    }
+    };
+    int l = 0;
+    for (; l + 2 <= L; l += 2) { one_step(l); one_step(l + 1); }             // halve the loop overhead
+    if (l < L) one_step(l);
 #pragma unroll
     for (int j = 0; j < 4; ++j) p[j] = sub(p[j], mul(half, g[j]));           // :302
     if (TRAJ) {
@@ -124,6 +127,8 @@ struct RunArgs {
     const double* table;
     double* h_bar;
     double* eps_bar;
+    const float* eps_schedule;   // [S, C] teacher forcing (parity tests), may be null
+    float* eps_trace;            // [C, S] the kernel's own step size for iteration n+1, may be null
     // state / outputs
     const float* q_init;
     float* q_cur;
@@ -139,7 +144,7 @@ struct RunArgs {
 template <int TK, int MK, int K>
 __global__ void __launch_bounds__(K == 1 ? 1024 : (K == 2 ? 512 : 256))
 hmc_run_kernel(const RunArgs a) {
-    __shared__ float s_red[2][32 * 3];
+    __shared__ float s_red[2][100];
     __shared__ float s_eps[2];
 
     const int c = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
@@ -189,6 +194,7 @@ hmc_run_kernel(const RunArgs a) {
     }
 
     for (int n = a.it0; n < a.it1; ++n) {
+        if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
         const float half = mul(0.5f, eps);
         // ---- gibbs (:969): p = z (*sqrt(mass)) ----
         float kin0 = 0.0f;
@@ -215,24 +221,27 @@ hmc_run_kernel(const RunArgs a) {
         for (int k = 0; k < K; ++k)
             trajectory4<TK, MK, false>(q[k], p[k], vc[k], eps, half, a.L, nullptr, nullptr, 0);
         // ---- both Hamiltonians with one fused reduction (:971, :995) ----
-        float r[3] = {kin0, 0.0f, 0.0f};
+        float r0 = kin0, r1 = 0.0f, r2 = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                r[1] = add(r[1], uterm1<TK>(q[k][j], vc[k].mean[j], vc[k].ivar[j]));
-                r[2] = add(r[2], kterm1<MK>(p[k][j], vc[k].im[j]));
+                r1 = add(r1, uterm1<TK>(q[k][j], vc[k].mean[j], vc[k].ivar[j]));
+                r2 = add(r2, kterm1<MK>(p[k][j], vc[k].im[j]));
             }
-        block_sum<3>(r, s_red[n & 1]);
-        const float lp_new = log_prob_from_sum(r[1], t.log_norm);
-        const float h_old = add(-lp_cur, mul(0.5f, r[0]));                   // potential + kinetic (:815)
-        const float h_new = add(-lp_new, mul(0.5f, r[2]));
+        // the iteration's log-uniform is produced once (thread 0) and rides the reduction's shared buffer
+        float logu = 0.0f;
+        if (tid == 0)
+            logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * t.C + c]
+                                                     : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        block_sum3(r0, r1, r2, logu, s_red[n & 1]);
+        const float lp_new = log_prob_from_sum(r1, t.log_norm);
+        const float h_old = add(-lp_cur, mul(0.5f, r0));                     // potential + kinetic (:815)
+        const float h_new = add(-lp_new, mul(0.5f, r2));
         const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);            // LogProbError (:783-785)
         // ---- MH (:1000-1004) ----
         const float x = add(-h_new, h_old);                                  // acceptance(), :626
         const float rho = (x < 0.0f) ? x : 0.0f;                             // Python min(0., x): nan -> 0.
-        const float logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * t.C + c]
-                                                             : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
         const bool acc = !bad && (rho >= logu);
         if (acc) {
             lp_cur = lp_new;
@@ -289,9 +298,12 @@ hmc_run_kernel(const RunArgs a) {
                 }
                 if (n == a.burn) e = (float)eps_bar;                          // freeze (:1033-1034)
                 s_eps[n & 1] = e;
+                if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = e;
             }
             __syncthreads();
             eps = s_eps[n & 1];
+        } else if (a.eps_trace && tid == 0) {
+            a.eps_trace[(size_t)c * a.S + n] = eps;
         }
     }
 
@@ -499,6 +511,7 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
         if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
         a.delta = nuts->desired_accept_rate; a.mu = nuts->mu; a.table = nuts->table;
         a.h_bar = nuts->h_bar; a.eps_bar = nuts->eps_bar;
+        a.eps_schedule = nuts->eps_schedule; a.eps_trace = nuts->eps_trace;
     }
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;

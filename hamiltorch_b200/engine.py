@@ -204,12 +204,14 @@ class HMCResult:
 
 def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, inv_mass=None,
             nuts=False, desired_accept_rate=0.8, seed=0, chain_offset=0, normals=None, log_uniforms=None,
-            record_ham=False, out=None, device=None, tuning=0):
+            record_ham=False, out=None, device=None, tuning=0, eps_schedule=None, record_eps=False):
     """The reference's sample() loop for sampler in {HMC, HMC_NUTS} as one persistent kernel over C chains.
 
     params_init (C, D) | (D,).  Randomness: in-kernel Philox keyed by (seed, chain_offset+c, iteration), or -- when
     ``normals`` (S, C, D) and ``log_uniforms`` (S, C) are given -- the injected stream (parity mode).
     ``out``: optional pre-allocated (C, S-burn, ld) fp32 device tensor for the samples.
+    NUTS only: ``eps_schedule`` (S, C) forces the step size of every iteration (parity tests replay the reference's
+    schedule); ``record_eps`` returns the kernel's own adapted step sizes in ``result.eps_trace`` (C, S).
     """
     N.require_cuda()
     lib = N.load_library()
@@ -255,6 +257,7 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
         rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
 
     nuts_s = N.NutsStruct()
+    eps_trace = None
     if nuts:
         table = nuts_table(burn).to(device)
         h_bar = torch.zeros(Cn, dtype=torch.float64, device=device)
@@ -264,6 +267,13 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
         nuts_s.mu = nuts_mu(step_size if not torch.is_tensor(step_size) else float(step_size.reshape(-1)[0]))
         nuts_s.table, nuts_s.h_bar, nuts_s.eps_bar = table.data_ptr(), h_bar.data_ptr(), eps_bar.data_ptr()
         keep_alive += [table, h_bar, eps_bar]
+        if eps_schedule is not None:
+            sched = eps_schedule.detach().to(device=device, dtype=torch.float32).reshape(S, Cn).contiguous()
+            nuts_s.eps_schedule = sched.data_ptr()
+            keep_alive.append(sched)
+        if record_eps:
+            eps_trace = torch.zeros((Cn, S), dtype=torch.float32, device=device)
+            nuts_s.eps_trace = eps_trace.data_ptr()
 
     with torch.cuda.device(device):
         rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
@@ -271,5 +281,8 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
                               N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.stream_ptr(device))
     N.check(rc, 'hmcx_hmc_run')
     res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
+    res.eps_trace = eps_trace
+    if nuts:
+        res.eps_bar, res.h_bar = eps_bar, h_bar
     res._keep_alive = keep_alive          # buffers the asynchronous kernel still reads
     return res

@@ -87,6 +87,11 @@ typedef struct hmcx_nuts {
     const double* table;
     double* h_bar;                  /* [C] in/out, running H_t (starts at 0, samplers.py:938)          */
     double* eps_bar;                /* [C] in/out, running eps_bar (starts at 1, samplers.py:939)      */
+    const float* eps_schedule;      /* optional [num_samples, C]: use THIS step size in iteration n instead of
+                                       the adapted one ("teacher forcing": parity tests replay the reference's
+                                       schedule because adaptation amplifies fp32 summation-order noise)       */
+    float* eps_trace;               /* optional [C, num_samples]: the step size the kernel's own adaptation
+                                       yields after iteration n (i.e. for iteration n+1)                       */
 } hmcx_nuts_t;
 
 int         hmcx_abi_version(void);

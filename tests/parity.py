@@ -13,6 +13,16 @@ Tolerances (stated once, used everywhere):
 import numpy as np
 
 H_TOL_REL = 2e-6
+# dual averaging (samplers.py:629-674): fp32 exp/log (CUDA libm vs Sleef, <= 2 ulp) and the summation-order noise of
+# rho are amplified by sqrt(t)/(gamma*(t+t0)) <= ~2 into the proposed step size
+NUTS_EPS_RTOL = 2e-4
+
+
+def nuts_eps_rtol(h_scale):
+    """Tolerance on a dual-averaging step-size proposal when the Hamiltonians are of size ``h_scale``: rho is a
+    difference of two fp32 numbers of that size (ulp = 1.2e-7*h), the recursion multiplies its error by at most ~2
+    and accumulates it over the burn-in -> ~1e-6*h, floored at NUTS_EPS_RTOL."""
+    return max(NUTS_EPS_RTOL, 1e-6 * float(h_scale))
 
 
 def first_decision_mismatch(acc_a, acc_b):
