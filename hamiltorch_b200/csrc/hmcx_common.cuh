@@ -56,11 +56,30 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
     z1 = r * s;
 }
 
+// Canonical momentum stream (identical for every kernel geometry): one Philox call per float4 VECTOR of the chain
+// and per iteration; r = (x,y,z,w): elements 4v,4v+1 <- Box-Muller(x,y), elements 4v+2,4v+3 <- Box-Muller(z,w).
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t chain, uint64_t iter, uint32_t vec,
                                                float z[4]) {
     const uint4 r = philox_draw(seed, chain, iter, vec, STREAM_MOMENTUM);
     box_muller(r.x, r.y, z[0], z[1]);
     box_muller(r.z, r.w, z[2], z[3]);
+}
+// the two normals of element pair `pair` (= elements 2*pair, 2*pair+1): half of vector pair>>1
+__device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t chain, uint64_t iter, uint32_t pair,
+                                               float z[2]) {
+    const uint4 r = philox_draw(seed, chain, iter, pair >> 1, STREAM_MOMENTUM);
+    if (pair & 1) box_muller(r.z, r.w, z[0], z[1]);
+    else box_muller(r.x, r.y, z[0], z[1]);
+}
+template <int E> __device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t chain, uint64_t iter,
+                                                                uint32_t grp, float* z);
+template <> __device__ __forceinline__ void philox_normals<4>(uint64_t seed, uint64_t chain, uint64_t iter,
+                                                              uint32_t grp, float* z) {
+    philox_normal4(seed, chain, iter, grp, z);
+}
+template <> __device__ __forceinline__ void philox_normals<2>(uint64_t seed, uint64_t chain, uint64_t iter,
+                                                              uint32_t grp, float* z) {
+    philox_normal2(seed, chain, iter, grp, z);
 }
 
 __device__ __forceinline__ float philox_log_uniform(uint64_t seed, uint64_t chain, uint64_t iter) {
@@ -154,6 +173,29 @@ __device__ __forceinline__ void st4(float* p, const float v[4]) {
 }
 __device__ __forceinline__ void st4_stream(float* p, const float v[4]) {   // write-once data: evict first
     __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+
+// E-wide (E = 2 or 4) contiguous element groups
+template <int E> __device__ __forceinline__ void ldE(const float* p, float* v);
+template <> __device__ __forceinline__ void ldE<4>(const float* p, float* v) { ld4(p, v); }
+template <> __device__ __forceinline__ void ldE<2>(const float* p, float* v) {
+    const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+}
+template <int E> __device__ __forceinline__ void ldE_stream(const float* p, float* v);
+template <> __device__ __forceinline__ void ldE_stream<4>(const float* p, float* v) { ld4_stream(p, v); }
+template <> __device__ __forceinline__ void ldE_stream<2>(const float* p, float* v) {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y;
+}
+template <int E> __device__ __forceinline__ void stE(float* p, const float* v);
+template <> __device__ __forceinline__ void stE<4>(float* p, const float* v) { st4(p, v); }
+template <> __device__ __forceinline__ void stE<2>(float* p, const float* v) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+template <int E> __device__ __forceinline__ void stE_stream(float* p, const float* v);
+template <> __device__ __forceinline__ void stE_stream<4>(float* p, const float* v) { st4_stream(p, v); }
+template <> __device__ __forceinline__ void stE_stream<2>(float* p, const float* v) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
 }
 
 }  // namespace hmcx

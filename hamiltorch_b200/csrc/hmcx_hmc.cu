@@ -6,11 +6,12 @@
 //   samplers.py:185-202   (gibbs)                           samplers.py:629-674 (adaptation)
 //
 // Kernels
-//   hmc_run_kernel<TK,MK,K>  persistent: one CTA owns one chain for ALL iterations of the launch.  The chain's
-//       position, proposal and momentum live in registers (K float4 vectors per thread, D <= 4*K*blockDim), the
-//       whole L-step trajectory is thread-private for these targets, the only cross-thread traffic per iteration
-//       is ONE fused block reduction of (p0.M^-1.p0, U(q_L) terms, p_L.M^-1.p_L), and HBM sees one coalesced
-//       float4 store of the retained sample (+ one read of injected normals in parity mode).
+//   hmc_run_kernel<TK,MK,E,K>  persistent: one CTA owns one chain for ALL iterations of the launch.  The chain's
+//       position, proposal and momentum live in registers (K groups of E contiguous elements per thread,
+//       D <= E*K*blockDim), the whole L-step trajectory is thread-private for these targets, the only cross-thread
+//       traffic per iteration is ONE fused block reduction of (p0.M^-1.p0, U(q_L) terms, p_L.M^-1.p_L) that also
+//       carries the iteration's log-uniform, and HBM sees one coalesced store of the retained sample (+ one read
+//       of injected normals in parity mode).
 //   leapfrog_kernel<TK,MK>   streaming form of samplers.leapfrog for (C, ld) state arrays in HBM (grid-stride
 //       float4; 16 B/element moved once, all L steps in registers).  This is the HBM-roofline kernel.
 //   hamiltonian_kernel<TK,MK>, gibbs_kernel<MK>   the remaining stand-alone pieces of the reference surface.
@@ -28,13 +29,14 @@ struct ElemTarget {           // element-wise target + mass description, passed 
     float log_norm;
 };
 
-// per-vector constants kept in registers (dead members are eliminated for ISO / MASS_NONE)
-struct VecConst { float mean[4], ivar[4], im[4], sd[4]; };
+// per-group constants kept in registers (dead members are eliminated for ISO / MASS_NONE)
+template <int E>
+struct VecConst { float mean[E], ivar[E], im[E], sd[E]; };
 
-template <int TK, int MK>
-__device__ __forceinline__ void load_consts(const ElemTarget& t, int e0, VecConst& c) {
+template <int TK, int MK, int E>
+__device__ __forceinline__ void load_consts(const ElemTarget& t, int e0, VecConst<E>& c) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < E; ++j) {
         const bool ok = (e0 + j) < t.D;
         if (TK == HMCX_TARGET_GAUSS_DIAG) {
             c.mean[j] = (ok && t.mean) ? t.mean[e0 + j] : 0.0f;
@@ -76,27 +78,27 @@ __device__ __forceinline__ float kterm1(float p, float im) {
 // log p from the reduced sum, targets.py op order: -0.5*sum (+ log_norm)
 __device__ __forceinline__ float log_prob_from_sum(float s, float log_norm) { return add(mul(-0.5f, s), log_norm); }
 
-// One float4 vector through a whole trajectory (samplers.py:281-302).  Optionally records the L clones.
-template <int TK, int MK, bool TRAJ>
-__device__ __forceinline__ void trajectory4(float q[4], float p[4], const VecConst& c, float eps, float half,
-                                            int L, float* q_traj, float* p_traj, size_t traj_stride) {
-    float g[4];
+// One group of E elements through a whole trajectory (samplers.py:281-302).  Optionally records the L clones.
+template <int TK, int MK, int E, bool TRAJ>
+__device__ __forceinline__ void trajectory(float* q, float* p, const VecConst<E>& c, float eps, float half, int L,
+                                           float* q_traj, float* p_traj, size_t traj_stride) {
+    float g[E];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < E; ++j) {
         g[j] = grad1<TK>(q[j], c.mean[j], c.ivar[j]);
         p[j] = add(p[j], mul(half, g[j]));                                   // :281
     }
     auto one_step = [&](int l) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < E; ++j) {
             q[j] = drift1<MK>(q[j], eps, c.im[j], p[j]);                     // :284 / :296
             g[j] = grad1<TK>(q[j], c.mean[j], c.ivar[j]);                    // :297
             p[j] = add(p[j], mul(eps, g[j]));                                // :298
         }
         if (TRAJ) {
             if (l + 1 < L) {                                                 // :299-300
-                st4_stream(q_traj + (size_t)l * traj_stride, q);
-                st4_stream(p_traj + (size_t)l * traj_stride, p);
+                stE_stream<E>(q_traj + (size_t)l * traj_stride, q);
+                stE_stream<E>(p_traj + (size_t)l * traj_stride, p);
             }
         }
     };
@@ -104,10 +106,10 @@ __device__ __forceinline__ void trajectory4(float q[4], float p[4], const VecCon
     for (; l + 2 <= L; l += 2) { one_step(l); one_step(l + 1); }             // halve the loop overhead
     if (l < L) one_step(l);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) p[j] = sub(p[j], mul(half, g[j]));           // :302
+    for (int j = 0; j < E; ++j) p[j] = sub(p[j], mul(half, g[j]));           // :302
     if (TRAJ) {
-        st4_stream(q_traj + (size_t)(L - 1) * traj_stride, q);
-        st4_stream(p_traj + (size_t)(L - 1) * traj_stride, p);
+        stE_stream<E>(q_traj + (size_t)(L - 1) * traj_stride, q);
+        stE_stream<E>(p_traj + (size_t)(L - 1) * traj_stride, p);
     }
 }
 
@@ -141,8 +143,10 @@ struct RunArgs {
     int32_t* num_rejected;
 };
 
-template <int TK, int MK, int K>
-__global__ void __launch_bounds__(K == 1 ? 1024 : (K == 2 ? 512 : 256))
+constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * K <= 8 ? 512 : 256); }
+
+template <int TK, int MK, int E, int K>
+__global__ void __launch_bounds__(run_max_threads(E, K))
 hmc_run_kernel(const RunArgs a) {
     __shared__ float s_red[2][100];
     __shared__ float s_eps[2];
@@ -153,17 +157,17 @@ hmc_run_kernel(const RunArgs a) {
     const size_t row = (size_t)c * ld;
     const uint64_t chain_id = a.chain_offset + (uint64_t)c;
 
-    VecConst vc[K];
-    float qc[K][4], q[K][4], p[K][4];
-    bool live[K];                 // vector lies inside the padded row
+    VecConst<E> vc[K];
+    float qc[K][E], q[K][E], p[K][E];
+    bool live[K];                 // group lies inside the padded row
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int e0 = 4 * (tid + k * G);
+        const int e0 = E * (tid + k * G);
         live[k] = e0 < ld;
-        load_consts<TK, MK>(t, e0, vc[k]);
-        if (live[k]) ld4(a.q_cur + row + e0, qc[k]);
+        load_consts<TK, MK, E>(t, e0, vc[k]);
+        if (live[k]) ldE<E>(a.q_cur + row + e0, qc[k]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < E; ++j)
             if (!live[k] || e0 + j >= D) qc[k][j] = 0.0f;
     }
 
@@ -174,7 +178,7 @@ hmc_run_kernel(const RunArgs a) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) r[0] = add(r[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
+            for (int j = 0; j < E; ++j) r[0] = add(r[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
         block_sum<1>(r, s_red[1]);
         lp_cur = log_prob_from_sum(r[0], t.log_norm);
         __syncthreads();
@@ -190,7 +194,7 @@ hmc_run_kernel(const RunArgs a) {
     if (a.it0 == 0 && my_samples) {                // ret_params = [params_init] (:959)
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            if (live[k]) st4_stream(my_samples + 4 * (tid + k * G), qc[k]);
+            if (live[k]) stE_stream<E>(my_samples + E * (tid + k * G), qc[k]);
     }
 
     for (int n = a.it0; n < a.it1; ++n) {
@@ -200,16 +204,19 @@ hmc_run_kernel(const RunArgs a) {
         float kin0 = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int v = tid + k * G, e0 = 4 * v;
-            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            const int grp = tid + k * G, e0 = E * grp;
+            float z[E];
+#pragma unroll
+            for (int j = 0; j < E; ++j) z[j] = 0.0f;
             if (live[k]) {
-                if (a.rng_mode == HMCX_RNG_INJECTED)
-                    ld4_stream(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, z);
-                else
-                    philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)v, z);
+                if (a.rng_mode == HMCX_RNG_INJECTED) {
+                    ldE_stream<E>(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, z);
+                } else {
+                    philox_normals<E>(a.seed, chain_id, (uint64_t)n, (uint32_t)grp, z);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < E; ++j) {
                 if (e0 + j >= D) z[j] = 0.0f;
                 p[k][j] = (MK == HMCX_MASS_DIAG) ? mul(z[j], vc[k].sd[j]) : z[j];
                 kin0 = add(kin0, kterm1<MK>(p[k][j], vc[k].im[j]));
@@ -219,13 +226,13 @@ hmc_run_kernel(const RunArgs a) {
         // ---- leapfrog (:973) : thread-private ----
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            trajectory4<TK, MK, false>(q[k], p[k], vc[k], eps, half, a.L, nullptr, nullptr, 0);
+            trajectory<TK, MK, E, false>(q[k], p[k], vc[k], eps, half, a.L, nullptr, nullptr, 0);
         // ---- both Hamiltonians with one fused reduction (:971, :995) ----
         float r0 = kin0, r1 = 0.0f, r2 = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < E; ++j) {
                 r1 = add(r1, uterm1<TK>(q[k][j], vc[k].mean[j], vc[k].ivar[j]));
                 r2 = add(r2, kterm1<MK>(p[k][j], vc[k].im[j]));
             }
@@ -248,7 +255,7 @@ hmc_run_kernel(const RunArgs a) {
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) qc[k][j] = q[k][j];
+                for (int j = 0; j < E; ++j) qc[k][j] = q[k][j];
         } else {
             ++rejected;
             if (n == a.burn + 1) {
@@ -257,10 +264,10 @@ hmc_run_kernel(const RunArgs a) {
                 float s[1] = {0.0f};
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const int e0 = 4 * (tid + k * G);
-                    if (live[k]) ld4(a.q_init + row + e0, qc[k]);
+                    const int e0 = E * (tid + k * G);
+                    if (live[k]) ldE<E>(a.q_init + row + e0, qc[k]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < E; ++j) {
                         if (!live[k] || e0 + j >= D) qc[k][j] = 0.0f;
                         s[0] = add(s[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
                     }
@@ -275,7 +282,7 @@ hmc_run_kernel(const RunArgs a) {
             float* dst = my_samples + (size_t)(n - a.burn) * ld;
 #pragma unroll
             for (int k = 0; k < K; ++k)
-                if (live[k]) st4_stream(dst + 4 * (tid + k * G), qc[k]);
+                if (live[k]) stE_stream<E>(dst + E * (tid + k * G), qc[k]);
         }
         if (tid == 0) {
             const size_t o = (size_t)c * a.S + n;
@@ -310,7 +317,7 @@ hmc_run_kernel(const RunArgs a) {
     // final state for resumption
 #pragma unroll
     for (int k = 0; k < K; ++k)
-        if (live[k]) st4(a.q_cur + row + 4 * (tid + k * G), qc[k]);
+        if (live[k]) stE<E>(a.q_cur + row + E * (tid + k * G), qc[k]);
     if (tid == 0) {
         a.eps[c] = eps;
         if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
@@ -331,8 +338,8 @@ leapfrog_kernel(const ElemTarget t, const float* __restrict__ q_in, const float*
     const size_t traj_stride = (size_t)t.C * t.ld;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(v / vpr), e0 = 4 * (int)(v - (size_t)c * vpr);
-        VecConst vc;
-        load_consts<TK, MK>(t, e0, vc);
+        VecConst<4> vc;
+        load_consts<TK, MK, 4>(t, e0, vc);
         float q[4], p[4];
         ld4_stream(q_in + 4 * v, q);
         ld4_stream(p_in + 4 * v, p);
@@ -340,8 +347,8 @@ leapfrog_kernel(const ElemTarget t, const float* __restrict__ q_in, const float*
         for (int j = 0; j < 4; ++j)
             if (e0 + j >= t.D) { q[j] = 0.0f; p[j] = 0.0f; }
         const float eps = eps_c[c];
-        trajectory4<TK, MK, TRAJ>(q, p, vc, eps, mul(0.5f, eps), L, TRAJ ? q_traj + 4 * v : nullptr,
-                                  TRAJ ? p_traj + 4 * v : nullptr, traj_stride);
+        trajectory<TK, MK, 4, TRAJ>(q, p, vc, eps, mul(0.5f, eps), L, TRAJ ? q_traj + 4 * v : nullptr,
+                                    TRAJ ? p_traj + 4 * v : nullptr, traj_stride);
         st4_stream(q_out + 4 * v, q);
         st4_stream(p_out + 4 * v, p);
     }
@@ -356,8 +363,8 @@ hamiltonian_kernel(const ElemTarget t, const float* __restrict__ q, const float*
     const size_t row = (size_t)c * t.ld;
     float r[2] = {0.0f, 0.0f};
     for (int e0 = 4 * threadIdx.x; e0 < t.ld; e0 += 4 * blockDim.x) {
-        VecConst vc;
-        load_consts<TK, MK>(t, e0, vc);
+        VecConst<4> vc;
+        load_consts<TK, MK, 4>(t, e0, vc);
         float qv[4], pv[4];
         ld4_stream(q + row + e0, qv);
         ld4_stream(p + row + e0, pv);
@@ -380,18 +387,18 @@ hamiltonian_kernel(const ElemTarget t, const float* __restrict__ q, const float*
 template <int MK>
 __global__ void __launch_bounds__(256)
 gibbs_kernel(const ElemTarget t, uint64_t seed, uint64_t chain_offset, uint64_t iter, float* __restrict__ p_out) {
-    const int vpr = t.ld >> 2;
-    const size_t nvec = (size_t)t.C * vpr;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(v / vpr), vi = (int)(v - (size_t)c * vpr), e0 = 4 * vi;
-        float z[4];
-        philox_normal4(seed, chain_offset + (uint64_t)c, iter, (uint32_t)vi, z);
+    const int ppr = t.ld >> 1;                                  // element pairs per row
+    const size_t npair = (size_t)t.C * ppr;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < npair; v += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(v / ppr), pi = (int)(v - (size_t)c * ppr), e0 = 2 * pi;
+        float z[2];
+        philox_normal2(seed, chain_offset + (uint64_t)c, iter, (uint32_t)pi, z);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             if (e0 + j >= t.D) z[j] = 0.0f;
             else if (MK == HMCX_MASS_DIAG) z[j] = mul(z[j], t.sd[e0 + j]);
         }
-        st4(p_out + 4 * v, z);
+        stE<2>(p_out + 2 * v, z);
     }
 }
 
@@ -414,12 +421,16 @@ static int fill_elem_target(const hmcx_target_t* target, const hmcx_mass_t* mass
 
 static inline int cuda_status() { return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA; }
 
-static int stream_grid(size_t nvec, int block) {
+static int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+static int stream_grid(size_t nvec, int block) {
     const size_t want = (nvec + block - 1) / block;
-    const size_t cap = (size_t)sms * 8;                        // 8 resident CTAs of 256 threads per SM
+    const size_t cap = (size_t)sm_count() * 8;                 // 8 resident CTAs of 256 threads per SM
     return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
@@ -473,27 +484,34 @@ int elem_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int D, int C, int
     ElemTarget t;
     const int rc = fill_elem_target(&dummy, mass, C, ld, t);
     if (rc != HMCX_OK) return rc;
-    const int grid = stream_grid((size_t)C * (ld >> 2), 256);
+    const int grid = stream_grid((size_t)C * (ld >> 1), 256);
     if (t.mk == HMCX_MASS_NONE) gibbs_kernel<HMCX_MASS_NONE><<<grid, 256, 0, st>>>(t, rng->seed, rng->chain_offset, (uint64_t)iter, p_out);
     else gibbs_kernel<HMCX_MASS_DIAG><<<grid, 256, 0, st>>>(t, rng->seed, rng->chain_offset, (uint64_t)iter, p_out);
     return cuda_status();
 }
 
-// Register-resident geometry: K float4 vectors per thread, G threads per chain (one CTA per chain).
-//   K=1: G<=1024 (<=64 regs/thread)   K=2: G<=512   K=4: G<=256      =>  D <= 4096 in every case.
-// Prefer the widest CTA (most warps per chain => most latency hiding; BASELINE configs under-fill the GPU).
-static bool pick_geometry(int ld, int& K, int& G) {
-    const int nvec = ld >> 2;
-    if (nvec > 1024) return false;
-    K = 1;
-    G = (nvec + 31) / 32 * 32;
-    return true;
+// Register-resident geometry (one CTA per chain): each thread owns K groups of E contiguous elements.
+//   tuning 0 / 1 (auto): one float4 per thread (E=4,K=1), D <= 4096.  Measured best on B200 for BASELINE config 2
+//                    (profiles/README.md): the per-warp fixed cost of an iteration (reduction, loop, RNG for the MH test)
+//                    makes both thinner threads (E=2: 2.25 ms) and fatter threads (K=2: 2.14, K=4: 3.6 ms) slower
+//                    than float4 (1.94 ms).
+//   tuning 2 / 4: E=4 with K = 2 / 4 groups per thread;  21: E=2,K=1 (D <= 2048);  22: E=2,K=2.
+static bool pick_geometry(int ld, int tuning, int& E, int& K, int& G) {
+    if (ld > 4096) return false;
+    if (tuning == 0 || tuning == 1) { E = 4; K = 1; }
+    else if (tuning == 21) { E = 2; K = 1; }
+    else if (tuning == 2 || tuning == 4) { E = 4; K = tuning; }
+    else if (tuning == 22) { E = 2; K = 2; }
+    else return false;
+    const int groups = ld / E;
+    G = ((groups + K - 1) / K + 31) / 32 * 32;
+    return G <= run_max_threads(E, K);
 }
 
 int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
                  const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int C, int ld, int L,
                  int S, int burn, int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged,
-                 float* ham, int32_t* num_rejected, int force_k, cudaStream_t st) {
+                 float* ham, int32_t* num_rejected, int tuning, cudaStream_t st) {
     RunArgs a = {};
     const int rc = fill_elem_target(target, mass, C, ld, a.t);
     if (rc != HMCX_OK) return rc;
@@ -516,17 +534,14 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
 
-    int K, G;
-    if (!pick_geometry(ld, K, G)) return HMCX_ERR_UNSUPPORTED;
-    if (force_k == 2 || force_k == 4) {          // test / tuning hook: fewer, fatter threads
-        K = force_k;
-        G = ((ld >> 2) + K - 1) / K;
-        G = (G + 31) / 32 * 32;
-    }
+    int E, K, G;
+    if (!pick_geometry(ld, tuning, E, K, G)) return tuning ? HMCX_ERR_INVALID_ARG : HMCX_ERR_UNSUPPORTED;
 #define CALL(TK, MK)                                                                                    \
-    if (K == 1) hmc_run_kernel<TK, MK, 1><<<C, G, 0, st>>>(a);                                          \
-    else if (K == 2) hmc_run_kernel<TK, MK, 2><<<C, G, 0, st>>>(a);                                     \
-    else hmc_run_kernel<TK, MK, 4><<<C, G, 0, st>>>(a)
+    if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1><<<C, G, 0, st>>>(a);                             \
+    else if (E == 2) hmc_run_kernel<TK, MK, 2, 2><<<C, G, 0, st>>>(a);                                  \
+    else if (K == 1) hmc_run_kernel<TK, MK, 4, 1><<<C, G, 0, st>>>(a);                                  \
+    else if (K == 2) hmc_run_kernel<TK, MK, 4, 2><<<C, G, 0, st>>>(a);                                  \
+    else hmc_run_kernel<TK, MK, 4, 4><<<C, G, 0, st>>>(a)
     DISPATCH_TK_MK(a.t, CALL);
 #undef CALL
     return cuda_status();

@@ -135,7 +135,8 @@ int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_
  *   samples_out [C, num_samples-burn, ld]  slot 0 = params_init (:959), slot n-burn = iteration n > burn
  *   accept_out / diverged_out  optional [C, num_samples] (uint8); ham_out optional [C, num_samples, 2] = (H_old, H_new)
  *   num_rejected optional [C] int32 in/out counter (:961, :1016, :1046)
- *   tuning       0 = automatic geometry; 2 / 4 = force that many float4 vectors per thread (tests, tuning)
+ *   tuning       0 = automatic register geometry (= 1, one float4 per thread); 2 / 4 = that many float4 groups per
+ *                thread; 21 / 22 = one / two float2 groups per thread (tests and tuning sweeps; results never depend on it)
  */
 int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
                  const hmcx_nuts_t* nuts,

@@ -66,9 +66,10 @@ def test_golden_chain_parity(name):
             assert float(res.step_size[c]) == np.float32(case['kw']['step_size'])
 
 
-@pytest.mark.parametrize('tuning', [2, 4])
+@pytest.mark.parametrize('tuning', [2, 4, 21, 22])
 def test_register_geometry_variants_agree(tuning):
-    """K=2/4 float4 vectors per thread only change the reduction tree, never the element-wise state."""
+    """The register geometry (float2 / float4 groups, 1-4 groups per thread) only changes the reduction tree, never the
+    element-wise state -- and, in Philox mode, not the random stream either."""
     for name in ('iso256', 'diag48_mass'):
         case = cases.plain_cases()[name]
         d = np.load(os.path.join(GOLD, name + '.npz'))
@@ -76,6 +77,12 @@ def test_register_geometry_variants_agree(tuning):
         for c in range(len(case['seeds'])):
             assert np.array_equal(res.accepted[c].cpu().numpy(), d['accepted_%d' % c])
             assert np.array_equal(res.samples[c].cpu().numpy(), d['samples_%d' % c])
+    tgt = T.GaussianDiag(torch.zeros(200), torch.linspace(0.5, 2, 200))
+    init = 0.1 * torch.randn(3, 200, generator=torch.Generator().manual_seed(0))
+    kw = dict(num_samples=21, num_steps_per_sample=5, step_size=0.3, burn=2, seed=9)
+    a = engine.hmc_run(tgt, init, **kw)
+    b = engine.hmc_run(tgt, init, tuning=tuning, **kw)
+    assert torch.equal(a.accepted, b.accepted) and torch.equal(a.samples, b.samples)
 
 
 def test_leapfrog_matches_reference_trajectory_and_reverses():
