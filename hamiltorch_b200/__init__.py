@@ -7,6 +7,7 @@ fails loudly if libhmcx.so is missing or no GPU is present: there is no CPU fall
 __version__ = '0.1.0'
 
 from . import targets, util
-from .samplers import (sample, sample_chains, Sampler, Integrator, Metric, leapfrog, hamiltonian, gibbs,
-                       acceptance, adaptation)
+from .samplers import (sample, sample_chains, sample_model, sample_split_model, predict_model, Sampler, Integrator,
+                       Metric, leapfrog, hamiltonian, gibbs, acceptance, adaptation, define_model_log_prob,
+                       define_split_model_log_prob)
 from .util import set_random_seed

@@ -22,9 +22,23 @@ class NativeError(RuntimeError):
     pass
 
 
+MLP_MAX_LAYERS, MLP_MAX_SPLITS = 8, 64
+SCHEME_PLAIN, SCHEME_SPLIT_SYM, SCHEME_SPLIT_RAND, SCHEME_SPLIT_KMID = 0, 1, 2, 3
+
+
+class MlpStruct(C.Structure):
+    _fields_ = [('num_layers', C.c_int32), ('widths', C.c_int32 * (MLP_MAX_LAYERS + 1)),
+                ('activation', C.c_int32 * MLP_MAX_LAYERS), ('loss', C.c_int32), ('tau_out', C.c_float),
+                ('prior_scale', C.c_float), ('prior_two_var', C.c_float * (2 * MLP_MAX_LAYERS)),
+                ('prior_log_scale', C.c_float * (2 * MLP_MAX_LAYERS)),
+                ('prior_grad_coef', C.c_float * (2 * MLP_MAX_LAYERS)), ('x', C.c_void_p), ('y', C.c_void_p),
+                ('num_rows', C.c_int32), ('num_splits', C.c_int32), ('split_begin', C.c_int32 * (MLP_MAX_SPLITS + 1))]
+
+
 class TargetStruct(C.Structure):
     _fields_ = [('kind', C.c_int32), ('dim', C.c_int32), ('mean', C.c_void_p), ('inv_var', C.c_void_p),
-                ('prec', C.c_void_p), ('log_norm', C.c_float), ('funnel_inv_var_v', C.c_float)]
+                ('prec', C.c_void_p), ('log_norm', C.c_float), ('funnel_inv_var_v', C.c_float),
+                ('mlp', C.POINTER(MlpStruct))]
 
 
 class MassStruct(C.Structure):
@@ -33,7 +47,7 @@ class MassStruct(C.Structure):
 
 class RngStruct(C.Structure):
     _fields_ = [('mode', C.c_int32), ('seed', C.c_uint64), ('chain_offset', C.c_uint64),
-                ('normals', C.c_void_p), ('log_uniforms', C.c_void_p)]
+                ('normals', C.c_void_p), ('log_uniforms', C.c_void_p), ('perms', C.c_void_p)]
 
 
 class NutsStruct(C.Structure):
@@ -56,6 +70,14 @@ _PROTOS = {
                                C.POINTER(NutsStruct), C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'hmcx_split_run': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(MassStruct), C.POINTER(RngStruct),
+                                 C.POINTER(NutsStruct), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hmcx_grad_log_prob': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hmcx_mlp_predict': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

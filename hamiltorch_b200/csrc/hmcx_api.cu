@@ -10,6 +10,11 @@ int elem_gibbs(const hmcx_mass_t*, const hmcx_rng_t*, int, int, int, int64_t, fl
 int elem_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*,
                  float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                  int, cudaStream_t);
+int mlp_split_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, int, const float*,
+                  float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
+                  cudaStream_t);
+int mlp_grad_log_prob(const hmcx_target_t*, const float*, int, int, int, float*, float*, cudaStream_t);
+int mlp_predict(const hmcx_target_t*, const float*, int, int, float*, float*, cudaStream_t);
 }  // namespace hmcx
 
 static inline bool is_elem(const hmcx_target_t* t) {
@@ -63,7 +68,38 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
         return hmcx::elem_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
                                   num_rejected, tuning, (cudaStream_t)stream);
+    if (target->kind == HMCX_TARGET_MLP)      // un-split Bayesian NN == sample_model (samplers.py:1261)
+        return hmcx::mlp_split_run(target, mass, rng, nuts, HMCX_SCHEME_PLAIN, q_init, q_cur, eps, C, ld, L,
+                                   num_samples, burn, iter_begin, iter_end, samples_out, accept_out, diverged_out,
+                                   ham_out, num_rejected, (cudaStream_t)stream);
     return HMCX_ERR_UNSUPPORTED;
+}
+
+int hmcx_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                   const hmcx_nuts_t* nuts, int32_t scheme, const float* q_init, float* q_cur, float* eps, int32_t C,
+                   int32_t ld, int32_t L, int32_t num_samples, int32_t burn, int32_t iter_begin, int32_t iter_end,
+                   float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                   int32_t* num_rejected, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (target->kind != HMCX_TARGET_MLP) return HMCX_ERR_UNSUPPORTED;
+    return hmcx::mlp_split_run(target, mass, rng, nuts, scheme, q_init, q_cur, eps, C, ld, L, num_samples, burn,
+                               iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out, num_rejected,
+                               (cudaStream_t)stream);
+}
+
+int hmcx_grad_log_prob(const hmcx_target_t* target, const float* q, int32_t C, int32_t ld, int32_t split,
+                       float* grad_out, float* log_prob_out, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (target->kind == HMCX_TARGET_MLP)
+        return hmcx::mlp_grad_log_prob(target, q, C, ld, split, grad_out, log_prob_out, (cudaStream_t)stream);
+    return HMCX_ERR_UNSUPPORTED;
+}
+
+int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t S, int32_t ld, float* pred_out,
+                     float* log_prob_out, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (target->kind != HMCX_TARGET_MLP) return HMCX_ERR_UNSUPPORTED;
+    return hmcx::mlp_predict(target, samples, S, ld, pred_out, log_prob_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,688 @@
+// hmcx_mlp.cu -- Bayesian dense-stack (MLP) HMC on sm_100a: the BNN rows of the hot path.
+//
+//   define_model_log_prob / define_split_model_log_prob   samplers.py:1093-1258  -> mlp_log_prob(), mlp_grad_split()
+//   leapfrog SPLITTING / SPLITTING_RAND / SPLITTING_KMID  samplers.py:465-603    -> trajectory in mlp_run_kernel
+//   sample() loop around them (sample_model / sample_split_model, :1261-1466)    -> mlp_run_kernel (persistent)
+//   predict_model                                          samplers.py:1468-1562  -> mlp_predict_kernel
+//   collect_gradients (autograd) is replaced by a hand-written backward pass      -> mlp_grad_split()
+//
+// Design (round 1, fp32 SIMT; the tensor-core batched-over-chains form is the next step):
+// one CTA of 256 threads owns one chain for the whole run.  The chain's flat parameter vector q, its momentum p and
+// the split gradient g live in SHARED MEMORY in the reference's flat layout (util.py:121-136), so every weight is
+// read from smem by the GEMM loops and the leapfrog kick/drift are conflict-free element-wise passes.  A gradient
+// evaluation streams the split's data rows through in tiles of 32 rows: forward (Linear+activation per layer,
+// register micro-tiles 4x4 with interleaved columns and a per-lane k-rotation that makes the strided weight reads
+// bank-conflict-free), loss gradient, backward (dW += dZ^T A, db, dA = dZ W) accumulating straight into g.
+// Multiply-adds inside the GEMM loops use FMA: these sums have no bit-parity counterpart in the reference (its
+// sgemm order is unknowable); everything element-wise (kicks, drifts, prior, Hamiltonian assembly, MH) keeps the
+// reference's separately-rounded fp32 operation order.
+#include "hmcx_common.cuh"
+
+namespace hmcx {
+
+constexpr int MLP_THREADS = 256;
+constexpr int MLP_T = 32;                 // data rows per tile
+constexpr int MLP_RG = MLP_T / 4;         // row groups of the 4x4 micro-tiles (rows rg, rg+8, rg+16, rg+24)
+
+struct MlpDev {
+    int L, D, Dp, N, M, has_data;
+    int n[HMCX_MLP_MAX_LAYERS + 1], act[HMCX_MLP_MAX_LAYERS];
+    int woff[HMCX_MLP_MAX_LAYERS], boff[HMCX_MLP_MAX_LAYERS];
+    int aoff[HMCX_MLP_MAX_LAYERS + 1];    // smem offsets (floats, relative to the tile area) of A[l] (T x n[l])
+    int dzoff[2];                         // two delta buffers (T x maxw)
+    int tile_floats;
+    float tau_out, prior_scale, c_ll;     // c_ll = fp32(-0.5*tau_out)   (samplers.py:1184)
+    float two_var[2 * HMCX_MLP_MAX_LAYERS], log_scale[2 * HMCX_MLP_MAX_LAYERS], gcoef[2 * HMCX_MLP_MAX_LAYERS];
+    const float* x;
+    const float* y;
+    int sb[HMCX_MLP_MAX_SPLITS + 1];
+};
+
+__device__ __forceinline__ float act_fwd(float z, int a) {
+    if (a == HMCX_ACT_RELU) return z > 0.0f ? z : 0.0f;
+    if (a == HMCX_ACT_TANH) return tanhf(z);
+    if (a == HMCX_ACT_SIGMOID) return 1.0f / (1.0f + expf(-z));
+    return z;
+}
+// derivative expressed through the activation's OUTPUT (what the backward pass has at hand)
+__device__ __forceinline__ float act_bwd(float aout, int a) {
+    if (a == HMCX_ACT_RELU) return aout > 0.0f ? 1.0f : 0.0f;
+    if (a == HMCX_ACT_TANH) return 1.0f - aout * aout;
+    if (a == HMCX_ACT_SIGMOID) return aout * (1.0f - aout);
+    return 1.0f;
+}
+
+// ---- tile primitives (all 256 threads; callers place the __syncthreads) ---------------------------------------
+__device__ __forceinline__ void mlp_load_x(const MlpDev& m, float* A0, int r0, int cnt) {
+    const int n0 = m.n[0];
+    for (int i = threadIdx.x; i < MLP_T * n0; i += MLP_THREADS)
+        A0[i] = (i < cnt * n0) ? __ldg(m.x + (size_t)r0 * n0 + i) : 0.0f;
+}
+
+// Aout[T x n_out] = act(Ain[T x n_in] . W^T + b),  W row-major (n_out, n_in) in shared memory
+__device__ __forceinline__ void mlp_linear_fwd(const float* Ain, const float* W, const float* b, float* Aout,
+                                               int n_in, int n_out, int act) {
+    const int ncg = (n_out + 3) >> 2;
+    for (int tile = threadIdx.x; tile < MLP_RG * ncg; tile += MLP_THREADS) {
+        const int cg = tile % ncg, rg = tile / ncg;
+        int jc[4];
+        float acc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = cg + jj * ncg;
+            jc[jj] = j < n_out ? j : n_out - 1;
+            const float bj = b[jc[jj]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][jj] = bj;
+        }
+        int kk = cg % n_in;                                   // per-lane rotation of the reduction index
+        for (int k = 0; k < n_in; ++k) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Ain[(rg + i * MLP_RG) * n_in + kk];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) w[jj] = W[jc[jj] * n_in + kk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], w[jj], acc[i][jj]);
+            if (++kk == n_in) kk = 0;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = cg + jj * ncg;
+            if (j < n_out) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Aout[(rg + i * MLP_RG) * n_out + j] = act_fwd(acc[i][jj], act);
+            }
+        }
+    }
+}
+
+// gW[n_out x n_in] += dz^T[n_out x T] . Ain[T x n_in];   gb[n_out] += column sums of dz
+__device__ __forceinline__ void mlp_weight_grad(const float* Ain, const float* dz, float* gW, float* gb, int n_in,
+                                                int n_out) {
+    const int nkg = (n_in + 3) >> 2, njg = (n_out + 3) >> 2;
+    for (int tile = threadIdx.x; tile < njg * nkg; tile += MLP_THREADS) {
+        const int kg = tile % nkg, jg = tile / nkg;
+        int jc[4], kc[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = jg + t * njg, k = kg + t * nkg;
+            jc[t] = j < n_out ? j : n_out - 1;
+            kc[t] = k < n_in ? k : n_in - 1;
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[jj][t] = 0.0f;
+        for (int r = 0; r < MLP_T; ++r) {
+            float d[4], a[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { d[t] = dz[r * n_out + jc[t]]; a[t] = Ain[r * n_in + kc[t]]; }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[jj][t] = fmaf(d[jj], a[t], acc[jj][t]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = jg + jj * njg;
+            if (j >= n_out) continue;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int k = kg + t * nkg;
+                if (k < n_in) gW[j * n_in + k] += acc[jj][t];
+            }
+        }
+    }
+    for (int j = threadIdx.x; j < n_out; j += MLP_THREADS) {
+        float s = 0.0f;
+        for (int r = 0; r < MLP_T; ++r) s += dz[r * n_out + j];
+        gb[j] += s;
+    }
+}
+
+// dz_prev[T x n_in] = (dz[T x n_out] . W[n_out x n_in]) * act'(A[T x n_in])
+__device__ __forceinline__ void mlp_input_grad(const float* dz, const float* W, const float* A, float* dz_prev,
+                                               int n_in, int n_out, int act_prev) {
+    const int nkg = (n_in + 3) >> 2;
+    for (int tile = threadIdx.x; tile < MLP_RG * nkg; tile += MLP_THREADS) {
+        const int kg = tile % nkg, rg = tile / nkg;
+        int kc[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int k = kg + t * nkg; kc[t] = k < n_in ? k : n_in - 1; }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[i][t] = 0.0f;
+        for (int j = 0; j < n_out; ++j) {
+            float d[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = dz[(rg + i * MLP_RG) * n_out + j];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) w[t] = W[j * n_in + kc[t]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[i][t] = fmaf(d[i], w[t], acc[i][t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = kg + t * nkg;
+            if (k >= n_in) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int o = (rg + i * MLP_RG) * n_in + k;
+                dz_prev[o] = acc[i][t] * act_bwd(A[o], act_prev);
+            }
+        }
+    }
+}
+
+// forward pass of one tile; returns nothing, leaves A[0..L] in the tile area
+__device__ __forceinline__ void mlp_forward_tile(const MlpDev& m, const float* q, float* tile, int r0, int cnt) {
+    mlp_load_x(m, tile + m.aoff[0], r0, cnt);
+    __syncthreads();
+    for (int l = 0; l < m.L; ++l) {
+        mlp_linear_fwd(tile + m.aoff[l], q + m.woff[l], q + m.boff[l], tile + m.aoff[l + 1], m.n[l], m.n[l + 1],
+                       m.act[l]);
+        __syncthreads();
+    }
+}
+
+// sum of squared residuals of a forwarded tile (thread partial) and, optionally, dz_L = d ll / d out
+__device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, const float* out, float* dz, int r0, int cnt) {
+    const int nL = m.n[m.L];
+    float sse = 0.0f;
+    const float c2 = mul(m.c_ll, 2.0f);                                   // autograd: ds * (2*diff)
+    for (int i = threadIdx.x; i < MLP_T * nL; i += MLP_THREADS) {
+        float d = 0.0f;
+        if (i < cnt * nL) {
+            d = sub(out[i], __ldg(m.y + (size_t)r0 * nL + i));
+            sse = add(sse, mul(d, d));
+        }
+        if (dz) dz[i] = mul(c2, d);
+    }
+    return sse;
+}
+
+// g += d ll_split / dq over the rows [r_begin, r_end)  (g must already hold the prior part)
+__device__ __forceinline__ void mlp_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, int r_begin,
+                                                  int r_end) {
+    for (int r0 = r_begin; r0 < r_end; r0 += MLP_T) {
+        const int cnt = min(MLP_T, r_end - r0);
+        mlp_forward_tile(m, q, tile, r0, cnt);
+        float* dz = tile + m.dzoff[m.L & 1];
+        mlp_loss_tile(m, tile + m.aoff[m.L], dz, r0, cnt);
+        __syncthreads();
+        for (int l = m.L - 1; l >= 0; --l) {
+            float* dz_prev = tile + m.dzoff[l & 1];
+            mlp_weight_grad(tile + m.aoff[l], dz, g + m.woff[l], g + m.boff[l], m.n[l], m.n[l + 1]);
+            if (l > 0)
+                mlp_input_grad(dz, q + m.woff[l], tile + m.aoff[l], dz_prev, m.n[l], m.n[l + 1], m.act[l - 1]);
+            __syncthreads();
+            dz = dz_prev;
+        }
+    }
+}
+
+// prior part of the gradient: d(prior/prior_scale)/dw = -(coef_i * (2w))   (pow/div backward order)
+__device__ __forceinline__ void mlp_prior_grad(const MlpDev& m, const float* q, float* g) {
+    for (int l = 0; l < m.L; ++l) {
+        const int nw = m.n[l] * m.n[l + 1];
+        const float cw = m.gcoef[2 * l], cb = m.gcoef[2 * l + 1];
+        for (int i = threadIdx.x; i < nw; i += MLP_THREADS) g[m.woff[l] + i] = -mul(cw, mul(2.0f, q[m.woff[l] + i]));
+        for (int i = threadIdx.x; i < m.n[l + 1]; i += MLP_THREADS)
+            g[m.boff[l] + i] = -mul(cb, mul(2.0f, q[m.boff[l] + i]));
+    }
+}
+
+// g = d log p_split / dq for split s (s < 0: all rows as one potential)
+__device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, float* g, float* tile, int s) {
+    mlp_prior_grad(m, q, g);
+    __syncthreads();
+    if (m.has_data) {
+        const int rb = s < 0 ? 0 : m.sb[s], re = s < 0 ? m.N : m.sb[s + 1];
+        mlp_backprop_rows(m, q, g, tile, rb, re);
+    }
+}
+
+// l_prior = sum_i Normal(0, scale_i).log_prob(w_i).sum(), accumulated tensor by tensor (samplers.py:1153-1157)
+__device__ __forceinline__ float mlp_log_prior(const MlpDev& m, const float* q, float* sred) {
+    float l_prior = 0.0f;
+    for (int t = 0; t < 2 * m.L; ++t) {
+        const int l = t >> 1;
+        const int off = (t & 1) ? m.boff[l] : m.woff[l];
+        const int cnt = (t & 1) ? m.n[l + 1] : m.n[l] * m.n[l + 1];
+        float s[1] = {0.0f};
+        for (int i = threadIdx.x; i < cnt; i += MLP_THREADS) {
+            const float w = q[off + i];
+            // -((w - 0)**2) / (2*var) - log_scale - log(sqrt(2*pi))
+            const float v = sub(sub(__fdiv_rn(-mul(w, w), m.two_var[t]), m.log_scale[t]), 0.9189385332046727f);
+            s[0] = add(s[0], v);
+        }
+        block_sum<1>(s, sred);
+        __syncthreads();
+        l_prior = add(s[0], l_prior);
+    }
+    return l_prior;
+}
+
+// log p(q) = sum over splits of (ll_m + l_prior/prior_scale)  (hamiltonian's split loop, samplers.py:787-796);
+// with s >= 0 only that split.  Optionally writes the network outputs (predict_model).
+__device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, float* tile, float* sred, int s,
+                                              float* pred_out) {
+    const float prior_term = __fdiv_rn(mlp_log_prior(m, q, sred), m.prior_scale);
+    if (!m.has_data) return prior_term;
+    float lp = 0.0f;
+    const int s0 = s < 0 ? 0 : s, s1 = s < 0 ? m.M : s + 1;
+    for (int sp = s0; sp < s1; ++sp) {
+        float sse[1] = {0.0f};
+        for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += MLP_T) {
+            const int cnt = min(MLP_T, m.sb[sp + 1] - r0);
+            mlp_forward_tile(m, q, tile, r0, cnt);
+            sse[0] = add(sse[0], mlp_loss_tile(m, tile + m.aoff[m.L], nullptr, r0, cnt));
+            if (pred_out) {
+                const int nL = m.n[m.L];
+                for (int i = threadIdx.x; i < cnt * nL; i += MLP_THREADS)
+                    pred_out[(size_t)r0 * nL + i] = tile[m.aoff[m.L] + i];
+            }
+            __syncthreads();
+        }
+        block_sum<1>(sse, sred);
+        __syncthreads();
+        const float ll = mul(m.c_ll, sse[0]);
+        lp = (sp == s0) ? add(ll, prior_term) : add(lp, add(ll, prior_term));
+    }
+    return lp;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// persistent sample() kernel for the BNN path
+// ---------------------------------------------------------------------------------------------------------
+struct MlpRunArgs {
+    MlpDev m;
+    int scheme, mk, C, ld;
+    const float* im;
+    const float* sd;
+    int rng_mode;
+    uint64_t seed, chain_offset;
+    const float* normals;
+    const float* logu;
+    const int32_t* perms;
+    int nuts;
+    double delta, mu;
+    const double* table;
+    double* h_bar;
+    double* eps_bar;
+    const float* eps_schedule;
+    float* eps_trace;
+    const float* q_init;
+    float* q_cur;
+    float* eps;
+    int L, S, burn, it0, it1;
+    float* samples;
+    uint8_t* accept;
+    uint8_t* diverged;
+    float* ham;
+    int32_t* num_rejected;
+};
+
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float sred[64];
+    __shared__ float s_bcast[4];
+    __shared__ int s_perm[HMCX_MLP_MAX_SPLITS];
+
+    const MlpDev& m = a.m;
+    const int c = blockIdx.x, tid = threadIdx.x, D = m.D, M = m.M;
+    float* q = sm;
+    float* p = q + m.Dp;
+    float* g = p + m.Dp;
+    float* tile = g + m.Dp;
+    const size_t row = (size_t)c * a.ld;
+    const uint64_t chain_id = a.chain_offset + (uint64_t)c;
+
+    for (int i = tid; i < m.Dp; i += MLP_THREADS) { q[i] = i < D ? a.q_cur[row + i] : 0.0f; p[i] = 0.0f; g[i] = 0.0f; }
+    __syncthreads();
+    float lp_cur = mlp_log_prob(m, q, tile, sred, -1, nullptr);
+
+    float eps = a.eps[c];
+    double h_bar = 0.0, eps_bar = 1.0;
+    if (a.nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
+    int rejected = 0;
+    const int keep = a.S - a.burn;
+    float* const my_samples = a.samples ? a.samples + (size_t)c * keep * a.ld : nullptr;
+    if (a.it0 == 0 && my_samples)
+        for (int i = tid; i < a.ld; i += MLP_THREADS) my_samples[i] = i < D ? q[i] : 0.0f;
+
+    auto kinetic = [&]() {                                    // 2*K: p.p or p.(im*p)   (samplers.py:801, :814)
+        float s[1] = {0.0f};
+        for (int i = tid; i < D; i += MLP_THREADS)
+            s[0] = add(s[0], a.mk == HMCX_MASS_DIAG ? mul(p[i], mul(a.im[i], p[i])) : mul(p[i], p[i]));
+        block_sum<1>(s, sred);
+        __syncthreads();
+        return s[0];
+    };
+    auto kick = [&](float coef) {                              // momentum += coef * grad
+        for (int i = tid; i < D; i += MLP_THREADS) p[i] = add(p[i], mul(coef, g[i]));
+        __syncthreads();
+    };
+    auto drift = [&](float coef) {                             // params += coef * M^-1 momentum
+        for (int i = tid; i < D; i += MLP_THREADS)
+            q[i] = add(q[i], a.mk == HMCX_MASS_DIAG ? mul(mul(coef, a.im[i]), p[i]) : mul(coef, p[i]));
+        __syncthreads();
+    };
+
+    for (int n = a.it0; n < a.it1; ++n) {
+        if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * a.C + c];
+        const float half = mul(0.5f, eps);
+        // ---- gibbs ----
+        for (int v = tid; 4 * v < a.ld; v += MLP_THREADS) {
+            float z[4];
+            if (a.rng_mode == HMCX_RNG_INJECTED) ld4_stream(a.normals + ((size_t)(n - a.it0) * a.C + c) * a.ld + 4 * v, z);
+            else philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)v, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * v + j;
+                if (i < D) p[i] = a.mk == HMCX_MASS_DIAG ? mul(z[j], a.sd[i]) : z[j];
+            }
+        }
+        if (a.scheme == HMCX_SCHEME_SPLIT_RAND && tid == 0) {            // idx = randperm(M), once per trajectory (:550)
+            if (a.rng_mode == HMCX_RNG_INJECTED) {
+                for (int s = 0; s < M; ++s) s_perm[s] = a.perms[((size_t)(n - a.it0) * a.C + c) * M + s];
+            } else {
+                for (int s = 0; s < M; ++s) s_perm[s] = s;
+                for (int s = M - 1; s > 0; --s) {                        // Fisher-Yates on the PERM stream
+                    const uint4 r = philox_draw(a.seed, chain_id, (uint64_t)n, (uint32_t)s, STREAM_PERM);
+                    const int j = (int)(r.x % (uint32_t)(s + 1));
+                    const int t = s_perm[s]; s_perm[s] = s_perm[j]; s_perm[j] = t;
+                }
+            }
+        }
+        __syncthreads();
+        const float kin0 = kinetic();
+        // ---- trajectory ----
+        if (a.scheme == HMCX_SCHEME_PLAIN) {                              // samplers.py:281-302
+            mlp_grad_split(m, q, g, tile, -1);
+            kick(half);
+            for (int l = 0; l < a.L; ++l) {
+                drift(eps);
+                mlp_grad_split(m, q, g, tile, -1);
+                kick(eps);
+            }
+            kick(-half);                                                  // p - half*g == p + (-half)*g exactly
+        } else if (a.scheme == HMCX_SCHEME_SPLIT_SYM) {                   // :499-540
+            const float cd = (float)((double)eps / (double)((M - 1) * 2));
+            for (int l = 0; l < a.L; ++l) {
+                for (int s = 0; s < M; ++s) {
+                    mlp_grad_split(m, q, g, tile, s);
+                    kick(half);
+                    if (s < M - 1) drift(cd);
+                }
+                for (int s = M - 1; s >= 0; --s) {
+                    mlp_grad_split(m, q, g, tile, s);
+                    kick(half);
+                    if (s > 0) drift(cd);
+                }
+            }
+        } else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) {                  // :551-568
+            const float cd = (float)((double)eps / (double)M);
+            for (int l = 0; l < a.L; ++l)
+                for (int s = 0; s < M; ++s) {
+                    mlp_grad_split(m, q, g, tile, s_perm[s]);
+                    kick(half);
+                    drift(cd);
+                    mlp_grad_split(m, q, g, tile, s_perm[s]);
+                    kick(half);
+                }
+        } else {                                                          // KMID :579-598
+            for (int l = 0; l < a.L; ++l) {
+                for (int s = 0; s < M; ++s) { mlp_grad_split(m, q, g, tile, s); kick(half); }
+                drift(eps);
+                for (int s = M - 1; s >= 0; --s) { mlp_grad_split(m, q, g, tile, s); kick(half); }
+            }
+        }
+        // ---- Hamiltonians + MH ----
+        const float lp_new = mlp_log_prob(m, q, tile, sred, -1, nullptr);
+        const float kin1 = kinetic();
+        const float h_old = add(-lp_cur, mul(0.5f, kin0));
+        const float h_new = add(-lp_new, mul(0.5f, kin1));
+        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);
+        const float x = add(-h_new, h_old);
+        const float rho = (x < 0.0f) ? x : 0.0f;
+        if (tid == 0)
+            s_bcast[0] = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * a.C + c]
+                                                           : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        __syncthreads();
+        const float logu = s_bcast[0];
+        const bool acc = !bad && (rho >= logu);
+        if (acc) {
+            lp_cur = lp_new;
+            for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
+        } else {
+            ++rejected;
+            const float* src = (n == a.burn + 1) ? a.q_init : a.q_cur;    // the first-stored-iteration quirk (:1018)
+            for (int i = tid; i < D; i += MLP_THREADS) q[i] = src[row + i];
+            __syncthreads();
+            if (n == a.burn + 1) {
+                lp_cur = mlp_log_prob(m, q, tile, sred, -1, nullptr);
+                for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
+            }
+        }
+        if (n > a.burn && my_samples) {
+            float* dst = my_samples + (size_t)(n - a.burn) * a.ld;
+            for (int i = tid; i < a.ld; i += MLP_THREADS) dst[i] = i < D ? q[i] : 0.0f;
+        }
+        if (tid == 0) {
+            const size_t o = (size_t)c * a.S + n;
+            if (a.accept) a.accept[o] = acc ? 1 : 0;
+            if (a.diverged) a.diverged[o] = bad ? 1 : 0;
+            if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
+        }
+        if (a.nuts && n <= a.burn) {                                       // dual averaging, as hmc_run_kernel
+            if (tid == 0) {
+                float e = eps;
+                if (n < a.burn || bad) {
+                    const double* T = a.table + 5 * (size_t)n;
+                    const double alpha = bad ? 0.0 : (double)expf(rho);
+                    h_bar = __dadd_rn(__dmul_rn(T[0], h_bar), __dmul_rn(T[1], a.delta - alpha));
+                    const double x_new = a.mu - __dmul_rn(T[2], h_bar);
+                    e = expf((float)x_new);
+                    const float xb = add((float)__dmul_rn(T[3], x_new), mul((float)T[4], logf((float)eps_bar)));
+                    eps_bar = (double)expf(xb);
+                }
+                if (n == a.burn) e = (float)eps_bar;
+                s_bcast[1] = e;
+                if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = e;
+            }
+            __syncthreads();
+            eps = s_bcast[1];
+        } else if (a.eps_trace && tid == 0) {
+            a.eps_trace[(size_t)c * a.S + n] = eps;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.eps[c] = eps;
+        if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
+        if (a.num_rejected) a.num_rejected[c] += rejected;
+    }
+}
+
+// gradient / log-prob of C parameter vectors (collect_gradients mirror, also the unit-test hook of the backward pass)
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+mlp_grad_kernel(const MlpDev m, const float* __restrict__ qin, int ld, int split, float* __restrict__ gout,
+                float* __restrict__ lpout) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float sred[64];
+    float* q = sm;
+    float* g = q + m.Dp;
+    float* tile = g + m.Dp;
+    const size_t row = (size_t)blockIdx.x * ld;
+    for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) { q[i] = i < m.D ? qin[row + i] : 0.0f; g[i] = 0.0f; }
+    __syncthreads();
+    if (gout) {
+        mlp_grad_split(m, q, g, tile, split);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ld; i += MLP_THREADS) gout[row + i] = i < m.D ? g[i] : 0.0f;
+    }
+    if (lpout) {
+        const float lp = mlp_log_prob(m, q, tile, sred, split, nullptr);
+        if (threadIdx.x == 0) lpout[blockIdx.x] = lp;
+    }
+}
+
+// predict_model: one CTA per posterior sample
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+mlp_predict_kernel(const MlpDev m, const float* __restrict__ samples, int ld, float* __restrict__ pred,
+                   float* __restrict__ lpout) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float sred[64];
+    float* q = sm;
+    float* tile = q + m.Dp;
+    const size_t row = (size_t)blockIdx.x * ld;
+    for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) q[i] = i < m.D ? samples[row + i] : 0.0f;
+    __syncthreads();
+    float* my_pred = pred + (size_t)blockIdx.x * m.N * m.n[m.L];
+    const float lp = mlp_log_prob(m, q, tile, sred, -1, my_pred);
+    if (threadIdx.x == 0 && lpout) lpout[blockIdx.x] = lp;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
+    if (!target || target->kind != HMCX_TARGET_MLP || !target->mlp) return HMCX_ERR_INVALID_ARG;
+    const hmcx_mlp_t& h = *target->mlp;
+    if (h.num_layers < 1 || h.num_layers > HMCX_MLP_MAX_LAYERS) return HMCX_ERR_INVALID_ARG;
+    if (h.loss != HMCX_LOSS_REGRESSION) return HMCX_ERR_UNSUPPORTED;
+    if (h.activation[h.num_layers - 1] != HMCX_ACT_NONE) return HMCX_ERR_INVALID_ARG;
+    m.L = h.num_layers;
+    int off = 0, maxw = 0, aoff = 0;
+    for (int l = 0; l <= m.L; ++l) {
+        if (h.widths[l] < 1) return HMCX_ERR_INVALID_ARG;
+        m.n[l] = h.widths[l];
+        m.aoff[l] = aoff;
+        aoff += MLP_T * m.n[l];
+        if (m.n[l] > maxw) maxw = m.n[l];
+    }
+    for (int l = 0; l < m.L; ++l) {
+        m.act[l] = h.activation[l];
+        if (m.act[l] < 0 || m.act[l] > HMCX_ACT_SIGMOID) return HMCX_ERR_INVALID_ARG;
+        m.woff[l] = off; off += m.n[l] * m.n[l + 1];
+        m.boff[l] = off; off += m.n[l + 1];
+    }
+    m.D = off;
+    if (m.D != target->dim) return HMCX_ERR_INVALID_ARG;
+    m.Dp = (m.D + 3) / 4 * 4;
+    m.dzoff[0] = aoff;
+    m.dzoff[1] = aoff + MLP_T * maxw;
+    m.tile_floats = aoff + 2 * MLP_T * maxw;
+    m.tau_out = h.tau_out;
+    m.prior_scale = h.prior_scale;
+    m.c_ll = (float)(-0.5 * (double)h.tau_out);
+    for (int t = 0; t < 2 * m.L; ++t) {
+        m.two_var[t] = h.prior_two_var[t]; m.log_scale[t] = h.prior_log_scale[t]; m.gcoef[t] = h.prior_grad_coef[t];
+    }
+    m.x = h.x; m.y = h.y; m.N = h.num_rows;
+    m.has_data = (h.x != nullptr) ? 1 : 0;
+    m.M = h.num_splits;
+    if (m.M < 1 || m.M > HMCX_MLP_MAX_SPLITS) return HMCX_ERR_INVALID_ARG;
+    if (m.has_data) {
+        if (!h.y || h.num_rows < 1) return HMCX_ERR_INVALID_ARG;
+        if (h.split_begin[0] != 0 || h.split_begin[m.M] != h.num_rows) return HMCX_ERR_INVALID_ARG;
+        for (int s = 0; s <= m.M; ++s) {
+            m.sb[s] = h.split_begin[s];
+            if (s && m.sb[s] <= m.sb[s - 1]) return HMCX_ERR_INVALID_ARG;
+        }
+    } else {
+        for (int s = 0; s <= m.M; ++s) m.sb[s] = 0;
+    }
+    return HMCX_OK;
+}
+
+static inline int cuda_status() { return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA; }
+
+template <typename Kern>
+static int prepare_smem(Kern kern, size_t bytes) {
+    if (bytes > 227 * 1024) return HMCX_ERR_UNSUPPORTED;       // the chain state does not fit one SM's shared memory
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return HMCX_ERR_UNSUPPORTED;
+    }
+    return HMCX_OK;
+}
+
+int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, const hmcx_nuts_t* nuts,
+                  int scheme, const float* q_init, float* q_cur, float* eps, int C, int ld, int L, int S, int burn,
+                  int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged, float* ham,
+                  int32_t* num_rejected, cudaStream_t st) {
+    MlpRunArgs a = {};
+    int rc = fill_mlp(target, a.m);
+    if (rc != HMCX_OK) return rc;
+    const int mk = mass ? mass->kind : HMCX_MASS_NONE;
+    if (mk != HMCX_MASS_NONE && mk != HMCX_MASS_DIAG) return HMCX_ERR_UNSUPPORTED;
+    if (mk == HMCX_MASS_DIAG && (!mass->inv_mass || !mass->mass_factor)) return HMCX_ERR_INVALID_ARG;
+    if (!rng || !q_init || !q_cur || !eps || C < 1 || ld < a.m.D || (ld & 3) || L < 1 || S < 1 || burn < 0 || burn >= S ||
+        it0 < 0 || it1 > S || it0 > it1)
+        return HMCX_ERR_INVALID_ARG;
+    if (scheme < HMCX_SCHEME_PLAIN || scheme > HMCX_SCHEME_SPLIT_KMID) return HMCX_ERR_INVALID_ARG;
+    if ((scheme == HMCX_SCHEME_SPLIT_SYM || scheme == HMCX_SCHEME_SPLIT_KMID) && a.m.M < 2) return HMCX_ERR_INVALID_ARG;  // :497-498
+    if (rng->mode == HMCX_RNG_INJECTED) {
+        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+        if (scheme == HMCX_SCHEME_SPLIT_RAND && !rng->perms) return HMCX_ERR_INVALID_ARG;
+    } else if (rng->mode != HMCX_RNG_PHILOX) {
+        return HMCX_ERR_INVALID_ARG;
+    }
+    a.scheme = scheme; a.mk = mk; a.C = C; a.ld = ld;
+    a.im = mass ? mass->inv_mass : nullptr; a.sd = mass ? mass->mass_factor : nullptr;
+    a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_offset = rng->chain_offset;
+    a.normals = rng->normals; a.logu = rng->log_uniforms; a.perms = rng->perms;
+    a.nuts = (nuts && nuts->enabled) ? 1 : 0;
+    if (a.nuts) {
+        if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
+        a.delta = nuts->desired_accept_rate; a.mu = nuts->mu; a.table = nuts->table;
+        a.h_bar = nuts->h_bar; a.eps_bar = nuts->eps_bar;
+        a.eps_schedule = nuts->eps_schedule; a.eps_trace = nuts->eps_trace;
+    }
+    a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
+    a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
+    const size_t smem = (size_t)(3 * a.m.Dp + a.m.tile_floats) * sizeof(float);
+    rc = prepare_smem(mlp_run_kernel, smem);
+    if (rc != HMCX_OK) return rc;
+    mlp_run_kernel<<<C, MLP_THREADS, smem, st>>>(a);
+    return cuda_status();
+}
+
+int mlp_grad_log_prob(const hmcx_target_t* target, const float* q, int C, int ld, int split, float* grad_out,
+                      float* log_prob_out, cudaStream_t st) {
+    MlpDev m = {};
+    int rc = fill_mlp(target, m);
+    if (rc != HMCX_OK) return rc;
+    if (!q || C < 1 || ld < m.D || (ld & 3) || split < -1 || split >= m.M || (!grad_out && !log_prob_out))
+        return HMCX_ERR_INVALID_ARG;
+    const size_t smem = (size_t)(2 * m.Dp + m.tile_floats) * sizeof(float);
+    rc = prepare_smem(mlp_grad_kernel, smem);
+    if (rc != HMCX_OK) return rc;
+    mlp_grad_kernel<<<C, MLP_THREADS, smem, st>>>(m, q, ld, split, grad_out, log_prob_out);
+    return cuda_status();
+}
+
+int mlp_predict(const hmcx_target_t* target, const float* samples, int S, int ld, float* pred_out, float* log_prob_out,
+                cudaStream_t st) {
+    MlpDev m = {};
+    int rc = fill_mlp(target, m);
+    if (rc != HMCX_OK) return rc;
+    if (!samples || !pred_out || S < 1 || ld < m.D || (ld & 3) || !m.has_data) return HMCX_ERR_INVALID_ARG;
+    const size_t smem = (size_t)(m.Dp + m.tile_floats) * sizeof(float);
+    rc = prepare_smem(mlp_predict_kernel, smem);
+    if (rc != HMCX_OK) return rc;
+    mlp_predict_kernel<<<S, MLP_THREADS, smem, st>>>(m, samples, ld, pred_out, log_prob_out);
+    return cuda_status();
+}
+
+}  // namespace hmcx

@@ -15,14 +15,39 @@ from . import targets as T
 # ----------------------------------------------------------------------------------------------------------
 # descriptors -> native structs (tensors are kept alive on the wrapper object)
 # ----------------------------------------------------------------------------------------------------------
+def _combine_mlp_splits(splits):
+    """A list of MLPRegression descriptors (what define_split_model_log_prob returns: one per data batch, sharing the
+    network and the prior) -> (first descriptor, concatenated x, y, split_begin)."""
+    first = splits[0]
+    for d in splits:
+        if not isinstance(d, T.MLPRegression):
+            raise TypeError('a split log_prob_func list must hold MLPRegression descriptors')
+        if d.widths != first.widths or d.acts != first.acts or d.tau_out != first.tau_out or \
+                float(d.prior_scale) != float(first.prior_scale) or \
+                any(float(a) != float(b) for a, b in zip(d.tau_list, first.tau_list)):
+            raise RuntimeError('all splits must share the network, tau_list, tau_out and prior_scale')
+        if d.x is None:
+            raise RuntimeError('split descriptors need data')
+    x = torch.cat([d.x for d in splits])
+    y = torch.cat([d.y.reshape(d.x.shape[0], -1) for d in splits])
+    begin = [0]
+    for d in splits:
+        begin.append(begin[-1] + d.x.shape[0])
+    return first, x, y, begin
+
+
 class NativeTarget:
     def __init__(self, target, device):
+        self.device = torch.device(device)
+        self._keep = {}
+        if isinstance(target, list) or isinstance(target, T.MLPRegression):
+            self._init_mlp(target)
+            return
         if not T.is_target(target):
             raise TypeError('not a hamiltorch_b200 target descriptor: %r' % (target,))
         self.target = target
-        self.device = torch.device(device)
         self.dim = target.dim
-        self._keep = {}
+        self.num_splits = 1
         s = N.TargetStruct()
         s.kind, s.dim = target.kind, target.dim
         s.log_norm = float(getattr(target, 'log_norm', 0.0))
@@ -33,6 +58,48 @@ class NativeTarget:
                 self._keep[field] = t
                 setattr(s, field, t.data_ptr())
         s.funnel_inv_var_v = float(getattr(target, 'inv_var_v', 0.0))
+        self.struct = s
+
+    def _init_mlp(self, target):
+        if isinstance(target, list):
+            first, x, y, begin = _combine_mlp_splits(target)
+        else:
+            first = target
+            x = first.x
+            y = None if x is None else first.y.reshape(x.shape[0], -1)
+            begin = [0, 0 if x is None else x.shape[0]]
+        if len(begin) - 1 > N.MLP_MAX_SPLITS:
+            raise NotImplementedError('at most %d splits' % N.MLP_MAX_SPLITS)
+        self.target = target
+        self.dim = first.dim
+        self.num_splits = len(begin) - 1
+        self.mlp_desc = first
+        m = N.MlpStruct()
+        m.num_layers = first.num_layers
+        for i, w in enumerate(first.widths):
+            m.widths[i] = w
+        for i, a in enumerate(first.acts):
+            m.activation[i] = a
+        m.loss = T.LOSS_REGRESSION
+        m.tau_out = first.tau_out
+        m.prior_scale = float(first.prior_scale)
+        for i in range(2 * first.num_layers):
+            m.prior_two_var[i] = float(first.two_var[i])
+            m.prior_log_scale[i] = float(first.log_scale[i])
+            m.prior_grad_coef[i] = float(first.grad_coef[i])
+        if x is not None:
+            xd = x.detach().to(self.device, torch.float32).contiguous()
+            yd = y.detach().to(self.device, torch.float32).contiguous()
+            self._keep['x'], self._keep['y'] = xd, yd
+            m.x, m.y = xd.data_ptr(), yd.data_ptr()
+            m.num_rows = xd.shape[0]
+        m.num_splits = self.num_splits
+        for i, b in enumerate(begin):
+            m.split_begin[i] = b
+        self.mlp_struct = m
+        s = N.TargetStruct()
+        s.kind, s.dim = T.KIND_MLP, first.dim
+        s.mlp = C.pointer(m)
         self.struct = s
 
     def ref(self):
@@ -204,12 +271,15 @@ class HMCResult:
 
 def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, inv_mass=None,
             nuts=False, desired_accept_rate=0.8, seed=0, chain_offset=0, normals=None, log_uniforms=None,
-            record_ham=False, out=None, device=None, tuning=0, eps_schedule=None, record_eps=False):
+            record_ham=False, out=None, device=None, tuning=0, eps_schedule=None, record_eps=False, scheme=None,
+            perms=None):
     """The reference's sample() loop for sampler in {HMC, HMC_NUTS} as one persistent kernel over C chains.
 
     params_init (C, D) | (D,).  Randomness: in-kernel Philox keyed by (seed, chain_offset+c, iteration), or -- when
     ``normals`` (S, C, D) and ``log_uniforms`` (S, C) are given -- the injected stream (parity mode).
     ``out``: optional pre-allocated (C, S-burn, ld) fp32 device tensor for the samples.
+    Bayesian-NN targets (an MLPRegression or the list of split descriptors): ``scheme`` selects the integrator
+    (N.SCHEME_PLAIN / SPLIT_SYM / SPLIT_RAND / SPLIT_KMID); ``perms`` (S, C, M) injects SPLITTING_RAND's randperm.
     NUTS only: ``eps_schedule`` (S, C) forces the step size of every iteration (parity tests replay the reference's
     schedule); ``record_eps`` returns the kernel's own adapted step sizes in ``result.eps_trace`` (C, S).
     """
@@ -253,6 +323,10 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
         rng.mode = N.RNG_INJECTED
         rng.normals, rng.log_uniforms = z.data_ptr(), lu.data_ptr()
         keep_alive += [z, lu]
+        if perms is not None:
+            pm = perms.detach().to(device=device, dtype=torch.int32).reshape(S, Cn, -1).contiguous()
+            rng.perms = pm.data_ptr()
+            keep_alive.append(pm)
     else:
         rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
 
@@ -276,13 +350,57 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
             nuts_s.eps_trace = eps_trace.data_ptr()
 
     with torch.cuda.device(device):
-        rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
-                              N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),
-                              N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.stream_ptr(device))
-    N.check(rc, 'hmcx_hmc_run')
+        if scheme is None:
+            rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
+                                  N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),
+                                  N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning),
+                                  N.stream_ptr(device))
+            N.check(rc, 'hmcx_hmc_run')
+        else:
+            rc = lib.hmcx_split_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), int(scheme), N.ptr(q_init),
+                                    N.ptr(q_cur), N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples),
+                                    N.ptr(accepted), N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected),
+                                    N.stream_ptr(device))
+            N.check(rc, 'hmcx_split_run')
     res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
     res.eps_trace = eps_trace
     if nuts:
         res.eps_bar, res.h_bar = eps_bar, h_bar
     res._keep_alive = keep_alive          # buffers the asynchronous kernel still reads
     return res
+
+
+def grad_log_prob(target, q, split=-1, want_grad=True, want_log_prob=True, device=None):
+    """Batched collect_gradients (samplers.py:33-66): (grad (C, D), log_prob (C,)) of C parameter vectors for a
+    Bayesian-NN target; ``split`` selects one data split (-1: the whole potential)."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    qd = _as_rows(q, ld, device)
+    Cn = qd.shape[0]
+    g = torch.empty_like(qd) if want_grad else None
+    lp = torch.empty(Cn, dtype=torch.float32, device=device) if want_log_prob else None
+    with torch.cuda.device(device):
+        rc = lib.hmcx_grad_log_prob(nt.ref(), N.ptr(qd), Cn, ld, int(split), N.ptr(g), N.ptr(lp), N.stream_ptr(device))
+    N.check(rc, 'hmcx_grad_log_prob')
+    return (g[:, :D] if want_grad else None), lp
+
+
+def mlp_predict(target, samples, device=None):
+    """Batched predict_model (samplers.py:1468-1562): samples (S, D) -> (pred (S, N, O), log_prob (S,))."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (samples.device if samples.is_cuda else 'cuda'))
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    sd = _as_rows(samples, ld, device)
+    S = sd.shape[0]
+    m = nt.mlp_struct
+    pred = torch.empty((S, m.num_rows, m.widths[m.num_layers]), dtype=torch.float32, device=device)
+    lp = torch.empty(S, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_mlp_predict(nt.ref(), N.ptr(sd), S, ld, N.ptr(pred), N.ptr(lp), N.stream_ptr(device))
+    N.check(rc, 'hmcx_mlp_predict')
+    return pred, lp

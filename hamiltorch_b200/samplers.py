@@ -17,6 +17,7 @@ from enum import Enum
 
 import torch
 
+from . import _native as N
 from . import engine
 from . import targets as T
 from . import util
@@ -157,16 +158,21 @@ def _check_sample_args(params_init_dim_ok, num_samples, burn, sampler):
         raise RuntimeError('burn must be greater than 0 for NUTS.')             # :933-934
 
 
-def _draw_reference_stream(dim, num_samples, device):
+def _draw_reference_stream(dim, num_samples, device, num_perm=0):
     """Pre-draw one chain's randoms from torch's GLOBAL generators in exactly the order the reference consumes
     them: per iteration the momentum normals -- ``Normal(zeros_like(params),
     ones_like(params)).sample()`` (:186, :202), i.e. the generator of params' device -- then ``torch.rand(1)`` on
     the CPU generator (:1004).  Valid while no LogProbError occurs (that skips the iteration's rand(1))."""
     z = torch.empty((num_samples, dim), dtype=torch.float32, device=device)
     logu = torch.empty(num_samples, dtype=torch.float32)
+    perms = torch.empty((num_samples, num_perm), dtype=torch.int32) if num_perm else None
     for n in range(num_samples):
         z[n] = torch.randn(dim, dtype=torch.float32, device=device)
+        if num_perm:
+            perms[n] = torch.randperm(num_perm)             # SPLITTING_RAND: once per trajectory (:550)
         logu[n] = torch.log(torch.rand(1))[0]
+    if num_perm:
+        return z, logu, perms
     return z, logu
 
 
@@ -223,14 +229,17 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                   fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, jitter_max_tries=10,
                   sampler=Sampler.HMC, integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN,
                   desired_accept_rate=0.8, rng='philox', seed=0, chain_offset=0, normals=None, log_uniforms=None,
-                  record_ham=False, out=None):
+                  record_ham=False, out=None, perms=None):
     """The engine's native entry: C independent chains at once.  ``params_init`` is (C, D); every chain gets the
     reference's ``sample`` semantics.  Returns an ``engine.HMCResult`` whose ``.samples`` is (C, S-burn, D) on the
     GPU (row c = what ``sample`` would have returned for chain c, stacked).
 
     rng='philox'  in-kernel Philox4x32-10 keyed by (seed, chain_offset + c, iteration) -- results do not depend on
                   how chains are sharded over GPUs.
-    rng='injected'  consume ``normals`` (S, C, D) / ``log_uniforms`` (S, C) (parity mode).
+    rng='injected'  consume ``normals`` (S, C, D) / ``log_uniforms`` (S, C) (parity mode; SPLITTING_RAND also
+                  ``perms`` (S, C, M)).
+    ``log_prob_func`` may be a Gaussian / funnel descriptor, an ``MLPRegression`` (sample_model) or the list of split
+    descriptors ``define_split_model_log_prob`` returns (with a SPLITTING integrator).
     """
     if params_init.dim() != 2:
         raise RuntimeError('sample_chains: params_init must be (num_chains, D)')
@@ -240,13 +249,13 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                        inv_mass, softabs_const, explicit_binding_const, fixed_point_threshold,
                        fixed_point_max_iterations, jitter_max_tries, sampler, integrator, metric,
                        desired_accept_rate, rng=rng, seed=seed, chain_offset=chain_offset, normals=normals,
-                       log_uniforms=log_uniforms, record_ham=record_ham, out=out)
+                       log_uniforms=log_uniforms, record_ham=record_ham, out=out, injected_perms=perms)
 
 
 def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_mass, softabs_const,
                 explicit_binding_const, fixed_point_threshold, fixed_point_max_iterations, jitter_max_tries,
                 sampler, integrator, metric, desired_accept_rate, rng='philox', seed=None, chain_offset=0,
-                normals=None, log_uniforms=None, record_ham=False, out=None):
+                normals=None, log_uniforms=None, record_ham=False, out=None, injected_perms=None):
     nuts = sampler == Sampler.HMC_NUTS
     if nuts:
         sampler = Sampler.HMC                                                     # :932-936
@@ -272,11 +281,162 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
             raise ValueError('unknown rng mode %r' % (rng,))
         return engine.hmc_run(log_prob_func, q0, num_samples, L, step_size, burn=burn, inv_mass=inv_mass, nuts=nuts,
                               desired_accept_rate=desired_accept_rate, seed=seed or 0, chain_offset=chain_offset,
-                              normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out)
+                              normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out,
+                              scheme=N.SCHEME_PLAIN if isinstance(log_prob_func, T.MLPRegression) else None)
     if sampler == Sampler.HMC:
         if type(log_prob_func) is not list:
             raise RuntimeError('For splitting log_prob_func must be list of functions')            # :466-467
-        raise NotImplementedError('split HMC kernel: not built yet')
+        M = len(log_prob_func)
+        if M == 1 and integrator in (Integrator.SPLITTING, Integrator.SPLITTING_KMID):
+            raise RuntimeError('For symmetric splitting log_prob_func must be list of functions greater than '
+                               'length 1')                                                          # :497-498, :577-578
+        scheme = {Integrator.SPLITTING: N.SCHEME_SPLIT_SYM, Integrator.SPLITTING_RAND: N.SCHEME_SPLIT_RAND,
+                  Integrator.SPLITTING_KMID: N.SCHEME_SPLIT_KMID}[integrator]
+        D = log_prob_func[0].dim
+        if q0.shape[1] != D:
+            raise RuntimeError('params_init has %d entries, the target has %d' % (q0.shape[1], D))
+        perms = None
+        if rng == 'reference':
+            if q0.shape[0] != 1:
+                raise RuntimeError("rng='reference' replays torch's global stream and is defined for one chain")
+            drawn = _draw_reference_stream(D, num_samples, q0.device,
+                                           M if integrator == Integrator.SPLITTING_RAND else 0)
+            z, logu, pm = drawn if len(drawn) == 3 else (drawn[0], drawn[1], None)
+            normals, log_uniforms = z.unsqueeze(1), logu.unsqueeze(1)
+            perms = None if pm is None else pm.unsqueeze(1)
+        elif rng == 'injected':
+            if normals is None or log_uniforms is None:
+                raise RuntimeError("rng='injected' needs normals and log_uniforms")
+            perms = injected_perms
+        elif rng == 'philox':
+            normals = log_uniforms = None
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)))
+        else:
+            raise ValueError('unknown rng mode %r' % (rng,))
+        return engine.hmc_run(log_prob_func, q0, num_samples, L, step_size, burn=burn, inv_mass=inv_mass, nuts=nuts,
+                              desired_accept_rate=desired_accept_rate, seed=seed or 0, chain_offset=chain_offset,
+                              normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out,
+                              scheme=scheme, perms=perms)
     if sampler == Sampler.RMHMC and integrator in (Integrator.EXPLICIT, Integrator.IMPLICIT):
         raise NotImplementedError('RMHMC kernel: not built yet')
     raise NotImplementedError()                                                                     # :606, :844
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Bayesian neural networks: define_model_log_prob / sample_model / sample_split_model / predict_model
+# ----------------------------------------------------------------------------------------------------------
+def _check_loss(model_loss):
+    if model_loss != 'regression':
+        raise NotImplementedError(
+            "hamiltorch_b200: only model_loss='regression' has a CUDA kernel so far (classification likelihoods and "
+            "callable losses are the next rows of SURVEY.md section 8f); got %r" % (model_loss,))
+
+
+def define_model_log_prob(model, model_loss, x, y, params_flattened_list, params_shape_list, tau_list, tau_out,
+                          normalizing_const=1., predict=False, prior_scale=1.0, device='cpu'):
+    """samplers.py:1093-1201.  Returns the log_prob_func of a dense-stack model as a NATIVE descriptor
+    (``targets.MLPRegression``): callable like the reference's closure (same torch ops, same (O,)-shaped value, the
+    ``(log_prob, output)`` pair when ``predict``) and understood by the kernels."""
+    _check_loss(model_loss)
+    desc = T.MLPRegression.from_model(model, x, y, tau_list, tau_out, prior_scale)
+    if list(params_flattened_list) != desc.sizes:
+        raise RuntimeError('params_flattened_list does not match the model')
+    desc.predict_mode = bool(predict)
+    return desc
+
+
+def define_split_model_log_prob(model, model_loss, train_loader, num_splits, params_flattened_list, params_shape_list,
+                                tau_list, tau_out, normalizing_const=1., predict=False, device='cpu', verbose=True):
+    """samplers.py:1203-1258: one descriptor per DataLoader batch (the first ``num_splits`` batches), the prior divided
+    by ``num_splits`` (:1254)."""
+    log_prob_list = []
+    for batch_idx, (data, target) in enumerate(train_loader):
+        if batch_idx > num_splits - 1:
+            break
+        log_prob_list.append(define_model_log_prob(model, model_loss, data.clone().to('cpu'), target.clone().to('cpu'),
+                                                   params_flattened_list, params_shape_list, tau_list, tau_out,
+                                                   normalizing_const=normalizing_const, prior_scale=num_splits,
+                                                   predict=predict, device=device))
+    if verbose:
+        print('Number of splits: ', len(log_prob_list), ' , each of batch size ', train_loader.batch_size, '\n')
+    return log_prob_list
+
+
+def _model_lists(model, tau_list):
+    params_shape_list, params_flattened_list = [], []
+    build_tau = tau_list is None
+    if build_tau:
+        tau_list = []
+    for weights in model.parameters():                                                   # :1351-1355
+        params_shape_list.append(weights.shape)
+        params_flattened_list.append(weights.nelement())
+        if build_tau:
+            tau_list.append(torch.tensor(1.))
+    return params_shape_list, params_flattened_list, tau_list
+
+
+def sample_model(model, x, y, params_init, model_loss='multi_class_linear_output', num_samples=10,
+                 num_steps_per_sample=10, step_size=0.1, burn=0, inv_mass=None, jitter=None, normalizing_const=1.,
+                 softabs_const=None, explicit_binding_const=100, fixed_point_threshold=1e-5,
+                 fixed_point_max_iterations=1000, jitter_max_tries=10, sampler=Sampler.HMC,
+                 integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, debug=False, tau_out=1., tau_list=None,
+                 store_on_GPU=True, desired_accept_rate=0.8, verbose=True, **engine_kwargs):
+    """samplers.py:1261-1362: build the model's log_prob_func and delegate to ``sample``."""
+    shapes, flat, tau_list = _model_lists(model, tau_list)
+    log_prob_func = define_model_log_prob(model, model_loss, x, y, flat, shapes, tau_list, tau_out,
+                                          normalizing_const=normalizing_const, device=params_init.device)
+    return sample(log_prob_func, params_init, num_samples=num_samples, num_steps_per_sample=num_steps_per_sample,
+                  step_size=step_size, burn=burn, jitter=jitter, inv_mass=inv_mass, normalizing_const=normalizing_const,
+                  softabs_const=softabs_const, explicit_binding_const=explicit_binding_const,
+                  fixed_point_threshold=fixed_point_threshold, fixed_point_max_iterations=fixed_point_max_iterations,
+                  jitter_max_tries=jitter_max_tries, sampler=sampler, integrator=integrator, metric=metric, debug=debug,
+                  desired_accept_rate=desired_accept_rate, store_on_GPU=store_on_GPU, verbose=verbose, **engine_kwargs)
+
+
+def sample_split_model(model, train_loader, params_init, num_splits, model_loss='multi_class_linear_output',
+                       num_samples=10, num_steps_per_sample=10, step_size=0.1, burn=0, inv_mass=None, jitter=None,
+                       normalizing_const=1., softabs_const=None, explicit_binding_const=100,
+                       fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, jitter_max_tries=10,
+                       sampler=Sampler.HMC, integrator=Integrator.SPLITTING, metric=Metric.HESSIAN, debug=False,
+                       tau_out=1., tau_list=None, store_on_GPU=True, desired_accept_rate=0.8, verbose=True,
+                       **engine_kwargs):
+    """samplers.py:1364-1466: the first ``num_splits`` batches of ``train_loader`` become the data splits."""
+    shapes, flat, tau_list = _model_lists(model, tau_list)
+    log_prob_func = define_split_model_log_prob(model, model_loss, train_loader, num_splits, flat, shapes, tau_list,
+                                                tau_out, normalizing_const=1., predict=False,
+                                                device=params_init.device, verbose=verbose)
+    return sample(log_prob_func, params_init, num_samples=num_samples, num_steps_per_sample=num_steps_per_sample,
+                  step_size=step_size, burn=burn, jitter=jitter, inv_mass=inv_mass, normalizing_const=normalizing_const,
+                  softabs_const=softabs_const, explicit_binding_const=explicit_binding_const,
+                  fixed_point_threshold=fixed_point_threshold, fixed_point_max_iterations=fixed_point_max_iterations,
+                  jitter_max_tries=jitter_max_tries, sampler=sampler, integrator=integrator, metric=metric, debug=debug,
+                  desired_accept_rate=desired_accept_rate, store_on_GPU=store_on_GPU, verbose=verbose, **engine_kwargs)
+
+
+def predict_model(model, samples, x=None, y=None, test_loader=None, model_loss='multi_class_linear_output', tau_out=1.,
+                  tau_list=None, verbose=False):
+    """samplers.py:1468-1562: network outputs of every sample as a (S, N, O) tensor + the list of S log-probs, from ONE
+    launch (one CTA per sample).  With a DataLoader the batches are the splits and, like the reference (:1527), the
+    prior is divided by the number of batches."""
+    with torch.no_grad():
+        shapes, flat, tau_list = _model_lists(model, tau_list)
+        if test_loader.__class__ is torch.utils.data.dataloader.DataLoader:
+            if len(test_loader.dataset) % test_loader.batch_size == 0.0:
+                num_batches = len(test_loader.dataset) / test_loader.batch_size
+            else:
+                num_batches = int(round(len(test_loader.dataset) / test_loader.batch_size) + 1)
+            target = define_split_model_log_prob(model, model_loss, test_loader, num_batches, flat, shapes, tau_list,
+                                                 tau_out, normalizing_const=1., predict=True,
+                                                 device=samples[0].device, verbose=verbose)
+        elif x is not None and y is not None:
+            if x.device != samples[0].device:
+                raise RuntimeError('x on device: {} and samples on device: {}'.format(x.device, samples[0].device))
+            target = define_model_log_prob(model, model_loss, x, y, flat, shapes, tau_list, tau_out, predict=True,
+                                           device=samples[0].device)
+        else:
+            raise RuntimeError('Val data not defined (i.e. arguments x, y, val_loader are all not defined)')
+        dev = samples[0].device
+        pred, lp = engine.mlp_predict(target, torch.stack(list(samples)))
+        pred, lp = pred.to(dev), lp.to(dev)
+    return pred, [l.reshape(1) for l in lp.unbind(0)]

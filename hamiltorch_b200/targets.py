@@ -188,3 +188,158 @@ class Funnel(Target):
 
 def is_target(obj):
     return isinstance(obj, Target)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Bayesian MLP: the log_prob_func that define_model_log_prob builds (samplers.py:1093-1201)
+# ----------------------------------------------------------------------------------------------------------
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+_ACT_OF_MODULE = {'ReLU': ACT_RELU, 'Tanh': ACT_TANH, 'Sigmoid': ACT_SIGMOID}
+LOSS_REGRESSION = 0
+MLP_MAX_LAYERS = 8
+
+
+def mlp_spec(model):
+    """Recognise a dense stack: ``nn.Linear`` or ``nn.Sequential(Linear, [ReLU|Tanh|Sigmoid], Linear, ...)`` with
+    biases.  Returns (widths [n_0..n_L], activations [after layer l], list of Linear modules).  Anything else --
+    conv / recurrent / normalisation layers, or a module whose forward() is arbitrary Python -- cannot be turned into
+    a CUDA kernel the way util.make_functional (util.py:253-376) turns it into a closure, and is refused."""
+    import torch.nn as nn
+    mods = [model] if isinstance(model, nn.Linear) else (list(model) if isinstance(model, nn.Sequential) else None)
+    if mods is None:
+        raise NotImplementedError(
+            'hamiltorch_b200 runs Bayesian-NN sampling for dense stacks only: pass an nn.Sequential of '
+            'Linear / ReLU / Tanh / Sigmoid layers (got %s)' % type(model).__name__)
+    widths, acts, linears = [], [], []
+    for m in mods:
+        if isinstance(m, nn.Linear):
+            if m.bias is None:
+                raise NotImplementedError('Linear layers without bias are not supported')
+            if widths and widths[-1] != m.in_features:
+                raise ValueError('layer widths do not chain')
+            if not widths:
+                widths.append(m.in_features)
+            widths.append(m.out_features)
+            acts.append(ACT_NONE)
+            linears.append(m)
+        elif type(m).__name__ in _ACT_OF_MODULE:
+            if not linears or acts[-1] != ACT_NONE:
+                raise NotImplementedError('an activation must follow a Linear layer')
+            acts[-1] = _ACT_OF_MODULE[type(m).__name__]
+        else:
+            raise NotImplementedError('unsupported layer for the B200 dense-stack kernel: %s' % type(m).__name__)
+    if not linears:
+        raise NotImplementedError('no Linear layer found')
+    if acts[-1] != ACT_NONE:
+        raise NotImplementedError('the model must end with a Linear layer (linear output)')
+    if len(linears) > MLP_MAX_LAYERS:
+        raise NotImplementedError('at most %d Linear layers' % MLP_MAX_LAYERS)
+    return widths, acts, linears
+
+
+def _act(h, a):
+    if a == ACT_RELU:
+        return torch.relu(h)
+    if a == ACT_TANH:
+        return torch.tanh(h)
+    if a == ACT_SIGMOID:
+        return torch.sigmoid(h)
+    return h
+
+
+class MLPRegression(Target):
+    """log p(theta) = ll + prior/prior_scale for a dense stack with Gaussian likelihood (model_loss='regression'):
+
+        prior = sum over parameter tensors i of Normal(0, tau_i^-1/2).log_prob(w_i).sum()   (samplers.py:1141-1157)
+        ll    = -0.5 * tau_out * ((f(x; theta) - y)**2).sum(0)                              (samplers.py:1184)
+
+    ``theta`` is the flat vector in ``model.parameters()`` order, each tensor row-major (util.py:121-136): for every
+    Linear the (out, in) weight then the (out,) bias.  ``__call__`` restates the reference's closure with the same
+    torch ops (F.linear), so it is also a valid reference ``log_prob_func``; like the reference's it returns shape
+    (O,) -- (1,) for a scalar output.  ``x is None`` samples the prior (:1160-1162).
+    """
+
+    kind = KIND_MLP
+
+    def __init__(self, widths, acts, x, y, tau_list, tau_out=1., prior_scale=1.0):
+        self.widths = list(widths)
+        self.acts = list(acts)
+        self.num_layers = len(self.widths) - 1
+        self.dim = sum(self.widths[l] * self.widths[l + 1] + self.widths[l + 1] for l in range(self.num_layers))
+        self.x = None if x is None else x.detach().to(torch.float32)
+        self.y = None if y is None else y.detach().to(torch.float32)
+        if self.x is not None:
+            if self.x.dim() != 2 or self.x.shape[1] != self.widths[0]:
+                raise ValueError('x must be (N, %d)' % self.widths[0])
+            if self.y.reshape(self.x.shape[0], -1).shape[1] != self.widths[-1]:
+                raise ValueError('y must be (N, %d)' % self.widths[-1])
+        self.tau_out = float(tau_out)
+        self.prior_scale = prior_scale
+        tau_list = [torch.as_tensor(t, dtype=torch.float32) for t in tau_list]
+        if len(tau_list) != 2 * self.num_layers:
+            raise ValueError('tau_list needs one precision per parameter tensor (%d)' % (2 * self.num_layers))
+        self.tau_list = tau_list
+        self.sizes = []
+        for l in range(self.num_layers):
+            self.sizes += [self.widths[l] * self.widths[l + 1], self.widths[l + 1]]
+        # constants with the reference's fp32 roundings (torch.distributions.Normal.log_prob)
+        self.scale = [t ** -0.5 for t in tau_list]                       # samplers.py:1143
+        self.two_var = [2 * (s ** 2) for s in self.scale]
+        self.log_scale = [s.log() for s in self.scale]
+        self.grad_coef = [(torch.tensor(1.0) / prior_scale) / tv for tv in self.two_var]   # see DESIGN.md 3.4
+
+    @classmethod
+    def from_model(cls, model, x, y, tau_list=None, tau_out=1., prior_scale=1.0):
+        widths, acts, linears = mlp_spec(model)
+        if tau_list is None:
+            tau_list = [torch.tensor(1.)] * (2 * len(linears))           # samplers.py:1348-1355
+        return cls(widths, acts, x, y, tau_list, tau_out, prior_scale)
+
+    def _tensors(self):
+        d = {}
+        if self.x is not None:
+            d['x'], d['y'] = self.x, self.y
+        return d
+
+    def unflatten(self, params):
+        out, i = [], 0
+        for l in range(self.num_layers):
+            n_in, n_out = self.widths[l], self.widths[l + 1]
+            W = params[i:i + n_in * n_out].view(n_out, n_in)
+            i += n_in * n_out
+            b = params[i:i + n_out]
+            i += n_out
+            out.append((W, b))
+        return out
+
+    def forward(self, params, x):
+        h = x
+        for l, (W, b) in enumerate(self.unflatten(params)):
+            h = _act(torch.nn.functional.linear(h, W, b), self.acts[l])
+        return h
+
+    def log_prior(self, params):
+        i = 0
+        l_prior = torch.zeros_like(params[0])
+        for n, s in zip(self.sizes, self.scale):
+            w = params[i:i + n]
+            l_prior = torch.distributions.Normal(torch.zeros_like(s), s, validate_args=False).log_prob(w).sum() + l_prior
+            i += n
+        return l_prior
+
+    predict_mode = False       # define_model_log_prob(predict=True): the closure also returns the network output
+
+    def __call__(self, params, predict=None):
+        predict = self.predict_mode if predict is None else predict
+        l_prior = self.log_prior(params)
+        if self.x is None:
+            return l_prior / self.prior_scale
+        output = self.forward(params, self.x.to(params.device))
+        ll = - 0.5 * self.tau_out * ((output - self.y.to(params.device).view_as(output)) ** 2).sum(0)
+        if predict:
+            return (ll + l_prior / self.prior_scale), output
+        return ll + l_prior / self.prior_scale
+
+    def grad(self, params):
+        p = params.detach().requires_grad_()
+        return torch.autograd.grad(self(p), p)[0]

@@ -52,6 +52,37 @@ extern "C" {
 #define HMCX_RNG_INJECTED 0         /* host supplies the reference's own random stream (parity mode)   */
 #define HMCX_RNG_PHILOX   1         /* in-kernel Philox4x32-10 keyed by (seed, chain, iteration)       */
 
+/* Dense-stack Bayesian NN target == the closure define_model_log_prob builds (samplers.py:1093-1201) for a
+ * Linear/activation stack with model_loss='regression', plus its data-split form (define_split_model_log_prob,
+ * :1203-1258): split m owns data rows [split_begin[m], split_begin[m+1]) and divides the prior by prior_scale.
+ * Flat parameter layout = util.flatten (util.py:121-136): per Linear the (out,in) row-major weight, then the bias. */
+#define HMCX_MLP_MAX_LAYERS 8
+#define HMCX_MLP_MAX_SPLITS 64
+#define HMCX_ACT_NONE 0
+#define HMCX_ACT_RELU 1
+#define HMCX_ACT_TANH 2
+#define HMCX_ACT_SIGMOID 3
+#define HMCX_LOSS_REGRESSION 0
+
+typedef struct hmcx_mlp {
+    int32_t num_layers;                            /* number of Linear layers                                  */
+    int32_t widths[HMCX_MLP_MAX_LAYERS + 1];       /* n_0 (inputs) ... n_L (outputs)                           */
+    int32_t activation[HMCX_MLP_MAX_LAYERS];       /* applied after layer l (last must be NONE)                */
+    int32_t loss;
+    float   tau_out;                               /* likelihood precision (samplers.py:1184)                  */
+    float   prior_scale;                           /* l_prior / prior_scale (:1199); = num_splits when split   */
+    /* Gaussian prior per parameter tensor i = (W_0, b_0, W_1, b_1, ...), constants carrying the reference's fp32
+     * roundings of torch.distributions.Normal(0, tau_i^-1/2).log_prob (:1143, :1156):                           */
+    float   prior_two_var[2 * HMCX_MLP_MAX_LAYERS];    /* 2*scale_i^2                                          */
+    float   prior_log_scale[2 * HMCX_MLP_MAX_LAYERS];  /* log(scale_i)                                         */
+    float   prior_grad_coef[2 * HMCX_MLP_MAX_LAYERS];  /* (1/prior_scale)/(2*scale_i^2): d prior/dw = -(coef*2w) */
+    const float* x;                                /* [num_rows, n_0] device; NULL = sample the prior (:1160)    */
+    const float* y;                                /* [num_rows, n_L] device                                    */
+    int32_t num_rows;
+    int32_t num_splits;                            /* M >= 1                                                    */
+    int32_t split_begin[HMCX_MLP_MAX_SPLITS + 1];
+} hmcx_mlp_t;
+
 typedef struct hmcx_target {
     int32_t kind;
     int32_t dim;                    /* D                                                               */
@@ -60,6 +91,7 @@ typedef struct hmcx_target {
     const float* prec;              /* [D,D] device row-major symmetric, GAUSS_FULL                    */
     float log_norm;                 /* additive constant of log p                                      */
     float funnel_inv_var_v;         /* FUNNEL: 1/sigma_v^2                                             */
+    const hmcx_mlp_t* mlp;          /* MLP: HOST pointer to the network / data description             */
 } hmcx_target_t;
 
 typedef struct hmcx_mass {
@@ -75,6 +107,8 @@ typedef struct hmcx_rng {
     uint64_t chain_offset;          /* PHILOX: global id of local chain 0 (multi-GPU sharding)         */
     const float* normals;           /* INJECTED: standard normals [iter_end-iter_begin, C, ld]         */
     const float* log_uniforms;      /* INJECTED: log(U) of the MH test [iter_end-iter_begin, C]        */
+    const int32_t* perms;           /* INJECTED, SPLITTING_RAND only: randperm(M) per trajectory (:550)
+                                       [iter_end-iter_begin, C, M]                                     */
 } hmcx_rng_t;
 
 /* Dual-averaging step-size adaptation ("HMC_NUTS"), samplers.py:629-674, per chain.
@@ -145,6 +179,41 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
                  int32_t iter_begin, int32_t iter_end,
                  float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
                  int32_t* num_rejected, int32_t tuning, void* stream);
+
+/* integrators of the HMC family (samplers.py:269, :494, :548, :575) */
+#define HMCX_SCHEME_PLAIN       0   /* plain leapfrog on the whole potential (sample_model)             */
+#define HMCX_SCHEME_SPLIT_SYM   1   /* Integrator.SPLITTING       (:494-547)                             */
+#define HMCX_SCHEME_SPLIT_RAND  2   /* Integrator.SPLITTING_RAND  (:548-571)                             */
+#define HMCX_SCHEME_SPLIT_KMID  3   /* Integrator.SPLITTING_KMID  (:575-601)                             */
+
+/*
+ * hmcx_split_run == the sample() loop for a data-split potential U = sum_m U_m (sample_split_model, samplers.py:1364
+ * -> sample with integrator in {SPLITTING, SPLITTING_RAND, SPLITTING_KMID}), and with HMCX_SCHEME_PLAIN the same
+ * loop for the un-split Bayesian NN (sample_model, :1261).  Target must be HMCX_TARGET_MLP.  Arguments as
+ * hmcx_hmc_run; the Hamiltonian sums the split log-probs (:787-796).
+ */
+int hmcx_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                   const hmcx_nuts_t* nuts, int32_t scheme,
+                   const float* q_init, float* q_cur, float* eps,
+                   int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
+                   int32_t iter_begin, int32_t iter_end,
+                   float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                   int32_t* num_rejected, void* stream);
+
+/*
+ * hmcx_grad_log_prob == collect_gradients(log_prob_func(params), params) (samplers.py:33-66, :270-278) for C
+ * parameter vectors: grad_out[c] = d log p_split(q[c]) / dq.  split = -1 sums all splits.  Any target kind.
+ * log_prob_out optional [C].
+ */
+int hmcx_grad_log_prob(const hmcx_target_t* target, const float* q, int32_t C, int32_t ld, int32_t split,
+                       float* grad_out, float* log_prob_out, void* stream);
+
+/*
+ * hmcx_mlp_predict == predict_model (samplers.py:1468-1562): forward pass of every sample over the target's data.
+ *   samples [S, ld];  pred_out [S, num_rows, n_L];  log_prob_out [S] = ll + prior/prior_scale (:1197)
+ */
+int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t S, int32_t ld,
+                     float* pred_out, float* log_prob_out, void* stream);
 
 #ifdef __cplusplus
 }

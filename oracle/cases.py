@@ -55,3 +55,39 @@ def make_init(kind, dim, seed):
     if kind == 'randn0.1':
         return 0.1 * torch.randn(dim)
     raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Bayesian-NN cases (sample_model / sample_split_model / predict_model, samplers.py:1261-1562)
+# ----------------------------------------------------------------------------------------------------------
+def mlp_problem(seed=0, n=48, n_in=6, hidden=16, n_out=1, depth=1, act='ReLU'):
+    """Small synthetic regression problem + an nn.Sequential dense stack, deterministic in ``seed``."""
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, n_in, generator=g)
+    w = torch.randn(n_in, n_out, generator=g)
+    y = torch.sin(x @ w / 2) + 0.1 * torch.randn(n, n_out, generator=g)
+    torch.manual_seed(seed)                    # the layers' default init draws from the global generator
+    layers, last = [], n_in
+    for _ in range(depth):
+        layers += [nn.Linear(last, hidden), getattr(nn, act)()]
+        last = hidden
+    layers.append(nn.Linear(last, n_out))
+    model = nn.Sequential(*layers)
+    return model, x, y
+
+
+def mlp_cases():
+    """name -> dict(problem kwargs, sampler kwargs).  scheme: None (sample_model, full batch) or the splitting
+    integrator name; num_splits / batch as in sample_split_model."""
+    base = dict(num_samples=14, num_steps_per_sample=5, burn=2, tau_out=50., seeds=[3, 4])
+    cases = {
+        'mlp_full': dict(problem=dict(seed=0), scheme=None, step_size=0.01, **base),
+        'mlp_split_sym': dict(problem=dict(seed=1), scheme='SPLITTING', num_splits=3, step_size=0.01, **base),
+        'mlp_split_rand': dict(problem=dict(seed=2), scheme='SPLITTING_RAND', num_splits=3, step_size=0.01, **base),
+        'mlp_split_kmid': dict(problem=dict(seed=3), scheme='SPLITTING_KMID', num_splits=3, step_size=0.01, **base),
+        'mlp_deep_tanh_mass': dict(problem=dict(seed=4, depth=2, act='Tanh', hidden=12), scheme='SPLITTING',
+                                   num_splits=4, step_size=0.01, diag_mass=True,
+                                   tau_list=[1., 2., .5, 1., 3., 1.], **base),
+    }
+    return cases

@@ -106,13 +106,111 @@ def run_reversibility(ref):
     np.savez_compressed(os.path.join(OUT, 'ref_reversibility.npz'), **out)
 
 
+SCHEME_ID = {None: None, 'SPLITTING': O.SPLIT_SYM, 'SPLITTING_RAND': O.SPLIT_RAND, 'SPLITTING_KMID': O.SPLIT_KMID}
+
+
+def build_mlp_case(case):
+    """(model, x, y, descriptors, inv_mass, tau_list) of a case -- shared with the tests."""
+    from hamiltorch_b200 import targets as T
+    model, x, y = cases.mlp_problem(**case['problem'])
+    tau_list = case.get('tau_list')
+    tau_t = None if tau_list is None else [torch.tensor(t) for t in tau_list]
+    if case['scheme'] is None:
+        descs = T.MLPRegression.from_model(model, x, y, tau_t, case['tau_out'])
+    else:
+        M = case['num_splits']
+        B = x.shape[0] // M
+        descs = [T.MLPRegression.from_model(model, x[m * B:(m + 1) * B], y[m * B:(m + 1) * B], tau_t, case['tau_out'],
+                                            prior_scale=M) for m in range(M)]
+    D = sum(p.numel() for p in model.parameters())
+    inv_mass = None
+    if case.get('diag_mass'):
+        inv_mass = 0.5 + torch.rand(D, generator=torch.Generator().manual_seed(99))
+    return model, x, y, descs, inv_mass, tau_t
+
+
+def run_mlp_case(ref, name, case):
+    import torch.utils.data as tud
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+    S, L, burn, eps = case['num_samples'], case['num_steps_per_sample'], case['burn'], case['step_size']
+    D = sum(p.numel() for p in model.parameters())
+    scheme = case['scheme']
+    M = case.get('num_splits', 0)
+    out = {}
+    for ci, seed in enumerate(case['seeds']):
+        torch.manual_seed(seed)
+        init = ref.util.flatten(model).detach().clone() + 0.05 * torch.randn(D)
+        if scheme is None:
+            samples = ref.sample_model(model, x, y, params_init=init, model_loss='regression', num_samples=S,
+                                       num_steps_per_sample=L, step_size=eps, burn=burn, inv_mass=inv_mass,
+                                       tau_out=case['tau_out'], tau_list=tau_t, verbose=False)
+        else:
+            loader = tud.DataLoader(tud.TensorDataset(x, y), batch_size=x.shape[0] // M, shuffle=False)
+            samples = ref.sample_split_model(model, loader, params_init=init, num_splits=M, model_loss='regression',
+                                             num_samples=S, num_steps_per_sample=L, step_size=eps, burn=burn,
+                                             inv_mass=inv_mass, tau_out=case['tau_out'], tau_list=tau_t,
+                                             integrator=getattr(ref.Integrator, scheme), verbose=False)
+        samples = torch.stack(samples)
+        # oracle replay from the same RNG state (descriptors instead of the reference's closures).  NB: iterating a
+        # DataLoader draws its base seed from the global CPU generator (torch/utils/data/dataloader.py), which
+        # define_split_model_log_prob does once (samplers.py:1251) -- part of the stream the reference consumes.
+        torch.manual_seed(seed)
+        init2 = ref.util.flatten(model).detach().clone() + 0.05 * torch.randn(D)
+        if scheme is not None:
+            next(iter(loader))
+        res = O.sample_hmc(descs, init2, num_samples=S, num_steps_per_sample=L, step_size=eps, burn=burn,
+                           inv_mass=inv_mass, split_scheme=SCHEME_ID[scheme])
+        assert torch.equal(torch.stack(res['samples']), samples), name
+        # the stream
+        torch.manual_seed(seed)
+        _ = 0.05 * torch.randn(D)
+        if scheme is not None:
+            next(iter(loader))
+        nperm = M if scheme == 'SPLITTING_RAND' else 0
+        z = torch.empty(S, D)
+        logu = torch.empty(S)
+        perms = torch.zeros(S, max(nperm, 1), dtype=torch.long)
+        for n in range(S):
+            z[n] = torch.randn(D)
+            if nperm:
+                perms[n] = torch.randperm(nperm)
+            logu[n] = torch.log(torch.rand(1))[0]
+        res2 = O.sample_hmc(descs, init2, num_samples=S, num_steps_per_sample=L, step_size=eps, burn=burn,
+                            inv_mass=inv_mass, split_scheme=SCHEME_ID[scheme], normals=z, log_uniforms=logu,
+                            perms=perms if nperm else None)
+        assert torch.equal(torch.stack(res2['samples']), samples), name
+        assert not any(res['diverged'])
+        out['init_%d' % ci] = init.numpy()
+        out['samples_%d' % ci] = samples.numpy()
+        out['z_%d' % ci] = z.numpy()
+        out['logu_%d' % ci] = logu.numpy()
+        out['perms_%d' % ci] = perms.numpy()
+        out['accepted_%d' % ci] = np.array(res['accepted'], dtype=np.uint8)
+        out['ham_old_%d' % ci] = np.array(res['ham_old'], dtype=np.float64)
+        out['ham_new_%d' % ci] = np.array(res['ham_new'], dtype=np.float64)
+        if ci == 0:
+            # predict_model on the retained samples (samplers.py:1468-1562)
+            pred, lps = ref.predict_model(model, list(samples), x=x, y=y, model_loss='regression',
+                                          tau_out=case['tau_out'], tau_list=tau_t)
+            out['pred'] = pred.numpy()
+            out['pred_log_prob'] = torch.stack([l.reshape(-1) for l in lps]).numpy()
+    out['seeds'] = np.array(case['seeds'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, out['samples_0'].shape, 'acc', [out['accepted_%d' % c].mean() for c in range(len(case['seeds']))])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = import_reference()
     run_reversibility(ref)
-    for name, case in cases.plain_cases().items():
-        run_plain_case(ref, name, case)
+    which = sys.argv[1:] or ['plain', 'mlp']
+    if 'plain' in which:
+        for name, case in cases.plain_cases().items():
+            run_plain_case(ref, name, case)
+    if 'mlp' in which:
+        for name, case in cases.mlp_cases().items():
+            run_mlp_case(ref, name, case)
 
 
 if __name__ == '__main__':

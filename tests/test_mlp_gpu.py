@@ -1,0 +1,147 @@
+"""GPU parity tests of the Bayesian-NN path (define_model_log_prob, splitting integrators, sample_model /
+sample_split_model, predict_model) against golden fixtures from the unmodified reference and the live oracle.
+
+Tolerances: the likelihood gradient is a chain of GEMM-shaped sums whose order in the reference (CPU sgemm) is
+unknowable, so states are compared to MLP_RTOL instead of bit-exactly; accept decisions must still be identical
+(tests/parity.py reports the margin otherwise)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.utils.data as tud
+
+import hamiltorch_b200 as hb
+from hamiltorch_b200 import engine, targets as T, _native as N
+from oracle import cases, hmc_oracle as O
+from oracle.gen_golden import build_mlp_case
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+MLP_RTOL = 2e-4
+SCHEME = {None: N.SCHEME_PLAIN, 'SPLITTING': N.SCHEME_SPLIT_SYM, 'SPLITTING_RAND': N.SCHEME_SPLIT_RAND,
+          'SPLITTING_KMID': N.SCHEME_SPLIT_KMID}
+
+
+def _autograd(f, q):
+    q = q.detach().requires_grad_()
+    lp = f(q)
+    return torch.autograd.grad(lp, q)[0], lp.detach()
+
+
+@pytest.mark.parametrize('name', sorted(cases.mlp_cases()))
+def test_gradient_and_log_prob_match_autograd(name):
+    """hmcx_grad_log_prob (hand-written backward) == autograd through the reference's closure, per split and summed."""
+    case = cases.mlp_cases()[name]
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    q = torch.from_numpy(d['samples_0'])[:5]
+    splits = descs if isinstance(descs, list) else [descs]
+    for m, f in enumerate(splits):
+        g, lp = engine.grad_log_prob(descs, q, split=m if isinstance(descs, list) else -1)
+        for c in range(q.shape[0]):
+            gr, lr = _autograd(f, q[c])
+            scale = gr.abs().max().item()
+            assert (g[c].cpu() - gr).abs().max().item() <= 2e-5 * scale, (name, m, c)
+            assert abs(float(lp[c]) - float(lr)) <= 2e-5 * (abs(float(lr)) + 1)
+    if isinstance(descs, list):
+        g, lp = engine.grad_log_prob(descs, q, split=-1, want_grad=False)
+        for c in range(q.shape[0]):
+            tot = sum(float(f(q[c])) for f in descs)
+            assert abs(float(lp[c]) - tot) <= 2e-5 * (abs(tot) + 1)
+
+
+def test_gradient_at_config4_size():
+    """BASELINE config 4 shapes: Linear(64,128)-ReLU-Linear(128,1), D=8449, N=1024 in 4 splits of 256."""
+    model, x, y = cases.mlp_problem(seed=7, n=1024, n_in=64, hidden=128)
+    descs = [T.MLPRegression.from_model(model, x[m * 256:(m + 1) * 256], y[m * 256:(m + 1) * 256], None, 100.,
+                                        prior_scale=4) for m in range(4)]
+    assert descs[0].dim == 8449
+    torch.manual_seed(0)
+    q = hb.util.flatten(model).detach()[None] + 0.05 * torch.randn(3, 8449)
+    for m in (0, 3):
+        g, lp = engine.grad_log_prob(descs, q, split=m)
+        for c in range(3):
+            gr, lr = _autograd(descs[m], q[c])
+            assert (g[c].cpu() - gr).abs().max().item() <= 5e-5 * gr.abs().max().item()
+            assert abs(float(lp[c]) - float(lr)) <= 5e-5 * (abs(float(lr)) + 1)
+
+
+@pytest.mark.parametrize('name', sorted(cases.mlp_cases()))
+def test_golden_chain_parity(name):
+    """sample_model / sample_split_model chains of the reference, reproduced from the reference's random stream."""
+    case = cases.mlp_cases()[name]
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    nC = len(case['seeds'])
+    S, L, burn = case['num_samples'], case['num_steps_per_sample'], case['burn']
+    init = torch.stack([torch.from_numpy(d['init_%d' % c]) for c in range(nC)])
+    z = torch.stack([torch.from_numpy(d['z_%d' % c]) for c in range(nC)], 1)
+    logu = torch.stack([torch.from_numpy(d['logu_%d' % c]) for c in range(nC)], 1)
+    perms = torch.stack([torch.from_numpy(d['perms_%d' % c]) for c in range(nC)], 1)
+    res = engine.hmc_run(descs, init, S, L, case['step_size'], burn=burn, inv_mass=inv_mass, normals=z,
+                         log_uniforms=logu, perms=perms if case['scheme'] == 'SPLITTING_RAND' else None,
+                         record_ham=True, scheme=SCHEME[case['scheme']])
+    torch.cuda.synchronize()
+    assert int(res.diverged.sum()) == 0
+    for c in range(nC):
+        parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
+                                   res.ham[c].cpu().numpy(), d['samples_%d' % c], d['accepted_%d' % c],
+                                   d['ham_old_%d' % c], d['ham_new_%d' % c], d['logu_%d' % c], burn, exact=False,
+                                   rtol=MLP_RTOL)
+
+
+def test_sample_split_model_dropin_and_predict_model():
+    """The reference-facing calls: hb.sample_split_model consumes torch's global stream like the reference (including
+    the DataLoader's base-seed draw), hb.predict_model returns the reference's (S,N,O) tensor and log-prob list."""
+    name = 'mlp_split_sym'
+    case = cases.mlp_cases()[name]
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    seed = case['seeds'][0]
+    D = descs[0].dim
+    torch.manual_seed(seed)
+    init = hb.util.flatten(model).detach().clone() + 0.05 * torch.randn(D)
+    assert np.array_equal(init.numpy(), d['init_0'])
+    M = case['num_splits']
+    loader = tud.DataLoader(tud.TensorDataset(x, y), batch_size=x.shape[0] // M, shuffle=False)
+    samples = hb.sample_split_model(model, loader, params_init=init, num_splits=M, model_loss='regression',
+                                    num_samples=case['num_samples'], num_steps_per_sample=case['num_steps_per_sample'],
+                                    step_size=case['step_size'], burn=case['burn'], tau_out=case['tau_out'],
+                                    integrator=hb.Integrator.SPLITTING, verbose=False)
+    got = torch.stack(samples).numpy()
+    np.testing.assert_allclose(got, d['samples_0'], rtol=MLP_RTOL, atol=MLP_RTOL)
+    pred, lps = hb.predict_model(model, [torch.from_numpy(s) for s in d['samples_0']], x=x, y=y,
+                                 model_loss='regression', tau_out=case['tau_out'])
+    assert pred.shape == d['pred'].shape and len(lps) == d['pred'].shape[0] and lps[0].shape == (1,)
+    np.testing.assert_allclose(pred.numpy(), d['pred'], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(torch.stack(lps).numpy(), d['pred_log_prob'], rtol=2e-5)
+    with pytest.raises(NotImplementedError):
+        hb.sample_model(model, x, y, init, model_loss='multi_class_linear_output')
+    with pytest.raises(RuntimeError, match='greater than length 1'):
+        hb.sample(descs[:1], init, integrator=hb.Integrator.SPLITTING, rng='philox')
+
+
+def test_config4_shapes_philox_properties():
+    """BASELINE config 4 shapes on one GPU, 8 chains (the per-GPU share of the 64-chain run), short: symmetric
+    split HMC with the survey's settings accepts ~0.97; rejected stored iterations repeat the previous row."""
+    model, x, y = cases.mlp_problem(seed=0, n=1024, n_in=64, hidden=128)
+    M = 4
+    descs = [T.MLPRegression.from_model(model, x[m * 256:(m + 1) * 256], y[m * 256:(m + 1) * 256], None, 100.,
+                                        prior_scale=M) for m in range(M)]
+    D = descs[0].dim
+    init = hb.util.flatten(model).detach()[None] + 0.01 * torch.randn(8, D, generator=torch.Generator().manual_seed(0))
+    res = hb.sample_chains(descs, init, num_samples=12, num_steps_per_sample=10, step_size=5e-4,
+                           inv_mass=torch.ones(D), integrator=hb.Integrator.SPLITTING, rng='philox', seed=3,
+                           record_ham=True)
+    torch.cuda.synchronize()
+    acc = res.accepted.cpu().bool()
+    assert int(res.diverged.sum()) == 0
+    assert acc.float().mean().item() > 0.7
+    s = res.samples.cpu()
+    assert torch.equal(s[:, 0], init)
+    same = (s[:, 2:] == s[:, 1:-1]).all(-1)
+    assert torch.equal(same, ~acc[:, 2:])
+    dH = (res.ham[..., 1] - res.ham[..., 0]).cpu()
+    assert torch.isfinite(dH).all() and dH.abs().median() < 2.0
