@@ -47,7 +47,15 @@ class MassStruct(C.Structure):
 
 class RngStruct(C.Structure):
     _fields_ = [('mode', C.c_int32), ('seed', C.c_uint64), ('chain_offset', C.c_uint64),
-                ('normals', C.c_void_p), ('log_uniforms', C.c_void_p), ('perms', C.c_void_p)]
+                ('normals', C.c_void_p), ('log_uniforms', C.c_void_p), ('perms', C.c_void_p),
+                ('uniforms', C.c_void_p), ('uniforms_per_iter', C.c_int32)]
+
+
+class RmhmcStruct(C.Structure):
+    _fields_ = [('integrator', C.c_int32), ('metric', C.c_int32), ('softabs_const', C.c_float), ('jitter', C.c_float),
+                ('pi_term', C.c_float), ('cos_2we', C.c_float), ('sin_2we', C.c_float),
+                ('fixed_point_threshold', C.c_float), ('fixed_point_max_iterations', C.c_int32),
+                ('jitter_max_tries', C.c_int32)]
 
 
 class NutsStruct(C.Structure):
@@ -74,6 +82,10 @@ _PROTOS = {
                                  C.POINTER(NutsStruct), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hmcx_rmhmc_run': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(RmhmcStruct), C.POINTER(RngStruct), C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     'hmcx_grad_log_prob': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     'hmcx_mlp_predict': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

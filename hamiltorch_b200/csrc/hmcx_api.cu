@@ -15,6 +15,8 @@ int mlp_split_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, c
                   cudaStream_t);
 int mlp_grad_log_prob(const hmcx_target_t*, const float*, int, int, int, float*, float*, cudaStream_t);
 int mlp_predict(const hmcx_target_t*, const float*, int, int, float*, float*, cudaStream_t);
+int rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
+              int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
 }  // namespace hmcx
 
 static inline bool is_elem(const hmcx_target_t* t) {
@@ -85,6 +87,14 @@ int hmcx_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const h
     return hmcx::mlp_split_run(target, mass, rng, nuts, scheme, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out, num_rejected,
                                (cudaStream_t)stream);
+}
+
+int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng, const float* q_init,
+                   float* q_cur, const float* eps, int32_t C, int32_t ld, int32_t L, int32_t num_samples,
+                   int32_t burn, int32_t iter_begin, int32_t iter_end, float* samples_out, uint8_t* accept_out,
+                   uint8_t* diverged_out, float* ham_out, int32_t* num_rejected, void* stream) {
+    return hmcx::rmhmc_run(target, cfg, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin, iter_end,
+                           samples_out, accept_out, diverged_out, ham_out, num_rejected, (cudaStream_t)stream);
 }
 
 int hmcx_grad_log_prob(const hmcx_target_t* target, const float* q, int32_t C, int32_t ld, int32_t split,

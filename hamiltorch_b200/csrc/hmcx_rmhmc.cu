@@ -1,0 +1,540 @@
+// hmcx_rmhmc.cu -- Riemannian-manifold HMC (sampler=RMHMC) on sm_100a.
+//
+//   fisher + softabs          samplers.py:69-127      -> eval_metric()  (closed-form Hessian, Jacobi eigensolver)
+//   cholesky_inverse          samplers.py:130-149     -> via the eigen-decomposition (G~^-1 p = Q diag(1/lam~) Q^T p)
+//   rm_hamiltonian            samplers.py:677-736     -> rm_hamiltonian()
+//   gibbs, RMHMC branch       samplers.py:183-184     -> p = chol(G~) z
+//   leapfrog explicit         samplers.py:389-462     -> explicit_trajectory()  (A-B-C-B-A, sequential C update)
+//   leapfrog implicit         samplers.py:305-387     -> implicit_trajectory()  (fixed-point iterations)
+//   sample() loop             samplers.py:965-1067    -> rmhmc_run_kernel
+//
+// The reference obtains dH/dtheta by autograd THROUGH the Hessian, eigh and the Cholesky solve (third derivatives
+// of log p by double backward).  Here it is the closed form (Betancourt 2013, softabs):
+//     dH/dtheta_k = -d_k log p + sum_ab Z_ab (dG/dtheta_k)_ab ,     Z = Q B Q^T ,
+//     B_ij = 1/2 delta_ij lam~'_i/lam~_i - 1/2 u_i u_j F_ij ,   u = diag(1/lam~) Q^T p ,
+//     F_ij = (lam~_i - lam~_j)/(lam_i - lam_j)  (i != j),  F_ii = lam~'(lam_i) ,   lam~ = lam*coth(alpha*lam)
+// with the target supplying G = -Hessian(log p) and the contraction with its third-derivative tensor in closed form.
+// One THREAD owns one chain (D is small on this path: BASELINE config 3 has D=2; D <= 16 supported): every metric
+// evaluation is thread-private, so 512 chains need no synchronisation at all; the arithmetic is latency/SFU bound
+// (exp, tanh, sinh, sqrt, divisions), not a tensor-core or HBM problem at these sizes.
+#include "hmcx_common.cuh"
+
+namespace hmcx {
+
+struct RmTarget {
+    int kind, D;
+    float log_norm, inv_var_v;
+    const float* mean;
+    const float* ivar;
+};
+
+// ---- targets: log p, its gradient, G = -Hessian, and the contraction of Z with dG/dtheta_k ----------------------
+template <int DM>
+__device__ __forceinline__ float rm_log_prob(const RmTarget& t, const float* th) {
+    const int d = t.D;
+    if (t.kind == HMCX_TARGET_FUNNEL) {                       // targets.Funnel.__call__
+        const float v = th[0];
+        float s = 0.0f;
+        for (int i = 1; i < d; ++i) s = add(s, mul(th[i], th[i]));
+        const float t1 = mul((float)(-0.5 * (double)t.inv_var_v), mul(v, v));
+        const float t2 = mul(0.5f * (float)(d - 1), v);
+        const float t3 = mul(mul(0.5f, expf(v)), s);
+        return add(sub(add(t1, t2), t3), t.log_norm);
+    }
+    float s = 0.0f;
+    for (int i = 0; i < d; ++i) {
+        if (t.kind == HMCX_TARGET_GAUSS_ISO) s = add(s, mul(th[i], th[i]));
+        else { const float y = sub(th[i], t.mean ? t.mean[i] : 0.0f); s = add(s, mul(mul(y, y), t.ivar[i])); }
+    }
+    return add(mul(-0.5f, s), t.log_norm);
+}
+
+template <int DM>
+__device__ __forceinline__ void rm_grad_log_prob(const RmTarget& t, const float* th, float* g) {
+    const int d = t.D;
+    if (t.kind == HMCX_TARGET_FUNNEL) {
+        const float v = th[0], E = expf(v);
+        float s = 0.0f;
+        for (int i = 1; i < d; ++i) { s += th[i] * th[i]; g[i] = -(E * th[i]); }
+        g[0] = -(t.inv_var_v * v) + 0.5f * (float)(d - 1) - 0.5f * E * s;
+        return;
+    }
+    for (int i = 0; i < d; ++i)
+        g[i] = (t.kind == HMCX_TARGET_GAUSS_ISO) ? -th[i] : -(t.ivar[i] * (th[i] - (t.mean ? t.mean[i] : 0.0f)));
+}
+
+template <int DM>
+__device__ __forceinline__ void rm_fill_metric(const RmTarget& t, const float* th, float (*G)[DM]) {
+    const int d = t.D;
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) G[a][b] = 0.0f;
+    if (t.kind == HMCX_TARGET_FUNNEL) {
+        const float E = expf(th[0]);
+        float s = 0.0f;
+        for (int i = 1; i < d; ++i) { s += th[i] * th[i]; G[0][i] = G[i][0] = E * th[i]; G[i][i] = E; }
+        G[0][0] = t.inv_var_v + 0.5f * E * s;
+        return;
+    }
+    for (int i = 0; i < d; ++i) G[i][i] = (t.kind == HMCX_TARGET_GAUSS_ISO) ? 1.0f : t.ivar[i];
+}
+
+// out_k = sum_ab Z_ab (dG/dtheta_k)_ab ; Z symmetric
+template <int DM>
+__device__ __forceinline__ void rm_contract_dmetric(const RmTarget& t, const float* th, const float (*Z)[DM], float* out) {
+    const int d = t.D;
+    if (t.kind == HMCX_TARGET_FUNNEL) {
+        const float E = expf(th[0]);
+        float s = 0.0f, zx = 0.0f, tr = 0.0f;
+        for (int i = 1; i < d; ++i) { s += th[i] * th[i]; zx += Z[0][i] * th[i]; tr += Z[i][i]; }
+        out[0] = Z[0][0] * (0.5f * E * s) + 2.0f * E * zx + E * tr;
+        for (int i = 1; i < d; ++i) out[i] = Z[0][0] * E * th[i] + 2.0f * Z[0][i] * E;
+        return;
+    }
+    for (int i = 0; i < d; ++i) out[i] = 0.0f;            // Gaussian: constant metric
+}
+
+// ---- symmetric eigensolver (cyclic Jacobi), fp32 ------------------------------------------------------------------
+template <int DM>
+__device__ __forceinline__ void jacobi_eigh(int d, float (*A)[DM], float (*Q)[DM], float* lam) {
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) Q[a][b] = (a == b) ? 1.0f : 0.0f;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        float off = 0.0f, diag = 0.0f;
+        for (int a = 0; a < d; ++a) {
+            diag += A[a][a] * A[a][a];
+            for (int b = a + 1; b < d; ++b) off += A[a][b] * A[a][b];
+        }
+        if (!(off > 1e-14f * diag) ) break;
+        for (int p = 0; p < d - 1; ++p)
+            for (int q = p + 1; q < d; ++q) {
+                const float apq = A[p][q];
+                if (fabsf(apq) < 1e-30f) continue;
+                const float theta = (A[q][q] - A[p][p]) / (2.0f * apq);
+                const float tt = (theta >= 0.0f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+                const float c = rsqrtf(tt * tt + 1.0f), s = tt * c;
+                for (int k = 0; k < d; ++k) {                 // A <- A J
+                    const float akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < d; ++k) {                 // A <- J^T A
+                    const float apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < d; ++k) {                 // Q <- Q J
+                    const float qkp = Q[k][p], qkq = Q[k][q];
+                    Q[k][p] = c * qkp - s * qkq;
+                    Q[k][q] = s * qkp + c * qkq;
+                }
+            }
+    }
+    for (int a = 0; a < d; ++a) lam[a] = A[a][a];
+}
+
+template <int DM>
+struct Metric {
+    float Q[DM][DM];      // eigenvectors in columns
+    float lam[DM];        // eigenvalues of G (+ jitter)
+    float lt[DM];         // lam~ = softabs(lam) (or lam for the HESSIAN metric)
+    float dlt[DM];        // d lam~ / d lam
+};
+
+struct RmCfg {
+    int softabs;          // Metric.SOFTABS (1) or Metric.HESSIAN (0)
+    float alpha, jitter;  // softabs_const, jitter scale (jitter < 0: none)
+    float pi_term;        // D*log(2*pi) in fp32 as samplers.py:712
+};
+
+// fisher(): G = -Hess (+ diag(u*jitter)), eigh, softabs.  false <=> the reference raises LogProbError (:110-112, :717)
+template <int DM>
+__device__ __forceinline__ bool eval_metric(const RmTarget& t, const RmCfg& cfg, const float* th, const float* u,
+                                            Metric<DM>& M) {
+    const int d = t.D;
+    float G[DM][DM];
+    rm_fill_metric<DM>(t, th, G);
+    bool ok = true;
+    for (int a = 0; a < d; ++a) {
+        if (u) G[a][a] = add(G[a][a], mul(u[a], cfg.jitter));
+        for (int b = 0; b < d; ++b) ok = ok && finite_f(G[a][b]);
+    }
+    if (!ok) return false;
+    jacobi_eigh<DM>(d, G, M.Q, M.lam);
+    for (int i = 0; i < d; ++i) {
+        const float l = M.lam[i];
+        if (cfg.softabs) {
+            const float x = cfg.alpha * l, th_ = tanhf(x);
+            M.lt[i] = (1.0f / th_) * l;                                   // (1./tanh(alpha*lam))*lam   (:120)
+            const float sh = sinhf(x);
+            M.dlt[i] = 1.0f / th_ - x / (sh * sh);
+            if (!finite_f(M.dlt[i])) M.dlt[i] = (l >= 0.0f) ? 1.0f : -1.0f;   // saturated: |lam|' = sign
+        } else {
+            M.lt[i] = l;
+            M.dlt[i] = 1.0f;
+        }
+        ok = ok && finite_f(M.lt[i]);
+    }
+    return ok;
+}
+
+// rm_hamiltonian (:710-736) given the metric; also leaves w = Q^T p for the gradients.  ok=false <=> LogProbError
+template <int DM>
+__device__ __forceinline__ float rm_hamiltonian(const RmTarget& t, const RmCfg& cfg, const float* th, const float* p,
+                                                const Metric<DM>& M, float* w, bool& ok) {
+    const int d = t.D;
+    const float lp = rm_log_prob<DM>(t, th);
+    if (!finite_f(lp)) ok = false;
+    float logdet = 0.0f, quad = 0.0f;
+    for (int i = 0; i < d; ++i) {
+        float wi = 0.0f;
+        for (int a = 0; a < d; ++a) wi += M.Q[a][i] * p[a];
+        w[i] = wi;
+        if (cfg.softabs) logdet += logf(M.lt[i]);
+        else { logdet += logf(fabsf(M.lt[i])); if (!(M.lt[i] > 0.0f)) ok = false; }   // Cholesky of a non-PD metric
+        quad += wi * wi / M.lt[i];
+    }
+    const float H = add(add(add(-lp, mul(0.5f, cfg.pi_term)), mul(0.5f, logdet)), mul(0.5f, quad));
+    if (!finite_f(H)) ok = false;
+    return H;
+}
+
+// dH/dp = G~^-1 p
+template <int DM>
+__device__ __forceinline__ void grad_momentum(const RmTarget& t, const Metric<DM>& M, const float* p, float* out) {
+    const int d = t.D;
+    float u[DM];
+    for (int i = 0; i < d; ++i) {
+        float wi = 0.0f;
+        for (int a = 0; a < d; ++a) wi += M.Q[a][i] * p[a];
+        u[i] = wi / M.lt[i];
+    }
+    for (int a = 0; a < d; ++a) {
+        float s = 0.0f;
+        for (int i = 0; i < d; ++i) s += M.Q[a][i] * u[i];
+        out[a] = s;
+    }
+}
+
+// dH/dtheta (closed form, see header)
+template <int DM>
+__device__ __forceinline__ void grad_params(const RmTarget& t, const float* th, const Metric<DM>& M, const float* p,
+                                            float* out) {
+    const int d = t.D;
+    float u[DM], glp[DM];
+    for (int i = 0; i < d; ++i) {
+        float wi = 0.0f;
+        for (int a = 0; a < d; ++a) wi += M.Q[a][i] * p[a];
+        u[i] = wi / M.lt[i];
+    }
+    float B[DM][DM], Z[DM][DM];
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+            float F;
+            if (i == j) F = M.dlt[i];
+            else {
+                const float dl = M.lam[i] - M.lam[j];
+                F = (fabsf(dl) > 1e-12f * (fabsf(M.lam[i]) + fabsf(M.lam[j]))) ? (M.lt[i] - M.lt[j]) / dl : M.dlt[i];
+            }
+            B[i][j] = -0.5f * u[i] * u[j] * F + ((i == j) ? 0.5f * M.dlt[i] / M.lt[i] : 0.0f);
+        }
+    // Z = Q B Q^T
+    for (int a = 0; a < d; ++a)
+        for (int j = 0; j < d; ++j) {
+            float s = 0.0f;
+            for (int i = 0; i < d; ++i) s += M.Q[a][i] * B[i][j];
+            Z[a][j] = s;                                      // (Q B)[a][j]
+        }
+    for (int a = 0; a < d; ++a) {
+        float row[DM];
+        for (int b = 0; b < d; ++b) {
+            float s = 0.0f;
+            for (int j = 0; j < d; ++j) s += Z[a][j] * M.Q[b][j];
+            row[b] = s;
+        }
+        for (int b = 0; b < d; ++b) B[a][b] = row[b];         // reuse B as Z = Q B Q^T
+    }
+    rm_contract_dmetric<DM>(t, th, B, out);
+    rm_grad_log_prob<DM>(t, th, glp);
+    for (int k = 0; k < d; ++k) out[k] = out[k] - glp[k];
+}
+
+// gibbs (:183-184): p = chol(G~) z,  G~ = Q diag(lam~) Q^T
+template <int DM>
+__device__ __forceinline__ bool gibbs_rm(const RmTarget& t, const Metric<DM>& M, const float* z, float* p) {
+    const int d = t.D;
+    float G[DM][DM];
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b <= a; ++b) {
+            float s = 0.0f;
+            for (int i = 0; i < d; ++i) s += M.Q[a][i] * M.lt[i] * M.Q[b][i];
+            G[a][b] = s;
+        }
+    bool ok = true;
+    for (int j = 0; j < d; ++j) {                             // Cholesky, lower, in place
+        float s = G[j][j];
+        for (int k = 0; k < j; ++k) s -= G[j][k] * G[j][k];
+        if (!(s > 0.0f)) ok = false;
+        const float ljj = sqrtf(s);
+        G[j][j] = ljj;
+        for (int i = j + 1; i < d; ++i) {
+            float v = G[i][j];
+            for (int k = 0; k < j; ++k) v -= G[i][k] * G[j][k];
+            G[i][j] = v / ljj;
+        }
+    }
+    for (int a = 0; a < d; ++a) {
+        float s = 0.0f;
+        for (int b = 0; b <= a; ++b) s += G[a][b] * z[b];
+        p[a] = s;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// run kernel: one thread = one chain
+// ---------------------------------------------------------------------------------------------------------
+struct RmRunArgs {
+    RmTarget t;
+    RmCfg cfg;
+    int integrator;               // 1 explicit, 2 implicit (Integrator enum values)
+    float cosw, sinw;             // cos/sin(2*omega*eps) evaluated in fp32 like samplers.py:435-436
+    float fp_threshold;
+    int fp_max_iter, jitter_max_tries;
+    int C, ld;
+    int rng_mode;
+    uint64_t seed, chain_offset;
+    const float* normals;         // [S, C, ld]
+    const float* logu;            // [S, C]
+    const float* uniforms;        // [S, C, J, ld]  injected jitter draws
+    int J;
+    const float* q_init;
+    float* q_cur;
+    const float* eps;
+    int L, S, burn, it0, it1;
+    float* samples;
+    uint8_t* accept;
+    uint8_t* diverged;
+    float* ham;
+    int32_t* num_rejected;
+};
+
+template <int DM>
+struct JitterSrc {                // the jitter uniforms of fisher() (:115), one row of D per call
+    const RmRunArgs& a;
+    int c, n, idx;
+    uint64_t chain_id;
+    __device__ JitterSrc(const RmRunArgs& a_, int c_, int n_) : a(a_), c(c_), n(n_), idx(0),
+                                                               chain_id(a_.chain_offset + (uint64_t)c_) {}
+    __device__ const float* next(float* buf) {
+        if (a.cfg.jitter < 0.0f) return nullptr;
+        const int d = a.t.D;
+        if (a.rng_mode == HMCX_RNG_INJECTED) {
+            const int j = idx < a.J ? idx : a.J - 1;          // overflow (NaN retries) re-uses the last row
+            const float* src = a.uniforms + (((size_t)(n - a.it0) * a.C + c) * a.J + j) * a.ld;
+            for (int i = 0; i < d; ++i) buf[i] = src[i];
+        } else {
+            for (int v = 0; 4 * v < d; ++v) {
+                const uint4 r = philox_draw(a.seed, chain_id, (uint64_t)n, (uint32_t)(idx * 8 + v), STREAM_JITTER);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                for (int j = 0; j < 4 && 4 * v + j < d; ++j) buf[4 * v + j] = (float)(rr[j] >> 8) * 5.9604645e-8f;  // [0,1)
+            }
+        }
+        ++idx;
+        return buf;
+    }
+};
+
+template <int DM>
+__global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    const RmTarget& t = a.t;
+    const int d = t.D;
+    const size_t row = (size_t)c * a.ld;
+    const uint64_t chain_id = a.chain_offset + (uint64_t)c;
+
+    float qc[DM], q[DM], p[DM], qt[DM], pt[DM], g[DM], w[DM], ub[DM];
+    for (int i = 0; i < d; ++i) qc[i] = a.q_cur[row + i];
+    const float eps = a.eps[c];
+    const float half = mul(0.5f, eps);
+    int rejected = 0;
+    const int keep = a.S - a.burn;
+    float* const my_samples = a.samples ? a.samples + (size_t)c * keep * a.ld : nullptr;
+    if (a.it0 == 0 && my_samples)
+        for (int i = 0; i < a.ld; ++i) my_samples[i] = i < d ? qc[i] : 0.0f;
+
+    Metric<DM> M;
+    for (int n = a.it0; n < a.it1; ++n) {
+        JitterSrc<DM> jit(a, c, n);
+        bool ok = true;
+        float h_old = nanf(""), h_new = nanf("");
+        // dH/dtheta with the reference's NaN-retry loop (:402-410); dH/dp (:415-422)
+        auto dHdq = [&](const float* th, const float* pp, float* out) {
+            for (int tries = 0; ok; ++tries) {
+                if (!eval_metric<DM>(t, a.cfg, th, jit.next(ub), M)) { ok = false; break; }
+                bool okh = true;
+                rm_hamiltonian<DM>(t, a.cfg, th, pp, M, w, okh);
+                if (!okh) { ok = false; break; }
+                grad_params<DM>(t, th, M, pp, out);
+                bool fin = true;
+                for (int i = 0; i < d; ++i) fin = fin && finite_f(out[i]);
+                if (fin) break;
+                if (tries + 1 > a.jitter_max_tries) { ok = false; break; }
+            }
+        };
+        auto dHdp = [&](const float* th, const float* pp, float* out) {
+            if (!ok) return;
+            if (!eval_metric<DM>(t, a.cfg, th, jit.next(ub), M)) { ok = false; return; }
+            bool okh = true;
+            rm_hamiltonian<DM>(t, a.cfg, th, pp, M, w, okh);
+            if (!okh) { ok = false; return; }
+            grad_momentum<DM>(t, M, pp, out);
+        };
+
+        // ---- gibbs (:969 -> :183-184) ----
+        ok = eval_metric<DM>(t, a.cfg, qc, jit.next(ub), M);
+        {
+            float z[DM];
+            if (a.rng_mode == HMCX_RNG_INJECTED) {
+                for (int i = 0; i < d; ++i) z[i] = a.normals[((size_t)(n - a.it0) * a.C + c) * a.ld + i];
+            } else {
+                for (int v = 0; 4 * v < d; ++v) {
+                    float z4[4];
+                    philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)v, z4);
+                    for (int j = 0; j < 4 && 4 * v + j < d; ++j) z[4 * v + j] = z4[j];
+                }
+            }
+            if (ok) ok = gibbs_rm<DM>(t, M, z, p);
+        }
+        for (int i = 0; i < d; ++i) q[i] = qc[i];
+        // ---- H(theta, p) (:971; the explicit branch's 2*H ... /2 is exact) ----
+        if (ok && eval_metric<DM>(t, a.cfg, q, jit.next(ub), M)) h_old = rm_hamiltonian<DM>(t, a.cfg, q, p, M, w, ok);
+        else ok = false;
+        // ---- trajectory ----
+        if (ok && a.integrator == 1) {                                              // explicit (:423-461)
+            for (int i = 0; i < d; ++i) { qt[i] = q[i]; pt[i] = p[i]; }
+            for (int l = 0; l < a.L && ok; ++l) {
+                dHdq(q, pt, g);  if (ok) for (int i = 0; i < d; ++i) p[i] = sub(p[i], mul(half, g[i]));      // A
+                dHdp(q, pt, g);  if (ok) for (int i = 0; i < d; ++i) qt[i] = add(qt[i], mul(half, g[i]));
+                dHdp(qt, p, g);  if (ok) for (int i = 0; i < d; ++i) q[i] = add(q[i], mul(half, g[i]));       // B
+                dHdq(qt, p, g);  if (ok) for (int i = 0; i < d; ++i) pt[i] = sub(pt[i], mul(half, g[i]));
+                if (!ok) break;
+                for (int i = 0; i < d; ++i) {                                                                  // C, sequential
+                    const float cw = a.cosw, sw = a.sinw;
+                    const float qn = mul(0.5f, add(add(add(q[i], qt[i]), mul(cw, sub(q[i], qt[i]))), mul(sw, sub(p[i], pt[i]))));
+                    const float pn = mul(0.5f, add(sub(add(p[i], pt[i]), mul(sw, sub(qn, qt[i]))), mul(cw, sub(p[i], pt[i]))));
+                    const float qtn = mul(0.5f, sub(sub(add(qn, qt[i]), mul(cw, sub(qn, qt[i]))), mul(sw, sub(pn, pt[i]))));
+                    const float ptn = mul(0.5f, sub(add(add(pn, pt[i]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[i]))));
+                    q[i] = qn; p[i] = pn; qt[i] = qtn; pt[i] = ptn;
+                }
+                dHdp(qt, p, g);  if (ok) for (int i = 0; i < d; ++i) q[i] = add(q[i], mul(half, g[i]));       // B
+                dHdq(qt, p, g);  if (ok) for (int i = 0; i < d; ++i) pt[i] = sub(pt[i], mul(half, g[i]));
+                dHdq(q, pt, g);  if (ok) for (int i = 0; i < d; ++i) p[i] = sub(p[i], mul(half, g[i]));      // A
+                dHdp(q, pt, g);  if (ok) for (int i = 0; i < d; ++i) qt[i] = add(qt[i], mul(half, g[i]));
+            }
+        } else if (ok) {                                                            // implicit (:363-386)
+            for (int l = 0; l < a.L && ok; ++l) {
+                for (int i = 0; i < d; ++i) pt[i] = p[i];                           // momentum_old
+                for (int it = 0; it < a.fp_max_iter && ok; ++it) {                  // fixed_point_momentum
+                    dHdq(q, p, g);
+                    if (!ok) break;
+                    float diff = 0.0f;
+                    for (int i = 0; i < d; ++i) {
+                        const float pn = sub(pt[i], mul(half, g[i]));
+                        const float e = sub(p[i], pn);
+                        diff = fmaxf(diff, mul(e, e));
+                        p[i] = pn;
+                    }
+                    if (diff < a.fp_threshold) break;
+                }
+                if (!ok) break;
+                float g_old[DM];
+                for (int i = 0; i < d; ++i) qt[i] = q[i];                           // params_old
+                dHdp(q, p, g_old);
+                for (int it = 0; it < a.fp_max_iter && ok; ++it) {                  // fixed_point_params
+                    dHdp(q, p, g);
+                    if (!ok) break;
+                    float diff = 0.0f;
+                    for (int i = 0; i < d; ++i) {
+                        const float qn = add(add(qt[i], mul(half, g[i])), mul(half, g_old[i]));
+                        const float e = sub(q[i], qn);
+                        diff = fmaxf(diff, mul(e, e));
+                        q[i] = qn;
+                    }
+                    if (diff < a.fp_threshold) break;
+                }
+                if (!ok) break;
+                dHdq(q, p, g);
+                if (ok) for (int i = 0; i < d; ++i) p[i] = sub(p[i], mul(half, g[i]));
+            }
+        }
+        // ---- H(theta_L, p_L) on the un-augmented Hamiltonian (:989) ----
+        if (ok && eval_metric<DM>(t, a.cfg, q, jit.next(ub), M)) h_new = rm_hamiltonian<DM>(t, a.cfg, q, p, M, w, ok);
+        else ok = false;
+        // ---- MH + bookkeeping ----
+        const float x = add(-h_new, h_old);
+        const float rho = (x < 0.0f) ? x : 0.0f;
+        const float logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * a.C + c]
+                                                             : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        const bool acc = ok && (rho >= logu);
+        if (acc) {
+            for (int i = 0; i < d; ++i) qc[i] = q[i];
+        } else {
+            ++rejected;
+            if (n == a.burn + 1) for (int i = 0; i < d; ++i) qc[i] = a.q_init[row + i];   // :1018 quirk
+        }
+        if (n > a.burn && my_samples) {
+            float* dst = my_samples + (size_t)(n - a.burn) * a.ld;
+            for (int i = 0; i < a.ld; ++i) dst[i] = i < d ? qc[i] : 0.0f;
+        }
+        const size_t o = (size_t)c * a.S + n;
+        if (a.accept) a.accept[o] = acc ? 1 : 0;
+        if (a.diverged) a.diverged[o] = ok ? 0 : 1;
+        if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
+    }
+    for (int i = 0; i < d; ++i) a.q_cur[row + i] = qc[i];
+    if (a.num_rejected) a.num_rejected[c] += rejected;
+}
+
+int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng, const float* q_init,
+              float* q_cur, const float* eps, int C, int ld, int L, int S, int burn, int it0, int it1, float* samples,
+              uint8_t* accept, uint8_t* diverged, float* ham, int32_t* num_rejected, cudaStream_t st) {
+    if (!target || !cfg || !rng || !q_init || !q_cur || !eps) return HMCX_ERR_INVALID_ARG;
+    if (target->kind != HMCX_TARGET_FUNNEL && target->kind != HMCX_TARGET_GAUSS_ISO &&
+        target->kind != HMCX_TARGET_GAUSS_DIAG)
+        return HMCX_ERR_UNSUPPORTED;
+    const int D = target->dim;
+    if (D < 1 || C < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 || burn >= S || it0 < 0 || it1 > S || it0 > it1)
+        return HMCX_ERR_INVALID_ARG;
+    if (D > 16) return HMCX_ERR_UNSUPPORTED;
+    if (target->kind == HMCX_TARGET_FUNNEL && D < 2) return HMCX_ERR_INVALID_ARG;
+    if (target->kind == HMCX_TARGET_GAUSS_DIAG && !target->inv_var) return HMCX_ERR_INVALID_ARG;
+    if (cfg->integrator != 1 && cfg->integrator != 2) return HMCX_ERR_UNSUPPORTED;      // S3: out of scope
+    if (cfg->metric != 1 && cfg->metric != 2) return HMCX_ERR_UNSUPPORTED;              // JACOBIAN_DIAG: out of scope
+    RmRunArgs a = {};
+    a.t.kind = target->kind; a.t.D = D; a.t.log_norm = target->log_norm; a.t.inv_var_v = target->funnel_inv_var_v;
+    a.t.mean = target->mean; a.t.ivar = target->inv_var;
+    a.cfg.softabs = cfg->metric == 2; a.cfg.alpha = cfg->softabs_const; a.cfg.jitter = cfg->jitter;
+    a.cfg.pi_term = cfg->pi_term;
+    a.integrator = cfg->integrator; a.cosw = cfg->cos_2we; a.sinw = cfg->sin_2we;
+    a.fp_threshold = cfg->fixed_point_threshold; a.fp_max_iter = cfg->fixed_point_max_iterations;
+    a.jitter_max_tries = cfg->jitter_max_tries;
+    a.C = C; a.ld = ld;
+    a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_offset = rng->chain_offset;
+    a.normals = rng->normals; a.logu = rng->log_uniforms; a.uniforms = rng->uniforms; a.J = rng->uniforms_per_iter;
+    if (rng->mode == HMCX_RNG_INJECTED) {
+        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+        if (cfg->jitter >= 0.0f && (!rng->uniforms || rng->uniforms_per_iter < 1)) return HMCX_ERR_INVALID_ARG;
+    } else if (rng->mode != HMCX_RNG_PHILOX) {
+        return HMCX_ERR_INVALID_ARG;
+    }
+    a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
+    a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
+    const int block = 128, grid = (C + block - 1) / block;
+    if (D <= 2) rmhmc_run_kernel<2><<<grid, block, 0, st>>>(a);
+    else if (D <= 6) rmhmc_run_kernel<6><<<grid, block, 0, st>>>(a);
+    else rmhmc_run_kernel<16><<<grid, block, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
+}
+
+}  // namespace hmcx

@@ -404,3 +404,77 @@ def mlp_predict(target, samples, device=None):
         rc = lib.hmcx_mlp_predict(nt.ref(), N.ptr(sd), S, ld, N.ptr(pred), N.ptr(lp), N.stream_ptr(device))
     N.check(rc, 'hmcx_mlp_predict')
     return pred, lp
+
+
+def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, jitter=None,
+              softabs_const=None, explicit_binding_const=100, fixed_point_threshold=1e-5,
+              fixed_point_max_iterations=1000, jitter_max_tries=10, explicit=True, softabs=False, seed=0,
+              chain_offset=0, normals=None, log_uniforms=None, uniforms=None, record_ham=False, device=None):
+    """The reference's sample() loop for sampler=RMHMC over C chains (one thread per chain).
+
+    Injected (parity) mode: ``normals`` (S, C, D), ``log_uniforms`` (S, C) and -- when ``jitter`` is not None --
+    ``uniforms`` (S, C, J, D): the ``torch.rand(D)`` jitter draws of every ``fisher`` call of iteration n in the
+    reference's order (J = 8*L+3 for the explicit integrator)."""
+    N.require_cuda()
+    lib = N.load_library()
+    if device is None:
+        device = params_init.device if params_init.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    device = torch.device(device)
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    S, L, burn = int(num_samples), int(num_steps_per_sample), int(burn)
+    q_init = _as_rows(params_init, ld, device)
+    Cn = q_init.shape[0]
+    q_cur = q_init.clone()
+    eps = _eps_vector(step_size, Cn, device)
+    samples = torch.empty((Cn, S - burn, ld), dtype=torch.float32, device=device)
+    accepted = torch.empty((Cn, S), dtype=torch.uint8, device=device)
+    diverged = torch.empty((Cn, S), dtype=torch.uint8, device=device)
+    ham = torch.empty((Cn, S, 2), dtype=torch.float32, device=device) if record_ham else None
+    num_rejected = torch.zeros(Cn, dtype=torch.int32, device=device)
+    if softabs and softabs_const is None:
+        raise RuntimeError('Metric.SOFTABS needs softabs_const')
+
+    cfg = N.RmhmcStruct()
+    cfg.integrator = 1 if explicit else 2
+    cfg.metric = 2 if softabs else 1
+    cfg.softabs_const = float(softabs_const) if softabs_const is not None else 0.0
+    cfg.jitter = float(jitter) if jitter is not None else -1.0
+    cfg.pi_term = float(D * torch.log(2. * torch.tensor(math.pi)))                              # samplers.py:711-712
+    eps0 = float(step_size) if not torch.is_tensor(step_size) else float(step_size.reshape(-1)[0])
+    cfg.cos_2we = float(torch.cos(torch.FloatTensor([2 * explicit_binding_const * eps0])))    # :435
+    cfg.sin_2we = float(torch.sin(torch.FloatTensor([2 * explicit_binding_const * eps0])))    # :436
+    cfg.fixed_point_threshold = float(fixed_point_threshold)
+    cfg.fixed_point_max_iterations = int(fixed_point_max_iterations)
+    cfg.jitter_max_tries = int(jitter_max_tries)
+
+    rng = N.RngStruct()
+    keep_alive = []
+    if normals is not None:
+        z = normals.detach().to(device=device, dtype=torch.float32)
+        if z.dim() == 2:
+            z = z.unsqueeze(1)
+        z = N.pad_rows(z.contiguous(), ld)
+        lu = log_uniforms.detach().to(device=device, dtype=torch.float32).reshape(S, Cn).contiguous()
+        rng.mode, rng.normals, rng.log_uniforms = N.RNG_INJECTED, z.data_ptr(), lu.data_ptr()
+        keep_alive += [z, lu]
+        if jitter is not None:
+            if uniforms is None:
+                raise RuntimeError('injected RMHMC with jitter needs the uniforms stream')
+            u = uniforms.detach().to(device=device, dtype=torch.float32)
+            if u.dim() == 3:
+                u = u.unsqueeze(1)
+            u = N.pad_rows(u.contiguous(), ld)
+            rng.uniforms, rng.uniforms_per_iter = u.data_ptr(), u.shape[2]
+            keep_alive.append(u)
+    else:
+        rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_rmhmc_run(nt.ref(), C.byref(cfg), C.byref(rng), N.ptr(q_init), N.ptr(q_cur), N.ptr(eps), Cn, ld,
+                                L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted), N.ptr(diverged), N.ptr(ham),
+                                N.ptr(num_rejected), N.stream_ptr(device))
+    N.check(rc, 'hmcx_rmhmc_run')
+    res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
+    res.eps_trace = None
+    res._keep_alive = keep_alive
+    return res

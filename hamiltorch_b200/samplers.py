@@ -229,7 +229,7 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                   fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, jitter_max_tries=10,
                   sampler=Sampler.HMC, integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN,
                   desired_accept_rate=0.8, rng='philox', seed=0, chain_offset=0, normals=None, log_uniforms=None,
-                  record_ham=False, out=None, perms=None):
+                  record_ham=False, out=None, perms=None, uniforms=None):
     """The engine's native entry: C independent chains at once.  ``params_init`` is (C, D); every chain gets the
     reference's ``sample`` semantics.  Returns an ``engine.HMCResult`` whose ``.samples`` is (C, S-burn, D) on the
     GPU (row c = what ``sample`` would have returned for chain c, stacked).
@@ -249,13 +249,15 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                        inv_mass, softabs_const, explicit_binding_const, fixed_point_threshold,
                        fixed_point_max_iterations, jitter_max_tries, sampler, integrator, metric,
                        desired_accept_rate, rng=rng, seed=seed, chain_offset=chain_offset, normals=normals,
-                       log_uniforms=log_uniforms, record_ham=record_ham, out=out, injected_perms=perms)
+                       log_uniforms=log_uniforms, record_ham=record_ham, out=out, injected_perms=perms,
+                       injected_uniforms=uniforms)
 
 
 def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_mass, softabs_const,
                 explicit_binding_const, fixed_point_threshold, fixed_point_max_iterations, jitter_max_tries,
                 sampler, integrator, metric, desired_accept_rate, rng='philox', seed=None, chain_offset=0,
-                normals=None, log_uniforms=None, record_ham=False, out=None, injected_perms=None):
+                normals=None, log_uniforms=None, record_ham=False, out=None, injected_perms=None,
+                injected_uniforms=None):
     nuts = sampler == Sampler.HMC_NUTS
     if nuts:
         sampler = Sampler.HMC                                                     # :932-936
@@ -319,7 +321,54 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
                               normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out,
                               scheme=scheme, perms=perms)
     if sampler == Sampler.RMHMC and integrator in (Integrator.EXPLICIT, Integrator.IMPLICIT):
-        raise NotImplementedError('RMHMC kernel: not built yet')
+        if isinstance(log_prob_func, list) or not isinstance(log_prob_func, (T.Funnel, T.GaussianIso, T.GaussianDiag)):
+            raise NotImplementedError('RMHMC needs closed-form third derivatives: Funnel / GaussianIso / GaussianDiag')
+        if metric not in (Metric.HESSIAN, Metric.SOFTABS):
+            raise NotImplementedError('Metric.JACOBIAN_DIAG is out of scope (experimental in the reference)')
+        if inv_mass is not None:
+            pass                                            # the reference ignores inv_mass for RMHMC (:989 comment)
+        D = log_prob_func.dim
+        if q0.shape[1] != D:
+            raise RuntimeError('params_init has %d entries, the target has %d' % (q0.shape[1], D))
+        explicit = integrator == Integrator.EXPLICIT
+        uniforms = None
+        if rng == 'reference':
+            if q0.shape[0] != 1:
+                raise RuntimeError("rng='reference' replays torch's global stream and is defined for one chain")
+            if jitter is not None and not explicit:
+                raise NotImplementedError(
+                    "implicit RMHMC with jitter draws a data-dependent number of uniforms per iteration; its "
+                    "reference stream cannot be pre-drawn -- use rng='philox'")
+            J = (8 * L + 3) if jitter is not None else 0
+            z = torch.empty((num_samples, D), dtype=torch.float32, device=q0.device)
+            logu = torch.empty(num_samples, dtype=torch.float32)
+            uni = torch.zeros((num_samples, max(J, 1), D), dtype=torch.float32)
+            for n in range(num_samples):                     # fisher's rand(D) (:115) is always CPU, gibbs first (:184)
+                if J:
+                    uni[n, 0] = torch.rand(D)
+                z[n] = torch.randn(D, dtype=torch.float32, device=q0.device)
+                for j in range(1, J):
+                    uni[n, j] = torch.rand(D)
+                logu[n] = torch.log(torch.rand(1))[0]
+            normals, log_uniforms = z.unsqueeze(1), logu.unsqueeze(1)
+            uniforms = uni.unsqueeze(1) if J else None
+        elif rng == 'injected':
+            if normals is None or log_uniforms is None:
+                raise RuntimeError("rng='injected' needs normals and log_uniforms")
+            uniforms = injected_uniforms
+        elif rng == 'philox':
+            normals = log_uniforms = None
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)))
+        else:
+            raise ValueError('unknown rng mode %r' % (rng,))
+        return engine.rmhmc_run(log_prob_func, q0, num_samples, L, step_size, burn=burn, jitter=jitter,
+                                softabs_const=softabs_const, explicit_binding_const=explicit_binding_const,
+                                fixed_point_threshold=fixed_point_threshold,
+                                fixed_point_max_iterations=fixed_point_max_iterations,
+                                jitter_max_tries=jitter_max_tries, explicit=explicit,
+                                softabs=(metric == Metric.SOFTABS), seed=seed or 0, chain_offset=chain_offset,
+                                normals=normals, log_uniforms=log_uniforms, uniforms=uniforms, record_ham=record_ham)
     raise NotImplementedError()                                                                     # :606, :844
 
 

@@ -109,6 +109,9 @@ typedef struct hmcx_rng {
     const float* log_uniforms;      /* INJECTED: log(U) of the MH test [iter_end-iter_begin, C]        */
     const int32_t* perms;           /* INJECTED, SPLITTING_RAND only: randperm(M) per trajectory (:550)
                                        [iter_end-iter_begin, C, M]                                     */
+    const float* uniforms;          /* INJECTED, RMHMC with jitter: the torch.rand(D) draws of fisher()
+                                       (:115) in call order [iter_end-iter_begin, C, uniforms_per_iter, ld]   */
+    int32_t uniforms_per_iter;      /* explicit integrator: 8*L+3 (gibbs, H, 8 per step, H_new)        */
 } hmcx_rng_t;
 
 /* Dual-averaging step-size adaptation ("HMC_NUTS"), samplers.py:629-674, per chain.
@@ -180,6 +183,19 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
                  float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
                  int32_t* num_rejected, int32_t tuning, void* stream);
 
+/* sampler=RMHMC configuration (samplers.py:850 arguments that only this sampler reads) */
+typedef struct hmcx_rmhmc {
+    int32_t integrator;             /* Integrator enum value: 1 EXPLICIT (:389-462), 2 IMPLICIT (:305-387)         */
+    int32_t metric;                 /* Metric enum value: 1 HESSIAN, 2 SOFTABS (:116-122)                          */
+    float   softabs_const;          /* alpha                                                                      */
+    float   jitter;                 /* scale of the uniform diagonal jitter (:113-115); < 0 = None                */
+    float   pi_term;                /* D*log(2*pi) evaluated in fp32 as :712                                      */
+    float   cos_2we, sin_2we;       /* cos/sin(2*explicit_binding_const*step_size) in fp32 as :435-436            */
+    float   fixed_point_threshold;  /* implicit: :337, :356                                                       */
+    int32_t fixed_point_max_iterations;
+    int32_t jitter_max_tries;       /* NaN-gradient retries before LogProbError (:402-410)                        */
+} hmcx_rmhmc_t;
+
 /* integrators of the HMC family (samplers.py:269, :494, :548, :575) */
 #define HMCX_SCHEME_PLAIN       0   /* plain leapfrog on the whole potential (sample_model)             */
 #define HMCX_SCHEME_SPLIT_SYM   1   /* Integrator.SPLITTING       (:494-547)                             */
@@ -195,6 +211,19 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
 int hmcx_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
                    const hmcx_nuts_t* nuts, int32_t scheme,
                    const float* q_init, float* q_cur, float* eps,
+                   int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
+                   int32_t iter_begin, int32_t iter_end,
+                   float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                   int32_t* num_rejected, void* stream);
+
+/*
+ * hmcx_rmhmc_run == the sample() loop for sampler=RMHMC (samplers.py:965-1067 with gibbs :183-184, rm_hamiltonian
+ * :677-736, fisher :69-127, explicit :389-462 / implicit :305-387 leapfrog).  Targets: FUNNEL, GAUSS_ISO, GAUSS_DIAG
+ * with dim <= 16 (closed-form Hessian and third-derivative contraction).  One thread per chain.  Arguments as
+ * hmcx_hmc_run (eps is read-only: the reference never adapts the step size of RMHMC).
+ */
+int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng,
+                   const float* q_init, float* q_cur, const float* eps,
                    int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
                    int32_t iter_begin, int32_t iter_end,
                    float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,

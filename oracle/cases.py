@@ -91,3 +91,32 @@ def mlp_cases():
                                    tau_list=[1., 2., .5, 1., 3., 1.], **base),
     }
     return cases
+
+
+# ----------------------------------------------------------------------------------------------------------
+# RMHMC cases (sampler=RMHMC, explicit / implicit integrators, HESSIAN / SOFTABS metrics)
+# ----------------------------------------------------------------------------------------------------------
+def rmhmc_cases():
+    funnel_kw = dict(softabs_const=1e6, metric='SOFTABS', jitter=1e-3)
+    cases = {
+        # small twin of BASELINE config 3: 2-D funnel, explicit integrator, omega=10, eps=.05
+        'rmhmc_exp_funnel2': dict(target=T.Funnel(2), init=[0., 1.], integrator='EXPLICIT', num_samples=12,
+                                  num_steps_per_sample=5, step_size=0.05, burn=2, explicit_binding_const=10,
+                                  seeds=[1, 2], **funnel_kw),
+        # general-D path (the notebook funnel has D=11): 5-D
+        'rmhmc_exp_funnel5': dict(target=T.Funnel(5), init=[0., 1., 1., 1., 1.], integrator='EXPLICIT', num_samples=8,
+                                  num_steps_per_sample=3, step_size=0.05, burn=0, explicit_binding_const=10,
+                                  seeds=[3], **funnel_kw),
+        # implicit (generalised leapfrog), no jitter so that the number of metric evaluations does not touch the RNG
+        'rmhmc_imp_funnel2': dict(target=T.Funnel(2), init=[0., 1.], integrator='IMPLICIT', num_samples=8,
+                                  num_steps_per_sample=4, step_size=0.1, burn=1, softabs_const=1e6, metric='SOFTABS',
+                                  jitter=None, fixed_point_threshold=1e-5, fixed_point_max_iterations=1000,
+                                  seeds=[5, 9]),          # seeds whose chains hit no LogProbError
+        # HESSIAN metric on a Gaussian (constant metric = precision)
+        'rmhmc_exp_hess_gauss3': dict(target=T.GaussianDiag(torch.tensor([0., 1., -1.]),
+                                                            torch.tensor([.5, 1., 2.]) ** 2),
+                                      init=[0.2, 0.8, -1.5], integrator='EXPLICIT', num_samples=10,
+                                      num_steps_per_sample=4, step_size=0.15, burn=0, explicit_binding_const=5,
+                                      metric='HESSIAN', jitter=None, softabs_const=None, seeds=[6]),
+    }
+    return cases

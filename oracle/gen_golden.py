@@ -20,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from oracle import cases, hmc_oracle as O          # noqa: E402
+from oracle import rmhmc_oracle as R               # noqa: E402
 from oracle.ref_import import import_reference     # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -199,18 +200,74 @@ def run_mlp_case(ref, name, case):
     print('wrote', name, out['samples_0'].shape, 'acc', [out['accepted_%d' % c].mean() for c in range(len(case['seeds']))])
 
 
+def run_rmhmc_case(ref, name, case):
+    tgt, D = case['target'], case['target'].dim
+    S, L = case['num_samples'], case['num_steps_per_sample']
+    explicit = case['integrator'] == 'EXPLICIT'
+    kw = dict(num_samples=S, num_steps_per_sample=L, step_size=case['step_size'], burn=case['burn'],
+              jitter=case['jitter'], softabs_const=case['softabs_const'])
+    if explicit:
+        kw['explicit_binding_const'] = case['explicit_binding_const']
+    else:
+        kw.update(fixed_point_threshold=case['fixed_point_threshold'],
+                  fixed_point_max_iterations=case['fixed_point_max_iterations'])
+    out = {}
+    for ci, seed in enumerate(case['seeds']):
+        init = torch.tensor(case['init'])
+        torch.manual_seed(seed)
+        samples = ref.sample(log_prob_func=tgt, params_init=init, sampler=ref.Sampler.RMHMC,
+                             integrator=getattr(ref.Integrator, case['integrator']),
+                             metric=getattr(ref.Metric, case['metric']), verbose=False, **kw)
+        samples = torch.stack(samples)
+        okw = dict(kw, integrator=R.EXPLICIT if explicit else R.IMPLICIT,
+                   metric=R.SOFTABS if case['metric'] == 'SOFTABS' else R.HESSIAN)
+        torch.manual_seed(seed)
+        res = R.sample_rmhmc(tgt, init, **okw)
+        assert torch.equal(torch.stack(res['samples']), samples), name
+        # the consumed stream: per iteration jitter(gibbs), normals, jitter(ham), 8L jitters (explicit), jitter(new_ham),
+        # rand(1) -- only recorded when the count per iteration is fixed (explicit, or no jitter at all)
+        J = (8 * L + 3) if (explicit and case['jitter'] is not None) else 0
+        assert not any(res['diverged'])
+        torch.manual_seed(seed)
+        z = torch.empty(S, D)
+        logu = torch.empty(S)
+        uni = torch.zeros(S, max(J, 1), D)
+        for n in range(S):
+            if J:
+                uni[n, 0] = torch.rand(D)
+            z[n] = torch.randn(D)
+            for j in range(1, J):
+                uni[n, j] = torch.rand(D)
+            logu[n] = torch.log(torch.rand(1))[0]
+        res2 = R.sample_rmhmc(tgt, init, normals=z, log_uniforms=logu, uniforms=uni if J else None, **okw)
+        assert torch.equal(torch.stack(res2['samples']), samples), name + ' (injected)'
+        out['samples_%d' % ci] = samples.numpy()
+        out['z_%d' % ci] = z.numpy()
+        out['logu_%d' % ci] = logu.numpy()
+        out['uniforms_%d' % ci] = uni.numpy()
+        out['accepted_%d' % ci] = np.array(res['accepted'], dtype=np.uint8)
+        out['ham_old_%d' % ci] = np.array(res['ham_old'], dtype=np.float64)
+        out['ham_new_%d' % ci] = np.array(res['ham_new'], dtype=np.float64)
+    out['seeds'] = np.array(case['seeds'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, out['samples_0'].shape, 'acc', [float(out['accepted_%d' % c].mean()) for c in range(len(case['seeds']))])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = import_reference()
     run_reversibility(ref)
-    which = sys.argv[1:] or ['plain', 'mlp']
+    which = sys.argv[1:] or ['plain', 'mlp', 'rmhmc']
     if 'plain' in which:
         for name, case in cases.plain_cases().items():
             run_plain_case(ref, name, case)
     if 'mlp' in which:
         for name, case in cases.mlp_cases().items():
             run_mlp_case(ref, name, case)
+    if 'rmhmc' in which:
+        for name, case in cases.rmhmc_cases().items():
+            run_rmhmc_case(ref, name, case)
 
 
 if __name__ == '__main__':

@@ -1,0 +1,88 @@
+"""GPU parity tests of sampler=RMHMC (explicit / implicit integrators, SOFTABS / HESSIAN metrics) against golden
+fixtures from the unmodified reference.
+
+Tolerance: the reference differentiates H by autograd through the Hessian, LAPACK eigh and a Cholesky solve in fp32;
+the kernel evaluates the closed form with a Jacobi eigensolver.  Both are fp32 evaluations of the same function, but
+of different expression trees, so states agree to RM_RTOL (not bit-exactly); accept decisions must be identical."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hamiltorch_b200 as hb
+from hamiltorch_b200 import engine, targets as T
+from oracle import cases
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RM_RTOL = 2e-3
+
+
+@pytest.mark.parametrize('name', sorted(cases.rmhmc_cases()))
+def test_golden_chain_parity(name):
+    case = cases.rmhmc_cases()[name]
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    nC = len(case['seeds'])
+    S, L = case['num_samples'], case['num_steps_per_sample']
+    explicit = case['integrator'] == 'EXPLICIT'
+    init = torch.tensor(case['init']).repeat(nC, 1)
+    z = torch.stack([torch.from_numpy(d['z_%d' % c]) for c in range(nC)], 1)
+    logu = torch.stack([torch.from_numpy(d['logu_%d' % c]) for c in range(nC)], 1)
+    uni = torch.stack([torch.from_numpy(d['uniforms_%d' % c]) for c in range(nC)], 1)      # (S, C, J, D)
+    res = engine.rmhmc_run(case['target'], init, S, L, case['step_size'], burn=case['burn'], jitter=case['jitter'],
+                           softabs_const=case['softabs_const'],
+                           explicit_binding_const=case.get('explicit_binding_const', 100),
+                           fixed_point_threshold=case.get('fixed_point_threshold', 1e-5),
+                           fixed_point_max_iterations=case.get('fixed_point_max_iterations', 1000),
+                           explicit=explicit, softabs=case['metric'] == 'SOFTABS', normals=z, log_uniforms=logu,
+                           uniforms=uni if case['jitter'] is not None else None, record_ham=True)
+    torch.cuda.synchronize()
+    for c in range(nC):
+        ham = res.ham[c].cpu().numpy().astype(np.float64)
+        div = res.diverged[c].cpu().numpy().astype(bool)
+        # A non-convergent implicit fixed-point iteration is chaotic: where the reference ends such a trajectory with
+        # a large energy error (-> reject) the kernel may overflow to a non-finite H (-> "diverged", also a reject).
+        # That is the only place a diverged flag is tolerated.
+        dH_ref = d['ham_new_%d' % c] - d['ham_old_%d' % c]
+        assert not np.any(div & ~(dH_ref > 1.0)), 'kernel diverged where the reference integrated fine'
+        if explicit:
+            assert not div.any()
+        ok = ~div
+        np.testing.assert_allclose(ham[ok, 0], d['ham_old_%d' % c][ok], rtol=RM_RTOL, atol=RM_RTOL)
+        np.testing.assert_allclose(ham[ok, 1], d['ham_new_%d' % c][ok], rtol=RM_RTOL, atol=RM_RTOL)
+        m = parity.first_decision_mismatch(res.accepted[c].cpu().numpy(), d['accepted_%d' % c])
+        assert m is None, 'accept decision differs at iteration %d' % m
+        np.testing.assert_allclose(res.samples[c].cpu().numpy(), d['samples_%d' % c], rtol=RM_RTOL, atol=RM_RTOL)
+
+
+def test_sample_dropin_rmhmc_explicit_reference_stream():
+    """hb.sample(sampler=RMHMC, integrator=EXPLICIT, metric=SOFTABS, jitter=...) after manual_seed == the reference."""
+    name = 'rmhmc_exp_funnel2'
+    case = cases.rmhmc_cases()[name]
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    torch.manual_seed(case['seeds'][0])
+    samples = hb.sample(case['target'], torch.tensor(case['init']), num_samples=case['num_samples'],
+                        num_steps_per_sample=case['num_steps_per_sample'], step_size=case['step_size'],
+                        burn=case['burn'], jitter=case['jitter'], softabs_const=case['softabs_const'],
+                        explicit_binding_const=case['explicit_binding_const'], sampler=hb.Sampler.RMHMC,
+                        integrator=hb.Integrator.EXPLICIT, metric=hb.Metric.SOFTABS, verbose=False)
+    np.testing.assert_allclose(torch.stack(samples).numpy(), d['samples_0'], rtol=RM_RTOL, atol=RM_RTOL)
+
+
+def test_config3_philox_funnel_statistics():
+    """BASELINE config 3: 512 chains of explicit RMHMC on the 2-D funnel (softabs alpha=1e6, omega=10, eps=.05, L=10,
+    jitter=1e-3).  The funnel's v-marginal is N(0, 3^2); RMHMC should explore it: pooled mean/sd of v over chains."""
+    C, S = 512, 120
+    tgt = T.Funnel(2)
+    init = torch.tensor([0., 1.]).repeat(C, 1)
+    res = hb.sample_chains(tgt, init, num_samples=S, num_steps_per_sample=10, step_size=0.05, jitter=1e-3,
+                           softabs_const=1e6, explicit_binding_const=10, sampler=hb.Sampler.RMHMC,
+                           integrator=hb.Integrator.EXPLICIT, metric=hb.Metric.SOFTABS, rng='philox', seed=2)
+    torch.cuda.synchronize()
+    acc = 1 - res.num_rejected.float().mean().item() / S
+    assert 0.4 < acc <= 1.0, acc
+    v = res.samples[:, S // 2:, 0].cpu()
+    assert abs(v.mean().item()) < 0.5
+    assert 1.5 < v.std().item() < 4.0
