@@ -15,6 +15,9 @@ int mlp_split_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, c
                   cudaStream_t);
 int mlp_grad_log_prob(const hmcx_target_t*, const float*, int, int, int, float*, float*, cudaStream_t);
 int mlp_predict(const hmcx_target_t*, const float*, int, int, float*, float*, cudaStream_t);
+int small_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*, float*,
+                  float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
+                  cudaStream_t);
 int rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
               int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
 }  // namespace hmcx
@@ -66,10 +69,16 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
                  float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
                  int32_t* num_rejected, int32_t tuning, void* stream) {
     if (!target) return HMCX_ERR_INVALID_ARG;
-    if (is_elem(target))
+    const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
+    if (is_elem(target) && !full_mass)
         return hmcx::elem_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
                                   num_rejected, tuning, (cudaStream_t)stream);
+    if (is_elem(target) || target->kind == HMCX_TARGET_GAUSS_FULL || target->kind == HMCX_TARGET_FUNNEL)
+        // coupled gradient or full mass matrix: thread-per-chain kernel, D <= 16 (samplers.py:293-294, :811-812, :198-199)
+        return hmcx::small_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
+                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
+                                   num_rejected, (cudaStream_t)stream);
     if (target->kind == HMCX_TARGET_MLP)      // un-split Bayesian NN == sample_model (samplers.py:1261)
         return hmcx::mlp_split_run(target, mass, rng, nuts, HMCX_SCHEME_PLAIN, q_init, q_cur, eps, C, ld, L,
                                    num_samples, burn, iter_begin, iter_end, samples_out, accept_out, diverged_out,

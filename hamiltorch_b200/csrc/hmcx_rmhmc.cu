@@ -26,12 +26,19 @@ struct RmTarget {
     float log_norm, inv_var_v;
     const float* mean;
     const float* ivar;
+    const float* prec;        // GAUSS_FULL: [D,D] row-major
 };
+
+// DM is the capacity of the per-thread arrays.  The DM == 2 instantiation is launched only for D == 2 (BASELINE
+// config 3), so there the dimension is a compile-time constant: every loop unrolls and the 2x2 metric algebra lives
+// in registers instead of local memory.
+template <int DM>
+__device__ __forceinline__ int rm_dim(const RmTarget& t) { return DM == 2 ? 2 : t.D; }
 
 // ---- targets: log p, its gradient, G = -Hessian, and the contraction of Z with dG/dtheta_k ----------------------
 template <int DM>
 __device__ __forceinline__ float rm_log_prob(const RmTarget& t, const float* th) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     if (t.kind == HMCX_TARGET_FUNNEL) {                       // targets.Funnel.__call__
         const float v = th[0];
         float s = 0.0f;
@@ -42,6 +49,14 @@ __device__ __forceinline__ float rm_log_prob(const RmTarget& t, const float* th)
         return add(sub(add(t1, t2), t3), t.log_norm);
     }
     float s = 0.0f;
+    if (t.kind == HMCX_TARGET_GAUSS_FULL) {                   // -0.5 * dot(y, P y) + log_norm
+        for (int a = 0; a < d; ++a) {
+            float r = 0.0f;
+            for (int b = 0; b < d; ++b) r += t.prec[a * d + b] * (th[b] - (t.mean ? t.mean[b] : 0.0f));
+            s += (th[a] - (t.mean ? t.mean[a] : 0.0f)) * r;
+        }
+        return add(mul(-0.5f, s), t.log_norm);
+    }
     for (int i = 0; i < d; ++i) {
         if (t.kind == HMCX_TARGET_GAUSS_ISO) s = add(s, mul(th[i], th[i]));
         else { const float y = sub(th[i], t.mean ? t.mean[i] : 0.0f); s = add(s, mul(mul(y, y), t.ivar[i])); }
@@ -51,12 +66,20 @@ __device__ __forceinline__ float rm_log_prob(const RmTarget& t, const float* th)
 
 template <int DM>
 __device__ __forceinline__ void rm_grad_log_prob(const RmTarget& t, const float* th, float* g) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     if (t.kind == HMCX_TARGET_FUNNEL) {
         const float v = th[0], E = expf(v);
         float s = 0.0f;
         for (int i = 1; i < d; ++i) { s += th[i] * th[i]; g[i] = -(E * th[i]); }
         g[0] = -(t.inv_var_v * v) + 0.5f * (float)(d - 1) - 0.5f * E * s;
+        return;
+    }
+    if (t.kind == HMCX_TARGET_GAUSS_FULL) {                   // -(P y)
+        for (int a = 0; a < d; ++a) {
+            float r = 0.0f;
+            for (int b = 0; b < d; ++b) r += t.prec[a * d + b] * (th[b] - (t.mean ? t.mean[b] : 0.0f));
+            g[a] = -r;
+        }
         return;
     }
     for (int i = 0; i < d; ++i)
@@ -65,7 +88,7 @@ __device__ __forceinline__ void rm_grad_log_prob(const RmTarget& t, const float*
 
 template <int DM>
 __device__ __forceinline__ void rm_fill_metric(const RmTarget& t, const float* th, float (*G)[DM]) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) G[a][b] = 0.0f;
     if (t.kind == HMCX_TARGET_FUNNEL) {
@@ -75,13 +98,18 @@ __device__ __forceinline__ void rm_fill_metric(const RmTarget& t, const float* t
         G[0][0] = t.inv_var_v + 0.5f * E * s;
         return;
     }
+    if (t.kind == HMCX_TARGET_GAUSS_FULL) {
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) G[a][b] = t.prec[a * d + b];
+        return;
+    }
     for (int i = 0; i < d; ++i) G[i][i] = (t.kind == HMCX_TARGET_GAUSS_ISO) ? 1.0f : t.ivar[i];
 }
 
 // out_k = sum_ab Z_ab (dG/dtheta_k)_ab ; Z symmetric
 template <int DM>
 __device__ __forceinline__ void rm_contract_dmetric(const RmTarget& t, const float* th, const float (*Z)[DM], float* out) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     if (t.kind == HMCX_TARGET_FUNNEL) {
         const float E = expf(th[0]);
         float s = 0.0f, zx = 0.0f, tr = 0.0f;
@@ -95,7 +123,8 @@ __device__ __forceinline__ void rm_contract_dmetric(const RmTarget& t, const flo
 
 // ---- symmetric eigensolver (cyclic Jacobi), fp32 ------------------------------------------------------------------
 template <int DM>
-__device__ __forceinline__ void jacobi_eigh(int d, float (*A)[DM], float (*Q)[DM], float* lam) {
+__device__ __forceinline__ void jacobi_eigh(int d_, float (*A)[DM], float (*Q)[DM], float* lam) {
+    const int d = DM == 2 ? 2 : d_;
     for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) Q[a][b] = (a == b) ? 1.0f : 0.0f;
     for (int sweep = 0; sweep < 16; ++sweep) {
@@ -150,7 +179,7 @@ struct RmCfg {
 template <int DM>
 __device__ __forceinline__ bool eval_metric(const RmTarget& t, const RmCfg& cfg, const float* th, const float* u,
                                             Metric<DM>& M) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     float G[DM][DM];
     rm_fill_metric<DM>(t, th, G);
     bool ok = true;
@@ -181,7 +210,7 @@ __device__ __forceinline__ bool eval_metric(const RmTarget& t, const RmCfg& cfg,
 template <int DM>
 __device__ __forceinline__ float rm_hamiltonian(const RmTarget& t, const RmCfg& cfg, const float* th, const float* p,
                                                 const Metric<DM>& M, float* w, bool& ok) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     const float lp = rm_log_prob<DM>(t, th);
     if (!finite_f(lp)) ok = false;
     float logdet = 0.0f, quad = 0.0f;
@@ -201,7 +230,7 @@ __device__ __forceinline__ float rm_hamiltonian(const RmTarget& t, const RmCfg& 
 // dH/dp = G~^-1 p
 template <int DM>
 __device__ __forceinline__ void grad_momentum(const RmTarget& t, const Metric<DM>& M, const float* p, float* out) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     float u[DM];
     for (int i = 0; i < d; ++i) {
         float wi = 0.0f;
@@ -219,7 +248,7 @@ __device__ __forceinline__ void grad_momentum(const RmTarget& t, const Metric<DM
 template <int DM>
 __device__ __forceinline__ void grad_params(const RmTarget& t, const float* th, const Metric<DM>& M, const float* p,
                                             float* out) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     float u[DM], glp[DM];
     for (int i = 0; i < d; ++i) {
         float wi = 0.0f;
@@ -261,7 +290,7 @@ __device__ __forceinline__ void grad_params(const RmTarget& t, const float* th, 
 // gibbs (:183-184): p = chol(G~) z,  G~ = Q diag(lam~) Q^T
 template <int DM>
 __device__ __forceinline__ bool gibbs_rm(const RmTarget& t, const Metric<DM>& M, const float* z, float* p) {
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     float G[DM][DM];
     for (int a = 0; a < d; ++a)
         for (int b = 0; b <= a; ++b) {
@@ -327,7 +356,7 @@ struct JitterSrc {                // the jitter uniforms of fisher() (:115), one
                                                                chain_id(a_.chain_offset + (uint64_t)c_) {}
     __device__ const float* next(float* buf) {
         if (a.cfg.jitter < 0.0f) return nullptr;
-        const int d = a.t.D;
+        const int d = rm_dim<DM>(a.t);
         if (a.rng_mode == HMCX_RNG_INJECTED) {
             const int j = idx < a.J ? idx : a.J - 1;          // overflow (NaN retries) re-uses the last row
             const float* src = a.uniforms + (((size_t)(n - a.it0) * a.C + c) * a.J + j) * a.ld;
@@ -349,7 +378,7 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.C) return;
     const RmTarget& t = a.t;
-    const int d = t.D;
+    const int d = rm_dim<DM>(t);
     const size_t row = (size_t)c * a.ld;
     const uint64_t chain_id = a.chain_offset + (uint64_t)c;
 
@@ -496,13 +525,210 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
     if (a.num_rejected) a.num_rejected[c] += rejected;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// plain HMC / HMC_NUTS for small coupled problems (D <= 16): one thread per chain
+//   targets GAUSS_FULL and FUNNEL (whose gradients couple the coordinates) and the full (2-D) inv_mass of
+//   samplers.py:293-294 (drift), :811-812 (kinetic), :198-199 (gibbs: MultivariateNormal(0, inverse(inv_mass)))
+//   -- e.g. the correlated variant of BASELINE config 1 and the notebook funnel under HMC / NUTS.
+// ---------------------------------------------------------------------------------------------------------
+struct SmallRunArgs {
+    RmTarget t;
+    int mk, C, ld;
+    const float* im;              // inv_mass: [D] or [D,D]
+    const float* mf;              // sqrt(mass) [D] or lower Cholesky factor of mass [D,D]
+    int rng_mode;
+    uint64_t seed, chain_offset;
+    const float* normals;
+    const float* logu;
+    int nuts;
+    double delta, mu;
+    const double* table;
+    double* h_bar;
+    double* eps_bar;
+    const float* eps_schedule;
+    float* eps_trace;
+    const float* q_init;
+    float* q_cur;
+    float* eps;
+    int L, S, burn, it0, it1;
+    float* samples;
+    uint8_t* accept;
+    uint8_t* diverged;
+    float* ham;
+    int32_t* num_rejected;
+};
+
+template <int DM>
+__global__ void __launch_bounds__(128) hmc_small_kernel(const SmallRunArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    const RmTarget& t = a.t;
+    const int d = rm_dim<DM>(t);
+    const size_t row = (size_t)c * a.ld;
+    const uint64_t chain_id = a.chain_offset + (uint64_t)c;
+    float qc[DM], q[DM], p[DM], g[DM], v[DM];
+    for (int i = 0; i < d; ++i) qc[i] = a.q_cur[row + i];
+    float eps = a.eps[c];
+    double h_bar = 0.0, eps_bar = 1.0;
+    if (a.nuts) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
+    int rejected = 0;
+    const int keep = a.S - a.burn;
+    float* const my_samples = a.samples ? a.samples + (size_t)c * keep * a.ld : nullptr;
+    if (a.it0 == 0 && my_samples)
+        for (int i = 0; i < a.ld; ++i) my_samples[i] = i < d ? qc[i] : 0.0f;
+
+    auto minv = [&](const float* pp, float* out) {            // M^-1 p
+        for (int i = 0; i < d; ++i) {
+            if (a.mk == HMCX_MASS_FULL) {
+                float s = 0.0f;
+                for (int j = 0; j < d; ++j) s += a.im[i * d + j] * pp[j];
+                out[i] = s;
+            } else {
+                out[i] = a.mk == HMCX_MASS_DIAG ? mul(a.im[i], pp[i]) : pp[i];
+            }
+        }
+    };
+    auto kinetic2 = [&](const float* pp) {                    // p . M^-1 p
+        float s = 0.0f;
+        minv(pp, v);
+        for (int i = 0; i < d; ++i) s = add(s, mul(pp[i], v[i]));
+        return s;
+    };
+    float lp_cur = rm_log_prob<DM>(t, qc);
+
+    for (int n = a.it0; n < a.it1; ++n) {
+        if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * a.C + c];
+        const float half = mul(0.5f, eps);
+        float z[DM];
+        if (a.rng_mode == HMCX_RNG_INJECTED) {
+            for (int i = 0; i < d; ++i) z[i] = a.normals[((size_t)(n - a.it0) * a.C + c) * a.ld + i];
+        } else {
+            for (int vv = 0; 4 * vv < d; ++vv) {
+                float z4[4];
+                philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)vv, z4);
+                for (int j = 0; j < 4 && 4 * vv + j < d; ++j) z[4 * vv + j] = z4[j];
+            }
+        }
+        for (int i = 0; i < d; ++i) {                         // gibbs
+            if (a.mk == HMCX_MASS_FULL) {
+                float s = 0.0f;
+                for (int j = 0; j <= i; ++j) s += a.mf[i * d + j] * z[j];
+                p[i] = s;
+            } else {
+                p[i] = a.mk == HMCX_MASS_DIAG ? mul(z[i], a.mf[i]) : z[i];
+            }
+            q[i] = qc[i];
+        }
+        const float kin0 = kinetic2(p);
+        rm_grad_log_prob<DM>(t, q, g);                                                          // :281
+        for (int i = 0; i < d; ++i) p[i] = add(p[i], mul(half, g[i]));
+        for (int l = 0; l < a.L; ++l) {
+            minv(p, v);
+            for (int i = 0; i < d; ++i) q[i] = add(q[i], a.mk == HMCX_MASS_DIAG ? mul(mul(eps, a.im[i]), p[i])
+                                                                                 : mul(eps, v[i]));   // :284/:294/:296
+            rm_grad_log_prob<DM>(t, q, g);
+            for (int i = 0; i < d; ++i) p[i] = add(p[i], mul(eps, g[i]));                          // :298
+        }
+        for (int i = 0; i < d; ++i) p[i] = sub(p[i], mul(half, g[i]));                             // :302
+        const float lp_new = rm_log_prob<DM>(t, q);
+        const float kin1 = kinetic2(p);
+        const float h_old = add(-lp_cur, mul(0.5f, kin0));
+        const float h_new = add(-lp_new, mul(0.5f, kin1));
+        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);
+        const float x = add(-h_new, h_old);
+        const float rho = (x < 0.0f) ? x : 0.0f;
+        const float logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * a.C + c]
+                                                             : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        const bool acc = !bad && (rho >= logu);
+        if (acc) {
+            lp_cur = lp_new;
+            for (int i = 0; i < d; ++i) qc[i] = q[i];
+        } else {
+            ++rejected;
+            if (n == a.burn + 1) {                                                                // :1018 quirk
+                for (int i = 0; i < d; ++i) qc[i] = a.q_init[row + i];
+                lp_cur = rm_log_prob<DM>(t, qc);
+            }
+        }
+        if (n > a.burn && my_samples) {
+            float* dst = my_samples + (size_t)(n - a.burn) * a.ld;
+            for (int i = 0; i < a.ld; ++i) dst[i] = i < d ? qc[i] : 0.0f;
+        }
+        const size_t o = (size_t)c * a.S + n;
+        if (a.accept) a.accept[o] = acc ? 1 : 0;
+        if (a.diverged) a.diverged[o] = bad ? 1 : 0;
+        if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
+        if (a.nuts && n <= a.burn) {                                                             // :1030-1035, :1060-1067
+            if (n < a.burn || bad) {
+                const double* T = a.table + 5 * (size_t)n;
+                const double alpha = bad ? 0.0 : (double)expf(rho);
+                h_bar = __dadd_rn(__dmul_rn(T[0], h_bar), __dmul_rn(T[1], a.delta - alpha));
+                const double x_new = a.mu - __dmul_rn(T[2], h_bar);
+                eps = expf((float)x_new);
+                const float xb = add((float)__dmul_rn(T[3], x_new), mul((float)T[4], logf((float)eps_bar)));
+                eps_bar = (double)expf(xb);
+            }
+            if (n == a.burn) eps = (float)eps_bar;
+        }
+        if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = eps;
+    }
+    for (int i = 0; i < d; ++i) a.q_cur[row + i] = qc[i];
+    a.eps[c] = eps;
+    if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
+    if (a.num_rejected) a.num_rejected[c] += rejected;
+}
+
+int small_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, const hmcx_nuts_t* nuts,
+                  const float* q_init, float* q_cur, float* eps, int C, int ld, int L, int S, int burn, int it0,
+                  int it1, float* samples, uint8_t* accept, uint8_t* diverged, float* ham, int32_t* num_rejected,
+                  cudaStream_t st) {
+    if (!target || !rng || !q_init || !q_cur || !eps) return HMCX_ERR_INVALID_ARG;
+    const int D = target->dim;
+    if (D < 1 || C < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 || burn >= S || it0 < 0 || it1 > S || it0 > it1)
+        return HMCX_ERR_INVALID_ARG;
+    if (D > 16) return HMCX_ERR_UNSUPPORTED;      // large dense targets / mass matrices: tensor-core path, next round
+    SmallRunArgs a = {};
+    a.t.kind = target->kind; a.t.D = D; a.t.log_norm = target->log_norm; a.t.inv_var_v = target->funnel_inv_var_v;
+    a.t.mean = target->mean; a.t.ivar = target->inv_var; a.t.prec = target->prec;
+    if (target->kind == HMCX_TARGET_GAUSS_DIAG && !target->inv_var) return HMCX_ERR_INVALID_ARG;
+    if (target->kind == HMCX_TARGET_GAUSS_FULL && !target->prec) return HMCX_ERR_INVALID_ARG;
+    if (target->kind == HMCX_TARGET_FUNNEL && D < 2) return HMCX_ERR_INVALID_ARG;
+    a.mk = mass ? mass->kind : HMCX_MASS_NONE;
+    if (a.mk != HMCX_MASS_NONE && (!mass->inv_mass || !mass->mass_factor)) return HMCX_ERR_INVALID_ARG;
+    a.im = mass ? mass->inv_mass : nullptr; a.mf = mass ? mass->mass_factor : nullptr;
+    a.C = C; a.ld = ld;
+    if (rng->mode == HMCX_RNG_INJECTED) {
+        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+    } else if (rng->mode != HMCX_RNG_PHILOX) {
+        return HMCX_ERR_INVALID_ARG;
+    }
+    a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_offset = rng->chain_offset;
+    a.normals = rng->normals; a.logu = rng->log_uniforms;
+    a.nuts = (nuts && nuts->enabled) ? 1 : 0;
+    if (a.nuts) {
+        if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
+        a.delta = nuts->desired_accept_rate; a.mu = nuts->mu; a.table = nuts->table;
+        a.h_bar = nuts->h_bar; a.eps_bar = nuts->eps_bar;
+        a.eps_schedule = nuts->eps_schedule; a.eps_trace = nuts->eps_trace;
+    }
+    a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
+    a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
+    const int block = 128, grid = (C + block - 1) / block;
+    if (D == 2) hmc_small_kernel<2><<<grid, block, 0, st>>>(a);
+    else if (D <= 6) hmc_small_kernel<6><<<grid, block, 0, st>>>(a);
+    else hmc_small_kernel<16><<<grid, block, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
+}
+
 int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng, const float* q_init,
               float* q_cur, const float* eps, int C, int ld, int L, int S, int burn, int it0, int it1, float* samples,
               uint8_t* accept, uint8_t* diverged, float* ham, int32_t* num_rejected, cudaStream_t st) {
     if (!target || !cfg || !rng || !q_init || !q_cur || !eps) return HMCX_ERR_INVALID_ARG;
     if (target->kind != HMCX_TARGET_FUNNEL && target->kind != HMCX_TARGET_GAUSS_ISO &&
-        target->kind != HMCX_TARGET_GAUSS_DIAG)
+        target->kind != HMCX_TARGET_GAUSS_DIAG && target->kind != HMCX_TARGET_GAUSS_FULL)
         return HMCX_ERR_UNSUPPORTED;
+    if (target->kind == HMCX_TARGET_GAUSS_FULL && !target->prec) return HMCX_ERR_INVALID_ARG;
     const int D = target->dim;
     if (D < 1 || C < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 || burn >= S || it0 < 0 || it1 > S || it0 > it1)
         return HMCX_ERR_INVALID_ARG;
@@ -513,7 +739,7 @@ int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_r
     if (cfg->metric != 1 && cfg->metric != 2) return HMCX_ERR_UNSUPPORTED;              // JACOBIAN_DIAG: out of scope
     RmRunArgs a = {};
     a.t.kind = target->kind; a.t.D = D; a.t.log_norm = target->log_norm; a.t.inv_var_v = target->funnel_inv_var_v;
-    a.t.mean = target->mean; a.t.ivar = target->inv_var;
+    a.t.mean = target->mean; a.t.ivar = target->inv_var; a.t.prec = target->prec;
     a.cfg.softabs = cfg->metric == 2; a.cfg.alpha = cfg->softabs_const; a.cfg.jitter = cfg->jitter;
     a.cfg.pi_term = cfg->pi_term;
     a.integrator = cfg->integrator; a.cosw = cfg->cos_2we; a.sinw = cfg->sin_2we;
@@ -531,7 +757,7 @@ int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_r
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
     const int block = 128, grid = (C + block - 1) / block;
-    if (D <= 2) rmhmc_run_kernel<2><<<grid, block, 0, st>>>(a);
+    if (D == 2) rmhmc_run_kernel<2><<<grid, block, 0, st>>>(a);
     else if (D <= 6) rmhmc_run_kernel<6><<<grid, block, 0, st>>>(a);
     else rmhmc_run_kernel<16><<<grid, block, 0, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;

@@ -44,6 +44,33 @@ def plain_cases():
         kw=dict(num_samples=60, num_steps_per_sample=10, step_size=0.1, burn=40, nuts=True,
                 desired_accept_rate=0.8),
         seeds=[21, 22], init='randn0.1')
+    # ---- coupled targets / full mass matrix: thread-per-chain kernel (matvec summation order differs from torch's,
+    #      so these compare to 'rtol' instead of bit-exactly)
+    g = torch.Generator().manual_seed(21)
+    A = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))[0]
+    cov = A @ torch.diag(torch.tensor([.25, 1., 4.], dtype=torch.float64)) @ A.t()
+    # the "3D correlated Gaussian" reading of BASELINE config 1: rotated cov diag(.25,1,4)
+    cases['cfg1_corr_gauss3'] = dict(
+        target=T.GaussianFull(torch.zeros(3), cov=cov),
+        kw=dict(num_samples=120, num_steps_per_sample=5, step_size=0.3, burn=0),
+        seeds=[123], init='zeros', rtol=2e-5)
+    # the notebook funnel (D=10+1) under plain HMC and under NUTS (hamiltorch_log_prob_examples.ipynb cells 24, 26)
+    # (the funnel's dynamics are chaotic: fp32 round-off differences -- expf vs Sleef exp, summation order -- grow
+    #  exponentially along the chain, so these fixtures are short and compared to 1e-3)
+    cases['funnel11_hmc'] = dict(
+        target=T.Funnel(11), kw=dict(num_samples=12, num_steps_per_sample=25, step_size=0.2, burn=0),
+        seeds=[123], init='funnel', rtol=1e-3)
+    cases['funnel11_nuts'] = dict(
+        target=T.Funnel(11), kw=dict(num_samples=14, num_steps_per_sample=25, step_size=0.01, burn=10, nuts=True,
+                                     desired_accept_rate=0.75),
+        seeds=[123], init='funnel', rtol=1e-3)
+    # full (2-D) inv_mass: gibbs :199, drift :294, kinetic :812
+    B = torch.randn(5, 5, generator=g)
+    im_full = (B @ B.t() / 5 + torch.eye(5)).contiguous()
+    cases['diag5_fullmass'] = dict(
+        target=T.GaussianDiag(torch.linspace(-1, 1, 5), _rand_var(5, 11)),
+        kw=dict(num_samples=50, num_steps_per_sample=6, step_size=0.25, burn=5, inv_mass=im_full),
+        seeds=[31, 32], init='randn0.1', rtol=2e-5)
     return cases
 
 
@@ -54,6 +81,10 @@ def make_init(kind, dim, seed):
         return torch.zeros(dim)
     if kind == 'randn0.1':
         return 0.1 * torch.randn(dim)
+    if kind == 'funnel':                           # notebook: ones(D+1) with v = 0
+        x = torch.ones(dim)
+        x[0] = 0.
+        return x
     raise ValueError(kind)
 
 

@@ -1,0 +1,91 @@
+"""Secondary measurements (not the driver's bench line): BASELINE configs 3, 4, 5 on one GPU, device-timed with CUDA
+events, next to the oracle port (the reference's algorithm) on one host core for a bounded sample.
+    python scripts/bench_paths.py > profiles/r1_paths.jsonl
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hamiltorch_b200 as hb                                    # noqa: E402
+from hamiltorch_b200 import targets as T                        # noqa: E402
+from oracle import cases, hmc_oracle as O, rmhmc_oracle as R    # noqa: E402
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, r
+
+
+def cfg5():
+    C, D, S, L, burn = 128, 4096, 150, 10, 100                  # per-GPU share of the 1024-chain / 8-GPU config
+    tgt = T.GaussianIso(D)
+    init = 0.1 * torch.randn(C, D, generator=torch.Generator().manual_seed(0))
+    ms, res = timed(lambda: hb.sample_chains(tgt, init.cuda(), num_samples=S, num_steps_per_sample=L, step_size=0.1,
+                                             burn=burn, sampler=hb.Sampler.HMC_NUTS, rng='philox', seed=1))
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    O.sample_hmc(tgt, init[0], num_samples=40, num_steps_per_sample=L, step_size=0.1, burn=30, nuts=True)
+    cpu = 40 * L / (time.perf_counter() - t0)
+    return dict(config='5: D=4096 iso, HMC_NUTS, 128 chains/GPU, L=10, burn=100, S=150', ms=ms,
+                chain_steps_per_s=C * S * L / (ms * 1e-3), cpu_port_1core_chain_steps_per_s=cpu,
+                median_adapted_eps=float(res.step_size.median()),
+                post_burn_accept=float(res.accepted[:, burn + 1:].float().mean()))
+
+
+def cfg4(C=64):
+    model, x, y = cases.mlp_problem(seed=0, n=1024, n_in=64, hidden=128)
+    M, S, L = 4, 30, 10
+    descs = [T.MLPRegression.from_model(model, x[m * 256:(m + 1) * 256], y[m * 256:(m + 1) * 256], None, 100.,
+                                        prior_scale=M) for m in range(M)]
+    D = descs[0].dim
+    init = hb.util.flatten(model).detach()[None] + 0.01 * torch.randn(C, D, generator=torch.Generator().manual_seed(0))
+    ms, res = timed(lambda: hb.sample_chains(descs, init.cuda(), num_samples=S, num_steps_per_sample=L, step_size=5e-4,
+                                             inv_mass=torch.ones(D), integrator=hb.Integrator.SPLITTING,
+                                             rng='philox', seed=3), reps=2)
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    O.sample_hmc(descs, init[0], num_samples=3, num_steps_per_sample=L, step_size=5e-4, inv_mass=torch.ones(D),
+                 split_scheme=O.SPLIT_SYM)
+    cpu = 3 * L / (time.perf_counter() - t0)
+    flops = 68.7e6 * C * S * L                                   # 68.7 MFLOP per chain-step
+    return dict(config='4: MLP 64-128-1 (D=8449), N=1024, M=4 symmetric split, %d chains on ONE GPU, L=10, S=%d' % (C, S),
+                ms=ms, chain_steps_per_s=C * S * L / (ms * 1e-3), achieved_tflops=flops / (ms * 1e-3) / 1e12,
+                cpu_port_1core_chain_steps_per_s=cpu, accept=float(res.accepted.float().mean()))
+
+
+def cfg3():
+    C, S, L = 512, 200, 10
+    tgt = T.Funnel(2)
+    init = torch.tensor([0., 1.]).repeat(C, 1)
+    kw = dict(num_samples=S, num_steps_per_sample=L, step_size=0.05, jitter=1e-3, softabs_const=1e6,
+              explicit_binding_const=10)
+    ms, res = timed(lambda: hb.sample_chains(tgt, init.cuda(), sampler=hb.Sampler.RMHMC,
+                                             integrator=hb.Integrator.EXPLICIT, metric=hb.Metric.SOFTABS,
+                                             rng='philox', seed=2, **kw))
+    torch.distributions.Distribution.set_default_validate_args(False)
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    R.sample_rmhmc(tgt, init[0], num_samples=6, num_steps_per_sample=L, step_size=0.05, jitter=1e-3,
+                   softabs_const=1e6, explicit_binding_const=10, integrator=R.EXPLICIT, metric=R.SOFTABS)
+    cpu = 6 * L / (time.perf_counter() - t0)
+    return dict(config='3: explicit RMHMC, 2-D funnel, softabs 1e6, omega=10, 512 chains, L=10, S=200', ms=ms,
+                chain_steps_per_s=C * S * L / (ms * 1e-3), cpu_port_1core_chain_steps_per_s=cpu,
+                accept=float(res.accepted.float().mean()))
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(1)
+    for f in (cfg5, cfg4, cfg3):
+        print(json.dumps(f()), flush=True)
+    print(json.dumps(cfg4(C=8)), flush=True)

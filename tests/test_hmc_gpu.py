@@ -46,22 +46,24 @@ def test_golden_chain_parity(name):
     case = cases.plain_cases()[name]
     d = np.load(os.path.join(GOLD, name + '.npz'))
     res, nuts = _run_case(case, d)
-    assert int(res.diverged.sum()) == 0
+    exact = 'rtol' not in case          # coupled targets / full mass: matvec summation order differs from torch's
     for c in range(len(case['seeds'])):
+        # LogProbError iterations (non-finite log-prob -> reject, samplers.py:1045) must be the reference's
+        assert np.array_equal(res.diverged[c].cpu().numpy(), d['diverged_%d' % c])
         parity.assert_chain_parity(
             res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(), res.ham[c].cpu().numpy(),
             d['samples_%d' % c], d['accepted_%d' % c], d['ham_old_%d' % c], d['ham_new_%d' % c],
-            d['logu_%d' % c], case['kw']['burn'], exact=True)
+            d['logu_%d' % c], case['kw']['burn'], exact=exact, rtol=case.get('rtol', 0.0))
         assert int(res.num_rejected[c]) == int((d['accepted_%d' % c] == 0).sum())
         if nuts:
             # the kernel's own dual averaging, fed the same history, proposes the reference's step sizes
             S, burn = case['kw']['num_samples'], case['kw']['burn']
             own = res.eps_trace[c].cpu().numpy().astype(np.float64)          # own[n] = eps for iteration n+1
             ref = d['step_sizes_%d' % c]
-            np.testing.assert_allclose(own[:S - 1], ref[1:], rtol=parity.NUTS_EPS_RTOL)
-            np.testing.assert_allclose(own[burn], float(d['final_step_size_%d' % c]), rtol=parity.NUTS_EPS_RTOL)
-            np.testing.assert_allclose(float(res.eps_bar[c]), float(d['final_step_size_%d' % c]),
-                                       rtol=parity.NUTS_EPS_RTOL)
+            rt = max(parity.NUTS_EPS_RTOL, 10 * case.get('rtol', 0.0))
+            np.testing.assert_allclose(own[:S - 1], ref[1:], rtol=rt)
+            np.testing.assert_allclose(own[burn], float(d['final_step_size_%d' % c]), rtol=rt)
+            np.testing.assert_allclose(float(res.eps_bar[c]), float(d['final_step_size_%d' % c]), rtol=rt)
         else:
             assert float(res.step_size[c]) == np.float32(case['kw']['step_size'])
 
