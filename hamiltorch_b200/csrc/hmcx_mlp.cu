@@ -20,9 +20,9 @@
 
 namespace hmcx {
 
-constexpr int MLP_THREADS = 256;
-constexpr int MLP_T = 32;                 // data rows per tile
-constexpr int MLP_RG = MLP_T / 4;         // row groups of the 4x4 micro-tiles (rows rg, rg+8, rg+16, rg+24)
+constexpr int MLP_THREADS = 512;
+constexpr int MLP_T_MAX = 64;             // data rows per tile: 64 when the tile buffers fit next to q,p,g, else 32 / 16
+// (rows of a 4x4 micro-tile are rg, rg+T/4, rg+2T/4, rg+3T/4)
 
 struct MlpDev {
     int L, D, Dp, N, M, has_data;
@@ -31,6 +31,7 @@ struct MlpDev {
     int aoff[HMCX_MLP_MAX_LAYERS + 1];    // smem offsets (floats, relative to the tile area) of A[l] (T x n[l])
     int dzoff[2];                         // two delta buffers (T x maxw)
     int tile_floats;
+    int T;                                // rows per tile (multiple of 4)
     float tau_out, prior_scale, c_ll;     // c_ll = fp32(-0.5*tau_out)   (samplers.py:1184)
     float two_var[2 * HMCX_MLP_MAX_LAYERS], log_scale[2 * HMCX_MLP_MAX_LAYERS], gcoef[2 * HMCX_MLP_MAX_LAYERS];
     const float* x;
@@ -55,15 +56,45 @@ __device__ __forceinline__ float act_bwd(float aout, int a) {
 // ---- tile primitives (all 256 threads; callers place the __syncthreads) ---------------------------------------
 __device__ __forceinline__ void mlp_load_x(const MlpDev& m, float* A0, int r0, int cnt) {
     const int n0 = m.n[0];
-    for (int i = threadIdx.x; i < MLP_T * n0; i += MLP_THREADS)
+    for (int i = threadIdx.x; i < m.T * n0; i += MLP_THREADS)
         A0[i] = (i < cnt * n0) ? __ldg(m.x + (size_t)r0 * n0 + i) : 0.0f;
 }
 
-// Aout[T x n_out] = act(Ain[T x n_in] . W^T + b),  W row-major (n_out, n_in) in shared memory
+// ---- "thin" layers (few outputs, e.g. the scalar regression head): split the reduction over a lane group ---------
+// S = lanes per output (power of two, S | 32); each group's lanes stride the reduction index, then shuffle-reduce.
+__device__ __forceinline__ int thin_group(int outputs) {
+    int s = 32;
+    while (s > 1 && outputs * s > MLP_THREADS) s >>= 1;
+    return s;
+}
+__device__ __forceinline__ float group_sum(float v, int S) {
+    for (int o = S >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void mlp_linear_fwd_thin(const float* Ain, const float* W, const float* b, float* Aout,
+                                                    int n_in, int n_out, int act, int T) {
+    const int outputs = T * n_out, S = thin_group(outputs);
+    for (int base = 0; base < outputs; base += MLP_THREADS / S) {
+        const int o = base + threadIdx.x / S, s = threadIdx.x % S;
+        const bool live = o < outputs;
+        const int r = live ? o / n_out : 0, j = live ? o % n_out : 0;
+        float acc = 0.0f;
+        for (int k = s; k < n_in; k += S) acc = fmaf(Ain[r * n_in + k], W[j * n_in + k], acc);
+        acc = group_sum(acc, S);
+        if (live && s == 0) Aout[r * n_out + j] = act_fwd(acc + b[j], act);
+    }
+}
+
+// Aout[T x n_out] = act(Ain[T x n_in] . W^T + b),  W row-major (n_out, n_in) in shared memory.
+// 4x4 register micro-tiles (rows rg+8i, columns cg+ncg*jj); the reduction index is rotated per lane so that the
+// strided weight reads are bank-conflict-free; with n_in % 4 == 0 and 16-byte aligned rows the loads are float4.
 __device__ __forceinline__ void mlp_linear_fwd(const float* Ain, const float* W, const float* b, float* Aout,
-                                               int n_in, int n_out, int act) {
-    const int ncg = (n_out + 3) >> 2;
-    for (int tile = threadIdx.x; tile < MLP_RG * ncg; tile += MLP_THREADS) {
+                                               int n_in, int n_out, int act, int T) {
+    const int ncg = (n_out + 3) >> 2, RG = T >> 2;
+    if (RG * ncg * 4 <= MLP_THREADS) { mlp_linear_fwd_thin(Ain, W, b, Aout, n_in, n_out, act, T); return; }
+    const bool vec = ((n_in & 3) == 0) && ((((size_t)W) & 15) == 0) && ((((size_t)Ain) & 15) == 0);
+    for (int tile = threadIdx.x; tile < RG * ncg; tile += MLP_THREADS) {
         const int cg = tile % ncg, rg = tile / ncg;
         int jc[4];
         float acc[4][4];
@@ -75,25 +106,63 @@ __device__ __forceinline__ void mlp_linear_fwd(const float* Ain, const float* W,
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i][jj] = bj;
         }
-        int kk = cg % n_in;                                   // per-lane rotation of the reduction index
-        for (int k = 0; k < n_in; ++k) {
-            float a[4], w[4];
+        if (vec) {
+            const int n4 = n_in >> 2, rot = cg % n4;          // rotation in units of float4
+            const float4* ap[4];
+            const float4* wp[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = Ain[(rg + i * MLP_RG) * n_in + kk];
+            for (int i = 0; i < 4; ++i) {
+                ap[i] = reinterpret_cast<const float4*>(Ain) + (rg + i * RG) * n4;
+                wp[i] = reinterpret_cast<const float4*>(W) + jc[i] * n4;
+            }
+            auto body = [&](int kk) {
+                float4 a[4], w[4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) w[jj] = W[jc[jj] * n_in + kk];
+                for (int i = 0; i < 4; ++i) { a[i] = ap[i][kk]; w[i] = wp[i][kk]; }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], w[jj], acc[i][jj]);
-            if (++kk == n_in) kk = 0;
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i].x, w[jj].x, acc[i][jj]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i].y, w[jj].y, acc[i][jj]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i].z, w[jj].z, acc[i][jj]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i].w, w[jj].w, acc[i][jj]);
+            };
+            int kk = rot;                                     // uniform trip count: no divergence across lanes
+#pragma unroll 2
+            for (int k = 0; k < n4; ++k) {
+                body(kk);
+                kk = (kk + 1 == n4) ? 0 : kk + 1;
+            }
+        } else {
+            int kk = cg % n_in;                               // per-lane rotation of the reduction index
+            for (int k = 0; k < n_in; ++k) {
+                float a[4], w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = Ain[(rg + i * RG) * n_in + kk];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) w[jj] = W[jc[jj] * n_in + kk];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], w[jj], acc[i][jj]);
+                if (++kk == n_in) kk = 0;
+            }
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int j = cg + jj * ncg;
             if (j < n_out) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) Aout[(rg + i * MLP_RG) * n_out + j] = act_fwd(acc[i][jj], act);
+                for (int i = 0; i < 4; ++i) Aout[(rg + i * RG) * n_out + j] = act_fwd(acc[i][jj], act);
             }
         }
     }
@@ -101,53 +170,100 @@ __device__ __forceinline__ void mlp_linear_fwd(const float* Ain, const float* W,
 
 // gW[n_out x n_in] += dz^T[n_out x T] . Ain[T x n_in];   gb[n_out] += column sums of dz
 __device__ __forceinline__ void mlp_weight_grad(const float* Ain, const float* dz, float* gW, float* gb, int n_in,
-                                                int n_out) {
-    const int nkg = (n_in + 3) >> 2, njg = (n_out + 3) >> 2;
-    for (int tile = threadIdx.x; tile < njg * nkg; tile += MLP_THREADS) {
-        const int kg = tile % nkg, jg = tile / nkg;
-        int jc[4], kc[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int j = jg + t * njg, k = kg + t * nkg;
-            jc[t] = j < n_out ? j : n_out - 1;
-            kc[t] = k < n_in ? k : n_in - 1;
+                                                int n_out, int T) {
+    const int njg = (n_out + 3) >> 2;
+    if (n_out * n_in * 2 <= MLP_THREADS * 4 && n_out * n_in <= MLP_THREADS) {
+        // thin: one output (j,k) per lane group, the T rows split over the group's lanes
+        const int outputs = n_out * n_in, S = thin_group(outputs);
+        for (int base = 0; base < outputs; base += MLP_THREADS / S) {
+            const int o = base + threadIdx.x / S, s = threadIdx.x % S;
+            const bool live = o < outputs;
+            const int j = live ? o / n_in : 0, k = live ? o % n_in : 0;
+            float acc = 0.0f;
+            for (int r = s; r < T; r += S) acc = fmaf(dz[r * n_out + j], Ain[r * n_in + k], acc);
+            acc = group_sum(acc, S);
+            if (live && s == 0) gW[j * n_in + k] += acc;
         }
-        float acc[4][4];
+    } else if (((n_in & 3) == 0) && ((((size_t)gW) & 15) == 0) && ((((size_t)Ain) & 15) == 0)) {
+        // 4 (rows of gW: j = jg + jj*njg) x 4 (contiguous k) micro-tiles, float4 activations and float4 RMW of gW
+        const int nk4 = n_in >> 2;
+        const float4* A4 = reinterpret_cast<const float4*>(Ain);
+        for (int tile = threadIdx.x; tile < njg * nk4; tile += MLP_THREADS) {
+            const int k4 = tile % nk4, jg = tile / nk4;
+            int jc[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
+            for (int t = 0; t < 4; ++t) { const int j = jg + t * njg; jc[t] = j < n_out ? j : n_out - 1; }
+            float4 acc[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) acc[jj][t] = 0.0f;
-        for (int r = 0; r < MLP_T; ++r) {
-            float d[4], a[4];
+            for (int jj = 0; jj < 4; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int r = 0; r < T; ++r) {
+                const float4 a = A4[r * nk4 + k4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { d[t] = dz[r * n_out + jc[t]]; a[t] = Ain[r * n_in + kc[t]]; }
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float d = dz[r * n_out + jc[jj]];
+                    acc[jj].x = fmaf(d, a.x, acc[jj].x); acc[jj].y = fmaf(d, a.y, acc[jj].y);
+                    acc[jj].z = fmaf(d, a.z, acc[jj].z); acc[jj].w = fmaf(d, a.w, acc[jj].w);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = jg + jj * njg;
+                if (j >= n_out) continue;
+                float4* dst = reinterpret_cast<float4*>(gW + j * n_in) + k4;
+                float4 v = *dst;
+                v.x += acc[jj].x; v.y += acc[jj].y; v.z += acc[jj].z; v.w += acc[jj].w;
+                *dst = v;
+            }
+        }
+    } else {
+        const int nkg = (n_in + 3) >> 2;
+        for (int tile = threadIdx.x; tile < njg * nkg; tile += MLP_THREADS) {
+            const int kg = tile % nkg, jg = tile / nkg;
+            int jc[4], kc[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = jg + t * njg, k = kg + t * nkg;
+                jc[t] = j < n_out ? j : n_out - 1;
+                kc[t] = k < n_in ? k : n_in - 1;
+            }
+            float acc[4][4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) acc[jj][t] = fmaf(d[jj], a[t], acc[jj][t]);
-        }
+                for (int t = 0; t < 4; ++t) acc[jj][t] = 0.0f;
+            for (int r = 0; r < T; ++r) {
+                float d[4], a[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = jg + jj * njg;
-            if (j >= n_out) continue;
+                for (int t = 0; t < 4; ++t) { d[t] = dz[r * n_out + jc[t]]; a[t] = Ain[r * n_in + kc[t]]; }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int k = kg + t * nkg;
-                if (k < n_in) gW[j * n_in + k] += acc[jj][t];
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[jj][t] = fmaf(d[jj], a[t], acc[jj][t]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = jg + jj * njg;
+                if (j >= n_out) continue;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int k = kg + t * nkg;
+                    if (k < n_in) gW[j * n_in + k] += acc[jj][t];
+                }
             }
         }
     }
     for (int j = threadIdx.x; j < n_out; j += MLP_THREADS) {
         float s = 0.0f;
-        for (int r = 0; r < MLP_T; ++r) s += dz[r * n_out + j];
+        for (int r = 0; r < T; ++r) s += dz[r * n_out + j];
         gb[j] += s;
     }
 }
 
 // dz_prev[T x n_in] = (dz[T x n_out] . W[n_out x n_in]) * act'(A[T x n_in])
 __device__ __forceinline__ void mlp_input_grad(const float* dz, const float* W, const float* A, float* dz_prev,
-                                               int n_in, int n_out, int act_prev) {
-    const int nkg = (n_in + 3) >> 2;
+                                               int n_in, int n_out, int act_prev, int T) {
+    const int nkg = (n_in + 3) >> 2, MLP_RG = T >> 2;
     for (int tile = threadIdx.x; tile < MLP_RG * nkg; tile += MLP_THREADS) {
         const int kg = tile % nkg, rg = tile / nkg;
         int kc[4];
@@ -188,7 +304,7 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpDev& m, const float* q
     __syncthreads();
     for (int l = 0; l < m.L; ++l) {
         mlp_linear_fwd(tile + m.aoff[l], q + m.woff[l], q + m.boff[l], tile + m.aoff[l + 1], m.n[l], m.n[l + 1],
-                       m.act[l]);
+                       m.act[l], m.T);
         __syncthreads();
     }
 }
@@ -198,7 +314,7 @@ __device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, const float* out
     const int nL = m.n[m.L];
     float sse = 0.0f;
     const float c2 = mul(m.c_ll, 2.0f);                                   // autograd: ds * (2*diff)
-    for (int i = threadIdx.x; i < MLP_T * nL; i += MLP_THREADS) {
+    for (int i = threadIdx.x; i < m.T * nL; i += MLP_THREADS) {
         float d = 0.0f;
         if (i < cnt * nL) {
             d = sub(out[i], __ldg(m.y + (size_t)r0 * nL + i));
@@ -212,17 +328,17 @@ __device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, const float* out
 // g += d ll_split / dq over the rows [r_begin, r_end)  (g must already hold the prior part)
 __device__ __forceinline__ void mlp_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, int r_begin,
                                                   int r_end) {
-    for (int r0 = r_begin; r0 < r_end; r0 += MLP_T) {
-        const int cnt = min(MLP_T, r_end - r0);
+    for (int r0 = r_begin; r0 < r_end; r0 += m.T) {
+        const int cnt = min(m.T, r_end - r0);
         mlp_forward_tile(m, q, tile, r0, cnt);
         float* dz = tile + m.dzoff[m.L & 1];
         mlp_loss_tile(m, tile + m.aoff[m.L], dz, r0, cnt);
         __syncthreads();
         for (int l = m.L - 1; l >= 0; --l) {
             float* dz_prev = tile + m.dzoff[l & 1];
-            mlp_weight_grad(tile + m.aoff[l], dz, g + m.woff[l], g + m.boff[l], m.n[l], m.n[l + 1]);
+            mlp_weight_grad(tile + m.aoff[l], dz, g + m.woff[l], g + m.boff[l], m.n[l], m.n[l + 1], m.T);
             if (l > 0)
-                mlp_input_grad(dz, q + m.woff[l], tile + m.aoff[l], dz_prev, m.n[l], m.n[l + 1], m.act[l - 1]);
+                mlp_input_grad(dz, q + m.woff[l], tile + m.aoff[l], dz_prev, m.n[l], m.n[l + 1], m.act[l - 1], m.T);
             __syncthreads();
             dz = dz_prev;
         }
@@ -281,8 +397,8 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
     const int s0 = s < 0 ? 0 : s, s1 = s < 0 ? m.M : s + 1;
     for (int sp = s0; sp < s1; ++sp) {
         float sse[1] = {0.0f};
-        for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += MLP_T) {
-            const int cnt = min(MLP_T, m.sb[sp + 1] - r0);
+        for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += m.T) {
+            const int cnt = min(m.T, m.sb[sp + 1] - r0);
             mlp_forward_tile(m, q, tile, r0, cnt);
             sse[0] = add(sse[0], mlp_loss_tile(m, tile + m.aoff[m.L], nullptr, r0, cnt));
             if (pred_out) {
@@ -555,6 +671,28 @@ mlp_predict_kernel(const MlpDev m, const float* __restrict__ samples, int ld, fl
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+static void mlp_layout_tiles(MlpDev& m, int T) {
+    int aoff = 0, maxw = 0;
+    for (int l = 0; l <= m.L; ++l) {
+        m.aoff[l] = aoff;
+        aoff += T * m.n[l];
+        if (m.n[l] > maxw) maxw = m.n[l];
+    }
+    m.dzoff[0] = aoff;
+    m.dzoff[1] = aoff + T * maxw;
+    m.tile_floats = aoff + 2 * T * maxw;
+    m.T = T;
+}
+
+// pick the largest tile height whose buffers fit next to `state_vectors` copies of the parameter vector
+static bool mlp_pick_tile(MlpDev& m, int state_vectors) {
+    for (int T = MLP_T_MAX; T >= 8; T >>= 1) {
+        mlp_layout_tiles(m, T);
+        if ((size_t)(state_vectors * m.Dp + m.tile_floats) * sizeof(float) <= 227 * 1024 - 4096) return true;
+    }
+    return false;
+}
+
 static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
     if (!target || target->kind != HMCX_TARGET_MLP || !target->mlp) return HMCX_ERR_INVALID_ARG;
     const hmcx_mlp_t& h = *target->mlp;
@@ -562,13 +700,10 @@ static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
     if (h.loss != HMCX_LOSS_REGRESSION) return HMCX_ERR_UNSUPPORTED;
     if (h.activation[h.num_layers - 1] != HMCX_ACT_NONE) return HMCX_ERR_INVALID_ARG;
     m.L = h.num_layers;
-    int off = 0, maxw = 0, aoff = 0;
+    int off = 0;
     for (int l = 0; l <= m.L; ++l) {
         if (h.widths[l] < 1) return HMCX_ERR_INVALID_ARG;
         m.n[l] = h.widths[l];
-        m.aoff[l] = aoff;
-        aoff += MLP_T * m.n[l];
-        if (m.n[l] > maxw) maxw = m.n[l];
     }
     for (int l = 0; l < m.L; ++l) {
         m.act[l] = h.activation[l];
@@ -579,9 +714,7 @@ static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
     m.D = off;
     if (m.D != target->dim) return HMCX_ERR_INVALID_ARG;
     m.Dp = (m.D + 3) / 4 * 4;
-    m.dzoff[0] = aoff;
-    m.dzoff[1] = aoff + MLP_T * maxw;
-    m.tile_floats = aoff + 2 * MLP_T * maxw;
+    mlp_layout_tiles(m, 8);
     m.tau_out = h.tau_out;
     m.prior_scale = h.prior_scale;
     m.c_ll = (float)(-0.5 * (double)h.tau_out);
@@ -651,6 +784,7 @@ int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     }
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
+    if (!mlp_pick_tile(a.m, 3)) return HMCX_ERR_UNSUPPORTED;    // q, p, g do not fit one SM's shared memory
     const size_t smem = (size_t)(3 * a.m.Dp + a.m.tile_floats) * sizeof(float);
     rc = prepare_smem(mlp_run_kernel, smem);
     if (rc != HMCX_OK) return rc;
@@ -665,6 +799,7 @@ int mlp_grad_log_prob(const hmcx_target_t* target, const float* q, int C, int ld
     if (rc != HMCX_OK) return rc;
     if (!q || C < 1 || ld < m.D || (ld & 3) || split < -1 || split >= m.M || (!grad_out && !log_prob_out))
         return HMCX_ERR_INVALID_ARG;
+    if (!mlp_pick_tile(m, 2)) return HMCX_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(2 * m.Dp + m.tile_floats) * sizeof(float);
     rc = prepare_smem(mlp_grad_kernel, smem);
     if (rc != HMCX_OK) return rc;
@@ -678,6 +813,7 @@ int mlp_predict(const hmcx_target_t* target, const float* samples, int S, int ld
     int rc = fill_mlp(target, m);
     if (rc != HMCX_OK) return rc;
     if (!samples || !pred_out || S < 1 || ld < m.D || (ld & 3) || !m.has_data) return HMCX_ERR_INVALID_ARG;
+    if (!mlp_pick_tile(m, 1)) return HMCX_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(m.Dp + m.tile_floats) * sizeof(float);
     rc = prepare_smem(mlp_predict_kernel, smem);
     if (rc != HMCX_OK) return rc;
