@@ -145,8 +145,10 @@ struct RunArgs {
 
 constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * K <= 8 ? 512 : 256); }
 
-template <int TK, int MK, int E, int K>
-__global__ void __launch_bounds__(run_max_threads(E, K))
+// MAXT = CTA size the instantiation is compiled for (register budget 64K/MAXT): chains of D <= 1024 run with <= 256
+// threads and get a generous budget, which lets the compiler software-pipeline the next iteration's RNG.
+template <int TK, int MK, int E, int K, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 hmc_run_kernel(const RunArgs a) {
     __shared__ float s_red[2][100];
     __shared__ float s_eps[2];
@@ -197,6 +199,26 @@ hmc_run_kernel(const RunArgs a) {
             if (live[k]) stE_stream<E>(my_samples + E * (tid + k * G), qc[k]);
     }
 
+    // the standard normals of iteration n: produced one iteration AHEAD (they do not depend on the MH decision), so
+    // that the Philox/Box-Muller arithmetic of iteration n+1 overlaps the shuffle/barrier latency of iteration n
+    float zn[K][E];
+    auto draw = [&](int n) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int grp = tid + k * G, e0 = E * grp;
+#pragma unroll
+            for (int j = 0; j < E; ++j) zn[k][j] = 0.0f;
+            if (live[k]) {
+                if (a.rng_mode == HMCX_RNG_INJECTED) ldE_stream<E>(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, zn[k]);
+                else philox_normals<E>(a.seed, chain_id, (uint64_t)n, (uint32_t)grp, zn[k]);
+            }
+#pragma unroll
+            for (int j = 0; j < E; ++j)
+                if (e0 + j >= D) zn[k][j] = 0.0f;
+        }
+    };
+    if (a.it0 < a.it1) draw(a.it0);
+
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
         const float half = mul(0.5f, eps);
@@ -204,21 +226,9 @@ hmc_run_kernel(const RunArgs a) {
         float kin0 = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int grp = tid + k * G, e0 = E * grp;
-            float z[E];
-#pragma unroll
-            for (int j = 0; j < E; ++j) z[j] = 0.0f;
-            if (live[k]) {
-                if (a.rng_mode == HMCX_RNG_INJECTED) {
-                    ldE_stream<E>(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, z);
-                } else {
-                    philox_normals<E>(a.seed, chain_id, (uint64_t)n, (uint32_t)grp, z);
-                }
-            }
 #pragma unroll
             for (int j = 0; j < E; ++j) {
-                if (e0 + j >= D) z[j] = 0.0f;
-                p[k][j] = (MK == HMCX_MASS_DIAG) ? mul(z[j], vc[k].sd[j]) : z[j];
+                p[k][j] = (MK == HMCX_MASS_DIAG) ? mul(zn[k][j], vc[k].sd[j]) : zn[k][j];
                 kin0 = add(kin0, kterm1<MK>(p[k][j], vc[k].im[j]));
                 q[k][j] = qc[k][j];
             }
@@ -236,6 +246,7 @@ hmc_run_kernel(const RunArgs a) {
                 r1 = add(r1, uterm1<TK>(q[k][j], vc[k].mean[j], vc[k].ivar[j]));
                 r2 = add(r2, kterm1<MK>(p[k][j], vc[k].im[j]));
             }
+        if (n + 1 < a.it1) draw(n + 1);                       // next iteration's normals: independent work for the scheduler
         // the iteration's log-uniform is produced once (thread 0) and rides the reduction's shared buffer
         float logu = 0.0f;
         if (tid == 0)
@@ -537,11 +548,12 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     int E, K, G;
     if (!pick_geometry(ld, tuning, E, K, G)) return tuning ? HMCX_ERR_INVALID_ARG : HMCX_ERR_UNSUPPORTED;
 #define CALL(TK, MK)                                                                                    \
-    if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1><<<C, G, 0, st>>>(a);                             \
-    else if (E == 2) hmc_run_kernel<TK, MK, 2, 2><<<C, G, 0, st>>>(a);                                  \
-    else if (K == 1) hmc_run_kernel<TK, MK, 4, 1><<<C, G, 0, st>>>(a);                                  \
-    else if (K == 2) hmc_run_kernel<TK, MK, 4, 2><<<C, G, 0, st>>>(a);                                  \
-    else hmc_run_kernel<TK, MK, 4, 4><<<C, G, 0, st>>>(a)
+    if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1, 1024><<<C, G, 0, st>>>(a);                       \
+    else if (E == 2) hmc_run_kernel<TK, MK, 2, 2, 1024><<<C, G, 0, st>>>(a);                            \
+    else if (K == 1 && G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256><<<C, G, 0, st>>>(a);                 \
+    else if (K == 1) hmc_run_kernel<TK, MK, 4, 1, 1024><<<C, G, 0, st>>>(a);                            \
+    else if (K == 2) hmc_run_kernel<TK, MK, 4, 2, 512><<<C, G, 0, st>>>(a);                             \
+    else hmc_run_kernel<TK, MK, 4, 4, 256><<<C, G, 0, st>>>(a)
     DISPATCH_TK_MK(a.t, CALL);
 #undef CALL
     return cuda_status();
