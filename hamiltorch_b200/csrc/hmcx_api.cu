@@ -9,7 +9,7 @@ int elem_hamiltonian(const hmcx_target_t*, const hmcx_mass_t*, const float*, con
 int elem_gibbs(const hmcx_mass_t*, const hmcx_rng_t*, int, int, int, int64_t, float*, cudaStream_t);
 int elem_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*,
                  float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
-                 int, cudaStream_t);
+                 int, float*, cudaStream_t);
 int mlp_split_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, int, const float*,
                   float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                   cudaStream_t);
@@ -29,6 +29,12 @@ static inline bool is_elem(const hmcx_target_t* t) {
 extern "C" {
 
 int hmcx_abi_version(void) { return HMCX_ABI_VERSION; }
+
+size_t hmcx_hmc_workspace_bytes(const hmcx_target_t* target, const hmcx_mass_t* mass, int32_t C, int32_t ld) {
+    const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
+    if (is_elem(target) && !full_mass && ld > 4096) return (size_t)C * (size_t)ld * sizeof(float);
+    return 0;
+}
 
 const char* hmcx_status_string(int status) {
     switch (status) {
@@ -67,13 +73,13 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
                  const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int32_t C, int32_t ld,
                  int32_t L, int32_t num_samples, int32_t burn, int32_t iter_begin, int32_t iter_end,
                  float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
-                 int32_t* num_rejected, int32_t tuning, void* stream) {
+                 int32_t* num_rejected, int32_t tuning, float* workspace, void* stream) {
     if (!target) return HMCX_ERR_INVALID_ARG;
     const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
     if (is_elem(target) && !full_mass)
         return hmcx::elem_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
-                                  num_rejected, tuning, (cudaStream_t)stream);
+                                  num_rejected, tuning, workspace, (cudaStream_t)stream);
     if (is_elem(target) || target->kind == HMCX_TARGET_GAUSS_FULL || target->kind == HMCX_TARGET_FUNNEL)
         // coupled gradient or full mass matrix: thread-per-chain kernel, D <= 16 (samplers.py:293-294, :811-812, :198-199)
         return hmcx::small_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,

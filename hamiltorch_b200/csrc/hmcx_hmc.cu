@@ -336,6 +336,148 @@ hmc_run_kernel(const RunArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// large-D form of the persistent kernel (D > 4096): same per-iteration logic, but the chain's state does not fit the
+// register file of one CTA, so it is streamed.  One CTA of 1024 threads per chain walks the chain's float4 vectors:
+//   pass A  load q_cur, draw p, integrate the (thread-private) trajectory, accumulate the three Hamiltonian sums,
+//           park the proposal in `work` (caller-provided (C, ld) scratch);
+//   decide  one fused block reduction + MH, exactly as hmc_run_kernel;
+//   pass B  commit proposal / keep / restore params_init (the :1018 quirk), write the retained row.
+// Pass B touches only vectors the same thread wrote in pass A: no extra barrier.  Traffic: 20*D bytes per iteration
+// and chain (L2-resident while C*ld*8 B < ~100 MB), i.e. HBM/L2-bound like the streaming leapfrog kernel.
+// ---------------------------------------------------------------------------------------------------------
+template <int TK, int MK>
+__global__ void __launch_bounds__(1024)
+hmc_run_big_kernel(const RunArgs a, float* __restrict__ work) {
+    __shared__ float s_red[2][100];
+    __shared__ float s_eps[2];
+    const int c = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
+    const ElemTarget& t = a.t;
+    const int ld = t.ld, D = t.D, nvec = ld >> 2;
+    const size_t row = (size_t)c * ld;
+    const uint64_t chain_id = a.chain_offset + (uint64_t)c;
+    float* const qcur = a.q_cur + row;
+    float* const prop = work + row;
+    const float* const qinit = a.q_init + row;
+
+    auto log_prob_of = [&](const float* src, float* sbuf) {     // full pass over a state row
+        float r[1] = {0.0f};
+        for (int v = tid; v < nvec; v += G) {
+            VecConst<4> vc;
+            load_consts<TK, MK, 4>(t, 4 * v, vc);
+            float x[4];
+            ld4(src + 4 * v, x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * v + j < D) r[0] = add(r[0], uterm1<TK>(x[j], vc.mean[j], vc.ivar[j]));
+        }
+        block_sum<1>(r, sbuf);
+        __syncthreads();
+        return log_prob_from_sum(r[0], t.log_norm);
+    };
+    float lp_cur = log_prob_of(qcur, s_red[1]);
+
+    float eps = a.eps[c];
+    double h_bar = 0.0, eps_bar = 1.0;
+    if (a.nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
+    int rejected = 0;
+    const int keep = a.S - a.burn;
+    float* const my_samples = a.samples ? a.samples + (size_t)c * keep * ld : nullptr;
+    if (a.it0 == 0 && my_samples)
+        for (int v = tid; v < nvec; v += G) { float x[4]; ld4(qcur + 4 * v, x); st4_stream(my_samples + 4 * v, x); }
+
+    for (int n = a.it0; n < a.it1; ++n) {
+        if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
+        const float half = mul(0.5f, eps);
+        float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+        for (int v = tid; v < nvec; v += G) {                   // ---- pass A ----
+            const int e0 = 4 * v;
+            VecConst<4> vc;
+            load_consts<TK, MK, 4>(t, e0, vc);
+            float q[4], p[4], z[4];
+            ld4(qcur + e0, q);
+            if (a.rng_mode == HMCX_RNG_INJECTED) ld4_stream(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, z);
+            else philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)v, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (e0 + j >= D) { z[j] = 0.0f; q[j] = 0.0f; }
+                p[j] = (MK == HMCX_MASS_DIAG) ? mul(z[j], vc.sd[j]) : z[j];
+                r0 = add(r0, kterm1<MK>(p[j], vc.im[j]));
+            }
+            trajectory<TK, MK, 4, false>(q, p, vc, eps, half, a.L, nullptr, nullptr, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r1 = add(r1, uterm1<TK>(q[j], vc.mean[j], vc.ivar[j]));
+                r2 = add(r2, kterm1<MK>(p[j], vc.im[j]));
+            }
+            st4(prop + e0, q);
+        }
+        float logu = 0.0f;
+        if (tid == 0)
+            logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * t.C + c]
+                                                     : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        block_sum3(r0, r1, r2, logu, s_red[n & 1]);
+        const float lp_new = log_prob_from_sum(r1, t.log_norm);
+        const float h_old = add(-lp_cur, mul(0.5f, r0));
+        const float h_new = add(-lp_new, mul(0.5f, r2));
+        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);
+        const float x = add(-h_new, h_old);
+        const float rho = (x < 0.0f) ? x : 0.0f;
+        const bool acc = !bad && (rho >= logu);
+        const bool quirk = !acc && (n == a.burn + 1);
+        if (!acc) ++rejected;
+        if (acc) lp_cur = lp_new;
+        const bool store = (n > a.burn) && my_samples;
+        if (acc || quirk || store) {                            // ---- pass B ----
+            float* dst = store ? my_samples + (size_t)(n - a.burn) * ld : nullptr;
+            const float* src = acc ? prop : (quirk ? qinit : qcur);
+            for (int v = tid; v < nvec; v += G) {
+                float xq[4];
+                ld4(src + 4 * v, xq);
+                if (acc || quirk) st4(qcur + 4 * v, xq);
+                if (dst) st4_stream(dst + 4 * v, xq);
+            }
+        }
+        if (quirk) {
+            __syncthreads();
+            lp_cur = log_prob_of(qcur, s_red[(n & 1) ^ 1]);
+        }
+        if (tid == 0) {
+            const size_t o = (size_t)c * a.S + n;
+            if (a.accept) a.accept[o] = acc ? 1 : 0;
+            if (a.diverged) a.diverged[o] = bad ? 1 : 0;
+            if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
+        }
+        if (a.nuts && n <= a.burn) {
+            if (tid == 0) {
+                float e = eps;
+                if (n < a.burn || bad) {
+                    const double* T = a.table + 5 * (size_t)n;
+                    const double alpha = bad ? 0.0 : (double)expf(rho);
+                    h_bar = __dadd_rn(__dmul_rn(T[0], h_bar), __dmul_rn(T[1], a.delta - alpha));
+                    const double x_new = a.mu - __dmul_rn(T[2], h_bar);
+                    e = expf((float)x_new);
+                    const float xb = add((float)__dmul_rn(T[3], x_new), mul((float)T[4], logf((float)eps_bar)));
+                    eps_bar = (double)expf(xb);
+                }
+                if (n == a.burn) e = (float)eps_bar;
+                s_eps[n & 1] = e;
+                if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = e;
+            }
+            __syncthreads();
+            eps = s_eps[n & 1];
+        } else if (a.eps_trace && tid == 0) {
+            a.eps_trace[(size_t)c * a.S + n] = eps;
+        }
+    }
+    if (tid == 0) {
+        a.eps[c] = eps;
+        if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
+        if (a.num_rejected) a.num_rejected[c] += rejected;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // streaming kernels
 // ---------------------------------------------------------------------------------------------------------
@@ -522,7 +664,7 @@ static bool pick_geometry(int ld, int tuning, int& E, int& K, int& G) {
 int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
                  const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int C, int ld, int L,
                  int S, int burn, int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged,
-                 float* ham, int32_t* num_rejected, int tuning, cudaStream_t st) {
+                 float* ham, int32_t* num_rejected, int tuning, float* workspace, cudaStream_t st) {
     RunArgs a = {};
     const int rc = fill_elem_target(target, mass, C, ld, a.t);
     if (rc != HMCX_OK) return rc;
@@ -546,6 +688,13 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
 
     int E, K, G;
+    if (ld > 4096 && tuning == 0) {                        // state does not fit one CTA's registers: streamed form
+        if (!workspace) return HMCX_ERR_INVALID_ARG;       // needs hmcx_hmc_workspace_bytes() of scratch
+#define CALLBIG(TK, MK) hmc_run_big_kernel<TK, MK><<<C, 1024, 0, st>>>(a, workspace)
+        DISPATCH_TK_MK(a.t, CALLBIG);
+#undef CALLBIG
+        return cuda_status();
+    }
     if (!pick_geometry(ld, tuning, E, K, G)) return tuning ? HMCX_ERR_INVALID_ARG : HMCX_ERR_UNSUPPORTED;
 #define CALL(TK, MK)                                                                                    \
     if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1, 1024><<<C, G, 0, st>>>(a);                       \

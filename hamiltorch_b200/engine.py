@@ -351,9 +351,11 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
 
     with torch.cuda.device(device):
         if scheme is None:
+            ws_bytes = lib.hmcx_hmc_workspace_bytes(nt.ref(), nm.ref(), Cn, ld)
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=device) if ws_bytes else None
             rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
                                   N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),
-                                  N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning),
+                                  N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.ptr(ws),
                                   N.stream_ptr(device))
             N.check(rc, 'hmcx_hmc_run')
         else:

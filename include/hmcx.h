@@ -22,13 +22,14 @@
 #ifndef HMCX_H
 #define HMCX_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define HMCX_ABI_VERSION 1
+#define HMCX_ABI_VERSION 2
 
 /* status codes */
 #define HMCX_OK                0
@@ -172,6 +173,7 @@ int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_
  *   samples_out [C, num_samples-burn, ld]  slot 0 = params_init (:959), slot n-burn = iteration n > burn
  *   accept_out / diverged_out  optional [C, num_samples] (uint8); ham_out optional [C, num_samples, 2] = (H_old, H_new)
  *   num_rejected optional [C] int32 in/out counter (:961, :1016, :1046)
+ *   workspace    hmcx_hmc_workspace_bytes() bytes of device scratch (NULL when that is 0)
  *   tuning       0 = automatic register geometry (= 1, one float4 per thread); 2 / 4 = that many float4 groups per
  *                thread; 21 / 22 = one / two float2 groups per thread (tests and tuning sweeps; results never depend on it)
  */
@@ -181,7 +183,11 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
                  int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
                  int32_t iter_begin, int32_t iter_end,
                  float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
-                 int32_t* num_rejected, int32_t tuning, void* stream);
+                 int32_t* num_rejected, int32_t tuning, float* workspace, void* stream);
+
+/* Scratch hmcx_hmc_run needs in `workspace` (device bytes; 0 = may pass NULL).  Element-wise targets with D > 4096 are
+ * advanced by a streamed form of the kernel that parks each proposal in a caller-provided (C, ld) buffer. */
+size_t hmcx_hmc_workspace_bytes(const hmcx_target_t* target, const hmcx_mass_t* mass, int32_t C, int32_t ld);
 
 /* sampler=RMHMC configuration (samplers.py:850 arguments that only this sampler reads) */
 typedef struct hmcx_rmhmc {

@@ -47,11 +47,11 @@ def test_invalid_arguments_are_rejected_without_cuda(built_library):
     nuts = N.NutsStruct()
     # ld not a multiple of 4
     rc = lib.hmcx_hmc_run(C.byref(tgt), C.byref(mass), C.byref(rng), C.byref(nuts), None, None, None,
-                          1, 7, 5, 10, 0, 0, 10, None, None, None, None, None, 0, None)
+                          1, 7, 5, 10, 0, 0, 10, None, None, None, None, None, 0, None, None)
     assert rc == N.ERR_INVALID_ARG
     # null state pointers
     rc = lib.hmcx_hmc_run(C.byref(tgt), C.byref(mass), C.byref(rng), C.byref(nuts), None, None, None,
-                          1, 8, 5, 10, 0, 0, 10, None, None, None, None, None, 0, None)
+                          1, 8, 5, 10, 0, 0, 10, None, None, None, None, None, 0, None, None)
     assert rc == N.ERR_INVALID_ARG
     # unknown target kind
     tgt.kind = 99
