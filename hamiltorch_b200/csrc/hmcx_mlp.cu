@@ -25,14 +25,14 @@ constexpr int MLP_T_MAX = 64;             // data rows per tile: 64 when the til
 // (rows of a 4x4 micro-tile are rg, rg+T/4, rg+2T/4, rg+3T/4)
 
 struct MlpDev {
-    int L, D, Dp, N, M, has_data;
+    int L, D, Dp, N, M, has_data, loss;
     int n[HMCX_MLP_MAX_LAYERS + 1], act[HMCX_MLP_MAX_LAYERS];
     int woff[HMCX_MLP_MAX_LAYERS], boff[HMCX_MLP_MAX_LAYERS];
     int aoff[HMCX_MLP_MAX_LAYERS + 1];    // smem offsets (floats, relative to the tile area) of A[l] (T x n[l])
     int dzoff[2];                         // two delta buffers (T x maxw)
     int tile_floats;
     int T;                                // rows per tile (multiple of 4)
-    float tau_out, prior_scale, c_ll;     // c_ll = fp32(-0.5*tau_out)   (samplers.py:1184)
+    float tau_out, prior_scale, c_ll;     // c_ll = fp32(-0.5*tau_out) (regression, :1184) or fp32(-tau_out) (:1172-1180)
     float two_var[2 * HMCX_MLP_MAX_LAYERS], log_scale[2 * HMCX_MLP_MAX_LAYERS], gcoef[2 * HMCX_MLP_MAX_LAYERS];
     const float* x;
     const float* y;
@@ -309,20 +309,61 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpDev& m, const float* q
     }
 }
 
-// sum of squared residuals of a forwarded tile (thread partial) and, optionally, dz_L = d ll / d out
-__device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, const float* out, float* dz, int r0, int cnt) {
+// Loss stage of a forwarded tile: returns the thread's partial of the loss sum (ll = c_ll * sum, or c_ll * sum / rows
+// for the mean-reduced nll_loss) and, when dz != nullptr, writes dz_L = d ll / d out.  `rows` = data rows of the closure
+// being evaluated (the split), only used by the mean reduction.  With log_softmax_out the tile's outputs are replaced
+// by their log-softmax (what predict_model returns for such a model).
+__device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, float* out, float* dz, int r0, int cnt, int rows,
+                                               bool log_softmax_out = false) {
     const int nL = m.n[m.L];
-    float sse = 0.0f;
-    const float c2 = mul(m.c_ll, 2.0f);                                   // autograd: ds * (2*diff)
-    for (int i = threadIdx.x; i < m.T * nL; i += MLP_THREADS) {
-        float d = 0.0f;
-        if (i < cnt * nL) {
-            d = sub(out[i], __ldg(m.y + (size_t)r0 * nL + i));
-            sse = add(sse, mul(d, d));
+    float sum = 0.0f;
+    if (m.loss == HMCX_LOSS_REGRESSION || m.loss == HMCX_LOSS_BINARY) {
+        const float c2 = mul(m.c_ll, 2.0f);                               // regression, autograd: ds * (2*diff)
+        for (int i = threadIdx.x; i < m.T * nL; i += MLP_THREADS) {
+            float d = 0.0f, gz = 0.0f;
+            if (i < cnt * nL) {
+                const float yv = __ldg(m.y + (size_t)r0 * nL + i), z = out[i];
+                if (m.loss == HMCX_LOSS_REGRESSION) {
+                    d = sub(z, yv);
+                    sum = add(sum, mul(d, d));
+                    gz = mul(c2, d);
+                } else {                                                  // BCE with logits, sum reduction
+                    sum += (1.0f - yv) * z + fmaxf(-z, 0.0f) + log1pf(expf(-fabsf(z)));
+                    gz = m.c_ll * (1.0f / (1.0f + expf(-z)) - yv);
+                }
+            }
+            if (dz) dz[i] = gz;
         }
-        if (dz) dz[i] = mul(c2, d);
+        return sum;
     }
-    return sse;
+    // multi-class: one thread per data row
+    const float cg = (m.loss == HMCX_LOSS_MULTICLASS_LOGSOFTMAX) ? m.c_ll / (float)rows : m.c_ll;
+    for (int r = threadIdx.x; r < m.T; r += MLP_THREADS) {
+        float* z = out + r * nL;
+        if (r < cnt) {
+            float mx = z[0];
+            for (int k = 1; k < nL; ++k) mx = fmaxf(mx, z[k]);
+            float se = 0.0f;
+            for (int k = 0; k < nL; ++k) se += expf(z[k] - mx);
+            const float lse = mx + logf(se);
+            int label = (int)__ldg(m.y + r0 + r);
+            label = label < 0 ? 0 : (label >= nL ? nL - 1 : label);
+            sum += lse - z[label];
+            for (int k = 0; k < nL; ++k) {
+                if (dz) dz[r * nL + k] = cg * (expf(z[k] - lse) - (k == label ? 1.0f : 0.0f));
+                if (log_softmax_out) z[k] = z[k] - lse;
+            }
+        } else if (dz) {
+            for (int k = 0; k < nL; ++k) dz[r * nL + k] = 0.0f;
+        }
+    }
+    return sum;
+}
+
+// ll of one closure from its reduced loss sum
+__device__ __forceinline__ float mlp_ll_from_sum(const MlpDev& m, float sum, int rows) {
+    if (m.loss == HMCX_LOSS_MULTICLASS_LOGSOFTMAX) return mul(m.c_ll, __fdiv_rn(sum, (float)rows));
+    return mul(m.c_ll, sum);
 }
 
 // g += d ll_split / dq over the rows [r_begin, r_end)  (g must already hold the prior part)
@@ -332,7 +373,7 @@ __device__ __forceinline__ void mlp_backprop_rows(const MlpDev& m, const float* 
         const int cnt = min(m.T, r_end - r0);
         mlp_forward_tile(m, q, tile, r0, cnt);
         float* dz = tile + m.dzoff[m.L & 1];
-        mlp_loss_tile(m, tile + m.aoff[m.L], dz, r0, cnt);
+        mlp_loss_tile(m, tile + m.aoff[m.L], dz, r0, cnt, r_end - r_begin);
         __syncthreads();
         for (int l = m.L - 1; l >= 0; --l) {
             float* dz_prev = tile + m.dzoff[l & 1];
@@ -400,8 +441,10 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
         for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += m.T) {
             const int cnt = min(m.T, m.sb[sp + 1] - r0);
             mlp_forward_tile(m, q, tile, r0, cnt);
-            sse[0] = add(sse[0], mlp_loss_tile(m, tile + m.aoff[m.L], nullptr, r0, cnt));
+            sse[0] = add(sse[0], mlp_loss_tile(m, tile + m.aoff[m.L], nullptr, r0, cnt, m.sb[sp + 1] - m.sb[sp],
+                                               pred_out != nullptr && m.loss == HMCX_LOSS_MULTICLASS_LOGSOFTMAX));
             if (pred_out) {
+                __syncthreads();
                 const int nL = m.n[m.L];
                 for (int i = threadIdx.x; i < cnt * nL; i += MLP_THREADS)
                     pred_out[(size_t)r0 * nL + i] = tile[m.aoff[m.L] + i];
@@ -410,7 +453,7 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
         }
         block_sum<1>(sse, sred);
         __syncthreads();
-        const float ll = mul(m.c_ll, sse[0]);
+        const float ll = mlp_ll_from_sum(m, sse[0], m.sb[sp + 1] - m.sb[sp]);
         lp = (sp == s0) ? add(ll, prior_term) : add(lp, add(ll, prior_term));
     }
     return lp;
@@ -697,7 +740,8 @@ static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
     if (!target || target->kind != HMCX_TARGET_MLP || !target->mlp) return HMCX_ERR_INVALID_ARG;
     const hmcx_mlp_t& h = *target->mlp;
     if (h.num_layers < 1 || h.num_layers > HMCX_MLP_MAX_LAYERS) return HMCX_ERR_INVALID_ARG;
-    if (h.loss != HMCX_LOSS_REGRESSION) return HMCX_ERR_UNSUPPORTED;
+    if (h.loss < HMCX_LOSS_REGRESSION || h.loss > HMCX_LOSS_MULTICLASS_LOGSOFTMAX) return HMCX_ERR_UNSUPPORTED;
+    m.loss = h.loss;
     if (h.activation[h.num_layers - 1] != HMCX_ACT_NONE) return HMCX_ERR_INVALID_ARG;
     m.L = h.num_layers;
     int off = 0;
@@ -717,7 +761,7 @@ static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
     mlp_layout_tiles(m, 8);
     m.tau_out = h.tau_out;
     m.prior_scale = h.prior_scale;
-    m.c_ll = (float)(-0.5 * (double)h.tau_out);
+    m.c_ll = (h.loss == HMCX_LOSS_REGRESSION) ? (float)(-0.5 * (double)h.tau_out) : (float)(-(double)h.tau_out);
     for (int t = 0; t < 2 * m.L; ++t) {
         m.two_var[t] = h.prior_two_var[t]; m.log_scale[t] = h.prior_log_scale[t]; m.gcoef[t] = h.prior_grad_coef[t];
     }

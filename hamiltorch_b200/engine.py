@@ -23,13 +23,14 @@ def _combine_mlp_splits(splits):
         if not isinstance(d, T.MLPRegression):
             raise TypeError('a split log_prob_func list must hold MLPRegression descriptors')
         if d.widths != first.widths or d.acts != first.acts or d.tau_out != first.tau_out or \
+                d.model_loss != first.model_loss or \
                 float(d.prior_scale) != float(first.prior_scale) or \
                 any(float(a) != float(b) for a, b in zip(d.tau_list, first.tau_list)):
             raise RuntimeError('all splits must share the network, tau_list, tau_out and prior_scale')
         if d.x is None:
             raise RuntimeError('split descriptors need data')
     x = torch.cat([d.x for d in splits])
-    y = torch.cat([d.y.reshape(d.x.shape[0], -1) for d in splits])
+    y = torch.cat([d.y.reshape(d.x.shape[0], first.y_cols) for d in splits])
     begin = [0]
     for d in splits:
         begin.append(begin[-1] + d.x.shape[0])
@@ -66,7 +67,7 @@ class NativeTarget:
         else:
             first = target
             x = first.x
-            y = None if x is None else first.y.reshape(x.shape[0], -1)
+            y = None if x is None else first.y.reshape(x.shape[0], first.y_cols)
             begin = [0, 0 if x is None else x.shape[0]]
         if len(begin) - 1 > N.MLP_MAX_SPLITS:
             raise NotImplementedError('at most %d splits' % N.MLP_MAX_SPLITS)
@@ -80,7 +81,7 @@ class NativeTarget:
             m.widths[i] = w
         for i, a in enumerate(first.acts):
             m.activation[i] = a
-        m.loss = T.LOSS_REGRESSION
+        m.loss = first.loss_id
         m.tau_out = first.tau_out
         m.prior_scale = float(first.prior_scale)
         for i in range(2 * first.num_layers):
@@ -400,7 +401,7 @@ def mlp_predict(target, samples, device=None):
     sd = _as_rows(samples, ld, device)
     S = sd.shape[0]
     m = nt.mlp_struct
-    pred = torch.empty((S, m.num_rows, m.widths[m.num_layers]), dtype=torch.float32, device=device)
+    pred = torch.empty((S, m.num_rows, m.widths[m.num_layers]), dtype=torch.float32, device=device)   # logits / log-probs
     lp = torch.empty(S, dtype=torch.float32, device=device)
     with torch.cuda.device(device):
         rc = lib.hmcx_mlp_predict(nt.ref(), N.ptr(sd), S, ld, N.ptr(pred), N.ptr(lp), N.stream_ptr(device))

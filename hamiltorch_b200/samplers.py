@@ -376,10 +376,10 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
 # Bayesian neural networks: define_model_log_prob / sample_model / sample_split_model / predict_model
 # ----------------------------------------------------------------------------------------------------------
 def _check_loss(model_loss):
-    if model_loss != 'regression':
+    if callable(model_loss) or model_loss not in T.LOSS_ID:
         raise NotImplementedError(
-            "hamiltorch_b200: only model_loss='regression' has a CUDA kernel so far (classification likelihoods and "
-            "callable losses are the next rows of SURVEY.md section 8f); got %r" % (model_loss,))
+            "hamiltorch_b200: model_loss must be one of %s -- a callable loss (samplers.py:1186-1188) cannot enter a "
+            "CUDA kernel and there is no CPU fallback; got %r" % (sorted(T.LOSS_ID), model_loss))
 
 
 def define_model_log_prob(model, model_loss, x, y, params_flattened_list, params_shape_list, tau_list, tau_out,
@@ -388,7 +388,7 @@ def define_model_log_prob(model, model_loss, x, y, params_flattened_list, params
     (``targets.MLPRegression``): callable like the reference's closure (same torch ops, same (O,)-shaped value, the
     ``(log_prob, output)`` pair when ``predict``) and understood by the kernels."""
     _check_loss(model_loss)
-    desc = T.MLPRegression.from_model(model, x, y, tau_list, tau_out, prior_scale)
+    desc = T.MLPTarget.from_model(model, x, y, tau_list, tau_out, prior_scale, model_loss)
     if list(params_flattened_list) != desc.sizes:
         raise RuntimeError('params_flattened_list does not match the model')
     desc.predict_mode = bool(predict)
@@ -488,4 +488,5 @@ def predict_model(model, samples, x=None, y=None, test_loader=None, model_loss='
         dev = samples[0].device
         pred, lp = engine.mlp_predict(target, torch.stack(list(samples)))
         pred, lp = pred.to(dev), lp.to(dev)
-    return pred, [l.reshape(1) for l in lp.unbind(0)]
+    shape = (1,) if model_loss == 'regression' else ()          # the reference's closure: (O,) vs 0-d
+    return pred, [l.reshape(shape) for l in lp.unbind(0)]

@@ -195,21 +195,31 @@ def is_target(obj):
 # ----------------------------------------------------------------------------------------------------------
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 _ACT_OF_MODULE = {'ReLU': ACT_RELU, 'Tanh': ACT_TANH, 'Sigmoid': ACT_SIGMOID}
-LOSS_REGRESSION = 0
+# model_loss (samplers.py:1170-1184) -> kernel loss id (include/hmcx.h HMCX_LOSS_*)
+LOSS_REGRESSION, LOSS_BINARY, LOSS_MULTICLASS, LOSS_MULTICLASS_LOGSOFTMAX = 0, 1, 2, 3
+LOSS_ID = {'regression': LOSS_REGRESSION, 'binary_class_linear_output': LOSS_BINARY,
+           'multi_class_linear_output': LOSS_MULTICLASS, 'multi_class_log_softmax_output': LOSS_MULTICLASS_LOGSOFTMAX}
 MLP_MAX_LAYERS = 8
 
 
 def mlp_spec(model):
-    """Recognise a dense stack: ``nn.Linear`` or ``nn.Sequential(Linear, [ReLU|Tanh|Sigmoid], Linear, ...)`` with
-    biases.  Returns (widths [n_0..n_L], activations [after layer l], list of Linear modules).  Anything else --
-    conv / recurrent / normalisation layers, or a module whose forward() is arbitrary Python -- cannot be turned into
-    a CUDA kernel the way util.make_functional (util.py:253-376) turns it into a closure, and is refused."""
+    """Recognise a dense stack: ``nn.Linear`` or ``nn.Sequential(Linear, [ReLU|Tanh|Sigmoid], Linear, ...
+    [, LogSoftmax])`` with biases.  Returns (widths [n_0..n_L], activations [after layer l], Linear modules,
+    final_log_softmax).  Anything else -- conv / recurrent / normalisation layers, or a module whose forward() is
+    arbitrary Python -- cannot be turned into a CUDA kernel the way util.make_functional (util.py:253-376) turns it
+    into a closure, and is refused."""
     import torch.nn as nn
     mods = [model] if isinstance(model, nn.Linear) else (list(model) if isinstance(model, nn.Sequential) else None)
     if mods is None:
         raise NotImplementedError(
             'hamiltorch_b200 runs Bayesian-NN sampling for dense stacks only: pass an nn.Sequential of '
             'Linear / ReLU / Tanh / Sigmoid layers (got %s)' % type(model).__name__)
+    final_log_softmax = False
+    if mods and isinstance(mods[-1], nn.LogSoftmax):
+        if mods[-1].dim not in (1, -1):
+            raise NotImplementedError('LogSoftmax must act on the class dimension (dim=1)')
+        final_log_softmax = True
+        mods = mods[:-1]
     widths, acts, linears = [], [], []
     for m in mods:
         if isinstance(m, nn.Linear):
@@ -231,10 +241,10 @@ def mlp_spec(model):
     if not linears:
         raise NotImplementedError('no Linear layer found')
     if acts[-1] != ACT_NONE:
-        raise NotImplementedError('the model must end with a Linear layer (linear output)')
+        raise NotImplementedError('the model must end with a Linear layer (optionally followed by LogSoftmax)')
     if len(linears) > MLP_MAX_LAYERS:
         raise NotImplementedError('at most %d Linear layers' % MLP_MAX_LAYERS)
-    return widths, acts, linears
+    return widths, acts, linears, final_log_softmax
 
 
 def _act(h, a):
@@ -247,32 +257,48 @@ def _act(h, a):
     return h
 
 
-class MLPRegression(Target):
-    """log p(theta) = ll + prior/prior_scale for a dense stack with Gaussian likelihood (model_loss='regression'):
+class MLPTarget(Target):
+    """log p(theta) = ll + prior/prior_scale for a dense stack -- the closure define_model_log_prob builds:
 
         prior = sum over parameter tensors i of Normal(0, tau_i^-1/2).log_prob(w_i).sum()   (samplers.py:1141-1157)
-        ll    = -0.5 * tau_out * ((f(x; theta) - y)**2).sum(0)                              (samplers.py:1184)
+        ll    = 'regression'                     -0.5*tau_out*((f(x)-y)**2).sum(0)                        (:1184)
+                'binary_class_linear_output'     -tau_out*BCEWithLogitsLoss(sum)(f(x), y)                  (:1170-1172)
+                'multi_class_linear_output'      -tau_out*CrossEntropyLoss(sum)(f(x), y.long().view(-1))   (:1173-1177)
+                'multi_class_log_softmax_output' -tau_out*nll_loss(f(x), y.long().view(-1))  [mean!]       (:1179-1180)
 
     ``theta`` is the flat vector in ``model.parameters()`` order, each tensor row-major (util.py:121-136): for every
     Linear the (out, in) weight then the (out,) bias.  ``__call__`` restates the reference's closure with the same
-    torch ops (F.linear), so it is also a valid reference ``log_prob_func``; like the reference's it returns shape
-    (O,) -- (1,) for a scalar output.  ``x is None`` samples the prior (:1160-1162).
+    torch ops, so it is also a valid reference ``log_prob_func`` (regression returns shape (O,) -- (1,) for a scalar
+    output; the classification losses return a 0-d tensor).  ``x is None`` samples the prior.
     """
 
     kind = KIND_MLP
+    predict_mode = False       # define_model_log_prob(predict=True): the closure also returns the network output
 
-    def __init__(self, widths, acts, x, y, tau_list, tau_out=1., prior_scale=1.0):
+    def __init__(self, widths, acts, x, y, tau_list, tau_out=1., prior_scale=1.0, model_loss='regression',
+                 final_log_softmax=False):
+        if model_loss not in LOSS_ID:
+            raise NotImplementedError(
+                'model_loss %r has no CUDA kernel (callable losses cannot enter a kernel); supported: %s'
+                % (model_loss, sorted(LOSS_ID)))
+        self.model_loss = model_loss
+        self.loss_id = LOSS_ID[model_loss]
+        self.final_log_softmax = bool(final_log_softmax)
+        if self.final_log_softmax != (model_loss == 'multi_class_log_softmax_output'):
+            raise NotImplementedError("a LogSoftmax output layer goes with model_loss='multi_class_log_softmax_output' "
+                                      "(and only with it)")
         self.widths = list(widths)
         self.acts = list(acts)
         self.num_layers = len(self.widths) - 1
         self.dim = sum(self.widths[l] * self.widths[l + 1] + self.widths[l + 1] for l in range(self.num_layers))
         self.x = None if x is None else x.detach().to(torch.float32)
         self.y = None if y is None else y.detach().to(torch.float32)
+        self.y_cols = self.widths[-1] if self.loss_id in (LOSS_REGRESSION, LOSS_BINARY) else 1
         if self.x is not None:
             if self.x.dim() != 2 or self.x.shape[1] != self.widths[0]:
                 raise ValueError('x must be (N, %d)' % self.widths[0])
-            if self.y.reshape(self.x.shape[0], -1).shape[1] != self.widths[-1]:
-                raise ValueError('y must be (N, %d)' % self.widths[-1])
+            if self.y.numel() != self.x.shape[0] * self.y_cols:
+                raise ValueError('y must have %d entries per data point for %s' % (self.y_cols, model_loss))
         self.tau_out = float(tau_out)
         self.prior_scale = prior_scale
         tau_list = [torch.as_tensor(t, dtype=torch.float32) for t in tau_list]
@@ -289,11 +315,11 @@ class MLPRegression(Target):
         self.grad_coef = [(torch.tensor(1.0) / prior_scale) / tv for tv in self.two_var]
 
     @classmethod
-    def from_model(cls, model, x, y, tau_list=None, tau_out=1., prior_scale=1.0):
-        widths, acts, linears = mlp_spec(model)
+    def from_model(cls, model, x, y, tau_list=None, tau_out=1., prior_scale=1.0, model_loss='regression'):
+        widths, acts, linears, fls = mlp_spec(model)
         if tau_list is None:
             tau_list = [torch.tensor(1.)] * (2 * len(linears))           # samplers.py:1348-1355
-        return cls(widths, acts, x, y, tau_list, tau_out, prior_scale)
+        return cls(widths, acts, x, y, tau_list, tau_out, prior_scale, model_loss, fls)
 
     def _tensors(self):
         d = {}
@@ -316,6 +342,8 @@ class MLPRegression(Target):
         h = x
         for l, (W, b) in enumerate(self.unflatten(params)):
             h = _act(torch.nn.functional.linear(h, W, b), self.acts[l])
+        if self.final_log_softmax:
+            h = torch.nn.functional.log_softmax(h, dim=1)
         return h
 
     def log_prior(self, params):
@@ -327,15 +355,21 @@ class MLPRegression(Target):
             i += n
         return l_prior
 
-    predict_mode = False       # define_model_log_prob(predict=True): the closure also returns the network output
-
     def __call__(self, params, predict=None):
         predict = self.predict_mode if predict is None else predict
         l_prior = self.log_prior(params)
         if self.x is None:
             return l_prior / self.prior_scale
         output = self.forward(params, self.x.to(params.device))
-        ll = - 0.5 * self.tau_out * ((output - self.y.to(params.device).view_as(output)) ** 2).sum(0)
+        y = self.y.to(params.device)
+        if self.loss_id == LOSS_BINARY:
+            ll = - self.tau_out * torch.nn.BCEWithLogitsLoss(reduction='sum')(output, y.view_as(output))
+        elif self.loss_id == LOSS_MULTICLASS:
+            ll = - self.tau_out * torch.nn.CrossEntropyLoss(reduction='sum')(output, y.long().view(-1))
+        elif self.loss_id == LOSS_MULTICLASS_LOGSOFTMAX:
+            ll = - self.tau_out * torch.nn.functional.nll_loss(output, y.long().view(-1))
+        else:
+            ll = - 0.5 * self.tau_out * ((output - y.view_as(output)) ** 2).sum(0)
         if predict:
             return (ll + l_prior / self.prior_scale), output
         return ll + l_prior / self.prior_scale
@@ -343,3 +377,6 @@ class MLPRegression(Target):
     def grad(self, params):
         p = params.detach().requires_grad_()
         return torch.autograd.grad(self(p), p)[0]
+
+
+MLPRegression = MLPTarget      # the regression-only name used by round-1 callers

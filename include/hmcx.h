@@ -63,7 +63,11 @@ extern "C" {
 #define HMCX_ACT_RELU 1
 #define HMCX_ACT_TANH 2
 #define HMCX_ACT_SIGMOID 3
-#define HMCX_LOSS_REGRESSION 0
+#define HMCX_LOSS_REGRESSION            0   /* 'regression'                      samplers.py:1182-1184          */
+#define HMCX_LOSS_BINARY                1   /* 'binary_class_linear_output'      :1170-1172 (BCE with logits)   */
+#define HMCX_LOSS_MULTICLASS            2   /* 'multi_class_linear_output'       :1173-1177 (cross entropy, sum) */
+#define HMCX_LOSS_MULTICLASS_LOGSOFTMAX 3   /* 'multi_class_log_softmax_output'  :1179-1180 (log-softmax output +
+                                               nll_loss with its default MEAN reduction)                        */
 
 typedef struct hmcx_mlp {
     int32_t num_layers;                            /* number of Linear layers                                  */
@@ -78,7 +82,8 @@ typedef struct hmcx_mlp {
     float   prior_log_scale[2 * HMCX_MLP_MAX_LAYERS];  /* log(scale_i)                                         */
     float   prior_grad_coef[2 * HMCX_MLP_MAX_LAYERS];  /* (1/prior_scale)/(2*scale_i^2): d prior/dw = -(coef*2w) */
     const float* x;                                /* [num_rows, n_0] device; NULL = sample the prior (:1160)    */
-    const float* y;                                /* [num_rows, n_L] device                                    */
+    const float* y;                                /* [num_rows, n_L] device (regression / binary) or [num_rows]
+                                                      class indices stored as float (multi-class)              */
     int32_t num_rows;
     int32_t num_splits;                            /* M >= 1                                                    */
     int32_t split_begin[HMCX_MLP_MAX_SPLITS + 1];

@@ -91,19 +91,27 @@ def make_init(kind, dim, seed):
 # ----------------------------------------------------------------------------------------------------------
 # Bayesian-NN cases (sample_model / sample_split_model / predict_model, samplers.py:1261-1562)
 # ----------------------------------------------------------------------------------------------------------
-def mlp_problem(seed=0, n=48, n_in=6, hidden=16, n_out=1, depth=1, act='ReLU'):
-    """Small synthetic regression problem + an nn.Sequential dense stack, deterministic in ``seed``."""
+def mlp_problem(seed=0, n=48, n_in=6, hidden=16, n_out=1, depth=1, act='ReLU', task='regression'):
+    """Small synthetic problem + an nn.Sequential dense stack, deterministic in ``seed``.  task: 'regression',
+    'binary' (labels in {0,1}, one logit), 'multiclass' (class indices, n_out logits), 'logsoftmax' (same, the model
+    ends in LogSoftmax)."""
     import torch.nn as nn
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(n, n_in, generator=g)
     w = torch.randn(n_in, n_out, generator=g)
     y = torch.sin(x @ w / 2) + 0.1 * torch.randn(n, n_out, generator=g)
+    if task == 'binary':
+        y = (y > 0).float()
+    elif task in ('multiclass', 'logsoftmax'):
+        y = y.argmax(1).float()
     torch.manual_seed(seed)                    # the layers' default init draws from the global generator
     layers, last = [], n_in
     for _ in range(depth):
         layers += [nn.Linear(last, hidden), getattr(nn, act)()]
         last = hidden
     layers.append(nn.Linear(last, n_out))
+    if task == 'logsoftmax':
+        layers.append(nn.LogSoftmax(dim=1))
     model = nn.Sequential(*layers)
     return model, x, y
 
@@ -120,6 +128,14 @@ def mlp_cases():
         'mlp_deep_tanh_mass': dict(problem=dict(seed=4, depth=2, act='Tanh', hidden=12), scheme='SPLITTING',
                                    num_splits=4, step_size=0.01, diag_mass=True,
                                    tau_list=[1., 2., .5, 1., 3., 1.], **base),
+        # classification likelihoods (samplers.py:1170-1180)
+        'mlp_binary': dict(problem=dict(seed=5, task='binary'), scheme=None, step_size=0.03,
+                           model_loss='binary_class_linear_output', **dict(base, tau_out=1.)),
+        'mlp_multiclass': dict(problem=dict(seed=6, task='multiclass', n_out=3), scheme=None, step_size=0.03,
+                               model_loss='multi_class_linear_output', **dict(base, tau_out=1.)),
+        'mlp_logsoftmax_split': dict(problem=dict(seed=7, task='logsoftmax', n_out=3), scheme='SPLITTING',
+                                     num_splits=3, step_size=0.05, model_loss='multi_class_log_softmax_output',
+                                     **dict(base, tau_out=20.)),
     }
     return cases
 

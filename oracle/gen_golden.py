@@ -119,13 +119,14 @@ def build_mlp_case(case):
     model, x, y = cases.mlp_problem(**case['problem'])
     tau_list = case.get('tau_list')
     tau_t = None if tau_list is None else [torch.tensor(t) for t in tau_list]
+    loss = case.get('model_loss', 'regression')
     if case['scheme'] is None:
-        descs = T.MLPRegression.from_model(model, x, y, tau_t, case['tau_out'])
+        descs = T.MLPTarget.from_model(model, x, y, tau_t, case['tau_out'], model_loss=loss)
     else:
         M = case['num_splits']
         B = x.shape[0] // M
-        descs = [T.MLPRegression.from_model(model, x[m * B:(m + 1) * B], y[m * B:(m + 1) * B], tau_t, case['tau_out'],
-                                            prior_scale=M) for m in range(M)]
+        descs = [T.MLPTarget.from_model(model, x[m * B:(m + 1) * B], y[m * B:(m + 1) * B], tau_t, case['tau_out'],
+                                        prior_scale=M, model_loss=loss) for m in range(M)]
     D = sum(p.numel() for p in model.parameters())
     inv_mass = None
     if case.get('diag_mass'):
@@ -140,17 +141,18 @@ def run_mlp_case(ref, name, case):
     D = sum(p.numel() for p in model.parameters())
     scheme = case['scheme']
     M = case.get('num_splits', 0)
+    loss = case.get('model_loss', 'regression')
     out = {}
     for ci, seed in enumerate(case['seeds']):
         torch.manual_seed(seed)
         init = ref.util.flatten(model).detach().clone() + 0.05 * torch.randn(D)
         if scheme is None:
-            samples = ref.sample_model(model, x, y, params_init=init, model_loss='regression', num_samples=S,
+            samples = ref.sample_model(model, x, y, params_init=init, model_loss=loss, num_samples=S,
                                        num_steps_per_sample=L, step_size=eps, burn=burn, inv_mass=inv_mass,
                                        tau_out=case['tau_out'], tau_list=tau_t, verbose=False)
         else:
             loader = tud.DataLoader(tud.TensorDataset(x, y), batch_size=x.shape[0] // M, shuffle=False)
-            samples = ref.sample_split_model(model, loader, params_init=init, num_splits=M, model_loss='regression',
+            samples = ref.sample_split_model(model, loader, params_init=init, num_splits=M, model_loss=loss,
                                              num_samples=S, num_steps_per_sample=L, step_size=eps, burn=burn,
                                              inv_mass=inv_mass, tau_out=case['tau_out'], tau_list=tau_t,
                                              integrator=getattr(ref.Integrator, scheme), verbose=False)
@@ -194,7 +196,7 @@ def run_mlp_case(ref, name, case):
         out['ham_new_%d' % ci] = np.array(res['ham_new'], dtype=np.float64)
         if ci == 0:
             # predict_model on the retained samples (samplers.py:1468-1562)
-            pred, lps = ref.predict_model(model, list(samples), x=x, y=y, model_loss='regression',
+            pred, lps = ref.predict_model(model, list(samples), x=x, y=y, model_loss=loss,
                                           tau_out=case['tau_out'], tau_list=tau_t)
             out['pred'] = pred.numpy()
             out['pred_log_prob'] = torch.stack([l.reshape(-1) for l in lps]).numpy()

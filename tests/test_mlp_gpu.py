@@ -118,7 +118,7 @@ def test_sample_split_model_dropin_and_predict_model():
     np.testing.assert_allclose(pred.numpy(), d['pred'], rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(torch.stack(lps).numpy(), d['pred_log_prob'], rtol=2e-5)
     with pytest.raises(NotImplementedError):
-        hb.sample_model(model, x, y, init, model_loss='multi_class_linear_output')
+        hb.sample_model(model, x, y, init, model_loss=lambda out, tgt: ((out - tgt) ** 2).sum(1))   # callable loss
     with pytest.raises(RuntimeError, match='greater than length 1'):
         hb.sample(descs[:1], init, integrator=hb.Integrator.SPLITTING, rng='philox')
 
@@ -145,3 +145,17 @@ def test_config4_shapes_philox_properties():
     assert torch.equal(same, ~acc[:, 2:])
     dH = (res.ham[..., 1] - res.ham[..., 0]).cpu()
     assert torch.isfinite(dH).all() and dH.abs().median() < 2.0
+
+
+@pytest.mark.parametrize('name', ['mlp_binary', 'mlp_multiclass', 'mlp_logsoftmax_split'])
+def test_classification_predict_model(name):
+    """predict_model for the classification likelihoods: logits (or log-probs for a LogSoftmax model) and the 0-d
+    log-prob per sample, vs the reference's own predict_model output."""
+    case = cases.mlp_cases()[name]
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    pred, lps = hb.predict_model(model, [torch.from_numpy(s) for s in d['samples_0']], x=x, y=y,
+                                 model_loss=case['model_loss'], tau_out=case['tau_out'])
+    assert pred.shape == d['pred'].shape and lps[0].shape == ()
+    np.testing.assert_allclose(pred.numpy(), d['pred'], rtol=5e-5, atol=5e-5)
+    np.testing.assert_allclose(torch.stack(lps).numpy(), d['pred_log_prob'].reshape(-1), rtol=5e-5)
