@@ -294,8 +294,11 @@ def run_b200_arm(args, rank, world, local_rank):
                        'chains_per_gpu': C, 'dim': D, 'L': L, 'iterations_per_step': S,
                        'l2_policy': 'each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
                        'parallelism': 'chains sharded over %d GPU(s), no data-path collective' % world},
-            'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,1>', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+            'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
+                         # profiles/r1a_prof_hmc_run_r1a.summary.txt (2.06 MB read + 990.65 MB written)
+                         'traffic': 992.7e6, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': t_kernel_ms,
                          'note': 'fused trajectory kernel: L=10 steps per 4*D bytes written, fp32-issue bound by design; '
                                  'see roofline_streaming for the HBM-bound form'},
