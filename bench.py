@@ -105,7 +105,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -208,7 +208,6 @@ def run_b200_arm(args, rank, world, local_rank):
     barrier()
     t_total_ms = ev[0].elapsed_time(ev[-1])
     t_kernel_ms = sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(args.steps)) / args.steps
-    clk = clocks.stop() if rank == 0 else None
     rejected = stats[..., 0].sum().item()
 
     # ---- e2e: public API, HOST buffers, H2D of the inputs and D2H of the result inside the timed region ----
@@ -268,6 +267,7 @@ def run_b200_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     t_stream_ms = s0.elapsed_time(s1) / n_s
     del qs, ps, qo, po
+    clk = clocks.stop() if rank == 0 else None        # sampled across all three timed regions (all under load)
 
     # max over ranks of every timing
     t = torch.tensor([t_total_ms, t_kernel_ms, t_e2e_ms, t_stream_ms], dtype=torch.float64, device=dev)

@@ -18,6 +18,7 @@ int mlp_predict(const hmcx_target_t*, const float*, int, int, float*, float*, cu
 int small_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*, float*,
                   float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                   cudaStream_t);
+int gemm_nt_tf32x3(const float*, const float*, float*, int, int, int, cudaStream_t);
 int rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
               int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
 }  // namespace hmcx
@@ -110,6 +111,10 @@ int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const h
                    uint8_t* diverged_out, float* ham_out, int32_t* num_rejected, void* stream) {
     return hmcx::rmhmc_run(target, cfg, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin, iter_end,
                            samples_out, accept_out, diverged_out, ham_out, num_rejected, (cudaStream_t)stream);
+}
+
+int hmcx_gemm_nt_tf32x3(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, void* stream) {
+    return hmcx::gemm_nt_tf32x3(A, B, D, M, N, K, (cudaStream_t)stream);
 }
 
 int hmcx_grad_log_prob(const hmcx_target_t* target, const float* q, int32_t C, int32_t ld, int32_t split,

@@ -481,3 +481,18 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
     res.eps_trace = None
     res._keep_alive = keep_alive
     return res
+
+
+def gemm_nt(A, B):
+    """D = A @ B.T on tcgen05 tensor cores with 3xTF32 split operands (fp32-accurate).  A (M,K), B (N,K) fp32 CUDA;
+    M, N multiples of 128, K a multiple of 32."""
+    N.require_cuda()
+    lib = N.load_library()
+    A = A.detach().to(torch.float32).contiguous()
+    B = B.detach().to(device=A.device, dtype=torch.float32).contiguous()
+    D = torch.empty((A.shape[0], B.shape[0]), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.hmcx_gemm_nt_tf32x3(N.ptr(A), N.ptr(B), N.ptr(D), A.shape[0], B.shape[0], A.shape[1],
+                                     N.stream_ptr(A.device))
+    N.check(rc, 'hmcx_gemm_nt_tf32x3')
+    return D

@@ -255,6 +255,14 @@ int hmcx_grad_log_prob(const hmcx_target_t* target, const float* q, int32_t C, i
 int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t S, int32_t ld,
                      float* pred_out, float* log_prob_out, void* stream);
 
+/*
+ * hmcx_gemm_nt_tf32x3: D[M,N] = A[M,K] . B[N,K]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32 with
+ * 3xTF32 split operands => fp32-accurate, fp32 accumulation in tensor memory).  Row-major fp32 device arrays;
+ * M, N multiples of 128, K a multiple of 32.  The dense contraction behind full-covariance targets / full mass
+ * matrices at large D (grad log p of ALL chains = -(Q - mu) P: M = chains, N = K = D; samplers.py:294, :812).
+ */
+int hmcx_gemm_nt_tf32x3(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
