@@ -19,6 +19,10 @@ int small_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, c
                   float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                   cudaStream_t);
 int gemm_nt_tf32x3(const float*, const float*, float*, int, int, int, cudaStream_t);
+size_t dense_workspace_floats(int, int);
+int dense_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*, float*,
+                  float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, float*,
+                  cudaStream_t);
 int rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
               int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
 }  // namespace hmcx
@@ -34,6 +38,8 @@ int hmcx_abi_version(void) { return HMCX_ABI_VERSION; }
 size_t hmcx_hmc_workspace_bytes(const hmcx_target_t* target, const hmcx_mass_t* mass, int32_t C, int32_t ld) {
     const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
     if (is_elem(target) && !full_mass && ld > 4096) return (size_t)C * (size_t)ld * sizeof(float);
+    if (target && target->kind == HMCX_TARGET_GAUSS_FULL && target->dim > 16 && !full_mass)
+        return hmcx::dense_workspace_floats(C, target->dim) * sizeof(float);
     return 0;
 }
 
@@ -81,6 +87,11 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
         return hmcx::elem_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
                                   num_rejected, tuning, workspace, (cudaStream_t)stream);
+    if (target->kind == HMCX_TARGET_GAUSS_FULL && target->dim > 16 && !full_mass)
+        // dense target at scale: one tcgen05 GEMM per leapfrog step over all chains (hmcx_tc.cu)
+        return hmcx::dense_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
+                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
+                                   num_rejected, workspace, (cudaStream_t)stream);
     if (is_elem(target) || target->kind == HMCX_TARGET_GAUSS_FULL || target->kind == HMCX_TARGET_FUNNEL)
         // coupled gradient or full mass matrix: thread-per-chain kernel, D <= 16 (samplers.py:293-294, :811-812, :198-199)
         return hmcx::small_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,

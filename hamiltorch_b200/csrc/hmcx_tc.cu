@@ -169,6 +169,399 @@ gemm_nt_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128));
 }
 
+
+// =========================================================================================================
+// Dense-target plain HMC / HMC_NUTS: full-covariance Gaussian at large D, all chains per step on the tensor cores
+//   grad log p (samplers.py:297 via autograd of targets.GaussianFull) for ALL chains = -(Q - mu) P : one tcgen05 GEMM
+//   per leapfrog step with the kick (:281/:298/:302) and the drift (:284/:296) fused into its epilogue.
+// Step-synchronous: a trajectory is L+1 launches of dense_step_kernel (each needs every column of the new Q, a
+// grid-wide dependency), bracketed by dense_gibbs_kernel and dense_mh_kernel; launched back-to-back on one stream
+// from hmcx_hmc_run, no host synchronisation.  State lives in the caller-provided workspace.
+// =========================================================================================================
+struct DenseArgs {
+    int C, Cp, D, Dp, NT;
+    const float* prec;        // [Dp, Dp] zero-padded precision
+    const float* mean;        // [Dp]
+    float log_norm;
+    int mk;
+    const float* im;          // [Dp] inverse mass (diag) or null
+    const float* sd;          // [Dp] sqrt(mass) or null
+};
+
+enum { DENSE_FIRST = 0, DENSE_MIDDLE = 1, DENSE_LAST = 2, DENSE_EVAL = 3 };
+
+// stage rows [row0, row0+128) x [k0, k0+32) of (X - mean) or of X (mean == nullptr)
+__device__ __forceinline__ void stage_rows(const float* __restrict__ X, int ld, int row0, int k0,
+                                           const float* __restrict__ mean, float* s_hi, float* s_lo) {
+    const int r = threadIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * ld + k0);
+#pragma unroll
+    for (int kc = 0; kc < TC_KC / 4; ++kc) {
+        float4 v = __ldg(src + kc);
+        if (mean) {
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + k0) + kc);
+            v.x = sub(v.x, mu.x); v.y = sub(v.y, mu.y); v.z = sub(v.z, mu.z); v.w = sub(v.w, mu.w);
+        }
+        float4 h, l;
+        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+        const int off = ((kc * 16 + (r >> 3)) * 128 + (r & 7) * 16) >> 2;
+        *reinterpret_cast<float4*>(s_hi + off) = h;
+        *reinterpret_cast<float4*>(s_lo + off) = l;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, float* __restrict__ Qout, float* __restrict__ P,
+                  const float* __restrict__ eps, int mode, float* __restrict__ upart) {
+    extern __shared__ __align__(1024) float smem[];
+    float* a_hi = smem;
+    float* a_lo = a_hi + TC_M * TC_KC;
+    float* b_hi = a_lo + TC_M * TC_KC;
+    float* b_lo = b_hi + TC_N * TC_KC;
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t mbar = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = make_idesc_tf32(TC_M, TC_N);
+    const int Dp = a.Dp;
+    uint32_t parity = 0;
+    for (int k0 = 0; k0 < Dp; k0 += TC_KC) {
+        stage_rows(Qin, Dp, tile_m * TC_M, k0, a.mean, a_hi, a_lo);           // A = Q - mu   (chains x D)
+        stage_rows(a.prec, Dp, tile_n * TC_N, k0, nullptr, b_hi, b_lo);       // B = P rows   (symmetric)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < TC_KC / 8; ++s) {
+                const uint32_t koff = (uint32_t)s * 2u * 2048u;
+                const uint64_t ah = make_kmajor_desc(smem_u32(a_hi) + koff, 2048, 128);
+                const uint64_t al = make_kmajor_desc(smem_u32(a_lo) + koff, 2048, 128);
+                const uint64_t bh = make_kmajor_desc(smem_u32(b_hi) + koff, 2048, 128);
+                const uint64_t bl = make_kmajor_desc(smem_u32(b_lo) + koff, 2048, 128);
+                umma_tf32(tmem, ah, bh, idesc, (k0 | s) != 0);
+                umma_tf32(tmem, ah, bl, idesc, true);
+                umma_tf32(tmem, al, bh, idesc, true);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        __syncthreads();
+    }
+    // ---- epilogue: acc = ((Q-mu) P)[row, cols]; g = -acc; kick, optional drift, partial of y.(P y) ----
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = tile_m * TC_M + warp * 32 + lane;
+    const bool live = row < a.C;
+    const float e = live ? eps[row] : 0.0f, half = mul(0.5f, e);
+    const float ck = (mode == DENSE_FIRST) ? half : e;
+    float udot = 0.0f;
+    const size_t base = (size_t)row * Dp + (size_t)tile_n * TC_N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int col = tile_n * TC_N + c0 + j;
+                const float4 q4 = *reinterpret_cast<const float4*>(Qin + base + c0 + j);
+                const float4 m4 = *reinterpret_cast<const float4*>(a.mean + col);
+                const float acc[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3])};
+                const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                float pn[4], qn[4];
+                float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mode != DENSE_EVAL) p4 = *reinterpret_cast<const float4*>(P + base + c0 + j);
+                const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    udot = add(udot, mul(sub(qv[t], mv[t]), acc[t]));
+                    const float g = -acc[t];
+                    pn[t] = add(pv[t], mul(ck, g));                                             // :281 / :298
+                    if (mode == DENSE_LAST) pn[t] = sub(pn[t], mul(half, g));                   // :302
+                    const float cd = (a.mk == HMCX_MASS_DIAG) ? mul(e, a.im[col + t]) : e;
+                    qn[t] = add(qv[t], mul(cd, pn[t]));                                         // :284 / :296
+                }
+                if (mode != DENSE_EVAL) *reinterpret_cast<float4*>(P + base + c0 + j) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+                if (mode == DENSE_FIRST || mode == DENSE_MIDDLE)
+                    *reinterpret_cast<float4*>(Qout + base + c0 + j) = make_float4(qn[0], qn[1], qn[2], qn[3]);
+            }
+        }
+    }
+    if (live && upart) upart[(size_t)row * a.NT + tile_n] = udot;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128));
+}
+
+// zero-padded copies into the workspace
+__global__ void dense_pad_matrix_kernel(const float* __restrict__ src, int D, float* __restrict__ dst, int Dp) {
+    const size_t n = (size_t)Dp * Dp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Dp), c = (int)(i % Dp);
+        dst[i] = (r < D && c < D) ? src[(size_t)r * D + c] : 0.0f;
+    }
+}
+__global__ void dense_pad_vector_kernel(const float* __restrict__ src, int D, float* __restrict__ dst, int Dp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dp; i += gridDim.x * blockDim.x)
+        dst[i] = (src && i < D) ? src[i] : 0.0f;
+}
+// rows of a caller (C, ld) array -> padded (Cp, Dp) work array
+__global__ void dense_load_rows_kernel(const float* __restrict__ src, int C, int ld, int D, float* __restrict__ dst,
+                                       int Cp, int Dp) {
+    const int r = blockIdx.x;
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) dst[(size_t)r * Dp + j] = (r < C && j < D) ? src[(size_t)r * ld + j] : 0.0f;
+}
+
+struct DenseRun {
+    DenseArgs a;
+    int ld, rng_mode;
+    uint64_t seed, chain_offset;
+    const float* normals;
+    const float* logu;
+    int nuts;
+    double delta, mu;
+    const double* table;
+    double* h_bar;
+    double* eps_bar;
+    const float* eps_schedule;
+    float* eps_trace;
+    const float* q_init;
+    float* q_cur;
+    float* eps;
+    int S, burn, it0;
+    float* samples;
+    uint8_t* accept;
+    uint8_t* diverged;
+    float* ham;
+    int32_t* num_rejected;
+    // workspace
+    float* kin0;
+    float* U_cur;
+    float* U_init;
+};
+
+// gibbs (:969) for iteration n: p = z * sqrt(mass) -> P rows, q_cur -> Q work rows, kinetic of p
+__global__ void __launch_bounds__(256)
+dense_gibbs_kernel(const DenseRun r, int n, float* __restrict__ Q, float* __restrict__ P, float* __restrict__ eps_work) {
+    __shared__ float sred[32];
+    const DenseArgs& a = r.a;
+    const int c = blockIdx.x, Dp = a.Dp, D = a.D;
+    const uint64_t chain_id = r.chain_offset + (uint64_t)c;
+    if (r.eps_schedule && threadIdx.x == 0) r.eps[c] = r.eps_schedule[(size_t)n * a.C + c];
+    float kin[1] = {0.0f};
+    for (int v = threadIdx.x; 4 * v < Dp; v += blockDim.x) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f}, qv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * v < r.ld) {
+            if (r.rng_mode == HMCX_RNG_INJECTED) ld4_stream(r.normals + ((size_t)(n - r.it0) * a.C + c) * r.ld + 4 * v, z);
+            else philox_normal4(r.seed, chain_id, (uint64_t)n, (uint32_t)v, z);
+            ld4(r.q_cur + (size_t)c * r.ld + 4 * v, qv);
+        }
+        float pv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = 4 * v + j;
+            if (i >= D) { z[j] = 0.0f; qv[j] = 0.0f; }
+            pv[j] = (a.mk == HMCX_MASS_DIAG) ? mul(z[j], a.sd[i]) : z[j];
+            kin[0] = add(kin[0], (a.mk == HMCX_MASS_DIAG) ? mul(pv[j], mul(a.im[i], pv[j])) : mul(pv[j], pv[j]));
+        }
+        st4(P + (size_t)c * Dp + 4 * v, pv);
+        st4(Q + (size_t)c * Dp + 4 * v, qv);
+    }
+    block_sum<1>(kin, sred);
+    if (threadIdx.x == 0) r.kin0[c] = kin[0];
+    (void)eps_work;
+}
+
+// log p from the per-tile partials of y.(P y)   (targets.GaussianFull: -0.5*dot(y, P y) + log_norm)
+__device__ __forceinline__ float dense_log_prob(const DenseArgs& a, const float* upart, int c) {
+    float s = 0.0f;
+    for (int t = 0; t < a.NT; ++t) s = add(s, upart[(size_t)c * a.NT + t]);
+    return add(mul(-0.5f, s), a.log_norm);
+}
+
+__global__ void dense_store_u_kernel(const DenseArgs a, const float* __restrict__ upart, float* __restrict__ U) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.C) U[c] = dense_log_prob(a, upart, c);
+}
+
+// MH + bookkeeping + dual averaging for iteration n (samplers.py:995-1067), one CTA per chain
+__global__ void __launch_bounds__(256)
+dense_mh_kernel(const DenseRun r, int n, const float* __restrict__ Qprop, const float* __restrict__ P,
+                const float* __restrict__ upart) {
+    __shared__ float sred[32];
+    __shared__ int s_flag[2];
+    const DenseArgs& a = r.a;
+    const int c = blockIdx.x, Dp = a.Dp, D = a.D, tid = threadIdx.x;
+    const uint64_t chain_id = r.chain_offset + (uint64_t)c;
+    float kin[1] = {0.0f};
+    for (int i = tid; i < D; i += blockDim.x) {
+        const float p = P[(size_t)c * Dp + i];
+        kin[0] = add(kin[0], (a.mk == HMCX_MASS_DIAG) ? mul(p, mul(a.im[i], p)) : mul(p, p));
+    }
+    block_sum<1>(kin, sred);
+    if (tid == 0) {
+        const float lp_cur = r.U_cur[c], lp_new = dense_log_prob(a, upart, c);
+        const float h_old = add(-lp_cur, mul(0.5f, r.kin0[c]));
+        const float h_new = add(-lp_new, mul(0.5f, kin[0]));
+        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);
+        const float x = add(-h_new, h_old);
+        const float rho = (x < 0.0f) ? x : 0.0f;
+        const float logu = (r.rng_mode == HMCX_RNG_INJECTED) ? r.logu[(size_t)(n - r.it0) * a.C + c]
+                                                             : philox_log_uniform(r.seed, chain_id, (uint64_t)n);
+        const bool acc = !bad && (rho >= logu);
+        const bool quirk = !acc && (n == r.burn + 1);
+        if (acc) r.U_cur[c] = lp_new;
+        else if (quirk) r.U_cur[c] = r.U_init[c];
+        if (!acc && r.num_rejected) r.num_rejected[c] += 1;
+        const size_t o = (size_t)c * r.S + n;
+        if (r.accept) r.accept[o] = acc ? 1 : 0;
+        if (r.diverged) r.diverged[o] = bad ? 1 : 0;
+        if (r.ham) { r.ham[2 * o] = h_old; r.ham[2 * o + 1] = h_new; }
+        float e = r.eps[c];
+        if (r.nuts && n <= r.burn) {                                         // :1030-1035, :1060-1067
+            double h_bar = r.h_bar[c], eps_bar = r.eps_bar[c];
+            if (n < r.burn || bad) {
+                const double* T = r.table + 5 * (size_t)n;
+                const double alpha = bad ? 0.0 : (double)expf(rho);
+                h_bar = __dadd_rn(__dmul_rn(T[0], h_bar), __dmul_rn(T[1], r.delta - alpha));
+                const double x_new = r.mu - __dmul_rn(T[2], h_bar);
+                e = expf((float)x_new);
+                const float xb = add((float)__dmul_rn(T[3], x_new), mul((float)T[4], logf((float)eps_bar)));
+                eps_bar = (double)expf(xb);
+            }
+            if (n == r.burn) e = (float)eps_bar;
+            r.h_bar[c] = h_bar; r.eps_bar[c] = eps_bar;
+            r.eps[c] = e;
+        }
+        if (r.eps_trace) r.eps_trace[o] = e;
+        s_flag[0] = acc ? 1 : 0;
+        s_flag[1] = quirk ? 1 : 0;
+    }
+    __syncthreads();
+    const bool acc = s_flag[0] != 0, quirk = s_flag[1] != 0;
+    float* qc = r.q_cur + (size_t)c * r.ld;
+    float* dst = (n > r.burn && r.samples) ? r.samples + ((size_t)c * (r.S - r.burn) + (n - r.burn)) * r.ld : nullptr;
+    for (int i = tid; i < r.ld; i += blockDim.x) {
+        float v;
+        if (acc) v = i < D ? Qprop[(size_t)c * Dp + i] : 0.0f;
+        else if (quirk) v = r.q_init[(size_t)c * r.ld + i];
+        else v = qc[i];
+        if (acc || quirk) qc[i] = v;
+        if (dst) dst[i] = v;
+    }
+}
+
+size_t dense_workspace_floats(int C, int D) {
+    const size_t Cp = (size_t)(C + 127) / 128 * 128, Dp = (size_t)(D + 127) / 128 * 128, NT = Dp / 128;
+    return 3 * Cp * Dp + Dp * Dp + 3 * Dp + Cp * NT + 3 * Cp + 64;
+}
+
+int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, const hmcx_nuts_t* nuts,
+                  const float* q_init, float* q_cur, float* eps, int C, int ld, int L, int S, int burn, int it0,
+                  int it1, float* samples, uint8_t* accept, uint8_t* diverged, float* ham, int32_t* num_rejected,
+                  float* ws, cudaStream_t st) {
+    if (!target || target->kind != HMCX_TARGET_GAUSS_FULL || !target->prec) return HMCX_ERR_INVALID_ARG;
+    const int D = target->dim;
+    if (!rng || !q_init || !q_cur || !eps || !ws || C < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 ||
+        burn >= S || it0 < 0 || it1 > S || it0 > it1)
+        return HMCX_ERR_INVALID_ARG;
+    const int mk = mass ? mass->kind : HMCX_MASS_NONE;
+    if (mk == HMCX_MASS_FULL) return HMCX_ERR_UNSUPPORTED;      // a second GEMM per step: next round
+    if (mk == HMCX_MASS_DIAG && (!mass->inv_mass || !mass->mass_factor)) return HMCX_ERR_INVALID_ARG;
+    if (rng->mode == HMCX_RNG_INJECTED) {
+        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+    } else if (rng->mode != HMCX_RNG_PHILOX) {
+        return HMCX_ERR_INVALID_ARG;
+    }
+    DenseRun r = {};
+    DenseArgs& a = r.a;
+    a.C = C; a.D = D; a.Cp = (C + 127) / 128 * 128; a.Dp = (D + 127) / 128 * 128; a.NT = a.Dp / 128;
+    a.log_norm = target->log_norm; a.mk = mk;
+    // carve the workspace
+    const size_t CD = (size_t)a.Cp * a.Dp;
+    float* Qbuf[2] = {ws, ws + CD};
+    float* P = ws + 2 * CD;
+    float* prec = ws + 3 * CD;
+    float* mean = prec + (size_t)a.Dp * a.Dp;
+    float* im = mean + a.Dp;
+    float* sd = im + a.Dp;
+    float* upart = sd + a.Dp;
+    r.kin0 = upart + (size_t)a.Cp * a.NT;
+    r.U_cur = r.kin0 + a.Cp;
+    r.U_init = r.U_cur + a.Cp;
+    a.prec = prec; a.mean = mean; a.im = (mk == HMCX_MASS_DIAG) ? im : nullptr; a.sd = (mk == HMCX_MASS_DIAG) ? sd : nullptr;
+    r.ld = ld; r.rng_mode = rng->mode; r.seed = rng->seed; r.chain_offset = rng->chain_offset;
+    r.normals = rng->normals; r.logu = rng->log_uniforms;
+    r.nuts = (nuts && nuts->enabled) ? 1 : 0;
+    if (r.nuts) {
+        if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
+        r.delta = nuts->desired_accept_rate; r.mu = nuts->mu; r.table = nuts->table;
+        r.h_bar = nuts->h_bar; r.eps_bar = nuts->eps_bar;
+        r.eps_schedule = nuts->eps_schedule; r.eps_trace = nuts->eps_trace;
+    }
+    r.q_init = q_init; r.q_cur = q_cur; r.eps = eps; r.S = S; r.burn = burn; r.it0 = it0;
+    r.samples = samples; r.accept = accept; r.diverged = diverged; r.ham = ham; r.num_rejected = num_rejected;
+
+    const size_t smem = (size_t)(2 * TC_M + 2 * TC_N) * TC_KC * sizeof(float);
+    if (cudaFuncSetAttribute(dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return HMCX_ERR_CUDA;
+    }
+    const dim3 ggrid(a.NT, a.Cp / 128);
+    dense_pad_matrix_kernel<<<296, 256, 0, st>>>(target->prec, D, prec, a.Dp);
+    dense_pad_vector_kernel<<<8, 256, 0, st>>>(target->mean, D, mean, a.Dp);
+    if (mk == HMCX_MASS_DIAG) {
+        dense_pad_vector_kernel<<<8, 256, 0, st>>>(mass->inv_mass, D, im, a.Dp);
+        dense_pad_vector_kernel<<<8, 256, 0, st>>>(mass->mass_factor, D, sd, a.Dp);
+    }
+    cudaMemsetAsync(P, 0, CD * sizeof(float), st);
+    // log p of params_init (needed again by the :1018 quirk) and of the current state
+    dense_load_rows_kernel<<<a.Cp, 256, 0, st>>>(q_init, C, ld, D, Qbuf[0], a.Cp, a.Dp);
+    dense_step_kernel<<<ggrid, TC_THREADS, smem, st>>>(a, Qbuf[0], Qbuf[1], P, eps, DENSE_EVAL, upart);
+    dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_init);
+    dense_load_rows_kernel<<<a.Cp, 256, 0, st>>>(q_cur, C, ld, D, Qbuf[0], a.Cp, a.Dp);
+    dense_step_kernel<<<ggrid, TC_THREADS, smem, st>>>(a, Qbuf[0], Qbuf[1], P, eps, DENSE_EVAL, upart);
+    dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_cur);
+    if (it0 == 0 && samples) {                                                      // slot 0 = params_init (:959)
+        cudaMemcpy2DAsync(samples, (size_t)(S - burn) * ld * sizeof(float), q_init, (size_t)ld * sizeof(float),
+                          (size_t)ld * sizeof(float), (size_t)C, cudaMemcpyDeviceToDevice, st);
+    }
+    for (int n = it0; n < it1; ++n) {
+        dense_gibbs_kernel<<<C, 256, 0, st>>>(r, n, Qbuf[0], P, nullptr);
+        for (int l = 0; l <= L; ++l) {
+            const int mode = (l == 0) ? DENSE_FIRST : (l == L ? DENSE_LAST : DENSE_MIDDLE);
+            dense_step_kernel<<<ggrid, TC_THREADS, smem, st>>>(a, Qbuf[l & 1], Qbuf[(l + 1) & 1], P, eps, mode, upart);
+        }
+        dense_mh_kernel<<<C, 256, 0, st>>>(r, n, Qbuf[L & 1], P, upart);
+    }
+    return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
+}
+
 int gemm_nt_tf32x3(const float* A, const float* B, float* D, int M, int N, int K, cudaStream_t st) {
     if (!A || !B || !D || M < 1 || N < 1 || K < 1) return HMCX_ERR_INVALID_ARG;
     if ((M % TC_M) || (N % TC_N) || (K % TC_KC)) return HMCX_ERR_UNSUPPORTED;

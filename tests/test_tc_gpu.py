@@ -22,3 +22,71 @@ def test_gemm_nt_tf32x3_is_fp32_accurate(shape):
     # 3xTF32 (hi*hi + hi*lo + lo*hi, the lo*lo term dropped): 22 significant bits per operand -> a few times the
     # rounding error of a plain fp32 GEMM, three orders of magnitude below a single tf32 product (~1e-3 relative)
     assert err <= 2e-5 * scale, (err, fp32, scale)
+
+
+def _corr_gaussian(D, seed):
+    import hamiltorch_b200.targets as T
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5
+    cov = A @ A.t() + 0.5 * torch.eye(D, dtype=torch.float64)
+    return T.GaussianFull(torch.randn(D, generator=g), cov=cov)
+
+
+@pytest.mark.parametrize('variant', ['hmc', 'diag_mass', 'nuts'])
+def test_dense_gaussian_full_chain_parity_vs_live_oracle(variant):
+    """Full-covariance Gaussian at D=200 (> 16: the tcgen05 step-synchronous path, one GEMM over all chains per
+    leapfrog step) against the oracle under the injected stream.  The gradient is a 3xTF32 tensor-core contraction
+    (~1e-6 relative), the reference's an fp32 mv: states agree to 2e-4, decisions identical."""
+    import numpy as np
+    import hamiltorch_b200 as hb
+    from hamiltorch_b200 import engine
+    from oracle import hmc_oracle as O
+    from tests import parity
+    D, C, S, L, burn = 200, 5, 12, 6, 3
+    tgt = _corr_gaussian(D, 1)
+    im = None
+    if variant == 'diag_mass':
+        im = 0.5 + torch.rand(D, generator=torch.Generator().manual_seed(2))
+    nuts = variant == 'nuts'
+    eps0 = 0.1 if nuts else 0.25
+    inits, zs, lus = [], [], []
+    for seed in range(C):
+        init, z, logu, _ = O.reference_stream(700 + seed, D, S, prior=lambda: tgt.mean + 0.3 * torch.randn(D))
+        inits.append(init), zs.append(z), lus.append(logu)
+    os_ = [O.sample_hmc(tgt, inits[c], num_samples=S, num_steps_per_sample=L, step_size=eps0, burn=burn, inv_mass=im,
+                        nuts=nuts, normals=zs[c], log_uniforms=lus[c]) for c in range(C)]
+    sched = torch.tensor([o['step_sizes'] for o in os_], dtype=torch.float32).t() if nuts else None
+    res = engine.hmc_run(tgt, torch.stack(inits), S, L, eps0, burn=burn, inv_mass=im, nuts=nuts,
+                         normals=torch.stack(zs, 1), log_uniforms=torch.stack(lus, 1), record_ham=True,
+                         eps_schedule=sched, record_eps=nuts)
+    torch.cuda.synchronize()
+    assert int(res.diverged.sum()) == 0
+    for c in range(C):
+        o = os_[c]
+        parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
+                                   res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
+                                   o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4)
+        if nuts:
+            own = res.eps_trace[c].cpu().numpy().astype(np.float64)
+            np.testing.assert_allclose(own[:S - 1], np.array(o['step_sizes'])[1:], rtol=2e-3)
+
+
+def test_dense_gaussian_full_philox_statistics_d1024():
+    """256 chains of a D=1024 correlated Gaussian (the 'full-covariance ... becomes tensor-core work' regime of SURVEY
+    8d): acceptance and energy errors of a working sampler; second moment along a random direction matches cov."""
+    import hamiltorch_b200 as hb
+    D, C, S, L = 1024, 256, 30, 8
+    tgt = _corr_gaussian(D, 3)
+    cov = torch.linalg.inv(tgt.prec.double())
+    Lc = torch.linalg.cholesky(cov)
+    init = tgt.mean[None] + (torch.randn(C, D, dtype=torch.float64, generator=torch.Generator().manual_seed(4)) @ Lc.t()).float()
+    res = hb.sample_chains(tgt, init, num_samples=S, num_steps_per_sample=L, step_size=0.12, rng='philox', seed=5,
+                           record_ham=True)
+    torch.cuda.synchronize()
+    assert int(res.diverged.sum()) == 0
+    acc = res.accepted.float().mean().item()
+    assert 0.6 < acc <= 1.0, acc
+    u = torch.randn(D, dtype=torch.float64, generator=torch.Generator().manual_seed(6))
+    u /= u.norm()
+    proj = ((res.samples[:, S // 2:].cpu().double() - tgt.mean.double()) @ u)
+    assert abs(proj.var().item() / float(u @ cov @ u) - 1.0) < 0.15
