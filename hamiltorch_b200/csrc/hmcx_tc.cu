@@ -179,7 +179,7 @@ gemm_nt_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, 
 // from hmcx_hmc_run, no host synchronisation.  State lives in the caller-provided workspace.
 // =========================================================================================================
 struct DenseArgs {
-    int C, Cp, D, Dp, NT;
+    int C, Cp, D, Dp, NT, BN;     // NT = Dp / BN column tiles
     const float* prec;        // [Dp, Dp] zero-padded precision
     const float* mean;        // [Dp]
     float log_norm;
@@ -190,89 +190,140 @@ struct DenseArgs {
 
 enum { DENSE_FIRST = 0, DENSE_MIDDLE = 1, DENSE_LAST = 2, DENSE_EVAL = 3 };
 
-// stage rows [row0, row0+128) x [k0, k0+32) of (X - mean) or of X (mean == nullptr)
-__device__ __forceinline__ void stage_rows(const float* __restrict__ X, int ld, int row0, int k0,
-                                           const float* __restrict__ mean, float* s_hi, float* s_lo) {
-    const int r = threadIdx.x;
-    const float4* src = reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * ld + k0);
-#pragma unroll
-    for (int kc = 0; kc < TC_KC / 4; ++kc) {
-        float4 v = __ldg(src + kc);
+// ---- packed operand layout ---------------------------------------------------------------------------------------
+// Operands are kept in global memory ALREADY in the canonical UMMA layout and ALREADY split into tf32 hi / lo, one
+// contiguous block per (row tile, 32-wide K chunk, hi|lo): a block of R rows is R*32 floats, element (r, k) at
+//     ((k/4) * (R/8) + r/8) * 32 + (r%8) * 4 + (k%4)            [8-row x 16-byte core matrices, K-major, no swizzle]
+// so that the GEMM main loop is nothing but 1-D bulk TMA copies (cp.async.bulk -> UBLKCP) into the stage buffers.
+__device__ __forceinline__ size_t pack_block_base(int tile, int kchunk, int hl, int kchunks, int R) {
+    return ((size_t)(tile * kchunks + kchunk) * 2 + hl) * (size_t)(R * TC_KC);
+}
+__device__ __forceinline__ int pack_elem_off(int r, int k, int R) {     // k in [0,32), multiple of 4 for float4 access
+    return ((k >> 2) * (R >> 3) + (r >> 3)) * 32 + (r & 7) * 4 + (k & 3);
+}
+__device__ __forceinline__ void split_store4(float* pack_hi, float* pack_lo, int off, const float v[4]) {
+    float4 h, l;
+    h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
+    l.x = to_tf32(v[0] - h.x); l.y = to_tf32(v[1] - h.y); l.z = to_tf32(v[2] - h.z); l.w = to_tf32(v[3] - h.w);
+    *reinterpret_cast<float4*>(pack_hi + off) = h;
+    *reinterpret_cast<float4*>(pack_lo + off) = l;
+}
+
+// pack a zero-padded row-major [rows x Dp] matrix (minus `mean` if given) into blocks of R rows
+__global__ void dense_pack_kernel(const float* __restrict__ src, const float* __restrict__ mean, int rows, int Dp, int R,
+                                  float* __restrict__ dst) {
+    const int kchunks = Dp / TC_KC, vec_per_row = Dp / 4;
+    const size_t n = (size_t)rows * vec_per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / vec_per_row), k = 4 * (int)(i % vec_per_row);
+        float v[4];
+        ld4(src + (size_t)row * Dp + k, v);
         if (mean) {
-            const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + k0) + kc);
-            v.x = sub(v.x, mu.x); v.y = sub(v.y, mu.y); v.z = sub(v.z, mu.z); v.w = sub(v.w, mu.w);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[t] = sub(v[t], mean[k + t]);
         }
-        float4 h, l;
-        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-        const int off = ((kc * 16 + (r >> 3)) * 128 + (r & 7) * 16) >> 2;
-        *reinterpret_cast<float4*>(s_hi + off) = h;
-        *reinterpret_cast<float4*>(s_lo + off) = l;
+        const int tile = row / R, kc = k / TC_KC;
+        const int off = pack_elem_off(row % R, k % TC_KC, R);
+        split_store4(dst + pack_block_base(tile, kc, 0, kchunks, R), dst + pack_block_base(tile, kc, 1, kchunks, R), off, v);
     }
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+
+__host__ __device__ constexpr int dense_stages(int BN) { return BN == 128 ? 3 : 4; }
+__host__ __device__ constexpr int dense_stage_floats(int BN) { return 2 * TC_M * TC_KC + 2 * BN * TC_KC; }
+
+// One leapfrog step for all chains:  acc = (Q - mu) P  on tcgen05, then kick / drift in the epilogue.
+//   grid (Dp/BN, Cp/128), 128 threads: thread 0 = TMA producer, thread 32 = MMA issuer, all 4 warps = epilogue.
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, float* __restrict__ Qout, float* __restrict__ P,
-                  const float* __restrict__ eps, int mode, float* __restrict__ upart) {
+dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float* __restrict__ QpIn,
+                  const float* __restrict__ Ppack, float* __restrict__ Qout, float* __restrict__ QpOut,
+                  float* __restrict__ P, const float* __restrict__ eps, int mode, float* __restrict__ upart) {
+    constexpr int ST = dense_stages(BN);
+    constexpr int A_BLK = TC_M * TC_KC, B_BLK = BN * TC_KC;                // floats per hi (or lo) block
+    constexpr uint32_t STAGE_BYTES = (uint32_t)dense_stage_floats(BN) * 4u;
     extern __shared__ __align__(1024) float smem[];
-    float* a_hi = smem;
-    float* a_lo = a_hi + TC_M * TC_KC;
-    float* b_hi = a_lo + TC_M * TC_KC;
-    float* b_lo = b_hi + TC_N * TC_KC;
-    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_full[ST], s_empty[ST], s_done;
     __shared__ uint32_t s_tmem;
     const int tile_n = blockIdx.x, tile_m = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t mbar = smem_u32(&s_mbar);
+    const int Dp = a.Dp, kchunks = Dp / TC_KC;
+
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+        mbar_init(smem_u32(&s_done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(BN < 32 ? 32 : BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = make_idesc_tf32(TC_M, TC_N);
-    const int Dp = a.Dp;
-    uint32_t parity = 0;
-    for (int k0 = 0; k0 < Dp; k0 += TC_KC) {
-        stage_rows(Qin, Dp, tile_m * TC_M, k0, a.mean, a_hi, a_lo);           // A = Q - mu   (chains x D)
-        stage_rows(a.prec, Dp, tile_n * TC_N, k0, nullptr, b_hi, b_lo);       // B = P rows   (symmetric)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
+
+    if (threadIdx.x == 0) {
+        // ===== TMA producer: 4 bulk copies per stage (A hi, A lo, B hi, B lo are adjacent pairs in global memory) =====
+        for (int i = 0; i < kchunks; ++i) {
+            const int s = i % ST;
+            mbar_wait(smem_u32(&s_empty[s]), ((i / ST) & 1) ^ 1);
+            const uint32_t full = smem_u32(&s_full[s]);
+            mbar_expect_tx(full, STAGE_BYTES);
+            float* st = smem + (size_t)s * dense_stage_floats(BN);
+            bulk_g2s(smem_u32(st), QpIn + pack_block_base(tile_m, i, 0, kchunks, TC_M), 2 * A_BLK * 4, full);
+            bulk_g2s(smem_u32(st + 2 * A_BLK), Ppack + pack_block_base(tile_n, i, 0, kchunks, BN), 2 * B_BLK * 4, full);
+        }
+    } else if (threadIdx.x == 32) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_tf32(TC_M, BN);
+        constexpr uint32_t A_LBO = (TC_M / 8) * 128, B_LBO = (BN / 8) * 128;
+        for (int i = 0; i < kchunks; ++i) {
+            const int s = i % ST;
+            mbar_wait(smem_u32(&s_full[s]), (i / ST) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + (size_t)s * dense_stage_floats(BN));
+            const uint32_t sb = sa + 2 * A_BLK * 4;
 #pragma unroll
-            for (int s = 0; s < TC_KC / 8; ++s) {
-                const uint32_t koff = (uint32_t)s * 2u * 2048u;
-                const uint64_t ah = make_kmajor_desc(smem_u32(a_hi) + koff, 2048, 128);
-                const uint64_t al = make_kmajor_desc(smem_u32(a_lo) + koff, 2048, 128);
-                const uint64_t bh = make_kmajor_desc(smem_u32(b_hi) + koff, 2048, 128);
-                const uint64_t bl = make_kmajor_desc(smem_u32(b_lo) + koff, 2048, 128);
-                umma_tf32(tmem, ah, bh, idesc, (k0 | s) != 0);
+            for (int k = 0; k < TC_KC / 8; ++k) {
+                const uint64_t ah = make_kmajor_desc(sa + k * 2 * A_LBO, A_LBO, 128);
+                const uint64_t al = make_kmajor_desc(sa + A_BLK * 4 + k * 2 * A_LBO, A_LBO, 128);
+                const uint64_t bh = make_kmajor_desc(sb + k * 2 * B_LBO, B_LBO, 128);
+                const uint64_t bl = make_kmajor_desc(sb + B_BLK * 4 + k * 2 * B_LBO, B_LBO, 128);
+                umma_tf32(tmem, ah, bh, idesc, (i | k) != 0);
                 umma_tf32(tmem, ah, bl, idesc, true);
                 umma_tf32(tmem, al, bh, idesc, true);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+            umma_commit(smem_u32(&s_empty[s]));                 // frees the stage when these MMAs have read it
         }
-        mbar_wait(mbar, parity);
-        parity ^= 1;
-        __syncthreads();
+        umma_commit(smem_u32(&s_done));
     }
-    // ---- epilogue: acc = ((Q-mu) P)[row, cols]; g = -acc; kick, optional drift, partial of y.(P y) ----
+    __syncwarp();
+    mbar_wait(smem_u32(&s_done), 0);
+    // ===== epilogue: acc = ((Q-mu) P)[row, cols]; g = -acc; kick, optional drift (+ packed copy for the next GEMM) =====
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = tile_m * TC_M + warp * 32 + lane;
     const bool live = row < a.C;
     const float e = live ? eps[row] : 0.0f, half = mul(0.5f, e);
     const float ck = (mode == DENSE_FIRST) ? half : e;
+    const bool drift = (mode == DENSE_FIRST || mode == DENSE_MIDDLE);
     float udot = 0.0f;
-    const size_t base = (size_t)row * Dp + (size_t)tile_n * TC_N;
+    const size_t base = (size_t)row * Dp + (size_t)tile_n * BN;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TC_N; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
         asm volatile(
@@ -285,15 +336,18 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, float* __res
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (live) {
+            const int colbase = tile_n * BN + c0;                           // a 32-aligned column block = one K chunk
+            float* qp_hi = QpOut + pack_block_base(tile_m, colbase / TC_KC, 0, kchunks, TC_M);
+            float* qp_lo = QpOut + pack_block_base(tile_m, colbase / TC_KC, 1, kchunks, TC_M);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const int col = tile_n * TC_N + c0 + j;
+                const int col = colbase + j;
                 const float4 q4 = *reinterpret_cast<const float4*>(Qin + base + c0 + j);
                 const float4 m4 = *reinterpret_cast<const float4*>(a.mean + col);
                 const float acc[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                       __uint_as_float(v[j + 3])};
                 const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
-                float pn[4], qn[4];
+                float pn[4], yn[4], qn[4];
                 float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (mode != DENSE_EVAL) p4 = *reinterpret_cast<const float4*>(P + base + c0 + j);
                 const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
@@ -305,17 +359,20 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, float* __res
                     if (mode == DENSE_LAST) pn[t] = sub(pn[t], mul(half, g));                   // :302
                     const float cd = (a.mk == HMCX_MASS_DIAG) ? mul(e, a.im[col + t]) : e;
                     qn[t] = add(qv[t], mul(cd, pn[t]));                                         // :284 / :296
+                    yn[t] = sub(qn[t], mv[t]);
                 }
                 if (mode != DENSE_EVAL) *reinterpret_cast<float4*>(P + base + c0 + j) = make_float4(pn[0], pn[1], pn[2], pn[3]);
-                if (mode == DENSE_FIRST || mode == DENSE_MIDDLE)
+                if (drift) {
                     *reinterpret_cast<float4*>(Qout + base + c0 + j) = make_float4(qn[0], qn[1], qn[2], qn[3]);
+                    split_store4(qp_hi, qp_lo, pack_elem_off(row % TC_M, j, TC_M), yn);       // next step's A operand
+                }
             }
         }
     }
     if (live && upart) upart[(size_t)row * a.NT + tile_n] = udot;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(BN < 32 ? 32 : BN));
 }
 
 // zero-padded copies into the workspace
@@ -367,7 +424,7 @@ struct DenseRun {
 
 // gibbs (:969) for iteration n: p = z * sqrt(mass) -> P rows, q_cur -> Q work rows, kinetic of p
 __global__ void __launch_bounds__(256)
-dense_gibbs_kernel(const DenseRun r, int n, float* __restrict__ Q, float* __restrict__ P, float* __restrict__ eps_work) {
+dense_gibbs_kernel(const DenseRun r, int n, float* __restrict__ Q, float* __restrict__ P, float* __restrict__ Qpack) {
     __shared__ float sred[32];
     const DenseArgs& a = r.a;
     const int c = blockIdx.x, Dp = a.Dp, D = a.D;
@@ -391,10 +448,15 @@ dense_gibbs_kernel(const DenseRun r, int n, float* __restrict__ Q, float* __rest
         }
         st4(P + (size_t)c * Dp + 4 * v, pv);
         st4(Q + (size_t)c * Dp + 4 * v, qv);
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = sub(qv[j], a.mean[4 * v + j]);
+        const int kchunks = Dp / TC_KC, kc = (4 * v) / TC_KC;
+        split_store4(Qpack + pack_block_base(c / TC_M, kc, 0, kchunks, TC_M),
+                     Qpack + pack_block_base(c / TC_M, kc, 1, kchunks, TC_M), pack_elem_off(c % TC_M, (4 * v) % TC_KC, TC_M), y);
     }
     block_sum<1>(kin, sred);
     if (threadIdx.x == 0) r.kin0[c] = kin[0];
-    (void)eps_work;
 }
 
 // log p from the per-tile partials of y.(P y)   (targets.GaussianFull: -0.5*dot(y, P y) + log_norm)
@@ -478,7 +540,10 @@ dense_mh_kernel(const DenseRun r, int n, const float* __restrict__ Qprop, const 
 
 size_t dense_workspace_floats(int C, int D) {
     const size_t Cp = (size_t)(C + 127) / 128 * 128, Dp = (size_t)(D + 127) / 128 * 128, NT = Dp / 128;
-    return 3 * Cp * Dp + Dp * Dp + 3 * Dp + Cp * NT + 3 * Cp + 64;
+    (void)NT;
+    return 7 * Cp * Dp            // Q[2], Qpack[2] (hi+lo each), P
+           + 3 * Dp * Dp          // padded precision + its packed hi/lo
+           + 3 * Dp + Cp * (Dp / 32) + 3 * Cp + 64;
 }
 
 int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, const hmcx_nuts_t* nuts,
@@ -502,16 +567,23 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     DenseArgs& a = r.a;
     a.C = C; a.D = D; a.Cp = (C + 127) / 128 * 128; a.Dp = (D + 127) / 128 * 128; a.NT = a.Dp / 128;
     a.log_norm = target->log_norm; a.mk = mk;
+    // column-tile width: the widest tile that still gives the GPU ~100 CTAs (each CTA re-streams its 128 chain rows)
+    const int mt = a.Cp / 128;
+    a.BN = 128;
+    while (a.BN > 32 && mt * (a.Dp / a.BN) < 96) a.BN >>= 1;
+    a.NT = a.Dp / a.BN;
     // carve the workspace
-    const size_t CD = (size_t)a.Cp * a.Dp;
+    const size_t CD = (size_t)a.Cp * a.Dp, DD = (size_t)a.Dp * a.Dp;
     float* Qbuf[2] = {ws, ws + CD};
-    float* P = ws + 2 * CD;
-    float* prec = ws + 3 * CD;
-    float* mean = prec + (size_t)a.Dp * a.Dp;
+    float* Qp[2] = {ws + 2 * CD, ws + 4 * CD};
+    float* P = ws + 6 * CD;
+    float* prec = ws + 7 * CD;
+    float* ppack = prec + DD;
+    float* mean = ppack + 2 * DD;
     float* im = mean + a.Dp;
     float* sd = im + a.Dp;
     float* upart = sd + a.Dp;
-    r.kin0 = upart + (size_t)a.Cp * a.NT;
+    r.kin0 = upart + (size_t)a.Cp * (a.Dp / 32);
     r.U_cur = r.kin0 + a.Cp;
     r.U_init = r.U_cur + a.Cp;
     a.prec = prec; a.mean = mean; a.im = (mk == HMCX_MASS_DIAG) ? im : nullptr; a.sd = (mk == HMCX_MASS_DIAG) ? sd : nullptr;
@@ -527,35 +599,56 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     r.q_init = q_init; r.q_cur = q_cur; r.eps = eps; r.S = S; r.burn = burn; r.it0 = it0;
     r.samples = samples; r.accept = accept; r.diverged = diverged; r.ham = ham; r.num_rejected = num_rejected;
 
-    const size_t smem = (size_t)(2 * TC_M + 2 * TC_N) * TC_KC * sizeof(float);
-    if (cudaFuncSetAttribute(dense_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return HMCX_ERR_CUDA;
+    const dim3 ggrid(a.NT, mt);
+    auto step = [&](const float* qin, const float* qpin, float* qout, float* qpout, int mode) -> bool {
+        if (a.BN == 128) {
+            const size_t sm = (size_t)dense_stages(128) * dense_stage_floats(128) * sizeof(float);
+            dense_step_kernel<128><<<ggrid, TC_THREADS, sm, st>>>(a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+        } else if (a.BN == 64) {
+            const size_t sm = (size_t)dense_stages(64) * dense_stage_floats(64) * sizeof(float);
+            dense_step_kernel<64><<<ggrid, TC_THREADS, sm, st>>>(a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+        } else {
+            const size_t sm = (size_t)dense_stages(32) * dense_stage_floats(32) * sizeof(float);
+            dense_step_kernel<32><<<ggrid, TC_THREADS, sm, st>>>(a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+        }
+        return true;
+    };
+    {
+        bool ok = true;
+        ok = ok && cudaFuncSetAttribute(dense_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)dense_stages(128) * dense_stage_floats(128) * 4)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(dense_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)dense_stages(64) * dense_stage_floats(64) * 4)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(dense_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)dense_stages(32) * dense_stage_floats(32) * 4)) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); return HMCX_ERR_CUDA; }
     }
-    const dim3 ggrid(a.NT, a.Cp / 128);
     dense_pad_matrix_kernel<<<296, 256, 0, st>>>(target->prec, D, prec, a.Dp);
+    dense_pack_kernel<<<296, 256, 0, st>>>(prec, nullptr, a.Dp, a.Dp, a.BN, ppack);
     dense_pad_vector_kernel<<<8, 256, 0, st>>>(target->mean, D, mean, a.Dp);
     if (mk == HMCX_MASS_DIAG) {
         dense_pad_vector_kernel<<<8, 256, 0, st>>>(mass->inv_mass, D, im, a.Dp);
         dense_pad_vector_kernel<<<8, 256, 0, st>>>(mass->mass_factor, D, sd, a.Dp);
     }
-    cudaMemsetAsync(P, 0, CD * sizeof(float), st);
+    cudaMemsetAsync(ws, 0, 7 * CD * sizeof(float), st);                              // Q, Qpack, P (incl. pad rows)
     // log p of params_init (needed again by the :1018 quirk) and of the current state
     dense_load_rows_kernel<<<a.Cp, 256, 0, st>>>(q_init, C, ld, D, Qbuf[0], a.Cp, a.Dp);
-    dense_step_kernel<<<ggrid, TC_THREADS, smem, st>>>(a, Qbuf[0], Qbuf[1], P, eps, DENSE_EVAL, upart);
+    dense_pack_kernel<<<296, 256, 0, st>>>(Qbuf[0], mean, a.Cp, a.Dp, TC_M, Qp[0]);
+    step(Qbuf[0], Qp[0], Qbuf[1], Qp[1], DENSE_EVAL);
     dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_init);
     dense_load_rows_kernel<<<a.Cp, 256, 0, st>>>(q_cur, C, ld, D, Qbuf[0], a.Cp, a.Dp);
-    dense_step_kernel<<<ggrid, TC_THREADS, smem, st>>>(a, Qbuf[0], Qbuf[1], P, eps, DENSE_EVAL, upart);
+    dense_pack_kernel<<<296, 256, 0, st>>>(Qbuf[0], mean, a.Cp, a.Dp, TC_M, Qp[0]);
+    step(Qbuf[0], Qp[0], Qbuf[1], Qp[1], DENSE_EVAL);
     dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_cur);
     if (it0 == 0 && samples) {                                                      // slot 0 = params_init (:959)
         cudaMemcpy2DAsync(samples, (size_t)(S - burn) * ld * sizeof(float), q_init, (size_t)ld * sizeof(float),
                           (size_t)ld * sizeof(float), (size_t)C, cudaMemcpyDeviceToDevice, st);
     }
     for (int n = it0; n < it1; ++n) {
-        dense_gibbs_kernel<<<C, 256, 0, st>>>(r, n, Qbuf[0], P, nullptr);
+        dense_gibbs_kernel<<<C, 256, 0, st>>>(r, n, Qbuf[0], P, Qp[0]);
         for (int l = 0; l <= L; ++l) {
             const int mode = (l == 0) ? DENSE_FIRST : (l == L ? DENSE_LAST : DENSE_MIDDLE);
-            dense_step_kernel<<<ggrid, TC_THREADS, smem, st>>>(a, Qbuf[l & 1], Qbuf[(l + 1) & 1], P, eps, mode, upart);
+            step(Qbuf[l & 1], Qp[l & 1], Qbuf[(l + 1) & 1], Qp[(l + 1) & 1], mode);
         }
         dense_mh_kernel<<<C, 256, 0, st>>>(r, n, Qbuf[L & 1], P, upart);
     }

@@ -89,3 +89,22 @@ if __name__ == '__main__':
     for f in (cfg5, cfg4, cfg3):
         print(json.dumps(f()), flush=True)
     print(json.dumps(cfg4(C=8)), flush=True)
+
+
+def dense(C=256, D=1024, S=20, L=10):
+    """Full-covariance Gaussian on the tcgen05 path: one GEMM (C x D) . (D x D) per leapfrog step."""
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5
+    cov = A @ A.t() + 0.5 * torch.eye(D, dtype=torch.float64)
+    tgt = T.GaussianFull(torch.zeros(D), cov=cov)
+    init = torch.randn(C, D, generator=g)
+    ms, res = timed(lambda: hb.sample_chains(tgt, init.cuda(), num_samples=S, num_steps_per_sample=L, step_size=0.1,
+                                             rng='philox', seed=5), reps=2)
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    O.sample_hmc(tgt, init[0], num_samples=5, num_steps_per_sample=L, step_size=0.1)
+    cpu = 5 * L / (time.perf_counter() - t0)
+    flops = 2.0 * C * D * D * (L + 1) * S                        # algorithmic: one (C x D)(D x D) product per gradient
+    return dict(config='dense: GaussianFull D=%d, %d chains, L=%d, S=%d (tcgen05 3xTF32)' % (D, C, L, S), ms=ms,
+                chain_steps_per_s=C * S * L / (ms * 1e-3), algorithmic_tflops=flops / (ms * 1e-3) / 1e12,
+                cpu_port_1core_chain_steps_per_s=cpu, accept=float(res.accepted.float().mean()))
