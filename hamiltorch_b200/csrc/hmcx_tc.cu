@@ -41,8 +41,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t lb
 }
 
 // 32-bit instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
@@ -654,6 +655,11 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     }
     return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
 }
+
+
+// NOTE (measured on B200): tf32 operands in MN-major form do NOT work with the no-swizzle canonical layout -- they need
+// the dedicated SWIZZLE_128B_BASE32B layout.  Every operand of this file is therefore kept K-major; an operand that an
+// epilogue produces "row per thread" is written transposed into its packed K-major block.
 
 int gemm_nt_tf32x3(const float* A, const float* B, float* D, int M, int N, int K, cudaStream_t st) {
     if (!A || !B || !D || M < 1 || N < 1 || K < 1) return HMCX_ERR_INVALID_ARG;

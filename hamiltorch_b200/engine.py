@@ -496,3 +496,4 @@ def gemm_nt(A, B):
                                      N.stream_ptr(A.device))
     N.check(rc, 'hmcx_gemm_nt_tf32x3')
     return D
+
