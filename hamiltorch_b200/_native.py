@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libhmcx.so')
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 MASS_NONE, MASS_DIAG, MASS_FULL = 0, 1, 2
 RNG_INJECTED, RNG_PHILOX = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):
@@ -32,7 +32,8 @@ class MlpStruct(C.Structure):
                 ('prior_scale', C.c_float), ('prior_two_var', C.c_float * (2 * MLP_MAX_LAYERS)),
                 ('prior_log_scale', C.c_float * (2 * MLP_MAX_LAYERS)),
                 ('prior_grad_coef', C.c_float * (2 * MLP_MAX_LAYERS)), ('x', C.c_void_p), ('y', C.c_void_p),
-                ('num_rows', C.c_int32), ('num_splits', C.c_int32), ('split_begin', C.c_int32 * (MLP_MAX_SPLITS + 1))]
+                ('num_rows', C.c_int32), ('num_splits', C.c_int32), ('split_begin', C.c_int32 * (MLP_MAX_SPLITS + 1)),
+                ('cluster_size', C.c_int32)]
 
 
 class TargetStruct(C.Structure):

@@ -17,6 +17,9 @@
 // sgemm order is unknowable); everything element-wise (kicks, drifts, prior, Hamiltonian assembly, MH) keeps the
 // reference's separately-rounded fp32 operation order.
 #include "hmcx_common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace hmcx {
 
@@ -366,10 +369,66 @@ __device__ __forceinline__ float mlp_ll_from_sum(const MlpDev& m, float sum, int
     return mul(m.c_ll, sum);
 }
 
-// g += d ll_split / dq over the rows [r_begin, r_end)  (g must already hold the prior part)
+// ---- thread-block clusters: a chain may be owned by CS cooperating CTAs (CS SMs) --------------------------------
+// Every CTA of the cluster keeps the full q, p, g in its own shared memory and does the (cheap) element-wise work
+// redundantly and identically; the expensive part -- the data rows of a gradient / log-prob evaluation -- is divided
+// by tile index (tile i -> rank i % CS), and the partial results are combined through DISTRIBUTED SHARED MEMORY in
+// the fixed order rank 0, 1, ... so that all CTAs hold bit-identical sums.  CS is a function of the data layout only
+// (never of the number of chains), so results do not depend on how chains are sharded over GPUs.
+struct ClusterCtx { int rank, size; };
+
+template <int CS>
+__device__ __forceinline__ void cluster_sum_vector(float* v, int n) {
+    if (CS == 1) return;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                            // every partial is complete
+    constexpr int MAXPT = 36;                                  // n <= 512*36 (the three state vectors must fit smem anyway)
+    float acc[MAXPT];
+#pragma unroll
+    for (int t = 0; t < MAXPT; ++t) {
+        const int i = threadIdx.x + t * MLP_THREADS;
+        float sum = 0.0f;
+        if (i < n) {
+#pragma unroll
+            for (int r = 0; r < CS; ++r) {
+                const float x = cluster.map_shared_rank(v, r)[i];
+                sum = (r == 0) ? x : add(sum, x);
+            }
+        }
+        acc[t] = sum;
+    }
+    cluster.sync();                                            // everybody has read everybody's partial
+#pragma unroll
+    for (int t = 0; t < MAXPT; ++t) {
+        const int i = threadIdx.x + t * MLP_THREADS;
+        if (i < n) v[i] = acc[t];
+    }
+    __syncthreads();
+}
+
+// scalar version: `slot` is a shared-memory word of this CTA; returns sum over ranks in rank order
+template <int CS>
+__device__ __forceinline__ float cluster_sum_scalar(float x, float* slot) {
+    if (CS == 1) return x;
+    cg::cluster_group cluster = cg::this_cluster();
+    if (threadIdx.x == 0) *slot = x;
+    cluster.sync();
+    float sum = 0.0f;
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {
+        const float y = *cluster.map_shared_rank(slot, r);
+        sum = (r == 0) ? y : add(sum, y);
+    }
+    cluster.sync();                                            // slot may be rewritten after this
+    return sum;
+}
+
+// g += d ll_split / dq over this rank's tiles of the rows [r_begin, r_end)  (g must already hold the prior part / zeros)
 __device__ __forceinline__ void mlp_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, int r_begin,
-                                                  int r_end) {
-    for (int r0 = r_begin; r0 < r_end; r0 += m.T) {
+                                                  int r_end, ClusterCtx cc) {
+    int ti = 0;
+    for (int r0 = r_begin; r0 < r_end; r0 += m.T, ++ti) {
+        if (ti % cc.size != cc.rank) continue;
         const int cnt = min(m.T, r_end - r0);
         mlp_forward_tile(m, q, tile, r0, cnt);
         float* dz = tile + m.dzoff[m.L & 1];
@@ -398,12 +457,16 @@ __device__ __forceinline__ void mlp_prior_grad(const MlpDev& m, const float* q, 
 }
 
 // g = d log p_split / dq for split s (s < 0: all rows as one potential)
-__device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, float* g, float* tile, int s) {
-    mlp_prior_grad(m, q, g);
+template <int CS>
+__device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, float* g, float* tile, int s,
+                                               ClusterCtx cc) {
+    if (cc.rank == 0) mlp_prior_grad(m, q, g);                 // the prior part enters the rank-ordered sum once
+    else for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) g[i] = 0.0f;
     __syncthreads();
     if (m.has_data) {
         const int rb = s < 0 ? 0 : m.sb[s], re = s < 0 ? m.N : m.sb[s + 1];
-        mlp_backprop_rows(m, q, g, tile, rb, re);
+        mlp_backprop_rows(m, q, g, tile, rb, re, cc);
+        cluster_sum_vector<CS>(g, m.D);
     }
 }
 
@@ -430,15 +493,18 @@ __device__ __forceinline__ float mlp_log_prior(const MlpDev& m, const float* q, 
 
 // log p(q) = sum over splits of (ll_m + l_prior/prior_scale)  (hamiltonian's split loop, samplers.py:787-796);
 // with s >= 0 only that split.  Optionally writes the network outputs (predict_model).
+template <int CS>
 __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, float* tile, float* sred, int s,
-                                              float* pred_out) {
+                                              float* pred_out, ClusterCtx cc, float* xslot) {
     const float prior_term = __fdiv_rn(mlp_log_prior(m, q, sred), m.prior_scale);
     if (!m.has_data) return prior_term;
     float lp = 0.0f;
     const int s0 = s < 0 ? 0 : s, s1 = s < 0 ? m.M : s + 1;
     for (int sp = s0; sp < s1; ++sp) {
         float sse[1] = {0.0f};
-        for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += m.T) {
+        int ti = 0;
+        for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += m.T, ++ti) {
+            if (ti % cc.size != cc.rank) continue;
             const int cnt = min(m.T, m.sb[sp + 1] - r0);
             mlp_forward_tile(m, q, tile, r0, cnt);
             sse[0] = add(sse[0], mlp_loss_tile(m, tile + m.aoff[m.L], nullptr, r0, cnt, m.sb[sp + 1] - m.sb[sp],
@@ -453,6 +519,7 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
         }
         block_sum<1>(sse, sred);
         __syncthreads();
+        sse[0] = cluster_sum_scalar<CS>(sse[0], xslot);
         const float ll = mlp_ll_from_sum(m, sse[0], m.sb[sp + 1] - m.sb[sp]);
         lp = (sp == s0) ? add(ll, prior_term) : add(lp, add(ll, prior_term));
     }
@@ -490,14 +557,19 @@ struct MlpRunArgs {
     int32_t* num_rejected;
 };
 
+template <int CS>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArgs a) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float sred[64];
     __shared__ float s_bcast[4];
+    __shared__ float s_xchg;
     __shared__ int s_perm[HMCX_MLP_MAX_SPLITS];
 
     const MlpDev& m = a.m;
-    const int c = blockIdx.x, tid = threadIdx.x, D = m.D, M = m.M;
+    ClusterCtx cc = {0, 1};
+    if (CS > 1) { cc.rank = (int)cg::this_cluster().block_rank(); cc.size = CS; }
+    const bool lead = cc.rank == 0;                            // rank 0 owns every global-memory output
+    const int c = blockIdx.x / CS, tid = threadIdx.x, D = m.D, M = m.M;
     float* q = sm;
     float* p = q + m.Dp;
     float* g = p + m.Dp;
@@ -507,14 +579,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
 
     for (int i = tid; i < m.Dp; i += MLP_THREADS) { q[i] = i < D ? a.q_cur[row + i] : 0.0f; p[i] = 0.0f; g[i] = 0.0f; }
     __syncthreads();
-    float lp_cur = mlp_log_prob(m, q, tile, sred, -1, nullptr);
+    float lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg);
 
     float eps = a.eps[c];
     double h_bar = 0.0, eps_bar = 1.0;
     if (a.nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
     int rejected = 0;
     const int keep = a.S - a.burn;
-    float* const my_samples = a.samples ? a.samples + (size_t)c * keep * a.ld : nullptr;
+    float* const my_samples = (a.samples && lead) ? a.samples + (size_t)c * keep * a.ld : nullptr;
     if (a.it0 == 0 && my_samples)
         for (int i = tid; i < a.ld; i += MLP_THREADS) my_samples[i] = i < D ? q[i] : 0.0f;
 
@@ -566,11 +638,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         const float kin0 = kinetic();
         // ---- trajectory ----
         if (a.scheme == HMCX_SCHEME_PLAIN) {                              // samplers.py:281-302
-            mlp_grad_split(m, q, g, tile, -1);
+            mlp_grad_split<CS>(m, q, g, tile, -1, cc);
             kick(half);
             for (int l = 0; l < a.L; ++l) {
                 drift(eps);
-                mlp_grad_split(m, q, g, tile, -1);
+                mlp_grad_split<CS>(m, q, g, tile, -1, cc);
                 kick(eps);
             }
             kick(-half);                                                  // p - half*g == p + (-half)*g exactly
@@ -578,12 +650,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             const float cd = (float)((double)eps / (double)((M - 1) * 2));
             for (int l = 0; l < a.L; ++l) {
                 for (int s = 0; s < M; ++s) {
-                    mlp_grad_split(m, q, g, tile, s);
+                    mlp_grad_split<CS>(m, q, g, tile, s, cc);
                     kick(half);
                     if (s < M - 1) drift(cd);
                 }
                 for (int s = M - 1; s >= 0; --s) {
-                    mlp_grad_split(m, q, g, tile, s);
+                    mlp_grad_split<CS>(m, q, g, tile, s, cc);
                     kick(half);
                     if (s > 0) drift(cd);
                 }
@@ -592,21 +664,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             const float cd = (float)((double)eps / (double)M);
             for (int l = 0; l < a.L; ++l)
                 for (int s = 0; s < M; ++s) {
-                    mlp_grad_split(m, q, g, tile, s_perm[s]);
+                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc);
                     kick(half);
                     drift(cd);
-                    mlp_grad_split(m, q, g, tile, s_perm[s]);
+                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc);
                     kick(half);
                 }
         } else {                                                          // KMID :579-598
             for (int l = 0; l < a.L; ++l) {
-                for (int s = 0; s < M; ++s) { mlp_grad_split(m, q, g, tile, s); kick(half); }
+                for (int s = 0; s < M; ++s) { mlp_grad_split<CS>(m, q, g, tile, s, cc); kick(half); }
                 drift(eps);
-                for (int s = M - 1; s >= 0; --s) { mlp_grad_split(m, q, g, tile, s); kick(half); }
+                for (int s = M - 1; s >= 0; --s) { mlp_grad_split<CS>(m, q, g, tile, s, cc); kick(half); }
             }
         }
         // ---- Hamiltonians + MH ----
-        const float lp_new = mlp_log_prob(m, q, tile, sred, -1, nullptr);
+        const float lp_new = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg);
         const float kin1 = kinetic();
         const float h_old = add(-lp_cur, mul(0.5f, kin0));
         const float h_new = add(-lp_new, mul(0.5f, kin1));
@@ -621,22 +693,23 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         const bool acc = !bad && (rho >= logu);
         if (acc) {
             lp_cur = lp_new;
-            for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
+            if (lead) for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
         } else {
             ++rejected;
             const float* src = (n == a.burn + 1) ? a.q_init : a.q_cur;    // the first-stored-iteration quirk (:1018)
             for (int i = tid; i < D; i += MLP_THREADS) q[i] = src[row + i];
             __syncthreads();
             if (n == a.burn + 1) {
-                lp_cur = mlp_log_prob(m, q, tile, sred, -1, nullptr);
-                for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
+                lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg);
+                if (lead) for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
             }
         }
+        if (CS > 1) cg::this_cluster().sync();                 // q_cur is stable before any rank re-reads it
         if (n > a.burn && my_samples) {
             float* dst = my_samples + (size_t)(n - a.burn) * a.ld;
             for (int i = tid; i < a.ld; i += MLP_THREADS) dst[i] = i < D ? q[i] : 0.0f;
         }
-        if (tid == 0) {
+        if (tid == 0 && lead) {
             const size_t o = (size_t)c * a.S + n;
             if (a.accept) a.accept[o] = acc ? 1 : 0;
             if (a.diverged) a.diverged[o] = bad ? 1 : 0;
@@ -656,16 +729,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                 }
                 if (n == a.burn) e = (float)eps_bar;
                 s_bcast[1] = e;
-                if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = e;
+                if (a.eps_trace && lead) a.eps_trace[(size_t)c * a.S + n] = e;
             }
             __syncthreads();
             eps = s_bcast[1];
-        } else if (a.eps_trace && tid == 0) {
+        } else if (a.eps_trace && tid == 0 && lead) {
             a.eps_trace[(size_t)c * a.S + n] = eps;
         }
         __syncthreads();
     }
-    if (tid == 0) {
+    if (tid == 0 && lead) {
         a.eps[c] = eps;
         if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
         if (a.num_rejected) a.num_rejected[c] += rejected;
@@ -685,12 +758,12 @@ mlp_grad_kernel(const MlpDev m, const float* __restrict__ qin, int ld, int split
     for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) { q[i] = i < m.D ? qin[row + i] : 0.0f; g[i] = 0.0f; }
     __syncthreads();
     if (gout) {
-        mlp_grad_split(m, q, g, tile, split);
+        mlp_grad_split<1>(m, q, g, tile, split, ClusterCtx{0, 1});
         __syncthreads();
         for (int i = threadIdx.x; i < ld; i += MLP_THREADS) gout[row + i] = i < m.D ? g[i] : 0.0f;
     }
     if (lpout) {
-        const float lp = mlp_log_prob(m, q, tile, sred, split, nullptr);
+        const float lp = mlp_log_prob<1>(m, q, tile, sred, split, nullptr, ClusterCtx{0, 1}, nullptr);
         if (threadIdx.x == 0) lpout[blockIdx.x] = lp;
     }
 }
@@ -707,7 +780,7 @@ mlp_predict_kernel(const MlpDev m, const float* __restrict__ samples, int ld, fl
     for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) q[i] = i < m.D ? samples[row + i] : 0.0f;
     __syncthreads();
     float* my_pred = pred + (size_t)blockIdx.x * m.N * m.n[m.L];
-    const float lp = mlp_log_prob(m, q, tile, sred, -1, my_pred);
+    const float lp = mlp_log_prob<1>(m, q, tile, sred, -1, my_pred, ClusterCtx{0, 1}, nullptr);
     if (threadIdx.x == 0 && lpout) lpout[blockIdx.x] = lp;
 }
 
@@ -830,9 +903,34 @@ int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
     if (!mlp_pick_tile(a.m, 3)) return HMCX_ERR_UNSUPPORTED;    // q, p, g do not fit one SM's shared memory
     const size_t smem = (size_t)(3 * a.m.Dp + a.m.tile_floats) * sizeof(float);
-    rc = prepare_smem(mlp_run_kernel, smem);
-    if (rc != HMCX_OK) return rc;
-    mlp_run_kernel<<<C, MLP_THREADS, smem, st>>>(a);
+    // CTAs per chain (thread-block cluster size): at most the tiles of the smallest split, at most 4, and -- unless the
+    // caller pins it (hmcx_mlp_t.cluster_size) -- no more than keeps every chain's cluster resident at once.  The
+    // partial gradients are associated per cluster rank, so low-order bits depend on this number: pin it to make
+    // chains bit-reproducible across launches with different chain counts (e.g. different multi-GPU shardings).
+    int cs = 1;
+    if (a.m.has_data && a.m.D <= MLP_THREADS * 36) {
+        int min_tiles = 1 << 30;
+        for (int s = 0; s < a.m.M; ++s) min_tiles = min(min_tiles, (a.m.sb[s + 1] - a.m.sb[s] + a.m.T - 1) / a.m.T);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int pinned = target->mlp->cluster_size;
+        while (cs * 2 <= 4 && cs * 2 <= min_tiles && (pinned ? cs * 2 <= pinned : C * cs * 2 <= sms)) cs *= 2;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C * cs);
+    cfg.blockDim = dim3(MLP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t err;
+    if (cs == 4) { rc = prepare_smem(mlp_run_kernel<4>, smem); if (rc != HMCX_OK) return rc; err = cudaLaunchKernelEx(&cfg, mlp_run_kernel<4>, a); }
+    else if (cs == 2) { rc = prepare_smem(mlp_run_kernel<2>, smem); if (rc != HMCX_OK) return rc; err = cudaLaunchKernelEx(&cfg, mlp_run_kernel<2>, a); }
+    else { rc = prepare_smem(mlp_run_kernel<1>, smem); if (rc != HMCX_OK) return rc; err = cudaLaunchKernelEx(&cfg, mlp_run_kernel<1>, a); }
+    if (err != cudaSuccess) { cudaGetLastError(); return HMCX_ERR_CUDA; }
     return cuda_status();
 }
 

@@ -95,6 +95,7 @@ class NativeTarget:
             m.x, m.y = xd.data_ptr(), yd.data_ptr()
             m.num_rows = xd.shape[0]
         m.num_splits = self.num_splits
+        m.cluster_size = int(getattr(first, 'cluster_size', 0))      # 0 = auto; 1/2/4 pins CTAs per chain
         for i, b in enumerate(begin):
             m.split_begin[i] = b
         self.mlp_struct = m

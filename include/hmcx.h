@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HMCX_ABI_VERSION 2
+#define HMCX_ABI_VERSION 3
 
 /* status codes */
 #define HMCX_OK                0
@@ -87,6 +87,8 @@ typedef struct hmcx_mlp {
     int32_t num_rows;
     int32_t num_splits;                            /* M >= 1                                                    */
     int32_t split_begin[HMCX_MLP_MAX_SPLITS + 1];
+    int32_t cluster_size;                          /* CTAs (SMs) cooperating on one chain: 0 = automatic, 1 / 2 / 4 =
+                                                      pinned (bit-reproducibility across chain counts)          */
 } hmcx_mlp_t;
 
 typedef struct hmcx_target {

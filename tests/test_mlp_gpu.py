@@ -159,3 +159,52 @@ def test_classification_predict_model(name):
     assert pred.shape == d['pred'].shape and lps[0].shape == ()
     np.testing.assert_allclose(pred.numpy(), d['pred'], rtol=5e-5, atol=5e-5)
     np.testing.assert_allclose(torch.stack(lps).numpy(), d['pred_log_prob'].reshape(-1), rtol=5e-5)
+
+
+@pytest.mark.parametrize('rows_per_split,expect_ctas', [(192, 2), (320, 4)])
+def test_cluster_split_chain_parity_vs_live_oracle(rows_per_split, expect_ctas):
+    """Splits with several 64-row tiles are shared by a thread-block cluster (2 or 4 CTAs per chain, partial gradients
+    and log-likelihood sums combined through distributed shared memory in rank order): same chains as the oracle."""
+    M, S, L, burn = 2, 8, 3, 1
+    model, x, y = cases.mlp_problem(seed=11, n=M * rows_per_split, n_in=6, hidden=16)
+    descs = [T.MLPTarget.from_model(model, x[m * rows_per_split:(m + 1) * rows_per_split],
+                                    y[m * rows_per_split:(m + 1) * rows_per_split], None, 20., prior_scale=M)
+             for m in range(M)]
+    D = descs[0].dim
+    C = 3
+    inits, zs, lus = [], [], []
+    for seed in range(C):
+        init, z, logu, _ = O.reference_stream(40 + seed, D, S,
+                                              prior=lambda: hb.util.flatten(model).detach() + 0.05 * torch.randn(D))
+        inits.append(init), zs.append(z), lus.append(logu)
+    res = engine.hmc_run(descs, torch.stack(inits), S, L, 0.004, burn=burn, normals=torch.stack(zs, 1),
+                         log_uniforms=torch.stack(lus, 1), record_ham=True, scheme=N.SCHEME_SPLIT_SYM)
+    torch.cuda.synchronize()
+    assert int(res.diverged.sum()) == 0
+    for c in range(C):
+        o = O.sample_hmc(descs, inits[c], num_samples=S, num_steps_per_sample=L, step_size=0.004, burn=burn,
+                         split_scheme=O.SPLIT_SYM, normals=zs[c], log_uniforms=lus[c])
+        parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
+                                   res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
+                                   o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=MLP_RTOL)
+
+
+def test_pinned_cluster_size_is_bit_reproducible_across_chain_counts():
+    """hmcx_mlp_t.cluster_size pins the CTAs per chain, so a chain's bits do not depend on how many chains share the
+    launch (the automatic choice shrinks the cluster when chains outnumber SMs)."""
+    M, S, L, rows = 2, 6, 3, 320
+    model, x, y = cases.mlp_problem(seed=12, n=M * rows, n_in=6, hidden=16)
+    descs = [T.MLPTarget.from_model(model, x[m * rows:(m + 1) * rows], y[m * rows:(m + 1) * rows], None, 20.,
+                                    prior_scale=M) for m in range(M)]
+    descs[0].cluster_size = 2
+    D = descs[0].dim
+    g = torch.Generator().manual_seed(3)
+    big = 100
+    init = hb.util.flatten(model).detach()[None] + 0.05 * torch.randn(big, D, generator=g)
+    z = torch.randn(S, big, D, generator=g)
+    lu = torch.log(torch.rand(S, big, generator=g))
+    run = lambda c: engine.hmc_run(descs, init[:c], S, L, 0.004, normals=z[:, :c].contiguous(),
+                                   log_uniforms=lu[:, :c].contiguous(), scheme=N.SCHEME_SPLIT_SYM)
+    a, b = run(3), run(big)
+    torch.cuda.synchronize()
+    assert torch.equal(a.samples, b.samples[:3]) and torch.equal(a.accepted, b.accepted[:3])
