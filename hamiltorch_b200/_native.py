@@ -33,7 +33,7 @@ class MlpStruct(C.Structure):
                 ('prior_log_scale', C.c_float * (2 * MLP_MAX_LAYERS)),
                 ('prior_grad_coef', C.c_float * (2 * MLP_MAX_LAYERS)), ('x', C.c_void_p), ('y', C.c_void_p),
                 ('num_rows', C.c_int32), ('num_splits', C.c_int32), ('split_begin', C.c_int32 * (MLP_MAX_SPLITS + 1)),
-                ('cluster_size', C.c_int32)]
+                ('cluster_size', C.c_int32), ('tensor_cores', C.c_int32)]
 
 
 class TargetStruct(C.Structure):

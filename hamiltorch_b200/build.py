@@ -55,7 +55,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('HMCX_NVCC_EXTRA', '').split() + \
+            (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

@@ -17,6 +17,7 @@
 // sgemm order is unknowable); everything element-wise (kicks, drifts, prior, Hamiltonian assembly, MH) keeps the
 // reference's separately-rounded fp32 operation order.
 #include "hmcx_common.cuh"
+#include "hmcx_umma.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -34,7 +35,11 @@ struct MlpDev {
     int aoff[HMCX_MLP_MAX_LAYERS + 1];    // smem offsets (floats, relative to the tile area) of A[l] (T x n[l])
     int dzoff[2];                         // two delta buffers (T x maxw)
     int tile_floats;
+    int tile_base;                        // float offset of the tile area in dynamic shared memory (after the state vectors)
     int T;                                // rows per tile (multiple of 4)
+    int tc;                               // 1: the first layer's GEMMs run on tcgen05 (layout below), 0: SIMT tiles
+    int tc_w1hi, tc_w1lo, tc_xhi, tc_xlo, tc_part;   // tile-area offsets (floats) of the tensor-core staging buffers
+    int tc_raw, tc_yraw;                  // cp.async landing buffers: the next tile's raw X rows and targets
     float tau_out, prior_scale, c_ll;     // c_ll = fp32(-0.5*tau_out) (regression, :1184) or fp32(-tau_out) (:1172-1180)
     float two_var[2 * HMCX_MLP_MAX_LAYERS], log_scale[2 * HMCX_MLP_MAX_LAYERS], gcoef[2 * HMCX_MLP_MAX_LAYERS];
     const float* x;
@@ -317,7 +322,7 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpDev& m, const float* q
 // being evaluated (the split), only used by the mean reduction.  With log_softmax_out the tile's outputs are replaced
 // by their log-softmax (what predict_model returns for such a model).
 __device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, float* out, float* dz, int r0, int cnt, int rows,
-                                               bool log_softmax_out = false) {
+                                               bool log_softmax_out = false, const float* ytile = nullptr) {
     const int nL = m.n[m.L];
     float sum = 0.0f;
     if (m.loss == HMCX_LOSS_REGRESSION || m.loss == HMCX_LOSS_BINARY) {
@@ -325,7 +330,7 @@ __device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, float* out, floa
         for (int i = threadIdx.x; i < m.T * nL; i += MLP_THREADS) {
             float d = 0.0f, gz = 0.0f;
             if (i < cnt * nL) {
-                const float yv = __ldg(m.y + (size_t)r0 * nL + i), z = out[i];
+                const float yv = ytile ? ytile[i] : __ldg(m.y + (size_t)r0 * nL + i), z = out[i];
                 if (m.loss == HMCX_LOSS_REGRESSION) {
                     d = sub(z, yv);
                     sum = add(sum, mul(d, d));
@@ -349,7 +354,7 @@ __device__ __forceinline__ float mlp_loss_tile(const MlpDev& m, float* out, floa
             float se = 0.0f;
             for (int k = 0; k < nL; ++k) se += expf(z[k] - mx);
             const float lse = mx + logf(se);
-            int label = (int)__ldg(m.y + r0 + r);
+            int label = (int)(ytile ? ytile[r] : __ldg(m.y + r0 + r));
             label = label < 0 ? 0 : (label >= nL ? nL - 1 : label);
             sum += lse - z[label];
             for (int k = 0; k < nL; ++k) {
@@ -423,6 +428,415 @@ __device__ __forceinline__ float cluster_sum_scalar(float x, float* slot) {
     return sum;
 }
 
+
+// =========================================================================================================
+// First-layer GEMMs on the 5th-generation tensor cores (tcgen05 / TMEM), for one-hidden-layer stacks
+//   n0 -> 128 -> nL   (n0 in {16,32,48,64}, nL <= 4; BASELINE config 4 is 64-128-1)
+// where  H = X W1^T  (forward) and  dW1 = dH^T X  (backward) carry ~all of the flops.  Per 64-row tile of the split:
+//   forward, TRANSPOSED:  H^T[128 units x 64 rows] = W1[128 x n0] . X_tile^T   -- A = W1 (shared memory, K-major,
+//       packed from the flat q at the start of every evaluation), B = X tile (staged from global memory), fp32
+//       accumulators in TENSOR MEMORY; 3xTF32 split operands (hi*hi + hi*lo + lo*hi) keep fp32-level accuracy;
+//   epilogue 1: each thread owns ONE hidden unit (TMEM lane) and 16 rows (columns): bias + activation in registers,
+//       the thin output layer as an in-warp transpose-reduction -> z2 in shared memory -> the usual loss stage;
+//   epilogue 2: dH^T = (W2^T dz2) * act'(H) computed in the same registers; db1 and dW2 are THREAD-LOCAL sums in this
+//       orientation; dH^T is written back to TENSOR MEMORY (tcgen05.st) as tf32 hi / lo;
+//   backward:  dW1[128 x n0] += dH^T[128 x 64 rows] . X_tile  with the A operand read FROM TENSOR MEMORY and
+//       B = X tile re-staged rows-contiguous; the accumulator stays in TMEM across all tiles of the split.
+// The big activations never touch shared memory.  Everything around (prior, schedules, kicks, drifts, Hamiltonians,
+// MH, clusters) is the code of the SIMT path.
+// =========================================================================================================
+constexpr int TC_TR = 64;                 // data rows per tile (MMA N forward, MMA K backward)
+constexpr int TC_H = 128;                 // hidden units = MMA M = TMEM lanes
+constexpr int TC_NLMAX = 4;               // outputs handled by the register head
+constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COLS = 256;   // TMEM columns: H / dH hi | dH lo | dW1
+
+static_assert(TC_TR / 4 == MLP_THREADS / 32 && TC_TR == 64, "staging / epilogue thread maps assume 16 warps and 64-row tiles");
+
+struct TcCtx { uint32_t tmem, barH, barW, barX, parH, parW, parX; };
+
+#ifdef HMCX_TC_PROF
+__device__ long long g_tc_prof[64];
+__device__ int g_tc_prof_n;
+#define TC_MARK(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { int k_ = g_tc_prof_n; if (k_ < 62) { g_tc_prof[k_] = ((long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFll); g_tc_prof_n = k_ + 1; } } } while (0)
+#else
+#define TC_MARK(id) do {} while (0)
+#endif
+
+__device__ __forceinline__ void tc_init(TcCtx& tc, uint64_t* bars, uint32_t* slot) {
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        mbar_init(smem_u32(&bars[2]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(TC_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc.tmem = *slot;
+    tc.barH = smem_u32(&bars[0]);
+    tc.barW = smem_u32(&bars[1]);
+    tc.barX = smem_u32(&bars[2]);
+    tc.parH = tc.parW = tc.parX = 0;
+}
+__device__ __forceinline__ void tc_fini(const TcCtx& tc) {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tc.tmem), "r"(TC_COLS));
+}
+
+// round-to-nearest (ties away) tf32 in an fp32 container == cvt.rna.tf32.f32 for finite inputs, as two full-rate
+// integer instructions instead of a conversion-pipe instruction (the epilogues split ~50 values per thread per tile)
+__device__ __forceinline__ float tf32_rn(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void tc_split4(const float4 v, float4& h, float4& l) {
+    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+    l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+}
+
+// q's W1 (flat, row-major 128 x n0) -> A operand, canonical K-major / no-swizzle core matrices, tf32 hi and lo.
+// The chunk index is rotated per lane so that both the strided reads and the packed writes are conflict-free.
+__device__ __forceinline__ void tc_pack_w1(const MlpDev& m, const float* q, float* tile) {
+    const int n0 = m.n[0], nch = n0 >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* W = q + m.woff[0];
+    float* hi = tile + m.tc_w1hi;
+    float* lo = tile + m.tc_w1lo;
+    const int u = 32 * (warp & 3) + lane;
+    for (int j = warp >> 2; j < nch; j += MLP_THREADS / 128) {
+        int c = j + lane;
+        c -= (c / nch) * nch;
+        float4 h, l;
+        tc_split4(*reinterpret_cast<const float4*>(W + u * n0 + 4 * c), h, l);
+        const int off = (c * (TC_H >> 3) + (u >> 3)) * 32 + (u & 7) * 4;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
+    }
+}
+
+// Prefetch the raw rows [r0, r0 + cnt) of X -- contiguous in global memory -- with ONE bulk TMA copy (thread 0, completion
+// on barX) and their targets with 4-byte cp.async (warp 1), into the landing buffers; a ragged last tile zero-fills
+// the missing rows.  The staging passes then read shared memory instead of waiting on L2.
+__device__ __forceinline__ void tc_prefetch(const MlpDev& m, float* tile, const TcCtx& tc, int r0, int cnt) {
+    const int n0 = m.n[0];
+    float* raw = tile + m.tc_raw;
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(cnt * n0) * 4u;
+        mbar_expect_tx(tc.barX, bytes);
+        bulk_g2s(smem_u32(raw), m.x + (size_t)r0 * n0, bytes, tc.barX);
+    }
+    if (cnt < TC_TR)
+        for (int i = cnt * n0 + threadIdx.x; i < TC_TR * n0; i += MLP_THREADS) raw[i] = 0.0f;
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {
+        const int ycols = (m.loss == HMCX_LOSS_REGRESSION || m.loss == HMCX_LOSS_BINARY) ? m.n[2] : 1;
+        const uint32_t yraw = smem_u32(tile + m.tc_yraw);
+        for (int t = threadIdx.x - 32; t < cnt * ycols; t += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(yraw + 4u * (uint32_t)t), "l"(m.y + (size_t)r0 * ycols + t) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void tc_prefetch_wait(TcCtx& tc) {
+    if (threadIdx.x >= 32 && threadIdx.x < 64) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    mbar_wait(tc.barX, tc.parX);
+    tc.parX ^= 1;
+    __syncthreads();
+}
+
+// forward B operand: X tile as [64 rows (N)] x [n0 (K)], K-major, from the landing buffer (row and chunk index both
+// vary over an 8-lane phase: conflict-free reads and writes)
+__device__ __forceinline__ void tc_stage_x_fwd(const MlpDev& m, float* tile) {
+    const int n0 = m.n[0], nch = n0 >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* raw = tile + m.tc_raw;
+    float* hi = tile + m.tc_xhi;
+    float* lo = tile + m.tc_xlo;
+    const int r = 8 * (warp & 7) + (lane & 7);
+    for (int c0 = (lane >> 3) + 4 * (warp >> 3); c0 < nch; c0 += 8) {
+        int c = c0 + (lane & 7);
+        c -= (c >= nch) ? nch : 0;
+        c -= (c >= nch) ? nch : 0;                                // nch >= 4: two conditional subtractions are a modulo
+        float4 h, l;
+        tc_split4(*reinterpret_cast<const float4*>(raw + r * n0 + 4 * c), h, l);
+        const int off = (c * (TC_TR >> 3) + (r >> 3)) * 32 + (r & 7) * 4;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
+    }
+}
+
+// backward B operand: X tile as [n0 (N)] x [64 rows (K)], K-major (4 consecutive ROWS of one input column per 16 bytes)
+__device__ __forceinline__ void tc_stage_x_bwd(const MlpDev& m, float* tile) {
+    const int n0 = m.n[0];
+    const float* raw = tile + m.tc_raw;
+    float* hi = tile + m.tc_xhi;
+    float* lo = tile + m.tc_xlo;
+    const int a = threadIdx.x >> 5;                               // 16 warps <-> the 16 four-row groups of the tile
+    for (int n = threadIdx.x & 31; n < n0; n += 32) {
+        const float* src = raw + 4 * a * n0 + n;
+        float4 h, l;
+        tc_split4(make_float4(src[0], src[n0], src[2 * n0], src[3 * n0]), h, l);
+        const int off = (a * (n0 >> 3) + (n >> 3)) * 32 + (n & 7) * 4;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
+    }
+}
+
+// H^T = W1 . X^T  (one elected thread; completion -> barH).  The descriptors differ only in the start-address field
+// (bits 0-13, 16-byte units), so a k-step is an integer add.
+__device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, float* tile) {
+    const uint32_t idesc = make_idesc_tf32(TC_H, TC_TR);
+    constexpr uint32_t A_LBO = (TC_H / 8) * 128, B_LBO = (TC_TR / 8) * 128;
+    uint64_t ah = make_kmajor_desc(smem_u32(tile + m.tc_w1hi), A_LBO, 128);
+    uint64_t al = make_kmajor_desc(smem_u32(tile + m.tc_w1lo), A_LBO, 128);
+    uint64_t bh = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
+    uint64_t bl = make_kmajor_desc(smem_u32(tile + m.tc_xlo), B_LBO, 128);
+    const int ksteps = m.n[0] >> 3;
+    const uint32_t d = tc.tmem + TC_COL_H;
+    tc_fence_after();
+    for (int k = 0; k < ksteps; ++k) {
+        umma_tf32(d, al, bh, idesc, k != 0);
+        umma_tf32(d, ah, bl, idesc, true);
+        umma_tf32(d, ah, bh, idesc, true);
+        ah += (2 * A_LBO) >> 4; al += (2 * A_LBO) >> 4; bh += (2 * B_LBO) >> 4; bl += (2 * B_LBO) >> 4;
+    }
+    umma_commit(tc.barH);
+}
+
+// dW1 (+)= dH^T . X   (A from tensor memory; completion -> barW)
+__device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, float* tile, bool accumulate) {
+    const int n0 = m.n[0];
+    const uint32_t idesc = make_idesc_tf32(TC_H, n0);
+    const uint32_t B_LBO = (uint32_t)(n0 / 8) * 128;
+    uint64_t bh = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
+    uint64_t bl = make_kmajor_desc(smem_u32(tile + m.tc_xlo), B_LBO, 128);
+    const uint32_t d = tc.tmem + TC_COL_W;
+    uint32_t a_hi = tc.tmem + TC_COL_H, a_lo = tc.tmem + TC_COL_LO;
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < TC_TR / 8; ++k) {
+        umma_tf32_ta(d, a_lo, bh, idesc, accumulate || k != 0);
+        umma_tf32_ta(d, a_hi, bl, idesc, true);
+        umma_tf32_ta(d, a_hi, bh, idesc, true);
+        a_hi += 8; a_lo += 8; bh += (2 * B_LBO) >> 4; bl += (2 * B_LBO) >> 4;
+    }
+    umma_commit(tc.barW);
+}
+
+// v[i] = this lane's value for row i; returns the sum over the warp's 32 lanes for row (lane >> 1)
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16]) {
+    const int lane = threadIdx.x & 31;
+#define HMCX_TS_STEP(HALF, OFF)                                                          \
+    {                                                                                    \
+        const bool upper = (lane & OFF) != 0;                                            \
+        _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                               \
+            const float send = upper ? v[i] : v[i + HALF];                               \
+            const float keep = upper ? v[i + HALF] : v[i];                               \
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);                       \
+        }                                                                                \
+    }
+    HMCX_TS_STEP(8, 16) HMCX_TS_STEP(4, 8) HMCX_TS_STEP(2, 4) HMCX_TS_STEP(1, 2)
+#undef HMCX_TS_STEP
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// bias + activation / activation derivative over a thread's 16 values, the activation kind resolved once
+template <int A>
+__device__ __forceinline__ void tc_act16_t(const uint32_t (&v)[16], float b, float (&act)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) act[i] = act_fwd(__uint_as_float(v[i]) + b, A);
+}
+__device__ __forceinline__ void tc_act16(const uint32_t (&v)[16], float b, float (&act)[16], int a) {
+    if (a == HMCX_ACT_RELU) tc_act16_t<HMCX_ACT_RELU>(v, b, act);
+    else if (a == HMCX_ACT_TANH) tc_act16_t<HMCX_ACT_TANH>(v, b, act);
+    else if (a == HMCX_ACT_SIGMOID) tc_act16_t<HMCX_ACT_SIGMOID>(v, b, act);
+    else tc_act16_t<HMCX_ACT_NONE>(v, b, act);
+}
+template <int A>
+__device__ __forceinline__ void tc_dact16_t(const float (&act)[16], float (&d)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = act_bwd(act[i], A);
+}
+__device__ __forceinline__ void tc_dact16(const float (&act)[16], float (&d)[16], int a) {
+    if (a == HMCX_ACT_RELU) tc_dact16_t<HMCX_ACT_RELU>(act, d);
+    else if (a == HMCX_ACT_TANH) tc_dact16_t<HMCX_ACT_TANH>(act, d);
+    else if (a == HMCX_ACT_SIGMOID) tc_dact16_t<HMCX_ACT_SIGMOID>(act, d);
+    else tc_dact16_t<HMCX_ACT_NONE>(act, d);
+}
+
+// per-thread constants / accumulators of the register epilogues: thread <-> hidden unit u, 16 rows of the tile
+struct TcEpi {
+    int u, cq, lq;
+    float b1u, w2[TC_NLMAX];
+    float db1, dw2[TC_NLMAX], db2;
+};
+__device__ __forceinline__ void tc_epi_begin(const MlpDev& m, const float* q, TcEpi& e) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    e.lq = warp & 3; e.cq = warp >> 2; e.u = 32 * e.lq + lane;
+    e.b1u = q[m.boff[0] + e.u];
+#pragma unroll
+    for (int j = 0; j < TC_NLMAX; ++j) {
+        e.w2[j] = j < m.n[2] ? q[m.woff[1] + j * TC_H + e.u] : 0.0f;
+        e.dw2[j] = 0.0f;
+    }
+    e.db1 = 0.0f; e.db2 = 0.0f;
+}
+
+// forward of one (prefetched) tile up to the network outputs: out[r * nL + j] (the loss stage's layout); the hidden
+// activations of this thread's (unit, 16 rows) block stay in `act`.  Ends with every thread past a __syncthreads.
+__device__ __forceinline__ void tc_forward_tile(const MlpDev& m, const float* q, float* tile, TcCtx& tc, const TcEpi& e,
+                                                float (&act)[16]) {
+    const int nL = m.n[2], lane = threadIdx.x & 31;
+    tc_prefetch_wait(tc);                                         // this tile's raw rows have landed
+    tc_stage_x_fwd(m, tile);
+    fence_async_smem();
+    __syncthreads();
+    TC_MARK(3);
+    if (threadIdx.x == 0) tc_issue_fwd(m, tc, tile);
+    TC_MARK(4);
+    mbar_wait(tc.barH, tc.parH);
+    tc.parH ^= 1;
+    tc_fence_after();
+    TC_MARK(5);
+    uint32_t v[16];
+    tmem_ld16(tc.tmem + ((uint32_t)(32 * e.lq) << 16) + TC_COL_H + 16 * e.cq, v);
+    tc_act16(v, e.b1u, act, m.act[0]);
+    float* part = tile + m.tc_part;
+#pragma unroll
+    for (int j = 0; j < TC_NLMAX; ++j) {
+        if (j < nL) {
+            float t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = e.w2[j] * act[i];
+            const float sum = warp_transpose_sum16(t);
+            if ((lane & 1) == 0) part[(e.lq * TC_TR + 16 * e.cq + (lane >> 1)) * TC_NLMAX + j] = sum;
+        }
+    }
+    __syncthreads();
+    TC_MARK(6);
+    float* out = tile + m.aoff[2];
+    for (int i = threadIdx.x; i < TC_TR * nL; i += MLP_THREADS) {
+        const int r = i / nL, j = i - r * nL;
+        const float s = ((part[(0 * TC_TR + r) * TC_NLMAX + j] + part[(1 * TC_TR + r) * TC_NLMAX + j]) +
+                         part[(2 * TC_TR + r) * TC_NLMAX + j]) + part[(3 * TC_TR + r) * TC_NLMAX + j];
+        out[i] = s + q[m.boff[1] + j];
+    }
+    __syncthreads();
+    TC_MARK(7);
+}
+
+// g += d ll_split / dq over this rank's 64-row tiles of [r_begin, r_end)
+__device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, TcCtx& tc,
+                                                 int r_begin, int r_end, ClusterCtx cc) {
+    const int nL = m.n[2], n0 = m.n[0];
+    TcEpi e;
+    tc_epi_begin(m, q, e);
+    float* out = tile + m.aoff[2];
+    float* dz = tile + m.dzoff[0];
+    const float* ytile = tile + m.tc_yraw;
+    const int stride = TC_TR * cc.size;
+    int done = 0;
+    int r0 = r_begin + TC_TR * cc.rank;                           // this rank's tiles: rank, rank + size, ...
+    if (r0 < r_end) tc_prefetch(m, tile, tc, r0, min(TC_TR, r_end - r0));
+    for (; r0 < r_end; r0 += stride) {
+        const int cnt = min(TC_TR, r_end - r0);
+        float act[16];
+        tc_forward_tile(m, q, tile, tc, e, act);                  // the forward MMA has completed: the X buffers are free
+        tc_stage_x_bwd(m, tile);
+        fence_async_smem();
+        mlp_loss_tile(m, out, dz, r0, cnt, r_end - r_begin, false, ytile);
+        __syncthreads();
+        TC_MARK(8);
+        if (r0 + stride < r_end) tc_prefetch(m, tile, tc, r0 + stride, min(TC_TR, r_end - r0 - stride));   // landing buffers are free
+        if (threadIdx.x < TC_TR * nL) e.db2 += dz[threadIdx.x];   // element (r, j) of every tile; reduced over r at the end
+        float dact[16];
+        tc_dact16(act, dact, m.act[0]);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = 16 * e.cq + i;
+            float da = 0.0f;
+#pragma unroll
+            for (int j = 0; j < TC_NLMAX; ++j) {
+                if (j < nL) {
+                    const float d = dz[r * nL + j];
+                    da = fmaf(d, e.w2[j], da);
+                    e.dw2[j] = fmaf(d, act[i], e.dw2[j]);
+                }
+            }
+            const float dh = da * dact[i];
+            e.db1 += dh;
+            const float h = tf32_rn(dh);
+            hi[i] = __float_as_uint(h);
+            lo[i] = __float_as_uint(tf32_rn(dh - h));
+        }
+        const uint32_t tl = tc.tmem + ((uint32_t)(32 * e.lq) << 16) + 16 * e.cq;
+        tmem_st16(tl + TC_COL_H, hi);
+        tmem_st16(tl + TC_COL_LO, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        TC_MARK(9);
+        __syncthreads();
+        TC_MARK(10);
+        if (threadIdx.x == 0) tc_issue_bwd(m, tc, tile, done != 0);
+        ++done;
+        TC_MARK(11);
+        mbar_wait(tc.barW, tc.parW);                              // X buffers and the dH columns are free again
+        tc.parW ^= 1;
+        TC_MARK(12);
+    }
+    if (done == 0) return;                                        // (uniform over the CTA)
+    tc_fence_after();
+    // ---- dW1: TMEM -> padded staging (the W1 operand area is idle now) -> g, conflict-free both ways
+    float* stg = tile + m.tc_w1hi;
+    const int pitch = n0 + 4;
+    if (16 * e.cq < n0) {
+        uint32_t v[16];
+        tmem_ld16(tc.tmem + ((uint32_t)(32 * e.lq) << 16) + TC_COL_W + 16 * e.cq, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(stg + e.u * pitch + 16 * e.cq + i) =
+                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    }
+    tc_fence_before();
+    __syncthreads();
+    float* gW = g + m.woff[0];
+    for (int i4 = threadIdx.x; i4 < TC_H * n0 / 4; i4 += MLP_THREADS) {
+        const int u = (4 * i4) / n0, k = 4 * i4 - u * n0;
+        const float4 d = *reinterpret_cast<const float4*>(stg + u * pitch + k);
+        float4 a = *reinterpret_cast<float4*>(gW + 4 * i4);
+        a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+        *reinterpret_cast<float4*>(gW + 4 * i4) = a;
+    }
+    // ---- db1, dW2: four per-unit partials (one per 16-row column group) summed in a fixed order; db2
+    float* red = tile + m.tc_part;
+    red[(e.cq * TC_H + e.u) * (1 + TC_NLMAX)] = e.db1;
+#pragma unroll
+    for (int j = 0; j < TC_NLMAX; ++j) red[(e.cq * TC_H + e.u) * (1 + TC_NLMAX) + 1 + j] = e.dw2[j];
+    __syncthreads();
+    if (threadIdx.x < TC_H) {
+        const int u = threadIdx.x;
+        auto tot = [&](int f) {
+            return ((red[(0 * TC_H + u) * (1 + TC_NLMAX) + f] + red[(1 * TC_H + u) * (1 + TC_NLMAX) + f]) +
+                    red[(2 * TC_H + u) * (1 + TC_NLMAX) + f]) + red[(3 * TC_H + u) * (1 + TC_NLMAX) + f];
+        };
+        g[m.boff[0] + u] += tot(0);
+        for (int j = 0; j < nL; ++j) g[m.woff[1] + j * TC_H + u] += tot(1 + j);
+    }
+    __syncthreads();
+    if (threadIdx.x < TC_TR * nL) red[threadIdx.x] = e.db2;       // db2[j] = sum over rows r of the per-(r, j) sums
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        for (int j = 0; j < nL; ++j) {
+            const float sj = warp_sum(red[threadIdx.x * nL + j] + red[(threadIdx.x + 32) * nL + j]);
+            if (threadIdx.x == 0) g[m.boff[1] + j] += sj;
+        }
+    }
+    __syncthreads();
+    TC_MARK(13);
+}
+
 // g += d ll_split / dq over this rank's tiles of the rows [r_begin, r_end)  (g must already hold the prior part / zeros)
 __device__ __forceinline__ void mlp_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, int r_begin,
                                                   int r_end, ClusterCtx cc) {
@@ -459,13 +873,17 @@ __device__ __forceinline__ void mlp_prior_grad(const MlpDev& m, const float* q, 
 // g = d log p_split / dq for split s (s < 0: all rows as one potential)
 template <int CS>
 __device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, float* g, float* tile, int s,
-                                               ClusterCtx cc) {
+                                               ClusterCtx cc, TcCtx& tc) {
+    TC_MARK(1);
     if (cc.rank == 0) mlp_prior_grad(m, q, g);                 // the prior part enters the rank-ordered sum once
     else for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) g[i] = 0.0f;
+    if (m.tc) tc_pack_w1(m, q, tile);
     __syncthreads();
+    TC_MARK(2);
     if (m.has_data) {
         const int rb = s < 0 ? 0 : m.sb[s], re = s < 0 ? m.N : m.sb[s + 1];
-        mlp_backprop_rows(m, q, g, tile, rb, re, cc);
+        if (m.tc) tc_backprop_rows(m, q, g, tile, tc, rb, re, cc);
+        else mlp_backprop_rows(m, q, g, tile, rb, re, cc);
         cluster_sum_vector<CS>(g, m.D);
     }
 }
@@ -495,9 +913,14 @@ __device__ __forceinline__ float mlp_log_prior(const MlpDev& m, const float* q, 
 // with s >= 0 only that split.  Optionally writes the network outputs (predict_model).
 template <int CS>
 __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, float* tile, float* sred, int s,
-                                              float* pred_out, ClusterCtx cc, float* xslot) {
+                                              float* pred_out, ClusterCtx cc, float* xslot, TcCtx& tc) {
     const float prior_term = __fdiv_rn(mlp_log_prior(m, q, sred), m.prior_scale);
     if (!m.has_data) return prior_term;
+    TcEpi te;
+    if (m.tc) {
+        tc_pack_w1(m, q, tile);
+        tc_epi_begin(m, q, te);
+    }
     float lp = 0.0f;
     const int s0 = s < 0 ? 0 : s, s1 = s < 0 ? m.M : s + 1;
     for (int sp = s0; sp < s1; ++sp) {
@@ -506,9 +929,16 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
         for (int r0 = m.sb[sp]; r0 < m.sb[sp + 1]; r0 += m.T, ++ti) {
             if (ti % cc.size != cc.rank) continue;
             const int cnt = min(m.T, m.sb[sp + 1] - r0);
-            mlp_forward_tile(m, q, tile, r0, cnt);
+            if (m.tc) {
+                float act[16];
+                tc_prefetch(m, tile, tc, r0, cnt);
+                tc_forward_tile(m, q, tile, tc, te, act);
+            } else {
+                mlp_forward_tile(m, q, tile, r0, cnt);
+            }
             sse[0] = add(sse[0], mlp_loss_tile(m, tile + m.aoff[m.L], nullptr, r0, cnt, m.sb[sp + 1] - m.sb[sp],
-                                               pred_out != nullptr && m.loss == HMCX_LOSS_MULTICLASS_LOGSOFTMAX));
+                                               pred_out != nullptr && m.loss == HMCX_LOSS_MULTICLASS_LOGSOFTMAX,
+                                               m.tc ? tile + m.tc_yraw : nullptr));
             if (pred_out) {
                 __syncthreads();
                 const int nL = m.n[m.L];
@@ -559,11 +989,13 @@ struct MlpRunArgs {
 
 template <int CS>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArgs a) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ float sred[64];
     __shared__ float s_bcast[4];
     __shared__ float s_xchg;
     __shared__ int s_perm[HMCX_MLP_MAX_SPLITS];
+    __shared__ __align__(8) uint64_t s_bars[3];
+    __shared__ uint32_t s_tmem;
 
     const MlpDev& m = a.m;
     ClusterCtx cc = {0, 1};
@@ -573,13 +1005,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
     float* q = sm;
     float* p = q + m.Dp;
     float* g = p + m.Dp;
-    float* tile = g + m.Dp;
+    float* tile = sm + m.tile_base;
     const size_t row = (size_t)c * a.ld;
     const uint64_t chain_id = a.chain_offset + (uint64_t)c;
+    TcCtx tc = {};
+    if (m.tc) tc_init(tc, s_bars, &s_tmem);
 
     for (int i = tid; i < m.Dp; i += MLP_THREADS) { q[i] = i < D ? a.q_cur[row + i] : 0.0f; p[i] = 0.0f; g[i] = 0.0f; }
     __syncthreads();
-    float lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg);
+    float lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
 
     float eps = a.eps[c];
     double h_bar = 0.0, eps_bar = 1.0;
@@ -638,11 +1072,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         const float kin0 = kinetic();
         // ---- trajectory ----
         if (a.scheme == HMCX_SCHEME_PLAIN) {                              // samplers.py:281-302
-            mlp_grad_split<CS>(m, q, g, tile, -1, cc);
+            mlp_grad_split<CS>(m, q, g, tile, -1, cc, tc);
             kick(half);
             for (int l = 0; l < a.L; ++l) {
                 drift(eps);
-                mlp_grad_split<CS>(m, q, g, tile, -1, cc);
+                mlp_grad_split<CS>(m, q, g, tile, -1, cc, tc);
                 kick(eps);
             }
             kick(-half);                                                  // p - half*g == p + (-half)*g exactly
@@ -650,12 +1084,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             const float cd = (float)((double)eps / (double)((M - 1) * 2));
             for (int l = 0; l < a.L; ++l) {
                 for (int s = 0; s < M; ++s) {
-                    mlp_grad_split<CS>(m, q, g, tile, s, cc);
+                    mlp_grad_split<CS>(m, q, g, tile, s, cc, tc);
                     kick(half);
                     if (s < M - 1) drift(cd);
                 }
                 for (int s = M - 1; s >= 0; --s) {
-                    mlp_grad_split<CS>(m, q, g, tile, s, cc);
+                    mlp_grad_split<CS>(m, q, g, tile, s, cc, tc);
                     kick(half);
                     if (s > 0) drift(cd);
                 }
@@ -664,21 +1098,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             const float cd = (float)((double)eps / (double)M);
             for (int l = 0; l < a.L; ++l)
                 for (int s = 0; s < M; ++s) {
-                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc);
+                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc, tc);
                     kick(half);
                     drift(cd);
-                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc);
+                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc, tc);
                     kick(half);
                 }
         } else {                                                          // KMID :579-598
             for (int l = 0; l < a.L; ++l) {
-                for (int s = 0; s < M; ++s) { mlp_grad_split<CS>(m, q, g, tile, s, cc); kick(half); }
+                for (int s = 0; s < M; ++s) { mlp_grad_split<CS>(m, q, g, tile, s, cc, tc); kick(half); }
                 drift(eps);
-                for (int s = M - 1; s >= 0; --s) { mlp_grad_split<CS>(m, q, g, tile, s, cc); kick(half); }
+                for (int s = M - 1; s >= 0; --s) { mlp_grad_split<CS>(m, q, g, tile, s, cc, tc); kick(half); }
             }
         }
         // ---- Hamiltonians + MH ----
-        const float lp_new = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg);
+        const float lp_new = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
         const float kin1 = kinetic();
         const float h_old = add(-lp_cur, mul(0.5f, kin0));
         const float h_new = add(-lp_new, mul(0.5f, kin1));
@@ -700,7 +1134,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             for (int i = tid; i < D; i += MLP_THREADS) q[i] = src[row + i];
             __syncthreads();
             if (n == a.burn + 1) {
-                lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg);
+                lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
                 if (lead) for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
             }
         }
@@ -743,29 +1177,35 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
         if (a.num_rejected) a.num_rejected[c] += rejected;
     }
+    if (m.tc) tc_fini(tc);
 }
 
 // gradient / log-prob of C parameter vectors (collect_gradients mirror, also the unit-test hook of the backward pass)
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_grad_kernel(const MlpDev m, const float* __restrict__ qin, int ld, int split, float* __restrict__ gout,
                 float* __restrict__ lpout) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ float sred[64];
+    __shared__ __align__(8) uint64_t s_bars[3];
+    __shared__ uint32_t s_tmem;
     float* q = sm;
     float* g = q + m.Dp;
-    float* tile = g + m.Dp;
+    float* tile = sm + m.tile_base;
     const size_t row = (size_t)blockIdx.x * ld;
+    TcCtx tc = {};
+    if (m.tc) tc_init(tc, s_bars, &s_tmem);
     for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) { q[i] = i < m.D ? qin[row + i] : 0.0f; g[i] = 0.0f; }
     __syncthreads();
     if (gout) {
-        mlp_grad_split<1>(m, q, g, tile, split, ClusterCtx{0, 1});
+        mlp_grad_split<1>(m, q, g, tile, split, ClusterCtx{0, 1}, tc);
         __syncthreads();
         for (int i = threadIdx.x; i < ld; i += MLP_THREADS) gout[row + i] = i < m.D ? g[i] : 0.0f;
     }
     if (lpout) {
-        const float lp = mlp_log_prob<1>(m, q, tile, sred, split, nullptr, ClusterCtx{0, 1}, nullptr);
+        const float lp = mlp_log_prob<1>(m, q, tile, sred, split, nullptr, ClusterCtx{0, 1}, nullptr, tc);
         if (threadIdx.x == 0) lpout[blockIdx.x] = lp;
     }
+    if (m.tc) tc_fini(tc);
 }
 
 // predict_model: one CTA per posterior sample
@@ -775,12 +1215,13 @@ mlp_predict_kernel(const MlpDev m, const float* __restrict__ samples, int ld, fl
     extern __shared__ __align__(16) float sm[];
     __shared__ float sred[64];
     float* q = sm;
-    float* tile = q + m.Dp;
+    float* tile = sm + m.tile_base;
     const size_t row = (size_t)blockIdx.x * ld;
     for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) q[i] = i < m.D ? samples[row + i] : 0.0f;
     __syncthreads();
     float* my_pred = pred + (size_t)blockIdx.x * m.N * m.n[m.L];
-    const float lp = mlp_log_prob<1>(m, q, tile, sred, -1, my_pred, ClusterCtx{0, 1}, nullptr);
+    TcCtx tc = {};                                             // predict keeps the SIMT tiles (m.tc == 0)
+    const float lp = mlp_log_prob<1>(m, q, tile, sred, -1, my_pred, ClusterCtx{0, 1}, nullptr, tc);
     if (threadIdx.x == 0 && lpout) lpout[blockIdx.x] = lp;
 }
 
@@ -800,8 +1241,34 @@ static void mlp_layout_tiles(MlpDev& m, int T) {
     m.T = T;
 }
 
+// tensor-core layout of the tile area (one-hidden-layer stacks n0 -> 128 -> nL, see the tcgen05 section above)
+static bool mlp_layout_tc(MlpDev& m, int state_vectors) {
+    if (m.L != 2 || m.n[1] != TC_H || m.n[0] < 16 || m.n[0] > 64 || (m.n[0] & 15) || m.n[2] > TC_NLMAX || !m.has_data)
+        return false;
+    const int n0 = m.n[0];
+    int off = 0;
+    m.tc_w1hi = off; off += TC_H * n0;
+    m.tc_w1lo = off; off += TC_H * n0;          // adjacent to w1hi: together they stage dW1 (pitch n0 + 4)
+    m.tc_xhi = off; off += TC_TR * n0;
+    m.tc_xlo = off; off += TC_TR * n0;
+    m.tc_part = off; off += 4 * TC_H * (1 + TC_NLMAX);
+    m.tc_raw = off; off += TC_TR * n0;
+    m.tc_yraw = off; off += TC_TR * TC_NLMAX;
+    m.aoff[0] = m.aoff[1] = 0;
+    m.aoff[2] = off; off += TC_TR * TC_NLMAX;
+    m.dzoff[0] = m.dzoff[1] = off; off += TC_TR * TC_NLMAX;
+    m.tile_floats = off;
+    m.tile_base = (state_vectors * m.Dp + 31) / 32 * 32;      // 128-byte aligned operand buffers
+    m.T = TC_TR;
+    m.tc = 1;
+    return (size_t)(m.tile_base + m.tile_floats) * sizeof(float) <= 227 * 1024 - 2048;
+}
+
 // pick the largest tile height whose buffers fit next to `state_vectors` copies of the parameter vector
-static bool mlp_pick_tile(MlpDev& m, int state_vectors) {
+static bool mlp_pick_tile(MlpDev& m, int state_vectors, bool allow_tc = false) {
+    if (allow_tc && mlp_layout_tc(m, state_vectors)) return true;
+    m.tc = 0;
+    m.tile_base = state_vectors * m.Dp;
     for (int T = MLP_T_MAX; T >= 8; T >>= 1) {
         mlp_layout_tiles(m, T);
         if ((size_t)(state_vectors * m.Dp + m.tile_floats) * sizeof(float) <= 227 * 1024 - 4096) return true;
@@ -901,8 +1368,9 @@ int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     }
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
-    if (!mlp_pick_tile(a.m, 3)) return HMCX_ERR_UNSUPPORTED;    // q, p, g do not fit one SM's shared memory
-    const size_t smem = (size_t)(3 * a.m.Dp + a.m.tile_floats) * sizeof(float);
+    if (!mlp_pick_tile(a.m, 3, target->mlp->tensor_cores != HMCX_MLP_TC_OFF))
+        return HMCX_ERR_UNSUPPORTED;                            // q, p, g do not fit one SM's shared memory
+    const size_t smem = (size_t)(a.m.tile_base + a.m.tile_floats) * sizeof(float);
     // CTAs per chain (thread-block cluster size): at most the tiles of the smallest split, at most 4, and -- unless the
     // caller pins it (hmcx_mlp_t.cluster_size) -- no more than keeps every chain's cluster resident at once.  The
     // partial gradients are associated per cluster rank, so low-order bits depend on this number: pin it to make
@@ -941,8 +1409,8 @@ int mlp_grad_log_prob(const hmcx_target_t* target, const float* q, int C, int ld
     if (rc != HMCX_OK) return rc;
     if (!q || C < 1 || ld < m.D || (ld & 3) || split < -1 || split >= m.M || (!grad_out && !log_prob_out))
         return HMCX_ERR_INVALID_ARG;
-    if (!mlp_pick_tile(m, 2)) return HMCX_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)(2 * m.Dp + m.tile_floats) * sizeof(float);
+    if (!mlp_pick_tile(m, 2, target->mlp->tensor_cores != HMCX_MLP_TC_OFF)) return HMCX_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(m.tile_base + m.tile_floats) * sizeof(float);
     rc = prepare_smem(mlp_grad_kernel, smem);
     if (rc != HMCX_OK) return rc;
     mlp_grad_kernel<<<C, MLP_THREADS, smem, st>>>(m, q, ld, split, grad_out, log_prob_out);
@@ -956,11 +1424,23 @@ int mlp_predict(const hmcx_target_t* target, const float* samples, int S, int ld
     if (rc != HMCX_OK) return rc;
     if (!samples || !pred_out || S < 1 || ld < m.D || (ld & 3) || !m.has_data) return HMCX_ERR_INVALID_ARG;
     if (!mlp_pick_tile(m, 1)) return HMCX_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)(m.Dp + m.tile_floats) * sizeof(float);
+    const size_t smem = (size_t)(m.tile_base + m.tile_floats) * sizeof(float);
     rc = prepare_smem(mlp_predict_kernel, smem);
     if (rc != HMCX_OK) return rc;
     mlp_predict_kernel<<<S, MLP_THREADS, smem, st>>>(m, samples, ld, pred_out, log_prob_out);
     return cuda_status();
 }
+
+#ifdef HMCX_TC_PROF
+extern "C" int hmcx_debug_tc_prof(long long* out) {           // developer build only (scripts/prof_tc_phases.py)
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_tc_prof_n, sizeof(int));
+    cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(long long) * 64);
+    int zero = 0;
+    cudaMemcpyToSymbol(g_tc_prof_n, &zero, sizeof(int));
+    return n;
+}
+#endif
 
 }  // namespace hmcx

@@ -14,56 +14,12 @@
 // Descriptor encodings follow the CUTLASS sm100 definitions (cute/arch/mma_sm100_desc.hpp: SmemDescriptor,
 // InstrDescriptor) -- re-derived here, no CUTLASS code is used.
 #include "hmcx_common.cuh"
+#include "hmcx_umma.cuh"
 
 namespace hmcx {
 
 constexpr int TC_M = 128, TC_N = 128, TC_KC = 32;        // CTA tile and K chunk (fp32 elements)
 constexpr int TC_THREADS = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ float to_tf32(float x) {      // round-to-nearest tf32, returned in an fp32 container
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// 64-bit shared-memory matrix descriptor: K-major, SWIZZLE_NONE.  Fields (16-byte units): start address [0,14),
-// leading byte offset = distance between the two core matrices along K [16,30), stride byte offset = distance
-// between 8-row groups [32,46), descriptor version 1 (Blackwell) [46,48), layout type 0 [61,64).
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-// 32-bit instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    while (!mbar_try_wait(mbar, parity)) {}
-}
 
 // Stage a [128 rows x KC] fp32 slab (row stride `ld`) into the canonical layout, split into tf32 hi and lo copies.
 // Core matrix (rg = row/8, kc = k/4) lives at ((kc * 16 + rg) * 128) bytes: SBO = 128 B, LBO = 16*128 = 2048 B.
@@ -227,20 +183,6 @@ __global__ void dense_pack_kernel(const float* __restrict__ src, const float* __
         const int off = pack_elem_off(row % R, k % TC_KC, R);
         split_store4(dst + pack_block_base(tile, kc, 0, kchunks, R), dst + pack_block_base(tile, kc, 1, kchunks, R), off, v);
     }
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }
 
 __host__ __device__ constexpr int dense_stages(int BN) { return BN == 128 ? 3 : 4; }

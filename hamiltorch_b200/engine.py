@@ -96,6 +96,7 @@ class NativeTarget:
             m.num_rows = xd.shape[0]
         m.num_splits = self.num_splits
         m.cluster_size = int(getattr(first, 'cluster_size', 0))      # 0 = auto; 1/2/4 pins CTAs per chain
+        m.tensor_cores = int(getattr(first, 'tensor_cores', 0))      # 0 = auto (tcgen05 when the shape fits); 1 = off
         for i, b in enumerate(begin):
             m.split_begin[i] = b
         self.mlp_struct = m

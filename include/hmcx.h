@@ -31,6 +31,9 @@ extern "C" {
 
 #define HMCX_ABI_VERSION 3
 
+#define HMCX_MLP_TC_AUTO 0
+#define HMCX_MLP_TC_OFF  1
+
 /* status codes */
 #define HMCX_OK                0
 #define HMCX_ERR_INVALID_ARG  -1
@@ -89,6 +92,9 @@ typedef struct hmcx_mlp {
     int32_t split_begin[HMCX_MLP_MAX_SPLITS + 1];
     int32_t cluster_size;                          /* CTAs (SMs) cooperating on one chain: 0 = automatic, 1 / 2 / 4 =
                                                       pinned (bit-reproducibility across chain counts)          */
+    int32_t tensor_cores;                          /* HMCX_MLP_TC_AUTO: first-layer GEMMs on tcgen05 (3xTF32, fp32-level
+                                                      accuracy) when the stack is n0 -> 128 -> nL with n0 in
+                                                      {16,32,48,64}, nL <= 4; HMCX_MLP_TC_OFF: fp32 SIMT tiles  */
 } hmcx_mlp_t;
 
 typedef struct hmcx_target {
