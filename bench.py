@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, C_PER_GPU, S, L, EPS = 1024, 256, 1000, 10, 0.05
+WARP_INST_PER_LAUNCH = 1092361880          # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
 METRIC = 'leapfrog-steps x chains / sec'
 UNIT = 'chain-steps/s'
 
@@ -285,6 +286,9 @@ def run_b200_arm(args, rank, world, local_rank):
         stream_bytes = Cs * D * 16                       # B_step = 16*D B per leapfrog-step x chain
         stream_gbs = stream_bytes / (t_stream_ms * 1e-3) / 1e9
         h2d, d2h = C * D * 4, C * S * ld * 4
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_mhz = float((clk or {}).get('sm_mhz') or 1965.0)
+        issue_peak = n_sm * 4 * sm_mhz * 1e6 / 1e9
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -302,6 +306,14 @@ def run_b200_arm(args, rank, world, local_rank):
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': t_kernel_ms,
                          'note': 'fused trajectory kernel: L=10 steps per 4*D bytes written, fp32-issue bound by design; '
                                  'see roofline_streaming for the HBM-bound form'},
+            # what actually bounds the fused kernel: warp-instruction issue.  Instructions per launch are static for this
+            # geometry (ncu smsp__inst_executed.sum, profiles/r1f_prof_hmc_run.summary.txt); time is measured live.
+            'roofline_issue': {'bound': 'issue', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>',
+                               'warp_instructions_per_launch': WARP_INST_PER_LAUNCH,
+                               'achieved': WARP_INST_PER_LAUNCH / (t_kernel_ms * 1e-3) / 1e9,
+                               'peak': issue_peak, 'unit': 'G warp-inst/s',
+                               'frac': WARP_INST_PER_LAUNCH / (t_kernel_ms * 1e-3) / 1e9 / issue_peak,
+                               'peak_source': '%d SMs x 4 schedulers x %.0f MHz (sampled under load)' % (n_sm, sm_mhz)},
             'roofline_streaming': {'bound': 'hbm', 'kernel': 'leapfrog_kernel<ISO,NONE> L=1, 32768x1024 state',
                                    'achieved': stream_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': stream_gbs / peak,
                                    'algorithmic_bytes_per_launch': stream_bytes, 'kernel_ms': t_stream_ms,

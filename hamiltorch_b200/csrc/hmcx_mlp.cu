@@ -448,7 +448,7 @@ __device__ __forceinline__ float cluster_sum_scalar(float x, float* slot) {
 constexpr int TC_TR = 64;                 // data rows per tile (MMA N forward, MMA K backward)
 constexpr int TC_H = 128;                 // hidden units = MMA M = TMEM lanes
 constexpr int TC_NLMAX = 4;               // outputs handled by the register head
-constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COLS = 256;   // TMEM columns: H / dH hi | dH lo | dW1
+constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COLS = 256;   // TMEM columns: H hh / dH hi | H hl / dH lo | dW1 hh | dW1 hl
 
 static_assert(TC_TR / 4 == MLP_THREADS / 32 && TC_TR == 64, "staging / epilogue thread maps assume 16 warps and 64-row tiles");
 
@@ -546,13 +546,13 @@ __device__ __forceinline__ void tc_prefetch_wait(TcCtx& tc) {
     __syncthreads();
 }
 
-// forward B operand: X tile as [64 rows (N)] x [n0 (K)], K-major, from the landing buffer (row and chunk index both
-// vary over an 8-lane phase: conflict-free reads and writes)
+// forward B operand: X tile as [64 rows hi | 64 rows lo (N = 128)] x [n0 (K)], K-major, from the landing buffer (row and
+// chunk index both vary over an 8-lane phase: conflict-free reads and writes).  Stacking hi|lo along N lets ONE UMMA
+// produce W1_hi X_hi^T and W1_hi X_lo^T side by side (the A tile is fetched once for both).
 __device__ __forceinline__ void tc_stage_x_fwd(const MlpDev& m, float* tile) {
     const int n0 = m.n[0], nch = n0 >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* raw = tile + m.tc_raw;
-    float* hi = tile + m.tc_xhi;
-    float* lo = tile + m.tc_xlo;
+    float* xb = tile + m.tc_xhi;
     const int r = 8 * (warp & 7) + (lane & 7);
     for (int c0 = (lane >> 3) + 4 * (warp >> 3); c0 < nch; c0 += 8) {
         int c = c0 + (lane & 7);
@@ -560,9 +560,9 @@ __device__ __forceinline__ void tc_stage_x_fwd(const MlpDev& m, float* tile) {
         c -= (c >= nch) ? nch : 0;                                // nch >= 4: two conditional subtractions are a modulo
         float4 h, l;
         tc_split4(*reinterpret_cast<const float4*>(raw + r * n0 + 4 * c), h, l);
-        const int off = (c * (TC_TR >> 3) + (r >> 3)) * 32 + (r & 7) * 4;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
+        const int off = (c * (2 * TC_TR >> 3) + (r >> 3)) * 32 + (r & 7) * 4;      // hi|lo stacked along N: 128 "rows"
+        *reinterpret_cast<float4*>(xb + off) = h;
+        *reinterpret_cast<float4*>(xb + off + (TC_TR >> 3) * 32) = l;
     }
 }
 
@@ -570,56 +570,53 @@ __device__ __forceinline__ void tc_stage_x_fwd(const MlpDev& m, float* tile) {
 __device__ __forceinline__ void tc_stage_x_bwd(const MlpDev& m, float* tile) {
     const int n0 = m.n[0];
     const float* raw = tile + m.tc_raw;
-    float* hi = tile + m.tc_xhi;
-    float* lo = tile + m.tc_xlo;
+    float* xb = tile + m.tc_xhi;
     const int a = threadIdx.x >> 5;                               // 16 warps <-> the 16 four-row groups of the tile
     for (int n = threadIdx.x & 31; n < n0; n += 32) {
         const float* src = raw + 4 * a * n0 + n;
         float4 h, l;
         tc_split4(make_float4(src[0], src[n0], src[2 * n0], src[3 * n0]), h, l);
-        const int off = (a * (n0 >> 3) + (n >> 3)) * 32 + (n & 7) * 4;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
+        const int off = (a * (2 * n0 >> 3) + (n >> 3)) * 32 + (n & 7) * 4;         // hi|lo stacked along N: 2*n0 "rows"
+        *reinterpret_cast<float4*>(xb + off) = h;
+        *reinterpret_cast<float4*>(xb + off + (n0 >> 3) * 32) = l;
     }
 }
 
-// H^T = W1 . X^T  (one elected thread; completion -> barH).  The descriptors differ only in the start-address field
-// (bits 0-13, 16-byte units), so a k-step is an integer add.
+// H^T = W1 . X^T  (one elected thread; completion -> barH).  Two UMMAs per k-step: W1_hi . [X_hi | X_lo]^T (N = 128, the
+// two products land in columns [0,64) and [64,128)) and W1_lo . X_hi^T (N = 64, accumulated onto [0,64)); the epilogue
+// adds the two column blocks.  The descriptors differ only in the start-address field (bits 0-13, 16-byte units), so
+// a k-step is an integer add.
 __device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, float* tile) {
-    const uint32_t idesc = make_idesc_tf32(TC_H, TC_TR);
-    constexpr uint32_t A_LBO = (TC_H / 8) * 128, B_LBO = (TC_TR / 8) * 128;
+    const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * TC_TR), idesc1 = make_idesc_tf32(TC_H, TC_TR);
+    constexpr uint32_t A_LBO = (TC_H / 8) * 128, B_LBO = (2 * TC_TR / 8) * 128;
     uint64_t ah = make_kmajor_desc(smem_u32(tile + m.tc_w1hi), A_LBO, 128);
     uint64_t al = make_kmajor_desc(smem_u32(tile + m.tc_w1lo), A_LBO, 128);
-    uint64_t bh = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
-    uint64_t bl = make_kmajor_desc(smem_u32(tile + m.tc_xlo), B_LBO, 128);
+    uint64_t b = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
     const int ksteps = m.n[0] >> 3;
     const uint32_t d = tc.tmem + TC_COL_H;
     tc_fence_after();
     for (int k = 0; k < ksteps; ++k) {
-        umma_tf32(d, al, bh, idesc, k != 0);
-        umma_tf32(d, ah, bl, idesc, true);
-        umma_tf32(d, ah, bh, idesc, true);
-        ah += (2 * A_LBO) >> 4; al += (2 * A_LBO) >> 4; bh += (2 * B_LBO) >> 4; bl += (2 * B_LBO) >> 4;
+        umma_tf32(d, ah, b, idesc2, k != 0);
+        umma_tf32(d, al, b, idesc1, true);
+        ah += (2 * A_LBO) >> 4; al += (2 * A_LBO) >> 4; b += (2 * B_LBO) >> 4;
     }
     umma_commit(tc.barH);
 }
 
-// dW1 (+)= dH^T . X   (A from tensor memory; completion -> barW)
+// dW1 (+)= dH^T . X   (A from tensor memory; completion -> barW): dH_hi . [X_hi | X_lo] (N = 2 n0) and dH_lo . X_hi (N = n0)
 __device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, float* tile, bool accumulate) {
     const int n0 = m.n[0];
-    const uint32_t idesc = make_idesc_tf32(TC_H, n0);
-    const uint32_t B_LBO = (uint32_t)(n0 / 8) * 128;
-    uint64_t bh = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
-    uint64_t bl = make_kmajor_desc(smem_u32(tile + m.tc_xlo), B_LBO, 128);
+    const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * n0), idesc1 = make_idesc_tf32(TC_H, n0);
+    const uint32_t B_LBO = (uint32_t)(2 * n0 / 8) * 128;
+    uint64_t b = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
     const uint32_t d = tc.tmem + TC_COL_W;
     uint32_t a_hi = tc.tmem + TC_COL_H, a_lo = tc.tmem + TC_COL_LO;
     tc_fence_after();
 #pragma unroll
     for (int k = 0; k < TC_TR / 8; ++k) {
-        umma_tf32_ta(d, a_lo, bh, idesc, accumulate || k != 0);
-        umma_tf32_ta(d, a_hi, bl, idesc, true);
-        umma_tf32_ta(d, a_hi, bh, idesc, true);
-        a_hi += 8; a_lo += 8; bh += (2 * B_LBO) >> 4; bl += (2 * B_LBO) >> 4;
+        umma_tf32_ta(d, a_hi, b, idesc2, accumulate || k != 0);
+        umma_tf32_ta(d, a_lo, b, idesc1, true);
+        a_hi += 8; a_lo += 8; b += (2 * B_LBO) >> 4;
     }
     umma_commit(tc.barW);
 }
@@ -699,8 +696,11 @@ __device__ __forceinline__ void tc_forward_tile(const MlpDev& m, const float* q,
     tc.parH ^= 1;
     tc_fence_after();
     TC_MARK(5);
-    uint32_t v[16];
+    uint32_t v[16], w[16];
     tmem_ld16(tc.tmem + ((uint32_t)(32 * e.lq) << 16) + TC_COL_H + 16 * e.cq, v);
+    tmem_ld16(tc.tmem + ((uint32_t)(32 * e.lq) << 16) + TC_COL_LO + 16 * e.cq, w);       // the W1_hi X_lo block
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
     tc_act16(v, e.b1u, act, m.act[0]);
     float* part = tile + m.tc_part;
 #pragma unroll
@@ -792,8 +792,11 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
     float* stg = tile + m.tc_w1hi;
     const int pitch = n0 + 4;
     if (16 * e.cq < n0) {
-        uint32_t v[16];
+        uint32_t v[16], w[16];
         tmem_ld16(tc.tmem + ((uint32_t)(32 * e.lq) << 16) + TC_COL_W + 16 * e.cq, v);
+        tmem_ld16(tc.tmem + ((uint32_t)(32 * e.lq) << 16) + TC_COL_W + n0 + 16 * e.cq, w);   // the dH_hi X_lo block
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
             *reinterpret_cast<float4*>(stg + e.u * pitch + 16 * e.cq + i) =
