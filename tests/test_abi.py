@@ -59,3 +59,32 @@ def test_invalid_arguments_are_rejected_without_cuda(built_library):
     assert rc == N.ERR_UNSUPPORTED
     assert b'unsupported' in lib.hmcx_status_string(rc)
     assert lib.hmcx_status_string(0) == b'ok'
+
+
+def test_ctypes_struct_layout_matches_the_c_header(tmp_path):
+    """Every struct of include/hmcx.h has the same size and field offsets in the ctypes binding (compiled with gcc)."""
+    import shutil
+    import subprocess
+    from hamiltorch_b200 import _native as N
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    pairs = {'hmcx_mlp_t': N.MlpStruct, 'hmcx_target_t': N.TargetStruct, 'hmcx_mass_t': N.MassStruct,
+             'hmcx_rng_t': N.RngStruct, 'hmcx_nuts_t': N.NutsStruct, 'hmcx_rmhmc_t': N.RmhmcStruct}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hmcx.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / 'probe.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'probe'
+    subprocess.check_call([gcc, '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname + '.sizeof']) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+    assert N.ABI_VERSION == int(re.search(r'#define HMCX_ABI_VERSION (\d+)',
+                                          open(os.path.join(ROOT, 'include', 'hmcx.h')).read()).group(1))
