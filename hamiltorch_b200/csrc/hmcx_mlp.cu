@@ -506,10 +506,10 @@ __device__ __forceinline__ void tc_pack_w1(const MlpDev& m, const float* q, floa
     const float* W = q + m.woff[0];
     float* hi = tile + m.tc_w1hi;
     float* lo = tile + m.tc_w1lo;
-    const int u = 32 * (warp & 3) + lane;
+    const int u = 32 * (warp & 3) + lane, rot = lane % nch;
     for (int j = warp >> 2; j < nch; j += MLP_THREADS / 128) {
-        int c = j + lane;
-        c -= (c / nch) * nch;
+        int c = j + rot;                                          // rotate the chunk index per lane
+        c -= (c >= nch) ? nch : 0;
         float4 h, l;
         tc_split4(*reinterpret_cast<const float4*>(W + u * n0 + 4 * c), h, l);
         const int off = (c * (TC_H >> 3) + (u >> 3)) * 32 + (u & 7) * 4;
@@ -867,7 +867,17 @@ __device__ __forceinline__ void mlp_prior_grad(const MlpDev& m, const float* q, 
     for (int l = 0; l < m.L; ++l) {
         const int nw = m.n[l] * m.n[l + 1];
         const float cw = m.gcoef[2 * l], cb = m.gcoef[2 * l + 1];
-        for (int i = threadIdx.x; i < nw; i += MLP_THREADS) g[m.woff[l] + i] = -mul(cw, mul(2.0f, q[m.woff[l] + i]));
+        if (((m.woff[l] | nw) & 3) == 0) {                         // 16-byte aligned tensor: four weights per access
+            const float4* q4 = reinterpret_cast<const float4*>(q + m.woff[l]);
+            float4* g4 = reinterpret_cast<float4*>(g + m.woff[l]);
+            for (int i = threadIdx.x; i < (nw >> 2); i += MLP_THREADS) {
+                const float4 w = q4[i];
+                g4[i] = make_float4(-mul(cw, mul(2.0f, w.x)), -mul(cw, mul(2.0f, w.y)), -mul(cw, mul(2.0f, w.z)),
+                                    -mul(cw, mul(2.0f, w.w)));
+            }
+        } else {
+            for (int i = threadIdx.x; i < nw; i += MLP_THREADS) g[m.woff[l] + i] = -mul(cw, mul(2.0f, q[m.woff[l] + i]));
+        }
         for (int i = threadIdx.x; i < m.n[l + 1]; i += MLP_THREADS)
             g[m.boff[l] + i] = -mul(cb, mul(2.0f, q[m.boff[l] + i]));
     }
@@ -1215,17 +1225,21 @@ mlp_grad_kernel(const MlpDev m, const float* __restrict__ qin, int ld, int split
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_predict_kernel(const MlpDev m, const float* __restrict__ samples, int ld, float* __restrict__ pred,
                    float* __restrict__ lpout) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ float sred[64];
+    __shared__ __align__(8) uint64_t s_bars[3];
+    __shared__ uint32_t s_tmem;
     float* q = sm;
     float* tile = sm + m.tile_base;
     const size_t row = (size_t)blockIdx.x * ld;
     for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) q[i] = i < m.D ? samples[row + i] : 0.0f;
     __syncthreads();
     float* my_pred = pred + (size_t)blockIdx.x * m.N * m.n[m.L];
-    TcCtx tc = {};                                             // predict keeps the SIMT tiles (m.tc == 0)
+    TcCtx tc = {};
+    if (m.tc) tc_init(tc, s_bars, &s_tmem);
     const float lp = mlp_log_prob<1>(m, q, tile, sred, -1, my_pred, ClusterCtx{0, 1}, nullptr, tc);
     if (threadIdx.x == 0 && lpout) lpout[blockIdx.x] = lp;
+    if (m.tc) tc_fini(tc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1426,7 +1440,7 @@ int mlp_predict(const hmcx_target_t* target, const float* samples, int S, int ld
     int rc = fill_mlp(target, m);
     if (rc != HMCX_OK) return rc;
     if (!samples || !pred_out || S < 1 || ld < m.D || (ld & 3) || !m.has_data) return HMCX_ERR_INVALID_ARG;
-    if (!mlp_pick_tile(m, 1)) return HMCX_ERR_UNSUPPORTED;
+    if (!mlp_pick_tile(m, 1, target->mlp->tensor_cores != HMCX_MLP_TC_OFF)) return HMCX_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(m.tile_base + m.tile_floats) * sizeof(float);
     rc = prepare_smem(mlp_predict_kernel, smem);
     if (rc != HMCX_OK) return rc;

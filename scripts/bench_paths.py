@@ -59,7 +59,16 @@ def cfg4(C=64):
                  split_scheme=O.SPLIT_SYM)
     cpu = 3 * L / (time.perf_counter() - t0)
     flops = 68.7e6 * C * S * L                                   # 68.7 MFLOP per chain-step
-    return dict(config='4: MLP 64-128-1 (D=8449), N=1024, M=4 symmetric split, %d chains on ONE GPU, L=10, S=%d' % (C, S),
+    # tensor roofline of the 3xTF32 path: tf32 runs at half the bf16 rate and every product costs three UMMAs
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))
+        peak, src = peaks['bf16_tflops_sustained'] / 6.0, 'MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32) / 3 (split)'
+    except Exception:
+        peak, src = 2250.0 / 6.0, 'nominal 2.25 PFLOP/s bf16 / 6'
+    tf = flops / (ms * 1e-3) / 1e12
+    roof = {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'peak_source': src,
+            'traffic': None}
+    return dict(roofline=roof, config='4: MLP 64-128-1 (D=8449), N=1024, M=4 symmetric split, %d chains on ONE GPU, L=10, S=%d' % (C, S),
                 ms=ms, chain_steps_per_s=C * S * L / (ms * 1e-3), achieved_tflops=flops / (ms * 1e-3) / 1e12,
                 cpu_port_1core_chain_steps_per_s=cpu, accept=float(res.accepted.float().mean()))
 

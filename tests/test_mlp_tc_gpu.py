@@ -95,3 +95,23 @@ def test_tc_chain_parity_vs_live_oracle(scheme, rows_per_split):
         parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
                                    res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
                                    o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4)
+
+
+@pytest.mark.parametrize('n_in,n_out,act,task,n,splits', [(64, 1, 'ReLU', 'regression', 200, 1),
+                                                          (48, 4, 'Tanh', 'logsoftmax', 150, 2)])
+def test_tc_predict_matches_the_model_and_the_simt_kernel(n_in, n_out, act, task, n, splits):
+    """predict_model's forward over posterior samples on the tensor-core path: network outputs == the torch model
+    evaluated at each sample (log-probabilities for a LogSoftmax model) == the fp32 SIMT kernel."""
+    model, descs = _problem(31, n, n_in, n_out, act, task, splits)
+    _, descs_simt = _problem(31, n, n_in, n_out, act, task, splits, tc=False)
+    D = descs[0].dim
+    torch.manual_seed(2)
+    samples = hb.util.flatten(model).detach()[None] + 0.05 * torch.randn(5, D)
+    pred, lp = engine.mlp_predict(descs, samples)
+    pred_s, lp_s = engine.mlp_predict(descs_simt, samples)
+    x = torch.cat([d.x for d in descs])
+    for s in range(samples.shape[0]):
+        ref = descs[0].forward(samples[s], x)
+        assert torch.allclose(pred[s].cpu(), ref, rtol=2e-5, atol=2e-5), s
+    assert torch.allclose(pred, pred_s, rtol=2e-5, atol=2e-5)
+    assert torch.allclose(lp, lp_s, rtol=2e-5, atol=1e-4)
