@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libhmcx.so')
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 MASS_NONE, MASS_DIAG, MASS_FULL = 0, 1, 2
 RNG_INJECTED, RNG_PHILOX = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class NativeError(RuntimeError):
@@ -59,6 +59,14 @@ class RmhmcStruct(C.Structure):
                 ('jitter_max_tries', C.c_int32)]
 
 
+class ConstMetricStruct(C.Structure):
+    _fields_ = [('metric_inv', C.c_void_p), ('metric_chol', C.c_void_p), ('log_det', C.c_float)]
+
+
+class SinkStruct(C.Structure):
+    _fields_ = [('thin', C.c_int32), ('sum', C.c_void_p), ('sumsq', C.c_void_p)]
+
+
 class NutsStruct(C.Structure):
     _fields_ = [('enabled', C.c_int32), ('desired_accept_rate', C.c_double), ('mu', C.c_double),
                 ('table', C.c_void_p), ('h_bar', C.c_void_p), ('eps_bar', C.c_void_p),
@@ -89,6 +97,16 @@ _PROTOS = {
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    'hmcx_rmhmc_dense_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'hmcx_rmhmc_dense_run': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(RmhmcStruct), C.POINTER(ConstMetricStruct),
+                                       C.POINTER(RngStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hmcx_hmc_run_sink': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(MassStruct), C.POINTER(RngStruct),
+                                    C.POINTER(NutsStruct), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.POINTER(SinkStruct), C.c_void_p]),
     'hmcx_gemm_nt_tf32x3': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'hmcx_grad_log_prob': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -52,18 +52,27 @@ def build(force=False, verbose=False):
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     procs, objs = [], []
+    flags = NVCC_FLAGS + os.environ.get('HMCX_NVCC_EXTRA', '').split()
+    stamp = ' '.join(flags)
+    common = [f for f in _deps() if not f.endswith('.cu')]
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('HMCX_NVCC_EXTRA', '').split() + \
-            (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for src, p in procs:
+        # per-object incremental rebuild: same flags, object newer than its source and every shared header
+        flagfile = obj + '.flags'
+        if (not force and os.path.exists(obj) and os.path.exists(flagfile) and open(flagfile).read() == stamp
+                and all(os.path.getmtime(f) <= os.path.getmtime(obj) for f in [src] + common)):
+            continue
+        cmd = [nvcc] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        procs.append((src, flagfile, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, flagfile, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on ' + src)
+        with open(flagfile, 'w') as f:
+            f.write(stamp)
     tmp = LIB + '.tmp'
     subprocess.check_call([nvcc, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
     os.replace(tmp, LIB)

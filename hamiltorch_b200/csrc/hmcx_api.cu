@@ -9,7 +9,11 @@ int elem_hamiltonian(const hmcx_target_t*, const hmcx_mass_t*, const float*, con
 int elem_gibbs(const hmcx_mass_t*, const hmcx_rng_t*, int, int, int, int64_t, float*, cudaStream_t);
 int elem_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*,
                  float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
-                 int, float*, cudaStream_t);
+                 int, float*, const hmcx_sink_t*, cudaStream_t);
+size_t dense_rmhmc_workspace_floats(int, int);
+int dense_rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_const_metric_t*, const hmcx_rng_t*,
+                    const float*, float*, const float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*,
+                    float*, int32_t*, float*, cudaStream_t);
 int mlp_split_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, int, const float*,
                   float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                   cudaStream_t);
@@ -19,7 +23,7 @@ int small_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, c
                   float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                   cudaStream_t);
 int gemm_nt_tf32x3(const float*, const float*, float*, int, int, int, cudaStream_t);
-size_t dense_workspace_floats(int, int);
+size_t dense_workspace_floats(int, int, int);
 int dense_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*, float*,
                   float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, float*,
                   cudaStream_t);
@@ -38,8 +42,9 @@ int hmcx_abi_version(void) { return HMCX_ABI_VERSION; }
 size_t hmcx_hmc_workspace_bytes(const hmcx_target_t* target, const hmcx_mass_t* mass, int32_t C, int32_t ld) {
     const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
     if (is_elem(target) && !full_mass && ld > 4096) return (size_t)C * (size_t)ld * sizeof(float);
-    if (target && target->kind == HMCX_TARGET_GAUSS_FULL && target->dim > 16 && !full_mass)
-        return hmcx::dense_workspace_floats(C, target->dim) * sizeof(float);
+    if (target && target->dim > 16 &&
+        (target->kind == HMCX_TARGET_GAUSS_FULL || (full_mass && is_elem(target))))
+        return hmcx::dense_workspace_floats(C, target->dim, full_mass ? 1 : 0) * sizeof(float);
     return 0;
 }
 
@@ -81,14 +86,27 @@ int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
                  int32_t L, int32_t num_samples, int32_t burn, int32_t iter_begin, int32_t iter_end,
                  float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
                  int32_t* num_rejected, int32_t tuning, float* workspace, void* stream) {
+    return hmcx_hmc_run_sink(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin,
+                             iter_end, samples_out, accept_out, diverged_out, ham_out, num_rejected, tuning, workspace,
+                             nullptr, stream);
+}
+
+int hmcx_hmc_run_sink(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                      const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int32_t C, int32_t ld,
+                      int32_t L, int32_t num_samples, int32_t burn, int32_t iter_begin, int32_t iter_end,
+                      float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                      int32_t* num_rejected, int32_t tuning, float* workspace, const hmcx_sink_t* sink, void* stream) {
     if (!target) return HMCX_ERR_INVALID_ARG;
+    if (sink && sink->thin < 1) return HMCX_ERR_INVALID_ARG;
+    if (sink && sink->thin == 1 && !sink->sum && !sink->sumsq) sink = nullptr;
     const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
     if (is_elem(target) && !full_mass)
         return hmcx::elem_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                   iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
-                                  num_rejected, tuning, workspace, (cudaStream_t)stream);
-    if (target->kind == HMCX_TARGET_GAUSS_FULL && target->dim > 16 && !full_mass)
-        // dense target at scale: one tcgen05 GEMM per leapfrog step over all chains (hmcx_tc.cu)
+                                  num_rejected, tuning, workspace, sink, (cudaStream_t)stream);
+    if (sink) return HMCX_ERR_UNSUPPORTED;
+    if (target->dim > 16 && (target->kind == HMCX_TARGET_GAUSS_FULL || (full_mass && is_elem(target))))
+        // dense target and / or full mass matrix at scale: tcgen05 GEMMs over all chains per leapfrog step (hmcx_tc.cu)
         return hmcx::dense_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                    iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out,
                                    num_rejected, workspace, (cudaStream_t)stream);
@@ -122,6 +140,20 @@ int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const h
                    uint8_t* diverged_out, float* ham_out, int32_t* num_rejected, void* stream) {
     return hmcx::rmhmc_run(target, cfg, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin, iter_end,
                            samples_out, accept_out, diverged_out, ham_out, num_rejected, (cudaStream_t)stream);
+}
+
+size_t hmcx_rmhmc_dense_workspace_bytes(int32_t C, int32_t D) {
+    return hmcx::dense_rmhmc_workspace_floats(C, D) * sizeof(float);
+}
+
+int hmcx_rmhmc_dense_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_const_metric_t* metric,
+                         const hmcx_rng_t* rng, const float* q_init, float* q_cur, const float* eps, int32_t C,
+                         int32_t ld, int32_t L, int32_t num_samples, int32_t burn, int32_t iter_begin, int32_t iter_end,
+                         float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                         int32_t* num_rejected, float* workspace, void* stream) {
+    return hmcx::dense_rmhmc_run(target, cfg, metric, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin,
+                                 iter_end, samples_out, accept_out, diverged_out, ham_out, num_rejected, workspace,
+                                 (cudaStream_t)stream);
 }
 
 int hmcx_gemm_nt_tf32x3(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, void* stream) {

@@ -141,13 +141,19 @@ struct RunArgs {
     uint8_t* diverged;
     float* ham;
     int32_t* num_rejected;
+    // sample sink (hmcx_sink_t): thinning + running first / second moments of the post-burn states
+    int thin;
+    float* msum;
+    float* msumsq;
 };
 
 constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * K <= 8 ? 512 : 256); }
 
 // MAXT = CTA size the instantiation is compiled for (register budget 64K/MAXT): chains of D <= 1024 run with <= 256
 // threads and get a generous budget, which lets the compiler software-pipeline the next iteration's RNG.
-template <int TK, int MK, int E, int K, int MAXT>
+// SINK = true adds the sample sink to the bookkeeping step (thinned stores, register-resident moment accumulators); it is
+// a separate instantiation so that the plain sample() loop keeps its register allocation and schedule.
+template <int TK, int MK, int E, int K, int MAXT, bool SINK = false>
 __global__ void __launch_bounds__(MAXT)
 hmc_run_kernel(const RunArgs a) {
     __shared__ float s_red[2][100];
@@ -190,8 +196,19 @@ hmc_run_kernel(const RunArgs a) {
     double h_bar = 0.0, eps_bar = 1.0;
     if (a.nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
     int rejected = 0;
-    const int keep = a.S - a.burn;                 // slots per chain in samples_out
+    const int thin = SINK ? a.thin : 1;
+    const int keep = SINK ? 1 + (a.S - a.burn - 1) / thin : a.S - a.burn;    // slots per chain in samples_out
     float* const my_samples = a.samples ? a.samples + (size_t)c * keep * ld : nullptr;
+    float msum[K][E], msq[K][E];
+    if (SINK) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) { msum[k][j] = 0.0f; msq[k][j] = 0.0f; }
+            if (live[k] && a.msum) ldE<E>(a.msum + row + E * (tid + k * G), msum[k]);
+            if (live[k] && a.msumsq) ldE<E>(a.msumsq + row + E * (tid + k * G), msq[k]);
+        }
+    }
 
     if (a.it0 == 0 && my_samples) {                // ret_params = [params_init] (:959)
 #pragma unroll
@@ -289,7 +306,23 @@ hmc_run_kernel(const RunArgs a) {
             }
         }
         // ---- bookkeeping (:1007-1026): store only for n > burn ----
-        if (n > a.burn && my_samples) {
+        if (SINK) {
+            if (n > a.burn) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        msum[k][j] = add(msum[k][j], qc[k][j]);
+                        msq[k][j] = add(msq[k][j], mul(qc[k][j], qc[k][j]));
+                    }
+                if (my_samples && (n - a.burn) % thin == 0) {
+                    float* dst = my_samples + (size_t)((n - a.burn) / thin) * ld;
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (live[k]) stE_stream<E>(dst + E * (tid + k * G), qc[k]);
+                }
+            }
+        } else if (n > a.burn && my_samples) {
             float* dst = my_samples + (size_t)(n - a.burn) * ld;
 #pragma unroll
             for (int k = 0; k < K; ++k)
@@ -329,6 +362,13 @@ hmc_run_kernel(const RunArgs a) {
 #pragma unroll
     for (int k = 0; k < K; ++k)
         if (live[k]) stE<E>(a.q_cur + row + E * (tid + k * G), qc[k]);
+    if (SINK) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (live[k] && a.msum) stE<E>(a.msum + row + E * (tid + k * G), msum[k]);
+            if (live[k] && a.msumsq) stE<E>(a.msumsq + row + E * (tid + k * G), msq[k]);
+        }
+    }
     if (tid == 0) {
         a.eps[c] = eps;
         if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
@@ -664,7 +704,8 @@ static bool pick_geometry(int ld, int tuning, int& E, int& K, int& G) {
 int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
                  const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int C, int ld, int L,
                  int S, int burn, int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged,
-                 float* ham, int32_t* num_rejected, int tuning, float* workspace, cudaStream_t st) {
+                 float* ham, int32_t* num_rejected, int tuning, float* workspace, const hmcx_sink_t* sink,
+                 cudaStream_t st) {
     RunArgs a = {};
     const int rc = fill_elem_target(target, mass, C, ld, a.t);
     if (rc != HMCX_OK) return rc;
@@ -688,6 +729,17 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
 
     int E, K, G;
+    if (sink) {                                            // thinning / moments: float4-per-thread geometry only
+        if (ld > 4096 || (tuning != 0 && tuning != 1)) return HMCX_ERR_UNSUPPORTED;
+        a.thin = sink->thin; a.msum = sink->sum; a.msumsq = sink->sumsq;
+        pick_geometry(ld, 0, E, K, G);
+#define CALLSINK(TK, MK)                                                                                \
+        if (G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256, true><<<C, G, 0, st>>>(a);                      \
+        else hmc_run_kernel<TK, MK, 4, 1, 1024, true><<<C, G, 0, st>>>(a)
+        DISPATCH_TK_MK(a.t, CALLSINK);
+#undef CALLSINK
+        return cuda_status();
+    }
     if (ld > 4096 && tuning == 0) {                        // state does not fit one CTA's registers: streamed form
         if (!workspace) return HMCX_ERR_INVALID_ARG;       // needs hmcx_hmc_workspace_bytes() of scratch
 #define CALLBIG(TK, MK) hmc_run_big_kernel<TK, MK><<<C, 1024, 0, st>>>(a, workspace)

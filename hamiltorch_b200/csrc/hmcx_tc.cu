@@ -143,6 +143,8 @@ struct DenseArgs {
     int mk;
     const float* im;          // [Dp] inverse mass (diag) or null
     const float* sd;          // [Dp] sqrt(mass) or null
+    int tk;                   // target kind (full-mass path: GAUSS_ISO / GAUSS_DIAG / GAUSS_FULL)
+    const float* ivar;        // [Dp] GAUSS_DIAG inverse variances
 };
 
 enum { DENSE_FIRST = 0, DENSE_MIDDLE = 1, DENSE_LAST = 2, DENSE_EVAL = 3 };
@@ -188,37 +190,16 @@ __global__ void dense_pack_kernel(const float* __restrict__ src, const float* __
 __host__ __device__ constexpr int dense_stages(int BN) { return BN == 128 ? 3 : 4; }
 __host__ __device__ constexpr int dense_stage_floats(int BN) { return 2 * TC_M * TC_KC + 2 * BN * TC_KC; }
 
-// One leapfrog step for all chains:  acc = (Q - mu) P  on tcgen05, then kick / drift in the epilogue.
-//   grid (Dp/BN, Cp/128), 128 threads: thread 0 = TMA producer, thread 32 = MMA issuer, all 4 warps = epilogue.
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float* __restrict__ QpIn,
-                  const float* __restrict__ Ppack, float* __restrict__ Qout, float* __restrict__ QpOut,
-                  float* __restrict__ P, const float* __restrict__ eps, int mode, float* __restrict__ upart) {
-    constexpr int ST = dense_stages(BN);
-    constexpr int A_BLK = TC_M * TC_KC, B_BLK = BN * TC_KC;                // floats per hi (or lo) block
+// The warp-specialised main loop shared by the dense kernels: thread 0 = TMA producer (1-D bulk copies of the packed
+// hi|lo operand blocks into an ST-stage ring), thread 32 = MMA issuer (three tf32 UMMAs per 8-wide k-step: hi*hi +
+// hi*lo + lo*hi, fp32 accumulators in tensor memory), tcgen05.commit releasing stages / signalling `s_done`.
+template <int BN, int ST>
+__device__ __forceinline__ void dense_mainloop(float* smem, uint64_t* s_full, uint64_t* s_empty, uint64_t* s_done_p,
+                                               uint32_t tmem, const float* __restrict__ QpIn,
+                                               const float* __restrict__ Ppack, int tile_m, int tile_n, int kchunks) {
+    constexpr int A_BLK = TC_M * TC_KC, B_BLK = BN * TC_KC;
     constexpr uint32_t STAGE_BYTES = (uint32_t)dense_stage_floats(BN) * 4u;
-    extern __shared__ __align__(1024) float smem[];
-    __shared__ __align__(8) uint64_t s_full[ST], s_empty[ST], s_done;
-    __shared__ uint32_t s_tmem;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Dp = a.Dp, kchunks = Dp / TC_KC;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
-        mbar_init(smem_u32(&s_done), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(BN < 32 ? 32 : BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-
+    uint64_t& s_done = *s_done_p;
     if (threadIdx.x == 0) {
         // ===== TMA producer: 4 bulk copies per stage (A hi, A lo, B hi, B lo are adjacent pairs in global memory) =====
         for (int i = 0; i < kchunks; ++i) {
@@ -256,6 +237,38 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float*
     }
     __syncwarp();
     mbar_wait(smem_u32(&s_done), 0);
+}
+
+// One leapfrog step for all chains:  acc = (Q - mu) P  on tcgen05, then kick / drift in the epilogue.
+//   grid (Dp/BN, Cp/128), 128 threads: thread 0 = TMA producer, thread 32 = MMA issuer, all 4 warps = epilogue.
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float* __restrict__ QpIn,
+                  const float* __restrict__ Ppack, float* __restrict__ Qout, float* __restrict__ QpOut,
+                  float* __restrict__ P, const float* __restrict__ eps, int mode, float* __restrict__ upart) {
+    constexpr int ST = dense_stages(BN);
+    extern __shared__ __align__(1024) float smem[];
+    __shared__ __align__(8) uint64_t s_full[ST], s_empty[ST], s_done;
+    __shared__ uint32_t s_tmem;
+    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Dp = a.Dp, kchunks = Dp / TC_KC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(BN < 32 ? 32 : BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    dense_mainloop<BN, ST>(smem, s_full, s_empty, &s_done, tmem, QpIn, Ppack, tile_m, tile_n, kchunks);
     // ===== epilogue: acc = ((Q-mu) P)[row, cols]; g = -acc; kick, optional drift (+ packed copy for the next GEMM) =====
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = tile_m * TC_M + warp * 32 + lane;
@@ -318,6 +331,142 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float*
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(BN < 32 ? 32 : BN));
 }
 
+
+// =========================================================================================================
+// Generic "linear flow" kernel on the tensor cores:  acc[row, col] = sum_k A[row, k] * B[col, k]   (all chains at once,
+// A = a packed state operand, B = a packed D x D matrix), with a fused update epilogue
+//     X[row, col]  <-  X + k1 * s*acc  [ - k2 * s*acc ]      (or X <- acc),     k = eps[row] or 0.5*eps[row]
+//     Xpack        <-  split_tf32(X_new - shift[col])          the NEXT GEMM's A operand, already packed
+//     part[row, tile_n] = sum_col (Y[row, col] - yshift[col]) * acc[row, col]       quadratic forms y.(B y)
+// It is the building block of everything on the path that is a (chains x D) . (D x D) contraction and not the
+// diagonal-mass dense step above:
+//   * full (2-D) inv_mass at D > 16 (samplers.py:294 drift q += eps*(M^-1 p), :812 kinetic 0.5 p.(M^-1 p), gibbs
+//     :199 p = chol(M) z) for GaussianIso / GaussianDiag / GaussianFull targets;
+//   * the constant-metric RMHMC flows dH/dp = G~^-1 p and dH/dtheta = P (theta - mu) (samplers.py:389-462).
+// =========================================================================================================
+enum { LIN_K_E = 1, LIN_K_HALF = 2 };
+struct LinEpi {
+    float* X;              // [Cp, Dp] updated in place (null: no update)
+    float* Xpack;          // packed copy of X_new - shift (null: none)
+    const float* shift;    // [Dp] or null
+    const float* Y;        // [Cp, Dp] dot partner (null: no dot)
+    const float* yshift;   // [Dp] or null
+    float* part;           // [Cp, NT]
+    const float* eps;      // [C]
+    int assign;            // X <- s*acc
+    int k1, k2;            // LIN_K_* (k2 = 0: no second term)
+    int k2add;             // second term is added instead of subtracted
+    float sign;            // s = +1 / -1
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const float* __restrict__ Bpack, const LinEpi ep) {
+    constexpr int ST = dense_stages(BN);
+    extern __shared__ __align__(1024) float smem[];
+    __shared__ __align__(8) uint64_t s_full[ST], s_empty[ST], s_done;
+    __shared__ uint32_t s_tmem;
+    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = Dp / TC_KC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(BN < 32 ? 32 : BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    dense_mainloop<BN, ST>(smem, s_full, s_empty, &s_done, tmem, Apack, Bpack, tile_m, tile_n, kchunks);
+
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = tile_m * TC_M + warp * 32 + lane;
+    const bool live = row < C;
+    const float e = (live && ep.eps) ? ep.eps[row] : 0.0f, half = mul(0.5f, e);
+    const float k1 = (ep.k1 == LIN_K_HALF) ? half : e, k2 = (ep.k2 == LIN_K_HALF) ? half : e;
+    const bool neg = ep.sign < 0.0f;
+    float dot = 0.0f;
+    const size_t base = (size_t)row * Dp + (size_t)tile_n * BN;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (live) {
+            const int colbase = tile_n * BN + c0;                           // a 32-aligned column block = one K chunk
+            float* xp_hi = ep.Xpack ? ep.Xpack + pack_block_base(tile_m, colbase / TC_KC, 0, kchunks, TC_M) : nullptr;
+            float* xp_lo = ep.Xpack ? ep.Xpack + pack_block_base(tile_m, colbase / TC_KC, 1, kchunks, TC_M) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int col = colbase + j;
+                const float acc[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3])};
+                if (ep.Y) {
+                    float yv[4];
+                    ld4(ep.Y + base + c0 + j, yv);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float y = ep.yshift ? sub(yv[t], ep.yshift[col + t]) : yv[t];
+                        dot = add(dot, mul(y, acc[t]));
+                    }
+                }
+                if (ep.X) {
+                    float xv[4] = {0.f, 0.f, 0.f, 0.f}, xn[4], yn[4];
+                    if (!ep.assign) ld4(ep.X + base + c0 + j, xv);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float g = neg ? -acc[t] : acc[t];
+                        xn[t] = ep.assign ? g : add(xv[t], mul(k1, g));
+                        if (ep.k2) xn[t] = ep.k2add ? add(xn[t], mul(k2, g)) : sub(xn[t], mul(k2, g));
+                        yn[t] = ep.shift ? sub(xn[t], ep.shift[col + t]) : xn[t];
+                    }
+                    st4(ep.X + base + c0 + j, xn);
+                    if (ep.Xpack) split_store4(xp_hi, xp_lo, pack_elem_off(row % TC_M, j, TC_M), yn);
+                }
+            }
+        }
+    }
+    if (live && ep.part) ep.part[(size_t)row * NT + tile_n] = dot;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(BN < 32 ? 32 : BN));
+}
+
+static bool lin_launch(int BN, dim3 grid, cudaStream_t st, int C, int Dp, int NT, const float* Apack, const float* Bpack,
+                       const LinEpi& ep) {
+    const size_t sm = (size_t)dense_stages(BN) * dense_stage_floats(BN) * sizeof(float);
+    if (BN == 128) dense_lin_kernel<128><<<grid, TC_THREADS, sm, st>>>(C, Dp, NT, Apack, Bpack, ep);
+    else if (BN == 64) dense_lin_kernel<64><<<grid, TC_THREADS, sm, st>>>(C, Dp, NT, Apack, Bpack, ep);
+    else dense_lin_kernel<32><<<grid, TC_THREADS, sm, st>>>(C, Dp, NT, Apack, Bpack, ep);
+    return true;
+}
+static bool lin_configure() {
+    bool ok = true;
+    ok = ok && cudaFuncSetAttribute(dense_lin_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)dense_stages(128) * dense_stage_floats(128) * 4)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(dense_lin_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)dense_stages(64) * dense_stage_floats(64) * 4)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(dense_lin_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)dense_stages(32) * dense_stage_floats(32) * 4)) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    return ok;
+}
+
 // zero-padded copies into the workspace
 __global__ void dense_pad_matrix_kernel(const float* __restrict__ src, int D, float* __restrict__ dst, int Dp) {
     const size_t n = (size_t)Dp * Dp;
@@ -363,6 +512,13 @@ struct DenseRun {
     float* kin0;
     float* U_cur;
     float* U_init;
+    // full (2-D) inv_mass: gibbs packs z (p = chol(M) z is a GEMM), kinetic energies arrive as per-tile partials
+    float* zpack;
+    const float* kpart0;
+    const float* kpartL;
+    // constant-metric RMHMC: H = -log p + 0.5*D*log(2 pi) + 0.5*log det G + 0.5 p.(G^-1 p)   (samplers.py:731)
+    int rm;
+    float ham_c1, ham_c2;
 };
 
 // gibbs (:969) for iteration n: p = z * sqrt(mass) -> P rows, q_cur -> Q work rows, kinetic of p
@@ -389,17 +545,21 @@ dense_gibbs_kernel(const DenseRun r, int n, float* __restrict__ Q, float* __rest
             pv[j] = (a.mk == HMCX_MASS_DIAG) ? mul(z[j], a.sd[i]) : z[j];
             kin[0] = add(kin[0], (a.mk == HMCX_MASS_DIAG) ? mul(pv[j], mul(a.im[i], pv[j])) : mul(pv[j], pv[j]));
         }
-        st4(P + (size_t)c * Dp + 4 * v, pv);
+        const int kchunks = Dp / TC_KC, kc = (4 * v) / TC_KC;
+        if (a.mk == HMCX_MASS_FULL)                                              // :199: p = scale_tril . z, a GEMM
+            split_store4(r.zpack + pack_block_base(c / TC_M, kc, 0, kchunks, TC_M),
+                         r.zpack + pack_block_base(c / TC_M, kc, 1, kchunks, TC_M), pack_elem_off(c % TC_M, (4 * v) % TC_KC, TC_M), z);
+        else
+            st4(P + (size_t)c * Dp + 4 * v, pv);
         st4(Q + (size_t)c * Dp + 4 * v, qv);
         float y[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = sub(qv[j], a.mean[4 * v + j]);
-        const int kchunks = Dp / TC_KC, kc = (4 * v) / TC_KC;
         split_store4(Qpack + pack_block_base(c / TC_M, kc, 0, kchunks, TC_M),
                      Qpack + pack_block_base(c / TC_M, kc, 1, kchunks, TC_M), pack_elem_off(c % TC_M, (4 * v) % TC_KC, TC_M), y);
     }
     block_sum<1>(kin, sred);
-    if (threadIdx.x == 0) r.kin0[c] = kin[0];
+    if (threadIdx.x == 0 && r.kin0) r.kin0[c] = kin[0];
 }
 
 // log p from the per-tile partials of y.(P y)   (targets.GaussianFull: -0.5*dot(y, P y) + log_norm)
@@ -424,16 +584,33 @@ dense_mh_kernel(const DenseRun r, int n, const float* __restrict__ Qprop, const 
     const int c = blockIdx.x, Dp = a.Dp, D = a.D, tid = threadIdx.x;
     const uint64_t chain_id = r.chain_offset + (uint64_t)c;
     float kin[1] = {0.0f};
-    for (int i = tid; i < D; i += blockDim.x) {
-        const float p = P[(size_t)c * Dp + i];
-        kin[0] = add(kin[0], (a.mk == HMCX_MASS_DIAG) ? mul(p, mul(a.im[i], p)) : mul(p, p));
+    if (a.mk != HMCX_MASS_FULL) {
+        for (int i = tid; i < D; i += blockDim.x) {
+            const float p = P[(size_t)c * Dp + i];
+            kin[0] = add(kin[0], (a.mk == HMCX_MASS_DIAG) ? mul(p, mul(a.im[i], p)) : mul(p, p));
+        }
+        block_sum<1>(kin, sred);
     }
-    block_sum<1>(kin, sred);
     if (tid == 0) {
+        float kin_old = 0.0f;
+        if (a.mk == HMCX_MASS_FULL) {                                        // p.(M^-1 p): per-tile partials, fixed order
+            for (int t = 0; t < a.NT; ++t) {
+                kin_old = add(kin_old, r.kpart0[(size_t)c * a.NT + t]);
+                kin[0] = add(kin[0], r.kpartL[(size_t)c * a.NT + t]);
+            }
+        } else {
+            kin_old = r.kin0[c];
+        }
         const float lp_cur = r.U_cur[c], lp_new = dense_log_prob(a, upart, c);
-        const float h_old = add(-lp_cur, mul(0.5f, r.kin0[c]));
-        const float h_new = add(-lp_new, mul(0.5f, kin[0]));
-        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new);
+        float h_old, h_new;
+        if (r.rm) {
+            h_old = add(add(add(-lp_cur, r.ham_c1), r.ham_c2), mul(0.5f, kin_old));
+            h_new = add(add(add(-lp_new, r.ham_c1), r.ham_c2), mul(0.5f, kin[0]));
+        } else {
+            h_old = add(-lp_cur, mul(0.5f, kin_old));
+            h_new = add(-lp_new, mul(0.5f, kin[0]));
+        }
+        const bool bad = !finite_f(lp_cur) || !finite_f(lp_new) || (r.rm && (!finite_f(h_old) || !finite_f(h_new)));
         const float x = add(-h_new, h_old);
         const float rho = (x < 0.0f) ? x : 0.0f;
         const float logu = (r.rng_mode == HMCX_RNG_INJECTED) ? r.logu[(size_t)(n - r.it0) * a.C + c]
@@ -481,35 +658,210 @@ dense_mh_kernel(const DenseRun r, int n, const float* __restrict__ Qprop, const 
     }
 }
 
-size_t dense_workspace_floats(int C, int D) {
-    const size_t Cp = (size_t)(C + 127) / 128 * 128, Dp = (size_t)(D + 127) / 128 * 128, NT = Dp / 128;
-    (void)NT;
+size_t dense_workspace_floats(int C, int D, int full_mass) {
+    const size_t Cp = (size_t)(C + 127) / 128 * 128, Dp = (size_t)(D + 127) / 128 * 128;
+    if (full_mass)
+        return 8 * Cp * Dp        // Q, P, Qpack, Ppack, Zpack (hi+lo each)
+               + 7 * Dp * Dp      // padding scratch + packed precision, inv_mass, chol(mass)
+               + 2 * Dp + 3 * Cp * (Dp / 32) + 2 * Cp + 64;
     return 7 * Cp * Dp            // Q[2], Qpack[2] (hi+lo each), P
            + 3 * Dp * Dp          // padded precision + its packed hi/lo
            + 3 * Dp + Cp * (Dp / 32) + 3 * Cp + 64;
+}
+
+// Element-wise targets under a full mass matrix: the kick has no contraction.  One CTA per chain: g = grad log p(q)
+// in the reference's op order, p <- p + k1*g [- k2*g], packed copy of p for the drift GEMM, and the U-terms sum
+// (slot 0 of the chain's partials; the other slots are zeroed so dense_log_prob's fixed-order sum is unchanged).
+__global__ void __launch_bounds__(256)
+dense_kick_elem_kernel(const DenseArgs a, const float* __restrict__ Q, float* __restrict__ P, float* __restrict__ Ppack,
+                       const float* __restrict__ eps, int k1m, int k2m, float* __restrict__ upart) {
+    __shared__ float sred[32];
+    const int c = blockIdx.x, Dp = a.Dp, D = a.D;
+    const float e = eps[c], half = mul(0.5f, e);
+    const float k1 = (k1m == LIN_K_HALF) ? half : e, k2 = (k2m == LIN_K_HALF) ? half : e;
+    const int kchunks = Dp / TC_KC;
+    float us[1] = {0.0f};
+    for (int v = threadIdx.x; 4 * v < Dp; v += blockDim.x) {
+        float qv[4], pv[4];
+        ld4(Q + (size_t)c * Dp + 4 * v, qv);
+        if (k1m) ld4(P + (size_t)c * Dp + 4 * v, pv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = 4 * v + j;
+            float g = 0.0f, u = 0.0f;
+            if (i < D) {
+                if (a.tk == HMCX_TARGET_GAUSS_ISO) { g = -qv[j]; u = mul(qv[j], qv[j]); }
+                else { const float y = sub(qv[j], a.mean[i]); g = -mul(a.ivar[i], y); u = mul(mul(y, y), a.ivar[i]); }
+            }
+            us[0] = add(us[0], u);
+            if (k1m) {
+                pv[j] = add(pv[j], mul(k1, g));                               // :281 / :298
+                if (k2m) pv[j] = sub(pv[j], mul(k2, g));                      // :302
+            }
+        }
+        if (k1m) {
+            st4(P + (size_t)c * Dp + 4 * v, pv);
+            const int kc = (4 * v) / TC_KC;
+            split_store4(Ppack + pack_block_base(c / TC_M, kc, 0, kchunks, TC_M),
+                         Ppack + pack_block_base(c / TC_M, kc, 1, kchunks, TC_M), pack_elem_off(c % TC_M, (4 * v) % TC_KC, TC_M), pv);
+        }
+    }
+    block_sum<1>(us, sred);
+    if (upart) for (int t = threadIdx.x; t < a.NT; t += blockDim.x) upart[(size_t)c * a.NT + t] = (t == 0) ? us[0] : 0.0f;
+}
+
+// sample() loop with a full (2-D) inv_mass at D > 16 (samplers.py:199, :294, :812): every drift, the momentum
+// refresh and both kinetic energies are (chains x D) . (D x D) GEMMs on tcgen05 (dense_lin_kernel); a GaussianFull
+// target adds the gradient GEMM, GaussianIso / GaussianDiag kick element-wise.  2L+4 (L+3) GEMMs per iteration.
+// K / N padding to multiples of 32 (one K chunk); column-tile width = the widest of 128/64/32 that divides Dp and still
+// gives the GPU ~100 CTAs (each CTA re-streams its 128 chain rows)
+static void dense_geometry(DenseArgs& a) {
+    a.Dp = (a.D + 31) / 32 * 32;
+    const int mt = a.Cp / 128;
+    a.BN = (a.Dp % 128 == 0) ? 128 : (a.Dp % 64 == 0) ? 64 : 32;
+    while (a.BN > 32 && mt * (a.Dp / a.BN) < 96) a.BN >>= 1;
+    a.NT = a.Dp / a.BN;
+}
+
+static inline float mul_host(float x, float y) { volatile float r = x * y; return r; }
+
+static int dense_fullmass_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                                  const hmcx_nuts_t* nuts, const float* q_init, float* q_cur, float* eps, int C, int ld,
+                                  int L, int S, int burn, int it0, int it1, float* samples, uint8_t* accept,
+                                  uint8_t* diverged, float* ham, int32_t* num_rejected, float* ws, cudaStream_t st) {
+    const int D = target->dim, tk = target->kind;
+    if (!mass->inv_mass || !mass->mass_factor) return HMCX_ERR_INVALID_ARG;
+    if (tk == HMCX_TARGET_GAUSS_DIAG && !target->inv_var) return HMCX_ERR_INVALID_ARG;
+    DenseRun r = {};
+    DenseArgs& a = r.a;
+    a.C = C; a.D = D; a.Cp = (C + 127) / 128 * 128;
+    a.log_norm = target->log_norm; a.mk = HMCX_MASS_FULL; a.tk = tk;
+    dense_geometry(a);
+    const size_t CD = (size_t)a.Cp * a.Dp, DD = (size_t)a.Dp * a.Dp;
+    float* Q = ws;
+    float* P = ws + CD;
+    float* Qpack = ws + 2 * CD;
+    float* Ppack = ws + 4 * CD;
+    float* Zpack = ws + 6 * CD;
+    float* scratch = ws + 8 * CD;
+    float* precpack = scratch + DD;
+    float* impack = precpack + 2 * DD;
+    float* trilpack = impack + 2 * DD;
+    float* mean = trilpack + 2 * DD;
+    float* ivar = mean + a.Dp;
+    float* upart = ivar + a.Dp;
+    float* kpart0 = upart + (size_t)a.Cp * (a.Dp / 32);
+    float* kpartL = kpart0 + (size_t)a.Cp * (a.Dp / 32);
+    r.U_cur = kpartL + (size_t)a.Cp * (a.Dp / 32);
+    r.U_init = r.U_cur + a.Cp;
+    r.kin0 = nullptr; r.zpack = Zpack; r.kpart0 = kpart0; r.kpartL = kpartL;
+    a.mean = mean; a.ivar = ivar; a.prec = nullptr; a.im = nullptr; a.sd = nullptr;
+    r.ld = ld; r.rng_mode = rng->mode; r.seed = rng->seed; r.chain_offset = rng->chain_offset;
+    r.normals = rng->normals; r.logu = rng->log_uniforms;
+    r.nuts = (nuts && nuts->enabled) ? 1 : 0;
+    if (r.nuts) {
+        if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
+        r.delta = nuts->desired_accept_rate; r.mu = nuts->mu; r.table = nuts->table;
+        r.h_bar = nuts->h_bar; r.eps_bar = nuts->eps_bar;
+        r.eps_schedule = nuts->eps_schedule; r.eps_trace = nuts->eps_trace;
+    }
+    r.q_init = q_init; r.q_cur = q_cur; r.eps = eps; r.S = S; r.burn = burn; r.it0 = it0;
+    r.samples = samples; r.accept = accept; r.diverged = diverged; r.ham = ham; r.num_rejected = num_rejected;
+    if (!lin_configure()) return HMCX_ERR_CUDA;
+
+    const bool gemm_target = tk == HMCX_TARGET_GAUSS_FULL;
+    auto pack_matrix = [&](const float* src, float* dst) {
+        dense_pad_matrix_kernel<<<296, 256, 0, st>>>(src, D, scratch, a.Dp);
+        dense_pack_kernel<<<296, 256, 0, st>>>(scratch, nullptr, a.Dp, a.Dp, a.BN, dst);
+    };
+    if (gemm_target) pack_matrix(target->prec, precpack);
+    pack_matrix(mass->inv_mass, impack);
+    pack_matrix(mass->mass_factor, trilpack);
+    dense_pad_vector_kernel<<<8, 256, 0, st>>>(tk == HMCX_TARGET_GAUSS_ISO ? nullptr : target->mean, D, mean, a.Dp);
+    dense_pad_vector_kernel<<<8, 256, 0, st>>>(tk == HMCX_TARGET_GAUSS_DIAG ? target->inv_var : nullptr, D, ivar, a.Dp);
+    cudaMemsetAsync(ws, 0, 8 * CD * sizeof(float), st);
+
+    const dim3 ggrid(a.NT, a.Cp / 128);
+    // kick: p <- p + k1*g [- k2*g], g = grad log p(q); also leaves the U-terms partials of q in `upart`.  k1 = 0: U only.
+    auto kick = [&](int k1, int k2) {
+        if (gemm_target) {
+            LinEpi ep = {};
+            ep.X = k1 ? P : nullptr; ep.Xpack = k1 ? Ppack : nullptr; ep.Y = Q; ep.yshift = mean; ep.part = upart;
+            ep.eps = eps; ep.k1 = k1; ep.k2 = k2; ep.sign = -1.0f;
+            lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, Qpack, precpack, ep);
+        } else {
+            dense_kick_elem_kernel<<<C, 256, 0, st>>>(a, Q, P, Ppack, eps, k1, k2, upart);
+        }
+    };
+    auto kinetic = [&](float* kpart) {                                       // :812  p.(M^-1 p)
+        LinEpi ep = {};
+        ep.Y = P; ep.part = kpart;
+        lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, Ppack, impack, ep);
+    };
+    auto load_q = [&](const float* src) {
+        dense_load_rows_kernel<<<a.Cp, 256, 0, st>>>(src, C, ld, D, Q, a.Cp, a.Dp);
+        if (gemm_target) dense_pack_kernel<<<296, 256, 0, st>>>(Q, mean, a.Cp, a.Dp, TC_M, Qpack);
+    };
+    load_q(q_init);
+    kick(0, 0);
+    dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_init);
+    load_q(q_cur);
+    kick(0, 0);
+    dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_cur);
+    if (it0 == 0 && samples) {                                                      // slot 0 = params_init (:959)
+        cudaMemcpy2DAsync(samples, (size_t)(S - burn) * ld * sizeof(float), q_init, (size_t)ld * sizeof(float),
+                          (size_t)ld * sizeof(float), (size_t)C, cudaMemcpyDeviceToDevice, st);
+    }
+    for (int n = it0; n < it1; ++n) {
+        dense_gibbs_kernel<<<C, 256, 0, st>>>(r, n, Q, P, Qpack);            // q_cur -> Q (+ packed), z -> Zpack
+        {
+            LinEpi ep = {};                                                  // :199  p = chol(M) z
+            ep.X = P; ep.Xpack = Ppack; ep.assign = 1; ep.sign = 1.0f;
+            lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, Zpack, trilpack, ep);
+        }
+        kinetic(kpart0);
+        kick(LIN_K_HALF, 0);                                                 // :281
+        for (int l = 1; l <= L; ++l) {
+            LinEpi ep = {};                                                  // :294  q <- q + eps*(M^-1 p)
+            ep.X = Q; ep.Xpack = gemm_target ? Qpack : nullptr; ep.shift = mean; ep.eps = eps; ep.k1 = LIN_K_E;
+            ep.sign = 1.0f;
+            lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, Ppack, impack, ep);
+            kick(LIN_K_E, l == L ? LIN_K_HALF : 0);                          // :298 (:302)
+        }
+        kinetic(kpartL);
+        dense_mh_kernel<<<C, 256, 0, st>>>(r, n, Q, P, upart);
+    }
+    return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
 }
 
 int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, const hmcx_nuts_t* nuts,
                   const float* q_init, float* q_cur, float* eps, int C, int ld, int L, int S, int burn, int it0,
                   int it1, float* samples, uint8_t* accept, uint8_t* diverged, float* ham, int32_t* num_rejected,
                   float* ws, cudaStream_t st) {
-    if (!target || target->kind != HMCX_TARGET_GAUSS_FULL || !target->prec) return HMCX_ERR_INVALID_ARG;
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
+    if (target->kind == HMCX_TARGET_GAUSS_FULL ? !target->prec
+                                               : !(full_mass && (target->kind == HMCX_TARGET_GAUSS_ISO ||
+                                                                 target->kind == HMCX_TARGET_GAUSS_DIAG)))
+        return HMCX_ERR_INVALID_ARG;
     const int D = target->dim;
     if (!rng || !q_init || !q_cur || !eps || !ws || C < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 ||
         burn >= S || it0 < 0 || it1 > S || it0 > it1)
         return HMCX_ERR_INVALID_ARG;
     const int mk = mass ? mass->kind : HMCX_MASS_NONE;
-    if (mk == HMCX_MASS_FULL) return HMCX_ERR_UNSUPPORTED;      // a second GEMM per step: next round
     if (mk == HMCX_MASS_DIAG && (!mass->inv_mass || !mass->mass_factor)) return HMCX_ERR_INVALID_ARG;
     if (rng->mode == HMCX_RNG_INJECTED) {
         if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
     } else if (rng->mode != HMCX_RNG_PHILOX) {
         return HMCX_ERR_INVALID_ARG;
     }
+    if (mk == HMCX_MASS_FULL)
+        return dense_fullmass_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, S, burn, it0, it1, samples,
+                                      accept, diverged, ham, num_rejected, ws, st);
     DenseRun r = {};
     DenseArgs& a = r.a;
     a.C = C; a.D = D; a.Cp = (C + 127) / 128 * 128; a.Dp = (D + 127) / 128 * 128; a.NT = a.Dp / 128;
-    a.log_norm = target->log_norm; a.mk = mk;
+    a.log_norm = target->log_norm; a.mk = mk; a.tk = target->kind;
     // column-tile width: the widest tile that still gives the GPU ~100 CTAs (each CTA re-streams its 128 chain rows)
     const int mt = a.Cp / 128;
     a.BN = 128;
@@ -594,6 +946,182 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
             step(Qbuf[l & 1], Qp[l & 1], Qbuf[(l + 1) & 1], Qp[(l + 1) & 1], mode);
         }
         dense_mh_kernel<<<C, 256, 0, st>>>(r, n, Qbuf[L & 1], P, upart);
+    }
+    return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sampler=RMHMC on Gaussian targets without jitter: the metric G = -Hessian (HESSIAN) or its softabs map is the SAME
+// matrix at every point, so dH/dtheta = -grad log p(theta) and dH/dp = G^-1 p (samplers.py:389-462 through autograd of
+// :677-736), and every flow of the explicit integrator (A-B-C-B-A on the augmented state, :427-458) and of the
+// implicit one (:363-386; its fixed points converge in two sweeps) is a (chains x D).(D x D) GEMM on tcgen05 with the
+// metric solve G^-1 p as one of them.  The host supplies G^-1, chol(G) (gibbs :183-184) and log det G, all computed
+// with the reference's torch ops.
+// ---------------------------------------------------------------------------------------------------------
+// H_C flow (:435-450): the SEQUENTIAL rotation of (theta, p, theta~, p~) with c = cos(2 w eps), s = sin(2 w eps)
+__global__ void __launch_bounds__(256)
+dense_rm_bind_kernel(const DenseArgs a, float cw, float sw, float* __restrict__ Q, float* __restrict__ P,
+                     float* __restrict__ Qc, float* __restrict__ Pc, float* __restrict__ Qpack, float* __restrict__ Ppack,
+                     float* __restrict__ Qcpack, float* __restrict__ Pcpack) {
+    const int c = blockIdx.x, Dp = a.Dp, kchunks = Dp / TC_KC;
+    for (int v = threadIdx.x; 4 * v < Dp; v += blockDim.x) {
+        const size_t o = (size_t)c * Dp + 4 * v;
+        float q[4], p[4], qt[4], pt[4], yq[4], yqt[4];
+        ld4(Q + o, q); ld4(P + o, p); ld4(Qc + o, qt); ld4(Pc + o, pt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float qn = mul(0.5f, add(add(add(q[j], qt[j]), mul(cw, sub(q[j], qt[j]))), mul(sw, sub(p[j], pt[j]))));
+            const float pn = mul(0.5f, add(sub(add(p[j], pt[j]), mul(sw, sub(qn, qt[j]))), mul(cw, sub(p[j], pt[j]))));
+            const float qtn = mul(0.5f, sub(sub(add(qn, qt[j]), mul(cw, sub(qn, qt[j]))), mul(sw, sub(pn, pt[j]))));
+            const float ptn = mul(0.5f, sub(add(add(pn, pt[j]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[j]))));
+            q[j] = qn; p[j] = pn; qt[j] = qtn; pt[j] = ptn;
+            yq[j] = sub(qn, a.mean[4 * v + j]); yqt[j] = sub(qtn, a.mean[4 * v + j]);
+        }
+        st4(Q + o, q); st4(P + o, p); st4(Qc + o, qt); st4(Pc + o, pt);
+        const int kc = (4 * v) / TC_KC, off = pack_elem_off(c % TC_M, (4 * v) % TC_KC, TC_M);
+        const size_t bh = pack_block_base(c / TC_M, kc, 0, kchunks, TC_M), bl = pack_block_base(c / TC_M, kc, 1, kchunks, TC_M);
+        split_store4(Ppack + bh, Ppack + bl, off, p);
+        split_store4(Pcpack + bh, Pcpack + bl, off, pt);
+        if (Qpack) { split_store4(Qpack + bh, Qpack + bl, off, yq); split_store4(Qcpack + bh, Qcpack + bl, off, yqt); }
+    }
+}
+
+size_t dense_rmhmc_workspace_floats(int C, int D) {
+    const size_t Cp = (size_t)(C + 127) / 128 * 128, Dp = (size_t)(D + 31) / 32 * 32;
+    return 14 * Cp * Dp + 7 * Dp * Dp + 2 * Dp + 3 * Cp * (Dp / 32) + 2 * Cp + 64;
+}
+
+int dense_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_const_metric_t* gm,
+                    const hmcx_rng_t* rng, const float* q_init, float* q_cur, const float* eps, int C, int ld, int L,
+                    int S, int burn, int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged, float* ham,
+                    int32_t* num_rejected, float* ws, cudaStream_t st) {
+    if (!target || !cfg || !gm || !rng || !q_init || !q_cur || !eps || !ws) return HMCX_ERR_INVALID_ARG;
+    const int D = target->dim, tk = target->kind;
+    if (tk != HMCX_TARGET_GAUSS_ISO && tk != HMCX_TARGET_GAUSS_DIAG && tk != HMCX_TARGET_GAUSS_FULL) return HMCX_ERR_UNSUPPORTED;
+    if (cfg->jitter >= 0.0f) return HMCX_ERR_UNSUPPORTED;                  // jitter makes the metric a per-call random matrix
+    if (cfg->integrator != 1 && cfg->integrator != 2) return HMCX_ERR_INVALID_ARG;
+    if (!gm->metric_inv || !gm->metric_chol || (tk == HMCX_TARGET_GAUSS_FULL && !target->prec) ||
+        (tk == HMCX_TARGET_GAUSS_DIAG && !target->inv_var))
+        return HMCX_ERR_INVALID_ARG;
+    if (C < 1 || D < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 || burn >= S || it0 < 0 || it1 > S || it0 > it1)
+        return HMCX_ERR_INVALID_ARG;
+    if (rng->mode == HMCX_RNG_INJECTED) {
+        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+    } else if (rng->mode != HMCX_RNG_PHILOX) {
+        return HMCX_ERR_INVALID_ARG;
+    }
+    DenseRun r = {};
+    DenseArgs& a = r.a;
+    a.C = C; a.D = D; a.Cp = (C + 127) / 128 * 128;
+    a.log_norm = target->log_norm; a.mk = HMCX_MASS_FULL; a.tk = tk;
+    dense_geometry(a);
+    const size_t CD = (size_t)a.Cp * a.Dp, DD = (size_t)a.Dp * a.Dp;
+    float* Q = ws;           float* P = ws + CD;          float* Qc = ws + 2 * CD;      float* Pc = ws + 3 * CD;
+    float* Qpack = ws + 4 * CD;  float* Ppack = ws + 6 * CD;  float* Qcpack = ws + 8 * CD;  float* Pcpack = ws + 10 * CD;
+    float* Zpack = ws + 12 * CD;
+    float* scratch = ws + 14 * CD;
+    float* precpack = scratch + DD;
+    float* ginvpack = precpack + 2 * DD;
+    float* cholpack = ginvpack + 2 * DD;
+    float* mean = cholpack + 2 * DD;
+    float* ivar = mean + a.Dp;
+    float* upart = ivar + a.Dp;
+    float* kpart0 = upart + (size_t)a.Cp * (a.Dp / 32);
+    float* kpartL = kpart0 + (size_t)a.Cp * (a.Dp / 32);
+    r.U_cur = kpartL + (size_t)a.Cp * (a.Dp / 32);
+    r.U_init = r.U_cur + a.Cp;
+    r.zpack = Zpack; r.kpart0 = kpart0; r.kpartL = kpartL;
+    a.mean = mean; a.ivar = ivar;
+    r.ld = ld; r.rng_mode = rng->mode; r.seed = rng->seed; r.chain_offset = rng->chain_offset;
+    r.normals = rng->normals; r.logu = rng->log_uniforms;
+    r.q_init = q_init; r.q_cur = q_cur; r.eps = const_cast<float*>(eps); r.S = S; r.burn = burn; r.it0 = it0;
+    r.samples = samples; r.accept = accept; r.diverged = diverged; r.ham = ham; r.num_rejected = num_rejected;
+    r.rm = 1; r.ham_c1 = mul_host(0.5f, cfg->pi_term); r.ham_c2 = mul_host(0.5f, gm->log_det);
+    if (!lin_configure()) return HMCX_ERR_CUDA;
+
+    const bool gemm_target = tk == HMCX_TARGET_GAUSS_FULL;
+    auto pack_matrix = [&](const float* src, float* dst) {
+        dense_pad_matrix_kernel<<<296, 256, 0, st>>>(src, D, scratch, a.Dp);
+        dense_pack_kernel<<<296, 256, 0, st>>>(scratch, nullptr, a.Dp, a.Dp, a.BN, dst);
+    };
+    if (gemm_target) pack_matrix(target->prec, precpack);
+    pack_matrix(gm->metric_inv, ginvpack);
+    pack_matrix(gm->metric_chol, cholpack);
+    dense_pad_vector_kernel<<<8, 256, 0, st>>>(tk == HMCX_TARGET_GAUSS_ISO ? nullptr : target->mean, D, mean, a.Dp);
+    dense_pad_vector_kernel<<<8, 256, 0, st>>>(tk == HMCX_TARGET_GAUSS_DIAG ? target->inv_var : nullptr, D, ivar, a.Dp);
+    cudaMemsetAsync(ws, 0, 14 * CD * sizeof(float), st);
+
+    const dim3 ggrid(a.NT, a.Cp / 128);
+    // p_ <- p_ - k*dH/dtheta(q_) = p_ + k*grad log p(q_)  (k = 0: U-terms of q_ only)
+    auto kick = [&](float* q_, float* qpack_, float* p_, float* ppack_, int k1, float* part) {
+        if (gemm_target) {
+            LinEpi ep = {};
+            ep.X = k1 ? p_ : nullptr; ep.Xpack = k1 ? ppack_ : nullptr; ep.Y = part ? q_ : nullptr; ep.yshift = mean;
+            ep.part = part; ep.eps = eps; ep.k1 = k1; ep.sign = -1.0f;
+            lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, qpack_, precpack, ep);
+        } else {
+            dense_kick_elem_kernel<<<C, 256, 0, st>>>(a, q_, p_, ppack_, eps, k1, 0, part);
+        }
+    };
+    // q_ <- q_ + k*G^-1 p_  [+ k*G^-1 p_]
+    auto drift = [&](float* q_, float* qpack_, float* ppack_, bool twice) {
+        LinEpi ep = {};
+        ep.X = q_; ep.Xpack = gemm_target ? qpack_ : nullptr; ep.shift = mean; ep.eps = eps; ep.k1 = LIN_K_HALF;
+        ep.k2 = twice ? LIN_K_HALF : 0; ep.k2add = 1; ep.sign = 1.0f;
+        lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, ppack_, ginvpack, ep);
+    };
+    auto kinetic = [&](float* kpart) {                                       // p.(G^-1 p)  (:729-730)
+        LinEpi ep = {};
+        ep.Y = P; ep.part = kpart;
+        lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, Ppack, ginvpack, ep);
+    };
+    auto load_q = [&](const float* src) {
+        dense_load_rows_kernel<<<a.Cp, 256, 0, st>>>(src, C, ld, D, Q, a.Cp, a.Dp);
+        if (gemm_target) dense_pack_kernel<<<296, 256, 0, st>>>(Q, mean, a.Cp, a.Dp, TC_M, Qpack);
+    };
+    load_q(q_init);
+    kick(Q, Qpack, P, Ppack, 0, upart);
+    dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_init);
+    load_q(q_cur);
+    kick(Q, Qpack, P, Ppack, 0, upart);
+    dense_store_u_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, upart, r.U_cur);
+    if (it0 == 0 && samples) {                                                      // slot 0 = params_init (:959)
+        cudaMemcpy2DAsync(samples, (size_t)(S - burn) * ld * sizeof(float), q_init, (size_t)ld * sizeof(float),
+                          (size_t)ld * sizeof(float), (size_t)C, cudaMemcpyDeviceToDevice, st);
+    }
+    const bool explicit_int = cfg->integrator == 1;
+    for (int n = it0; n < it1; ++n) {
+        dense_gibbs_kernel<<<C, 256, 0, st>>>(r, n, Q, P, Qpack);
+        {
+            LinEpi ep = {};                                                  // :183-184  p = chol(G) z
+            ep.X = P; ep.Xpack = Ppack; ep.assign = 1; ep.sign = 1.0f;
+            lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, Zpack, cholpack, ep);
+        }
+        kinetic(kpart0);
+        if (explicit_int) {
+            cudaMemcpyAsync(Qc, Q, 2 * CD * sizeof(float), cudaMemcpyDeviceToDevice, st);          // theta~, p~ (:425-426)
+            cudaMemcpyAsync(Qcpack, Qpack, 4 * CD * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            for (int l = 0; l < L; ++l) {
+                kick(Q, Qpack, P, Ppack, LIN_K_HALF, nullptr);                                      // A (:429-430)
+                drift(Qc, Qcpack, Pcpack, false);
+                drift(Q, Qpack, Ppack, false);                                                      // B (:432-433)
+                kick(Qc, Qcpack, Pc, Pcpack, LIN_K_HALF, nullptr);
+                dense_rm_bind_kernel<<<C, 256, 0, st>>>(a, cfg->cos_2we, cfg->sin_2we, Q, P, Qc, Pc,  // C (:435-450)
+                                                      gemm_target ? Qpack : nullptr, Ppack, Qcpack, Pcpack);
+                drift(Q, Qpack, Ppack, false);                                                      // B (:454-455)
+                kick(Qc, Qcpack, Pc, Pcpack, LIN_K_HALF, nullptr);
+                kick(Q, Qpack, P, Ppack, LIN_K_HALF, upart);                                        // A (:457-458)
+                drift(Qc, Qcpack, Pcpack, false);
+            }
+        } else {
+            for (int l = 0; l < L; ++l) {
+                kick(Q, Qpack, P, Ppack, LIN_K_HALF, nullptr);                                      // :363
+                drift(Q, Qpack, Ppack, true);                                                       // :364
+                kick(Q, Qpack, P, Ppack, LIN_K_HALF, upart);                                        // :368-383
+            }
+        }
+        kinetic(kpartL);
+        dense_mh_kernel<<<C, 256, 0, st>>>(r, n, Q, P, upart);
     }
     return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;
 }

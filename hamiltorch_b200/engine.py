@@ -265,6 +265,8 @@ class HMCResult:
 
     @property
     def samples(self):
+        if self.samples_padded is None:
+            raise RuntimeError('this run kept no samples (keep_samples=False): use moment_sum / moment_sumsq')
         return self.samples_padded[..., :self.dim]
 
     @property
@@ -275,7 +277,7 @@ class HMCResult:
 def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, inv_mass=None,
             nuts=False, desired_accept_rate=0.8, seed=0, chain_offset=0, normals=None, log_uniforms=None,
             record_ham=False, out=None, device=None, tuning=0, eps_schedule=None, record_eps=False, scheme=None,
-            perms=None):
+            perms=None, thin=1, moments=False, keep_samples=True, host_samples=False):
     """The reference's sample() loop for sampler in {HMC, HMC_NUTS} as one persistent kernel over C chains.
 
     params_init (C, D) | (D,).  Randomness: in-kernel Philox keyed by (seed, chain_offset+c, iteration), or -- when
@@ -285,6 +287,12 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     (N.SCHEME_PLAIN / SPLIT_SYM / SPLIT_RAND / SPLIT_KMID); ``perms`` (S, C, M) injects SPLITTING_RAND's randperm.
     NUTS only: ``eps_schedule`` (S, C) forces the step size of every iteration (parity tests replay the reference's
     schedule); ``record_eps`` returns the kernel's own adapted step sizes in ``result.eps_trace`` (C, S).
+    Sample sink (include/hmcx.h hmcx_sink_t; element-wise targets): ``thin`` keeps every thin-th post-burn state,
+    ``moments`` accumulates per-chain running sum / sum of squares over every post-burn iteration in the kernel's
+    registers (``result.moment_sum``, ``result.moment_sumsq``, ``result.moment_count``), ``keep_samples=False`` stores no
+    samples at all, ``host_samples=True`` makes the kernel stream the retained rows straight into pinned host memory
+    (the reference's ``store_on_GPU=False``, samplers.py:1008-1012) -- ``result.samples`` is then a CPU tensor, valid
+    after a stream synchronisation.
     """
     N.require_cuda()
     lib = N.load_library()
@@ -301,8 +309,20 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     Cn = q_init.shape[0]
     q_cur = q_init.clone()
     eps = _eps_vector(step_size, Cn, device)
-    keep = S - burn
-    if out is None:
+    thin = int(thin)
+    if thin < 1:
+        raise RuntimeError('thin must be >= 1')
+    use_sink = thin > 1 or moments or not keep_samples or host_samples
+    if use_sink and scheme is not None:
+        raise NotImplementedError('the sample sink is implemented for element-wise targets')
+    keep = 1 + (S - burn - 1) // thin
+    if not keep_samples:
+        samples = None
+    elif host_samples:
+        # pinned host memory is device-addressable under unified virtual addressing: the kernel's st.global.cs rows go
+        # over PCIe while the chains keep running (no device-side sample buffer, no separate D2H copy)
+        samples = torch.empty((Cn, keep, ld), dtype=torch.float32, pin_memory=True)
+    elif out is None:
         samples = torch.empty((Cn, keep, ld), dtype=torch.float32, device=device)
     else:
         samples = out
@@ -352,15 +372,29 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
             eps_trace = torch.zeros((Cn, S), dtype=torch.float32, device=device)
             nuts_s.eps_trace = eps_trace.data_ptr()
 
+    msum = msq = None
     with torch.cuda.device(device):
         if scheme is None:
             ws_bytes = lib.hmcx_hmc_workspace_bytes(nt.ref(), nm.ref(), Cn, ld)
             ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=device) if ws_bytes else None
-            rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
-                                  N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),
-                                  N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.ptr(ws),
-                                  N.stream_ptr(device))
-            N.check(rc, 'hmcx_hmc_run')
+            if use_sink:
+                sink = N.SinkStruct()
+                sink.thin = thin
+                if moments:
+                    msum = torch.zeros((Cn, ld), dtype=torch.float32, device=device)
+                    msq = torch.zeros((Cn, ld), dtype=torch.float32, device=device)
+                    sink.sum, sink.sumsq = msum.data_ptr(), msq.data_ptr()
+                rc = lib.hmcx_hmc_run_sink(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init),
+                                           N.ptr(q_cur), N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples),
+                                           N.ptr(accepted), N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected),
+                                           int(tuning), N.ptr(ws), C.byref(sink), N.stream_ptr(device))
+                N.check(rc, 'hmcx_hmc_run_sink')
+            else:
+                rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
+                                      N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),
+                                      N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.ptr(ws),
+                                      N.stream_ptr(device))
+                N.check(rc, 'hmcx_hmc_run')
         else:
             rc = lib.hmcx_split_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), int(scheme), N.ptr(q_init),
                                     N.ptr(q_cur), N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples),
@@ -369,6 +403,11 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
             N.check(rc, 'hmcx_split_run')
     res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
     res.eps_trace = eps_trace
+    res.thin = thin
+    res.moment_sum = None if msum is None else msum[:, :D]
+    res.moment_sumsq = None if msq is None else msq[:, :D]
+    res.moment_count = S - burn - 1
+    res.final_state = q_cur[:, :D]
     if nuts:
         res.eps_bar, res.h_bar = eps_bar, h_bar
     res._keep_alive = keep_alive          # buffers the asynchronous kernel still reads
@@ -409,6 +448,36 @@ def mlp_predict(target, samples, device=None):
         rc = lib.hmcx_mlp_predict(nt.ref(), N.ptr(sd), S, ld, N.ptr(pred), N.ptr(lp), N.stream_ptr(device))
     N.check(rc, 'hmcx_mlp_predict')
     return pred, lp
+
+
+def const_metric(target, softabs, softabs_const):
+    """The metric of a Gaussian target without jitter is one matrix: evaluate it ONCE on the host with the reference's
+    own torch ops (fisher, samplers.py:108-121: autograd Hessian of the descriptor, eigh + coth map for SOFTABS) and
+    derive what the kernels consume: G^-1 (the metric solve of cholesky_inverse :146-148 as a matrix), chol(G) (gibbs
+    :183-184 through MultivariateNormal's scale_tril) and log det G (:726 / :728)."""
+    D = target.dim
+    hess = torch.autograd.functional.hessian(target, torch.zeros(D), create_graph=False)
+    fish = -hess
+    if softabs:
+        lam, vec = torch.linalg.eigh(fish, UPLO='L')
+        abs_lam = (1. / torch.tanh(softabs_const * lam)) * lam
+        fish = torch.matmul(vec, torch.matmul(abs_lam.diag(), vec.t()))
+        log_det = float(abs_lam.log().sum())
+    else:
+        log_det = float(torch.slogdet(fish)[1])
+    lower = torch.linalg.cholesky(fish)
+    ginv = torch.cholesky_inverse(lower.double()).float()        # (L L^T)^-1 from the reference's fp32 factor
+    return ginv.contiguous(), lower.contiguous(), log_det
+
+
+def _rmhmc_is_dense(target, jitter):
+    """Gaussian targets without jitter have a constant metric: the tensor-core path (any D).  GaussianIso / GaussianDiag
+    at D <= 16 stay on the thread-per-chain kernel (which also handles jitter)."""
+    if jitter is not None:
+        return False
+    if isinstance(target, T.GaussianFull):
+        return True
+    return isinstance(target, (T.GaussianIso, T.GaussianDiag)) and target.dim > 16
 
 
 def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, jitter=None,
@@ -475,10 +544,23 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
     else:
         rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
     with torch.cuda.device(device):
-        rc = lib.hmcx_rmhmc_run(nt.ref(), C.byref(cfg), C.byref(rng), N.ptr(q_init), N.ptr(q_cur), N.ptr(eps), Cn, ld,
-                                L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted), N.ptr(diverged), N.ptr(ham),
-                                N.ptr(num_rejected), N.stream_ptr(device))
-    N.check(rc, 'hmcx_rmhmc_run')
+        if _rmhmc_is_dense(nt.target, jitter):
+            ginv, lower, log_det = const_metric(nt.target, softabs, softabs_const)
+            gm = N.ConstMetricStruct()
+            ginv_d, lower_d = ginv.to(device), lower.to(device)
+            gm.metric_inv, gm.metric_chol, gm.log_det = ginv_d.data_ptr(), lower_d.data_ptr(), log_det
+            ws = torch.empty(lib.hmcx_rmhmc_dense_workspace_bytes(Cn, D) // 4, dtype=torch.float32, device=device)
+            keep_alive += [ginv_d, lower_d, ws]
+            rc = lib.hmcx_rmhmc_dense_run(nt.ref(), C.byref(cfg), C.byref(gm), C.byref(rng), N.ptr(q_init),
+                                          N.ptr(q_cur), N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples),
+                                          N.ptr(accepted), N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected),
+                                          N.ptr(ws), N.stream_ptr(device))
+            N.check(rc, 'hmcx_rmhmc_dense_run')
+        else:
+            rc = lib.hmcx_rmhmc_run(nt.ref(), C.byref(cfg), C.byref(rng), N.ptr(q_init), N.ptr(q_cur), N.ptr(eps), Cn,
+                                    ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted), N.ptr(diverged), N.ptr(ham),
+                                    N.ptr(num_rejected), N.stream_ptr(device))
+            N.check(rc, 'hmcx_rmhmc_run')
     res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
     res.eps_trace = None
     res._keep_alive = keep_alive

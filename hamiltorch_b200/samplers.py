@@ -200,7 +200,14 @@ def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, 
     res = _run_chains(log_prob_func, params_init.unsqueeze(0), num_samples, num_steps_per_sample, step_size, burn,
                       jitter, inv_mass, softabs_const, explicit_binding_const, fixed_point_threshold,
                       fixed_point_max_iterations, jitter_max_tries, sampler, integrator, metric,
-                      desired_accept_rate, rng=rng, seed=seed, record_ham=(debug == 1))
+                      desired_accept_rate, rng=rng, seed=seed, record_ham=(debug == 1),
+                      sink=dict(host_samples=True) if (
+                          not store_on_GPU and sampler in (Sampler.HMC, Sampler.HMC_NUTS) and
+                          isinstance(log_prob_func, (T.GaussianIso, T.GaussianDiag)) and
+                          integrator not in _SPLIT_INTEGRATORS and
+                          not (torch.is_tensor(inv_mass) and inv_mass.dim() == 2)) else None)
+    if not res.samples_padded.is_cuda:
+        torch.cuda.current_stream().synchronize()       # the kernel wrote the samples into pinned host memory
     nuts = sampler == Sampler.HMC_NUTS
     out_dev = params_init.device if store_on_GPU else torch.device('cpu')
     samples = res.samples[0].to(out_dev)
@@ -229,7 +236,8 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                   fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, jitter_max_tries=10,
                   sampler=Sampler.HMC, integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN,
                   desired_accept_rate=0.8, rng='philox', seed=0, chain_offset=0, normals=None, log_uniforms=None,
-                  record_ham=False, out=None, perms=None, uniforms=None):
+                  record_ham=False, out=None, perms=None, uniforms=None, thin=1, moments=False, keep_samples=True,
+                  store_on_GPU=True):
     """The engine's native entry: C independent chains at once.  ``params_init`` is (C, D); every chain gets the
     reference's ``sample`` semantics.  Returns an ``engine.HMCResult`` whose ``.samples`` is (C, S-burn, D) on the
     GPU (row c = what ``sample`` would have returned for chain c, stacked).
@@ -240,6 +248,12 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                   ``perms`` (S, C, M)).
     ``log_prob_func`` may be a Gaussian / funnel descriptor, an ``MLPRegression`` (sample_model) or the list of split
     descriptors ``define_split_model_log_prob`` returns (with a SPLITTING integrator).
+
+    Sample sink (plain HMC / HMC_NUTS on GaussianIso / GaussianDiag): ``thin`` keeps every thin-th post-burn state;
+    ``moments=True`` returns per-chain running sums / sums of squares over all post-burn iterations
+    (``.moment_sum``, ``.moment_sumsq``, ``.moment_count``); ``keep_samples=False`` stores no samples;
+    ``store_on_GPU=False`` (the reference's flag, samplers.py:1008-1012) streams the retained samples from the kernel
+    straight into pinned host memory: ``.samples`` is then a CPU tensor (synchronise the stream before reading).
     """
     if params_init.dim() != 2:
         raise RuntimeError('sample_chains: params_init must be (num_chains, D)')
@@ -250,15 +264,22 @@ def sample_chains(log_prob_func, params_init, num_samples=10, num_steps_per_samp
                        fixed_point_max_iterations, jitter_max_tries, sampler, integrator, metric,
                        desired_accept_rate, rng=rng, seed=seed, chain_offset=chain_offset, normals=normals,
                        log_uniforms=log_uniforms, record_ham=record_ham, out=out, injected_perms=perms,
-                       injected_uniforms=uniforms)
+                       injected_uniforms=uniforms,
+                       sink=dict(thin=thin, moments=moments, keep_samples=keep_samples, host_samples=not store_on_GPU))
 
 
 def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_mass, softabs_const,
                 explicit_binding_const, fixed_point_threshold, fixed_point_max_iterations, jitter_max_tries,
                 sampler, integrator, metric, desired_accept_rate, rng='philox', seed=None, chain_offset=0,
                 normals=None, log_uniforms=None, record_ham=False, out=None, injected_perms=None,
-                injected_uniforms=None):
+                injected_uniforms=None, sink=None):
     nuts = sampler == Sampler.HMC_NUTS
+    sink = sink or {}
+    if (sink.get('thin', 1) != 1 or sink.get('moments') or not sink.get('keep_samples', True) or
+            sink.get('host_samples')) and not (sampler in (Sampler.HMC, Sampler.HMC_NUTS) and
+                                               isinstance(log_prob_func, (T.GaussianIso, T.GaussianDiag)) and
+                                               integrator not in _SPLIT_INTEGRATORS):
+        raise NotImplementedError('thin / moments / keep_samples / store_on_GPU=False: plain HMC on element-wise targets')
     if nuts:
         sampler = Sampler.HMC                                                     # :932-936
     if sampler == Sampler.HMC and integrator not in _SPLIT_INTEGRATORS:
@@ -284,7 +305,7 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
         return engine.hmc_run(log_prob_func, q0, num_samples, L, step_size, burn=burn, inv_mass=inv_mass, nuts=nuts,
                               desired_accept_rate=desired_accept_rate, seed=seed or 0, chain_offset=chain_offset,
                               normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out,
-                              scheme=N.SCHEME_PLAIN if isinstance(log_prob_func, T.MLPRegression) else None)
+                              scheme=N.SCHEME_PLAIN if isinstance(log_prob_func, T.MLPRegression) else None, **sink)
     if sampler == Sampler.HMC:
         if type(log_prob_func) is not list:
             raise RuntimeError('For splitting log_prob_func must be list of functions')            # :466-467
@@ -321,8 +342,14 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
                               normals=normals, log_uniforms=log_uniforms, record_ham=record_ham, out=out,
                               scheme=scheme, perms=perms)
     if sampler == Sampler.RMHMC and integrator in (Integrator.EXPLICIT, Integrator.IMPLICIT):
-        if isinstance(log_prob_func, list) or not isinstance(log_prob_func, (T.Funnel, T.GaussianIso, T.GaussianDiag)):
-            raise NotImplementedError('RMHMC needs closed-form third derivatives: Funnel / GaussianIso / GaussianDiag')
+        if isinstance(log_prob_func, list) or not isinstance(log_prob_func, (T.Funnel, T.GaussianIso, T.GaussianDiag,
+                                                                             T.GaussianFull)):
+            raise NotImplementedError('RMHMC needs closed-form third derivatives: Funnel / Gaussian descriptors')
+        if isinstance(log_prob_func, T.GaussianFull) and jitter is not None:
+            raise NotImplementedError('GaussianFull under RMHMC runs on the constant-metric tensor-core path: jitter=None')
+        if not isinstance(log_prob_func, T.GaussianFull) and log_prob_func.dim > 16 and \
+                (isinstance(log_prob_func, T.Funnel) or jitter is not None):
+            raise NotImplementedError('RMHMC at D > 16: Gaussian targets with jitter=None (constant metric, tensor cores)')
         if metric not in (Metric.HESSIAN, Metric.SOFTABS):
             raise NotImplementedError('Metric.JACOBIAN_DIAG is out of scope (experimental in the reference)')
         if inv_mass is not None:

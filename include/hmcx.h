@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HMCX_ABI_VERSION 3
+#define HMCX_ABI_VERSION 4
 
 #define HMCX_MLP_TC_AUTO 0
 #define HMCX_MLP_TC_OFF  1
@@ -270,6 +270,64 @@ int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t 
  * matrices at large D (grad log p of ALL chains = -(Q - mu) P: M = chains, N = K = D; samplers.py:294, :812).
  */
 int hmcx_gemm_nt_tf32x3(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, void* stream);
+
+/*
+ * Constant-metric RMHMC on the tensor cores.  For Gaussian targets without jitter the metric of samplers.py:69-127
+ * (G = -Hessian, or its softabs map V diag(lambda coth(alpha lambda)) V^T) is one matrix for every chain and every
+ * point, so the flows of the explicit (:427-458) and implicit (:363-386) integrators are (chains x D).(D x D)
+ * contractions: dH/dp = G^-1 p (the metric solve of cholesky_inverse, :130-149) and dH/dtheta = P (theta - mu).
+ * The caller evaluates, once, with the reference's own torch ops:
+ *   metric_inv  [D,D]  G^-1        metric_chol [D,D]  lower Cholesky factor of G (gibbs :183-184)
+ *   log_det            log det G   (sum log lambda~ for SOFTABS :726, slogdet for HESSIAN :728)
+ */
+typedef struct hmcx_const_metric {
+    const float* metric_inv;
+    const float* metric_chol;
+    float log_det;
+} hmcx_const_metric_t;
+
+size_t hmcx_rmhmc_dense_workspace_bytes(int32_t C, int32_t D);
+
+/*
+ * hmcx_rmhmc_dense_run == the sample() loop for sampler=RMHMC (as hmcx_rmhmc_run) for targets GAUSS_ISO / GAUSS_DIAG /
+ * GAUSS_FULL of ANY dimension with cfg->jitter < 0 (None): every flow is a tcgen05 GEMM over all chains (3xTF32,
+ * operands packed for 1-D bulk TMA), 8 per explicit leapfrog step.  workspace: hmcx_rmhmc_dense_workspace_bytes().
+ */
+int hmcx_rmhmc_dense_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_const_metric_t* metric,
+                         const hmcx_rng_t* rng, const float* q_init, float* q_cur, const float* eps,
+                         int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
+                         int32_t iter_begin, int32_t iter_end,
+                         float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                         int32_t* num_rejected, float* workspace, void* stream);
+
+/*
+ * Sample sink -- what consumes the retained samples (the store_on_GPU=False contract of samplers.py:1008-1012 and the
+ * step after the path), for runs whose C*S*D exceeds what the caller wants to keep:
+ *   thin   keep every thin-th post-burn iteration: samples_out is [C, 1 + (num_samples-burn-1)/thin, ld], slot 0 =
+ *          params_init, slot j = the chain state after iteration burn + j*thin  (thin = 1: the reference's list)
+ *   sum, sumsq   optional [C, ld] in/out accumulators: running sum / sum of squares of the chain state over EVERY
+ *          iteration n > burn (= elements 1.. of the reference's returned list), so posterior means and variances
+ *          need no sample storage at all (samples_out may then be NULL).  fp32; accumulate windows of iterations
+ *          (iter_begin/iter_end) and combine in higher precision for very long runs.
+ * samples_out may point to device-mapped pinned HOST memory: the kernel's retained-row stores are coalesced 16-byte
+ * streaming stores (st.global.cs), which is how samples leave the GPU while the chains keep running.
+ */
+typedef struct hmcx_sink {
+    int32_t thin;
+    float*  sum;
+    float*  sumsq;
+} hmcx_sink_t;
+
+/* hmcx_hmc_run with a sample sink (sink == NULL or {1, NULL, NULL}: identical to hmcx_hmc_run).  Element-wise
+ * targets (GAUSS_ISO / GAUSS_DIAG, mass none / diagonal, ld <= 4096); other combinations return HMCX_ERR_UNSUPPORTED
+ * when the sink asks for thinning or moments. */
+int hmcx_hmc_run_sink(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
+                      const hmcx_nuts_t* nuts,
+                      const float* q_init, float* q_cur, float* eps,
+                      int32_t C, int32_t ld, int32_t L, int32_t num_samples, int32_t burn,
+                      int32_t iter_begin, int32_t iter_end,
+                      float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
+                      int32_t* num_rejected, int32_t tuning, float* workspace, const hmcx_sink_t* sink, void* stream);
 
 #ifdef __cplusplus
 }

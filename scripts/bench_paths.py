@@ -93,13 +93,6 @@ def cfg3():
                 accept=float(res.accepted.float().mean()))
 
 
-if __name__ == '__main__':
-    torch.set_num_threads(1)
-    for f in (cfg5, cfg4, cfg3):
-        print(json.dumps(f()), flush=True)
-    print(json.dumps(cfg4(C=8)), flush=True)
-
-
 def dense(C=256, D=1024, S=20, L=10):
     """Full-covariance Gaussian on the tcgen05 path: one GEMM (C x D) . (D x D) per leapfrog step."""
     g = torch.Generator().manual_seed(3)
@@ -117,3 +110,86 @@ def dense(C=256, D=1024, S=20, L=10):
     return dict(config='dense: GaussianFull D=%d, %d chains, L=%d, S=%d (tcgen05 3xTF32)' % (D, C, L, S), ms=ms,
                 chain_steps_per_s=C * S * L / (ms * 1e-3), algorithmic_tflops=flops / (ms * 1e-3) / 1e12,
                 cpu_port_1core_chain_steps_per_s=cpu, accept=float(res.accepted.float().mean()))
+
+
+def _spd(D, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5
+    return A @ A.t() + 0.5 * torch.eye(D, dtype=torch.float64)
+
+
+def fullmass(C=256, D=1024, S=10, L=10, full_target=False):
+    """2-D inv_mass at scale (samplers.py:199, :294, :812): momentum refresh, every drift and both kinetic energies as
+    tcgen05 GEMMs; a GaussianFull target adds the gradient GEMM."""
+    tgt = T.GaussianFull(torch.zeros(D), cov=_spd(D, 3)) if full_target else T.GaussianIso(D)
+    im = _spd(D, 4).float()
+    init = torch.randn(C, D, generator=torch.Generator().manual_seed(5))
+    ms, res = timed(lambda: hb.sample_chains(tgt, init.cuda(), num_samples=S, num_steps_per_sample=L, step_size=0.1,
+                                             inv_mass=im, rng='philox', seed=5), reps=2)
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    O.sample_hmc(tgt, init[0], num_samples=5, num_steps_per_sample=L, step_size=0.1, inv_mass=im)
+    cpu = 5 * L / (time.perf_counter() - t0)
+    gemms = (2 * L + 4) if full_target else (L + 3)
+    flops = 2.0 * C * D * D * gemms * S
+    return dict(config='full inv_mass: %s D=%d, %d chains, L=%d, S=%d (%d tcgen05 GEMMs per iteration)' % (
+        type(tgt).__name__, D, C, L, S, gemms), ms=ms, chain_steps_per_s=C * S * L / (ms * 1e-3),
+        algorithmic_tflops=flops / (ms * 1e-3) / 1e12, cpu_port_1core_chain_steps_per_s=cpu,
+        accept=float(res.accepted.float().mean()))
+
+
+def rmhmc_dense(C=512, D=64, S=20, L=10, cpu_iters=2):
+    """the 'D=64 Gaussian-Hessian variant' of config 3 (and larger D): explicit RMHMC with the constant
+    metric G = P; 8 GEMMs per leapfrog step, the metric solve G^-1 p among them."""
+    tgt = T.GaussianFull(torch.zeros(D), cov=_spd(D, 3))
+    init = torch.randn(C, D, generator=torch.Generator().manual_seed(5))
+    kw = dict(num_steps_per_sample=L, step_size=0.1, explicit_binding_const=10)
+    ms, res = timed(lambda: hb.sample_chains(tgt, init.cuda(), num_samples=S, sampler=hb.Sampler.RMHMC,
+                                             integrator=hb.Integrator.EXPLICIT, metric=hb.Metric.HESSIAN,
+                                             rng='philox', seed=2, **kw), reps=2)
+    cpu = None
+    if cpu_iters:
+        torch.manual_seed(0)
+        t0 = time.perf_counter()
+        R.sample_rmhmc(tgt, init[0], num_samples=cpu_iters, integrator=R.EXPLICIT, metric=R.HESSIAN, **kw)
+        cpu = cpu_iters * L / (time.perf_counter() - t0)
+    flops = 2.0 * C * D * D * (8 * L + 3) * S
+    return dict(config='explicit RMHMC, GaussianFull D=%d (Hessian metric, jitter None), %d chains, L=%d, S=%d' % (D, C, L, S),
+                ms=ms, chain_steps_per_s=C * S * L / (ms * 1e-3), algorithmic_tflops=flops / (ms * 1e-3) / 1e12,
+                cpu_port_1core_chain_steps_per_s=cpu, accept=float(res.accepted.float().mean()))
+
+
+def saturation():
+    """SURVEY 8d saturation sweep of the persistent plain-HMC kernel: D=1024 isotropic Gaussian, C chains, L in {1, 10};
+    S sized so that the retained samples stay below 8 GiB.  Rows with C=256 are BASELINE config 2's shape."""
+    D, rows = 1024, []
+    for C in (256, 1024, 4096, 16384, 65536):
+        for L in (1, 10):
+            S = max(8, min(1000, (8 << 30) // (C * D * 4)))
+            out = torch.empty((C, S, D), dtype=torch.float32, device='cuda')
+            init = torch.zeros(C, D, device='cuda')
+            ms, res = timed(lambda: hb.sample_chains(T.GaussianIso(D), init, num_samples=S, num_steps_per_sample=L,
+                                                     step_size=0.05, rng='philox', seed=1, out=out), reps=2)
+            rows.append(dict(config='saturation: D=1024 iso, C=%d, L=%d, S=%d' % (C, L, S), ms=ms,
+                             chain_steps_per_s=C * S * L / (ms * 1e-3),
+                             sample_write_gbs=C * S * D * 4 / (ms * 1e-3) / 1e9,
+                             streaming_equiv_gbs=C * S * L * 16 * D / (ms * 1e-3) / 1e9))
+            del out
+    return rows
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(1)
+    if 'only-new' not in sys.argv:
+        for f in (cfg5, cfg4, cfg3):
+            print(json.dumps(f()), flush=True)
+        print(json.dumps(cfg4(C=8)), flush=True)
+    if 'new' in sys.argv or 'only-new' in sys.argv:
+        print(json.dumps(fullmass()), flush=True)
+        print(json.dumps(fullmass(full_target=True)), flush=True)
+        print(json.dumps(rmhmc_dense()), flush=True)
+        print(json.dumps(rmhmc_dense(C=1024, D=1024, S=4, cpu_iters=0)), flush=True)
+        for r in saturation():
+            print(json.dumps(r), flush=True)
+
+

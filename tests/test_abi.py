@@ -70,7 +70,8 @@ def test_ctypes_struct_layout_matches_the_c_header(tmp_path):
     if gcc is None:
         pytest.skip('gcc not available')
     pairs = {'hmcx_mlp_t': N.MlpStruct, 'hmcx_target_t': N.TargetStruct, 'hmcx_mass_t': N.MassStruct,
-             'hmcx_rng_t': N.RngStruct, 'hmcx_nuts_t': N.NutsStruct, 'hmcx_rmhmc_t': N.RmhmcStruct}
+             'hmcx_rng_t': N.RngStruct, 'hmcx_nuts_t': N.NutsStruct, 'hmcx_rmhmc_t': N.RmhmcStruct,
+             'hmcx_const_metric_t': N.ConstMetricStruct, 'hmcx_sink_t': N.SinkStruct}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hmcx.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))

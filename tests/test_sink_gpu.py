@@ -1,0 +1,65 @@
+"""GPU: the sample sink of the persistent HMC kernel (include/hmcx.h hmcx_sink_t / hmcx_hmc_run_sink): thinning, running
+moments in registers, no-sample runs and the store_on_GPU=False path (kernel streams retained rows into pinned host
+memory).  Everything is checked bit-exactly against the plain run of the same chains (same Philox stream)."""
+import pytest
+import torch
+
+import hamiltorch_b200 as hb
+from hamiltorch_b200 import targets as T
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(num_samples=50, num_steps_per_sample=4, step_size=0.25, burn=7, rng='philox', seed=21)
+
+
+def _setup(D=300, C=6):
+    g = torch.Generator().manual_seed(3)
+    tgt = T.GaussianDiag(torch.randn(D, generator=g), 0.3 + torch.rand(D, generator=g))
+    init = tgt.mean[None] + 0.3 * torch.randn(C, D, generator=g)
+    im = 0.5 + torch.rand(D, generator=g)
+    return tgt, init, im
+
+
+@pytest.mark.parametrize('nuts', [False, True])
+def test_thinning_and_moments_equal_the_plain_run(nuts):
+    tgt, init, im = _setup()
+    kw = dict(KW, inv_mass=im, sampler=hb.Sampler.HMC_NUTS if nuts else hb.Sampler.HMC)
+    full = hb.sample_chains(tgt, init, **kw)
+    thin = hb.sample_chains(tgt, init, thin=4, moments=True, **kw)
+    none = hb.sample_chains(tgt, init, keep_samples=False, moments=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(thin.accepted, full.accepted) and torch.equal(thin.step_size, full.step_size)
+    assert thin.samples.shape[1] == 1 + (50 - 7 - 1) // 4
+    assert torch.equal(thin.samples, full.samples[:, ::4])
+    # moments: sequential fp32 sums over the reference's returned list minus element 0 (params_init)
+    s = torch.zeros_like(full.samples[:, 0])
+    sq = torch.zeros_like(s)
+    for j in range(1, full.samples.shape[1]):
+        s = s + full.samples[:, j]
+        sq = sq + full.samples[:, j] * full.samples[:, j]
+    assert thin.moment_count == full.samples.shape[1] - 1
+    assert torch.equal(thin.moment_sum, s) and torch.equal(thin.moment_sumsq, sq)
+    assert torch.equal(none.moment_sum, s) and torch.equal(none.moment_sumsq, sq)
+    assert torch.equal(none.final_state, full.samples[:, -1])
+    with pytest.raises(RuntimeError):
+        none.samples
+
+
+def test_store_on_gpu_false_streams_samples_to_pinned_host_memory():
+    tgt, init, im = _setup(D=1024, C=16)
+    full = hb.sample_chains(tgt, init, **KW)
+    host = hb.sample_chains(tgt, init, store_on_GPU=False, **KW)
+    torch.cuda.synchronize()
+    assert not host.samples.is_cuda and host.samples_padded.is_pinned()
+    assert torch.equal(host.samples, full.samples.cpu())
+    # the reference-shaped entry point: list of CPU tensors (samplers.py:1008-1012)
+    torch.manual_seed(0)
+    a = hb.sample(tgt, init[0], num_samples=12, num_steps_per_sample=3, step_size=0.2, store_on_GPU=False, verbose=False)
+    assert len(a) == 12 and all(not t.is_cuda for t in a)
+
+
+def test_sink_is_refused_where_it_is_not_implemented():
+    D = 24
+    cov = torch.eye(D, dtype=torch.float64) * 2
+    with pytest.raises(NotImplementedError):
+        hb.sample_chains(T.GaussianFull(torch.zeros(D), cov=cov), torch.zeros(2, D), num_samples=5, thin=2)

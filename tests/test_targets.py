@@ -71,3 +71,26 @@ def test_funnel_matches_notebook_definition():
         w = torch.randn(D + 1)
         assert abs(float(tgt(w)) - float(funnel_ll(w))) < 1e-4 * (1 + abs(float(tgt(w))))
         torch.testing.assert_close(_autograd(tgt, w), tgt.grad(w), rtol=1e-5, atol=1e-5)
+
+
+def test_const_metric_matches_the_oracle_fisher():
+    """engine.const_metric (host side of the constant-metric RMHMC path) == oracle fisher() at any point for Gaussian
+    targets without jitter, for both metrics; G^-1 and chol(G) are consistent with it."""
+    from hamiltorch_b200 import engine
+    from oracle import rmhmc_oracle as R
+    D = 12
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5
+    cov = A @ A.t() + 0.5 * torch.eye(D, dtype=torch.float64)
+    for tgt in (T.GaussianFull(torch.randn(D, generator=g), cov=cov),
+                T.GaussianDiag(torch.randn(D, generator=g), 0.3 + torch.rand(D, generator=g)), T.GaussianIso(D)):
+        for softabs in (False, True):
+            ginv, lower, log_det = engine.const_metric(tgt, softabs, 0.7)
+            for _ in range(2):
+                q = torch.randn(D, generator=g)
+                fish, lam = R.fisher(q, tgt, None, 0.7, R.SOFTABS if softabs else R.HESSIAN, None)
+                fish = fish.detach()
+                assert torch.allclose(lower @ lower.t(), fish, rtol=1e-5, atol=1e-6)
+                assert torch.allclose(ginv @ fish, torch.eye(D), atol=2e-5)
+                ref_ld = float(lam.log().sum()) if softabs else float(torch.slogdet(fish)[1])
+                assert abs(log_det - ref_ld) <= 1e-5 * (1 + abs(ref_ld))
