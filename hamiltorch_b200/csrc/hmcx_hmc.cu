@@ -210,6 +210,14 @@ hmc_run_kernel(const RunArgs a) {
         }
     }
 
+    // the plain sample() loop stores one row per post-burn iteration: keep a running row pointer (one 64-bit add per
+    // iteration instead of re-deriving the address from n)
+    float* row_ptr = nullptr;
+    if (!SINK && my_samples) {
+        const int first = (a.it0 > a.burn + 1 ? a.it0 : a.burn + 1) - a.burn;
+        row_ptr = my_samples + (size_t)first * ld + E * tid;
+    }
+
     if (a.it0 == 0 && my_samples) {                // ret_params = [params_init] (:959)
 #pragma unroll
         for (int k = 0; k < K; ++k)
@@ -323,10 +331,10 @@ hmc_run_kernel(const RunArgs a) {
                 }
             }
         } else if (n > a.burn && my_samples) {
-            float* dst = my_samples + (size_t)(n - a.burn) * ld;
 #pragma unroll
             for (int k = 0; k < K; ++k)
-                if (live[k]) stE_stream<E>(dst + E * (tid + k * G), qc[k]);
+                if (live[k]) stE_stream<E>(row_ptr + E * k * G, qc[k]);
+            row_ptr += ld;
         }
         if (tid == 0) {
             const size_t o = (size_t)c * a.S + n;

@@ -456,8 +456,16 @@ def const_metric(target, softabs, softabs_const):
     derive what the kernels consume: G^-1 (the metric solve of cholesky_inverse :146-148 as a matrix), chol(G) (gibbs
     :183-184 through MultivariateNormal's scale_tril) and log det G (:726 / :728)."""
     D = target.dim
-    hess = torch.autograd.functional.hessian(target, torch.zeros(D), create_graph=False)
-    fish = -hess
+    # -Hessian of the quadratic log-density; what torch.autograd.functional.hessian(target, q) (:108) returns at ANY q
+    # (tests/test_targets.py::test_const_metric_matches_the_oracle_fisher) without its D backward passes
+    if isinstance(target, T.GaussianFull):
+        fish = target.prec.detach().clone()
+    elif isinstance(target, T.GaussianDiag):
+        fish = torch.diag(target.inv_var.detach().to(torch.float32))
+    elif isinstance(target, T.GaussianIso):
+        fish = torch.eye(D, dtype=torch.float32)
+    else:
+        fish = -torch.autograd.functional.hessian(target, torch.zeros(D), create_graph=False)
     if softabs:
         lam, vec = torch.linalg.eigh(fish, UPLO='L')
         abs_lam = (1. / torch.tanh(softabs_const * lam)) * lam
