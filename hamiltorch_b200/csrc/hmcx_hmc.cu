@@ -103,7 +103,10 @@ __device__ __forceinline__ void trajectory(float* q, float* p, const VecConst<E>
         }
     };
     int l = 0;
-    for (; l + 2 <= L; l += 2) { one_step(l); one_step(l + 1); }             // halve the loop overhead
+#pragma unroll 1
+    for (; l + 2 <= L; l += 2) { one_step(l); one_step(l + 1); }             // halve the loop overhead; no deeper
+                                                                             // unrolling: the sample() loop body must stay
+                                                                             // inside the instruction cache
     if (l < L) one_step(l);
 #pragma unroll
     for (int j = 0; j < E; ++j) p[j] = sub(p[j], mul(half, g[j]));           // :302
@@ -147,16 +150,46 @@ struct RunArgs {
     float* msumsq;
 };
 
+// block_sum3 for CTAs of at most 8 warps: the second level reads the warps' partials with broadcast LDS.128 and adds them
+// in warp order (3 independent 8-term chains) instead of a second shuffle butterfly: ~90 cycles less latency on the
+// per-iteration critical path, same instruction count, every thread ends with the same bits.
+// `sbuf` holds 4*8+1 floats; callers alternate between two buffers on consecutive calls.
+__device__ __forceinline__ void block_sum3_small(float& a, float& b, float& c, float& extra, float* sbuf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    if (nwarp == 1) {
+        warp_sum3(a, b, c, true);
+        extra = __shfl_sync(0xffffffffu, extra, 0);
+        return;
+    }
+    warp_sum3(a, b, c, false);
+    if ((lane & 7) == 0 && lane < 24) sbuf[4 * warp + (lane >> 3)] = a;
+    if (threadIdx.x == 0) sbuf[32] = extra;
+    __syncthreads();
+    float4 v = *reinterpret_cast<const float4*>(sbuf);
+    a = v.x; b = v.y; c = v.z;
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+        if (w < nwarp) {
+            v = *reinterpret_cast<const float4*>(sbuf + 4 * w);
+            a = add(a, v.x); b = add(b, v.y); c = add(c, v.z);
+        }
+    }
+    extra = sbuf[32];
+}
+
 constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * K <= 8 ? 512 : 256); }
 
 // MAXT = CTA size the instantiation is compiled for (register budget 64K/MAXT): chains of D <= 1024 run with <= 256
 // threads and get a generous budget, which lets the compiler software-pipeline the next iteration's RNG.
 // SINK = true adds the sample sink to the bookkeeping step (thinned stores, register-resident moment accumulators); it is
 // a separate instantiation so that the plain sample() loop keeps its register allocation and schedule.
-template <int TK, int MK, int E, int K, int MAXT, bool SINK = false>
+// PHILOX = true compiles the in-kernel counter RNG branch-free (no memory access, so dead lanes just compute and are
+// masked): the Philox / Box-Muller arithmetic of iteration n+1 and the shuffle chain of iteration n's reduction then
+// sit in one basic block and the scheduler interleaves them.
+template <int TK, int MK, int E, int K, int MAXT, bool SINK = false, bool PHILOX = false>
 __global__ void __launch_bounds__(MAXT)
 hmc_run_kernel(const RunArgs a) {
-    __shared__ float s_red[2][100];
+    __shared__ __align__(16) float s_red[2][100];
     __shared__ float s_eps[2];
 
     const int c = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
@@ -233,7 +266,9 @@ hmc_run_kernel(const RunArgs a) {
             const int grp = tid + k * G, e0 = E * grp;
 #pragma unroll
             for (int j = 0; j < E; ++j) zn[k][j] = 0.0f;
-            if (live[k]) {
+            if (PHILOX) {
+                philox_normals<E>(a.seed, chain_id, (uint64_t)n, (uint32_t)grp, zn[k]);
+            } else if (live[k]) {
                 if (a.rng_mode == HMCX_RNG_INJECTED) ldE_stream<E>(a.normals + ((size_t)(n - a.it0) * t.C + c) * ld + e0, zn[k]);
                 else philox_normals<E>(a.seed, chain_id, (uint64_t)n, (uint32_t)grp, zn[k]);
             }
@@ -244,9 +279,26 @@ hmc_run_kernel(const RunArgs a) {
     };
     if (a.it0 < a.it1) draw(a.it0);
 
+    // the MH test's log-uniforms: warp 0 produces them 32 iterations at a time, lane l for iteration n+l, so the ~70
+    // dependent instructions of Philox + logf leave the per-iteration critical path (every other warp waits for warp 0 at
+    // the reduction's barrier) and cost 1/32 of the issue slots
+    float logu_lanes = 0.0f;
+    const bool warp0 = tid < 32;
+
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
         const float half = mul(0.5f, eps);
+        // the iteration's log-uniform (warp 0; rides the reduction's shared buffer)
+        float logu = 0.0f;
+        if (warp0) {
+            const int phase = (n - a.it0) & 31;
+            if (phase == 0) {
+                const int m = n + tid;
+                if (a.rng_mode == HMCX_RNG_INJECTED) logu_lanes = m < a.it1 ? a.logu[(size_t)(m - a.it0) * t.C + c] : 0.0f;
+                else logu_lanes = philox_log_uniform(a.seed, chain_id, (uint64_t)m);
+            }
+            logu = __shfl_sync(0xffffffffu, logu_lanes, phase);
+        }
         // ---- gibbs (:969): p = z (*sqrt(mass)) ----
         float kin0 = 0.0f;
 #pragma unroll
@@ -271,13 +323,11 @@ hmc_run_kernel(const RunArgs a) {
                 r1 = add(r1, uterm1<TK>(q[k][j], vc[k].mean[j], vc[k].ivar[j]));
                 r2 = add(r2, kterm1<MK>(p[k][j], vc[k].im[j]));
             }
-        if (n + 1 < a.it1) draw(n + 1);                       // next iteration's normals: independent work for the scheduler
-        // the iteration's log-uniform is produced once (thread 0) and rides the reduction's shared buffer
-        float logu = 0.0f;
-        if (tid == 0)
-            logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * t.C + c]
-                                                     : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
-        block_sum3(r0, r1, r2, logu, s_red[n & 1]);
+        // next iteration's normals: independent work.  In Philox mode the draw is branch-free and unconditional (one
+        // unused draw after the last iteration) so that it shares a basic block with the reduction's shuffle chain.
+        if (PHILOX || n + 1 < a.it1) draw(n + 1);
+        if (MAXT <= 256) block_sum3_small(r0, r1, r2, logu, s_red[n & 1]);
+        else block_sum3(r0, r1, r2, logu, s_red[n & 1]);
         const float lp_new = log_prob_from_sum(r1, t.log_norm);
         const float h_old = add(-lp_cur, mul(0.5f, r0));                     // potential + kinetic (:815)
         const float h_new = add(-lp_new, mul(0.5f, r2));
@@ -756,10 +806,13 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
         return cuda_status();
     }
     if (!pick_geometry(ld, tuning, E, K, G)) return tuning ? HMCX_ERR_INVALID_ARG : HMCX_ERR_UNSUPPORTED;
+    const bool philox = a.rng_mode == HMCX_RNG_PHILOX;
 #define CALL(TK, MK)                                                                                    \
     if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1, 1024><<<C, G, 0, st>>>(a);                       \
     else if (E == 2) hmc_run_kernel<TK, MK, 2, 2, 1024><<<C, G, 0, st>>>(a);                            \
+    else if (K == 1 && G <= 256 && philox) hmc_run_kernel<TK, MK, 4, 1, 256, false, true><<<C, G, 0, st>>>(a); \
     else if (K == 1 && G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256><<<C, G, 0, st>>>(a);                 \
+    else if (K == 1 && philox) hmc_run_kernel<TK, MK, 4, 1, 1024, false, true><<<C, G, 0, st>>>(a);     \
     else if (K == 1) hmc_run_kernel<TK, MK, 4, 1, 1024><<<C, G, 0, st>>>(a);                            \
     else if (K == 2) hmc_run_kernel<TK, MK, 4, 2, 512><<<C, G, 0, st>>>(a);                             \
     else hmc_run_kernel<TK, MK, 4, 4, 256><<<C, G, 0, st>>>(a)

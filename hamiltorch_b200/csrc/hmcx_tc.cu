@@ -13,10 +13,24 @@
 //     tcgen05.ld (32x32b.x32: warp w owns TMEM lanes 32w..32w+31) and stores rows to global memory.
 // Descriptor encodings follow the CUTLASS sm100 definitions (cute/arch/mma_sm100_desc.hpp: SmemDescriptor,
 // InstrDescriptor) -- re-derived here, no CUTLASS code is used.
+#include <cstdlib>
 #include "hmcx_common.cuh"
 #include "hmcx_umma.cuh"
 
 namespace hmcx {
+
+// 32 lanes x 32 columns of the accumulator: thread (lane) <-> TMEM lane, register i <-> column i; waits for the data
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 constexpr int TC_M = 128, TC_N = 128, TC_KC = 32;        // CTA tile and K chunk (fp32 elements)
 constexpr int TC_THREADS = 128;
@@ -104,15 +118,7 @@ gemm_nt_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, 
     for (int c0 = 0; c0 < TC_N; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(taddr, v);
         if (row < M) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -190,6 +196,47 @@ __global__ void dense_pack_kernel(const float* __restrict__ src, const float* __
 __host__ __device__ constexpr int dense_stages(int BN) { return BN == 128 ? 3 : 4; }
 __host__ __device__ constexpr int dense_stage_floats(int BN) { return 2 * TC_M * TC_KC + 2 * BN * TC_KC; }
 
+// Programmatic dependent launch: the step-synchronous dense paths are chains of short GEMM launches on one stream.  Each
+// kernel lets its successor start launching at once (griddepcontrol.launch_dependents) and itself waits for its
+// predecessor's completion + memory flush (griddepcontrol.wait) only after its prologue (mbarrier init, TMEM allocation),
+// so launch latency and prologue overlap the previous kernel's main loop and epilogue.  All global reads and writes of a
+// kernel come after its wait.  HMCX_PDL=0 in the environment falls back to plain stream order.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("HMCX_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Prologue shared by the dense kernels: mbarrier ring + accumulator columns in tensor memory (warp 0 allocates).
+template <int BN, int ST>
+__device__ __forceinline__ uint32_t dense_prologue(uint64_t* s_full, uint64_t* s_empty, uint64_t* s_done, uint32_t* s_tmem) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+        mbar_init(smem_u32(s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(BN < 32 ? 32 : BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *s_tmem;
+}
+
 // The warp-specialised main loop shared by the dense kernels: thread 0 = TMA producer (1-D bulk copies of the packed
 // hi|lo operand blocks into an ST-stage ring), thread 32 = MMA issuer (three tf32 UMMAs per 8-wide k-step: hi*hi +
 // hi*lo + lo*hi, fp32 accumulators in tensor memory), tcgen05.commit releasing stages / signalling `s_done`.
@@ -250,24 +297,14 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float*
     extern __shared__ __align__(1024) float smem[];
     __shared__ __align__(8) uint64_t s_full[ST], s_empty[ST], s_done;
     __shared__ uint32_t s_tmem;
+    pdl_launch_dependents();
     const int tile_n = blockIdx.x, tile_m = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Dp = a.Dp, kchunks = Dp / TC_KC;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
-        mbar_init(smem_u32(&s_done), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(BN < 32 ? 32 : BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem = dense_prologue<BN, ST>(s_full, s_empty, &s_done, &s_tmem);
 
+    pdl_wait();               // everything above (barriers, TMEM) overlapped the previous launch's tail; its writes are visible now
     dense_mainloop<BN, ST>(smem, s_full, s_empty, &s_done, tmem, QpIn, Ppack, tile_m, tile_n, kchunks);
     // ===== epilogue: acc = ((Q-mu) P)[row, cols]; g = -acc; kick, optional drift (+ packed copy for the next GEMM) =====
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -282,15 +319,7 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float*
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(taddr, v);
         if (live) {
             const int colbase = tile_n * BN + c0;                           // a 32-aligned column block = one K chunk
             float* qp_hi = QpOut + pack_block_base(tile_m, colbase / TC_KC, 0, kchunks, TC_M);
@@ -366,24 +395,14 @@ dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const f
     extern __shared__ __align__(1024) float smem[];
     __shared__ __align__(8) uint64_t s_full[ST], s_empty[ST], s_done;
     __shared__ uint32_t s_tmem;
+    pdl_launch_dependents();
     const int tile_n = blockIdx.x, tile_m = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = Dp / TC_KC;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
-        mbar_init(smem_u32(&s_done), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(BN < 32 ? 32 : BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem = dense_prologue<BN, ST>(s_full, s_empty, &s_done, &s_tmem);
 
+    pdl_wait();
     dense_mainloop<BN, ST>(smem, s_full, s_empty, &s_done, tmem, Apack, Bpack, tile_m, tile_n, kchunks);
 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -398,15 +417,7 @@ dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const f
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(taddr, v);
         if (live) {
             const int colbase = tile_n * BN + c0;                           // a 32-aligned column block = one K chunk
             float* xp_hi = ep.Xpack ? ep.Xpack + pack_block_base(tile_m, colbase / TC_KC, 0, kchunks, TC_M) : nullptr;
@@ -450,9 +461,9 @@ dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const f
 static bool lin_launch(int BN, dim3 grid, cudaStream_t st, int C, int Dp, int NT, const float* Apack, const float* Bpack,
                        const LinEpi& ep) {
     const size_t sm = (size_t)dense_stages(BN) * dense_stage_floats(BN) * sizeof(float);
-    if (BN == 128) dense_lin_kernel<128><<<grid, TC_THREADS, sm, st>>>(C, Dp, NT, Apack, Bpack, ep);
-    else if (BN == 64) dense_lin_kernel<64><<<grid, TC_THREADS, sm, st>>>(C, Dp, NT, Apack, Bpack, ep);
-    else dense_lin_kernel<32><<<grid, TC_THREADS, sm, st>>>(C, Dp, NT, Apack, Bpack, ep);
+    if (BN == 128) launch_pdl(dense_lin_kernel<128>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
+    else if (BN == 64) launch_pdl(dense_lin_kernel<64>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
+    else launch_pdl(dense_lin_kernel<32>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
     return true;
 }
 static bool lin_configure() {
@@ -898,13 +909,13 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     auto step = [&](const float* qin, const float* qpin, float* qout, float* qpout, int mode) -> bool {
         if (a.BN == 128) {
             const size_t sm = (size_t)dense_stages(128) * dense_stage_floats(128) * sizeof(float);
-            dense_step_kernel<128><<<ggrid, TC_THREADS, sm, st>>>(a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            launch_pdl(dense_step_kernel<128>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
         } else if (a.BN == 64) {
             const size_t sm = (size_t)dense_stages(64) * dense_stage_floats(64) * sizeof(float);
-            dense_step_kernel<64><<<ggrid, TC_THREADS, sm, st>>>(a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            launch_pdl(dense_step_kernel<64>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
         } else {
             const size_t sm = (size_t)dense_stages(32) * dense_stage_floats(32) * sizeof(float);
-            dense_step_kernel<32><<<ggrid, TC_THREADS, sm, st>>>(a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            launch_pdl(dense_step_kernel<32>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
         }
         return true;
     };

@@ -282,7 +282,8 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
 
     params_init (C, D) | (D,).  Randomness: in-kernel Philox keyed by (seed, chain_offset+c, iteration), or -- when
     ``normals`` (S, C, D) and ``log_uniforms`` (S, C) are given -- the injected stream (parity mode).
-    ``out``: optional pre-allocated (C, S-burn, ld) fp32 device tensor for the samples.
+    ``out``: optional pre-allocated (C, S-burn, ld) fp32 tensor for the samples: a device tensor, or a PINNED host
+    tensor (the kernel then streams the retained rows straight into it, see ``host_samples``).
     Bayesian-NN targets (an MLPRegression or the list of split descriptors): ``scheme`` selects the integrator
     (N.SCHEME_PLAIN / SPLIT_SYM / SPLIT_RAND / SPLIT_KMID); ``perms`` (S, C, M) injects SPLITTING_RAND's randperm.
     NUTS only: ``eps_schedule`` (S, C) forces the step size of every iteration (parity tests replay the reference's
@@ -312,13 +313,17 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     thin = int(thin)
     if thin < 1:
         raise RuntimeError('thin must be >= 1')
+    if out is not None and not out.is_cuda:
+        if not out.is_pinned():
+            raise RuntimeError('a host `out` buffer must be pinned (page-locked) memory')
+        host_samples = True                        # caller-provided pinned sample block: the kernel streams into it
     use_sink = thin > 1 or moments or not keep_samples or host_samples
     if use_sink and scheme is not None:
         raise NotImplementedError('the sample sink is implemented for element-wise targets')
     keep = 1 + (S - burn - 1) // thin
     if not keep_samples:
         samples = None
-    elif host_samples:
+    elif host_samples and out is None:
         # pinned host memory is device-addressable under unified virtual addressing: the kernel's st.global.cs rows go
         # over PCIe while the chains keep running (no device-side sample buffer, no separate D2H copy)
         samples = torch.empty((Cn, keep, ld), dtype=torch.float32, pin_memory=True)

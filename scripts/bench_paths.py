@@ -1,6 +1,6 @@
 """Secondary measurements (not the driver's bench line): BASELINE configs 3, 4, 5 on one GPU, device-timed with CUDA
 events, next to the oracle port (the reference's algorithm) on one host core for a bounded sample.
-    python scripts/bench_paths.py > profiles/r1_paths.jsonl
+    python scripts/bench_paths.py [base] [dense] [sat] > profiles/<round>_paths.jsonl
 """
 import json
 import os
@@ -180,16 +180,17 @@ def saturation():
 
 if __name__ == '__main__':
     torch.set_num_threads(1)
-    if 'only-new' not in sys.argv:
+    sel = set(sys.argv[1:]) or {'base'}
+    if 'base' in sel:                       # BASELINE configs 5, 4, 3 (+ config 4's per-GPU share on 8 GPUs)
         for f in (cfg5, cfg4, cfg3):
             print(json.dumps(f()), flush=True)
         print(json.dumps(cfg4(C=8)), flush=True)
-    if 'new' in sys.argv or 'only-new' in sys.argv:
+    if 'dense' in sel:                      # tensor-core paths for dense targets / mass matrices / constant metrics
+        print(json.dumps(dense()), flush=True)
         print(json.dumps(fullmass()), flush=True)
         print(json.dumps(fullmass(full_target=True)), flush=True)
         print(json.dumps(rmhmc_dense()), flush=True)
         print(json.dumps(rmhmc_dense(C=1024, D=1024, S=4, cpu_iters=0)), flush=True)
+    if 'sat' in sel:
         for r in saturation():
             print(json.dumps(r), flush=True)
-
-
