@@ -25,7 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, C_PER_GPU, S, L, EPS = 1024, 256, 1000, 10, 0.05
-WARP_INST_PER_LAUNCH = 1092361880          # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
+WARP_INST_PER_LAUNCH = 1088380528          # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
+                                           # (profiles/r1h_prof_hmc_run.summary.txt)
 METRIC = 'leapfrog-steps x chains / sec'
 UNIT = 'chain-steps/s'
 
@@ -321,13 +322,13 @@ def run_b200_arm(args, rank, world, local_rank):
             'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
-                         # profiles/r1a_prof_hmc_run_r1a.summary.txt (2.06 MB read + 990.65 MB written)
-                         'traffic': 992.7e6, 'peak_source': peak_src,
+                         # profiles/r1h_prof_hmc_run.summary.txt (1.15 MB read + 990.76 MB written)
+                         'traffic': 991.9e6, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': t_kernel_ms,
                          'note': 'fused trajectory kernel: L=10 steps per 4*D bytes written, fp32-issue bound by design; '
                                  'see roofline_streaming for the HBM-bound form'},
             # what actually bounds the fused kernel: warp-instruction issue.  Instructions per launch are static for this
-            # geometry (ncu smsp__inst_executed.sum, profiles/r1f_prof_hmc_run.summary.txt); time is measured live.
+            # geometry (ncu smsp__inst_executed.sum, profiles/r1h_prof_hmc_run.summary.txt); time is measured live.
             'roofline_issue': {'bound': 'issue', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>',
                                'warp_instructions_per_launch': WARP_INST_PER_LAUNCH,
                                'achieved': WARP_INST_PER_LAUNCH / (t_kernel_ms * 1e-3) / 1e9,
