@@ -170,18 +170,22 @@ def run_b200_arm(args, rank, world, local_rank):
     q0 = q0_host.to(dev)
     out = torch.empty((C, S, ld), dtype=torch.float32, device=dev)           # 1 GiB: 8x the 126 MB L2
     host_out = torch.empty((C, S, ld), dtype=torch.float32).pin_memory()
-    stats = torch.empty((world, C, 2), dtype=torch.float32, device=dev)
+    stats_local = torch.zeros((max(args.steps, args.warmup, 1), C, 2), dtype=torch.float32, device=dev)
+    stats = torch.empty((world,) + tuple(stats_local.shape), dtype=torch.float32, device=dev)
 
     def step(seed):
         return engine.hmc_run(tgt, q0, S, L, EPS, seed=seed, chain_offset=chain_offset, out=out, device=dev,
                               tuning=int(os.environ.get('HMCX_TUNING', '0')))
 
-    def gather_stats(res):
-        mine = torch.stack([res.num_rejected.float(), res.step_size], 1)
+    def keep_stats(k, res):               # per-chain summary of step k (reject count, final step size), device side
+        stats_local[k, :, 0].copy_(res.num_rejected)
+        stats_local[k, :, 1].copy_(res.step_size)
+
+    def gather_stats():                   # the run's single (tiny) collective: every rank's per-chain summaries
         if world > 1:
-            dist.all_gather_into_tensor(stats.view(-1), mine.view(-1))        # the run's single (tiny) collective
+            dist.all_gather_into_tensor(stats.view(-1), stats_local.view(-1))
         else:
-            stats[0].copy_(mine)
+            stats[0].copy_(stats_local)
 
     def barrier():
         if world > 1:
@@ -190,7 +194,8 @@ def run_b200_arm(args, rank, world, local_rank):
 
     # ---- warm-up ----
     for w in range(args.warmup):
-        gather_stats(step(w))
+        keep_stats(w, step(w))
+    gather_stats()
     barrier()
 
     # ---- device-timed region: EXACTLY K steps, inputs resident in HBM ----
@@ -205,12 +210,13 @@ def run_b200_arm(args, rank, world, local_rank):
         ev[1 + 2 * k].record()
         res = step(100 + k)
         ev[2 + 2 * k].record()
-        gather_stats(res)
+        keep_stats(k, res)
+    gather_stats()
     ev[-1].record()
     barrier()
     t_total_ms = ev[0].elapsed_time(ev[-1])
     t_kernel_ms = sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(args.steps)) / args.steps
-    rejected = stats[..., 0].sum().item()
+    rejected = stats[:, :args.steps, :, 0].sum().item()
 
     # ---- e2e: public API, HOST buffers, H2D of the inputs and D2H of the result inside the timed region ----
     def e2e_step(seed):

@@ -10,6 +10,10 @@ int elem_gibbs(const hmcx_mass_t*, const hmcx_rng_t*, int, int, int, int64_t, fl
 int elem_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*,
                  float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
                  int, float*, const hmcx_sink_t*, cudaStream_t);
+int coupled_leapfrog(const hmcx_target_t*, const hmcx_mass_t*, const float*, const float*, const float*, int, int, int,
+                     float*, float*, float*, float*, cudaStream_t);
+int coupled_hamiltonian(const hmcx_target_t*, const hmcx_mass_t*, const float*, const float*, int, int, float*, uint8_t*,
+                        cudaStream_t);
 size_t dense_rmhmc_workspace_floats(int, int);
 int dense_rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_const_metric_t*, const hmcx_rng_t*,
                     const float*, float*, const float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*,
@@ -62,18 +66,20 @@ int hmcx_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass, const fl
                   const float* eps, int32_t C, int32_t ld, int32_t L, float* q_out, float* p_out, float* q_traj,
                   float* p_traj, void* stream) {
     if (!target) return HMCX_ERR_INVALID_ARG;
-    if (is_elem(target))
+    if (is_elem(target) && !(mass && mass->kind == HMCX_MASS_FULL))
         return hmcx::elem_leapfrog(target, mass, q_in, p_in, eps, C, ld, L, q_out, p_out, q_traj, p_traj,
                                    (cudaStream_t)stream);
-    return HMCX_ERR_UNSUPPORTED;
+    // coupled gradient (GAUSS_FULL, FUNNEL) or full mass matrix: one CTA per chain, any D (hmcx_coupled.cu)
+    return hmcx::coupled_leapfrog(target, mass, q_in, p_in, eps, C, ld, L, q_out, p_out, q_traj, p_traj,
+                                  (cudaStream_t)stream);
 }
 
 int hmcx_hamiltonian(const hmcx_target_t* target, const hmcx_mass_t* mass, const float* q, const float* p,
                      int32_t C, int32_t ld, float* H_out, uint8_t* flags_out, void* stream) {
     if (!target) return HMCX_ERR_INVALID_ARG;
-    if (is_elem(target))
+    if (is_elem(target) && !(mass && mass->kind == HMCX_MASS_FULL))
         return hmcx::elem_hamiltonian(target, mass, q, p, C, ld, H_out, flags_out, (cudaStream_t)stream);
-    return HMCX_ERR_UNSUPPORTED;
+    return hmcx::coupled_hamiltonian(target, mass, q, p, C, ld, H_out, flags_out, (cudaStream_t)stream);
 }
 
 int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_t C, int32_t ld, int64_t iter,

@@ -149,7 +149,9 @@ int         hmcx_abi_version(void);
 const char* hmcx_status_string(int status);
 
 /*
- * hmcx_leapfrog == samplers.leapfrog, plain-HMC branch (samplers.py:269-304) for C chains at once.
+ * hmcx_leapfrog == samplers.leapfrog, plain-HMC branch (samplers.py:269-304) for C chains at once.  Targets GAUSS_ISO /
+ * GAUSS_DIAG / GAUSS_FULL / FUNNEL, mass none / diagonal / full, any D (element-wise cases: the streaming HBM-roofline
+ * kernel; coupled gradients or a full mass matrix: one CTA per chain with the state in shared memory).
  *   q_in, p_in   [C, ld]   start state (not modified)
  *   eps          [C]       per-chain step size
  *   q_out, p_out [C, ld]   state after L steps, p_out with the half-step correction of :302 applied

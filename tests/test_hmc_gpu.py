@@ -321,3 +321,55 @@ def test_large_dimension_streamed_kernel_vs_live_oracle(D):
                          step_size=0.04, rng='philox', seed=1)
     assert 0.8 < float(r.accept_rate.mean()) <= 1.0
     assert abs(float(r.samples[:, 15:].var()) - 1.0) < 0.1         # started in stationarity, must stay there
+
+
+@pytest.mark.parametrize('D', [3, 11, 150])
+def test_standalone_leapfrog_and_hamiltonian_coupled_targets_vs_oracle(D):
+    """samplers.leapfrog / samplers.hamiltonian (the reference's utility entry points) for what is not element-wise:
+    GaussianFull and Funnel targets, and the 2-D inv_mass of :294 / :812, at small and large D (one CTA per chain,
+    hmcx_coupled.cu).  Matrix-vector sums differ from torch.mv in summation order only."""
+    g = torch.Generator().manual_seed(40 + D)
+    A = torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5
+    cov = A @ A.t() + 0.5 * torch.eye(D, dtype=torch.float64)
+    B = torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5
+    im_full = (B @ B.t() + 0.7 * torch.eye(D, dtype=torch.float64)).float()
+    im_diag = 0.5 + torch.rand(D, generator=g)
+    targets = [T.GaussianFull(torch.randn(D, generator=g), cov=cov), T.GaussianDiag(torch.randn(D, generator=g),
+                                                                                   0.3 + torch.rand(D, generator=g))]
+    if D <= 11:
+        targets.append(T.Funnel(D))
+    C, L = 4, 6
+    eps = torch.tensor([0.05, 0.1, 0.02, 0.08])
+    for tgt in targets:
+        for im in (None, im_diag, im_full):
+            if isinstance(tgt, T.GaussianDiag) and (im is None or im.dim() == 1):
+                continue                                # element-wise: covered by the bit-exact tests above
+            q = 0.5 * torch.randn(C, D, generator=g)
+            p = torch.randn(C, D, generator=g)
+            qt, pt = engine.leapfrog(tgt, q, p, L, eps, inv_mass=im, return_trajectory=True)
+            qf, pf = engine.leapfrog(tgt, q, p, L, eps, inv_mass=im)
+            H, flags = engine.hamiltonian(tgt, q, p, inv_mass=im)
+            torch.cuda.synchronize()
+            assert torch.equal(qf, qt[-1]) and torch.equal(pf, pt[-1]) and int(flags.sum()) == 0
+            for c in range(C):
+                oq, op = O.leapfrog_hmc(tgt, q[c], p[c], L, float(eps[c]), im)
+                np.testing.assert_allclose(qt[:, c].cpu().numpy(), torch.stack(oq).detach().numpy(), rtol=2e-4, atol=2e-5)
+                np.testing.assert_allclose(pt[:, c].cpu().numpy(), torch.stack(op).detach().numpy(), rtol=2e-4, atol=2e-4)
+                ref = float(O.hamiltonian_hmc(tgt, q[c], p[c], im))
+                assert abs(float(H[c]) - ref) <= 1e-5 * (1 + abs(ref))
+    # the drop-in wrappers: (D,) in, lists of (D,) out; reversibility (tests/test_util.py:97-110) on a coupled target
+    tgt = targets[0]
+    q0, p0 = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    qs, ps = hb.leapfrog(q0, p0, tgt, steps=8, step_size=0.05, inv_mass=im_full)
+    assert len(qs) == 8 and qs[0].shape == (D,)
+    qb, pb = hb.leapfrog(qs[-1], -ps[-1].clone(), tgt, steps=8, step_size=0.05, inv_mass=im_full)
+    assert torch.allclose(qb[-1], q0, atol=2e-4)
+    assert hb.hamiltonian(q0, p0, tgt, inv_mass=im_full).dim() == 0
+
+
+def test_standalone_hamiltonian_flags_nonfinite_funnel():
+    """A funnel point whose log-density overflows: samplers.hamiltonian raises LogProbError (:783-785)."""
+    tgt = T.Funnel(5)
+    q = torch.tensor([200., 1., 1., 1., 1.])          # exp(200) = inf
+    with pytest.raises(hb.util.LogProbError):
+        hb.hamiltonian(q, torch.zeros(5), tgt)

@@ -63,3 +63,23 @@ def test_sink_is_refused_where_it_is_not_implemented():
     cov = torch.eye(D, dtype=torch.float64) * 2
     with pytest.raises(NotImplementedError):
         hb.sample_chains(T.GaussianFull(torch.zeros(D), cov=cov), torch.zeros(2, D), num_samples=5, thin=2)
+
+
+def test_sink_edge_cases():
+    """burn = S-1 (nothing but params_init is ever retained: zero moment count), thin larger than the run, D % 4 != 0."""
+    g = torch.Generator().manual_seed(9)
+    D, C = 37, 3
+    tgt = T.GaussianDiag(torch.zeros(D), 0.5 + torch.rand(D, generator=g))
+    init = 0.2 * torch.randn(C, D, generator=g)
+    r = hb.sample_chains(tgt, init, num_samples=6, num_steps_per_sample=3, step_size=0.2, burn=5, moments=True, seed=2)
+    torch.cuda.synchronize()
+    assert r.samples.shape == (C, 1, D) and torch.equal(r.samples[:, 0].cpu(), init)
+    assert r.moment_count == 0 and float(r.moment_sum.abs().sum()) == 0.0
+    full = hb.sample_chains(tgt, init, num_samples=12, num_steps_per_sample=3, step_size=0.2, burn=2, seed=2)
+    thin = hb.sample_chains(tgt, init, num_samples=12, num_steps_per_sample=3, step_size=0.2, burn=2, seed=2, thin=50,
+                            moments=True)
+    torch.cuda.synchronize()
+    assert thin.samples.shape == (C, 1, D) and torch.equal(thin.samples[:, 0], full.samples[:, 0])
+    assert torch.allclose(thin.moment_sum, full.samples[:, 1:].sum(1), rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        hb.sample_chains(tgt, init, num_samples=5, thin=0)

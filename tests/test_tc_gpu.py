@@ -164,3 +164,35 @@ def test_full_inv_mass_philox_statistics_d512():
     assert abs(k0.mean().item() / D - 1.0) < 0.05, k0.mean().item()
     v = res.samples[:, S // 2:].cpu().double().var().item()
     assert abs(v - 1.0) < 0.1, v
+
+
+def test_dense_paths_edge_shapes():
+    """Ragged shapes on the tensor-core paths: D = 17 (the smallest dense dimension, padded to one 32-wide K chunk),
+    C = 130 chains (two 128-row tiles, the second almost empty), one iteration, and D = 33 (two chunks, last nearly empty):
+    chain c of the big launch equals the same chain launched alone (rows never interact), decisions equal the oracle's."""
+    import hamiltorch_b200.targets as T
+    from oracle import hmc_oracle as O
+    for D, C in ((17, 130), (33, 3)):
+        tgt = _corr_gaussian(D, 50 + D)
+        im = _spd(D, 60 + D)
+        S, L = 3, 4
+        g = torch.Generator().manual_seed(D)
+        init = tgt.mean[None] + 0.3 * torch.randn(C, D, generator=g)
+        z = torch.randn(S, C, D, generator=g)
+        logu = torch.log(torch.rand(S, C, generator=g))
+        for mass in (None, im):
+            res = engine.hmc_run(tgt, init, S, L, 0.2, inv_mass=mass, normals=z, log_uniforms=logu, record_ham=True)
+            torch.cuda.synchronize()
+            for c in (0, C - 1):
+                one = engine.hmc_run(tgt, init[c:c + 1], S, L, 0.2, inv_mass=mass, normals=z[:, c:c + 1],
+                                     log_uniforms=logu[:, c:c + 1], record_ham=True)
+                torch.cuda.synchronize()
+                assert torch.equal(one.samples[0], res.samples[c]) and torch.equal(one.accepted[0], res.accepted[c])
+                o = O.sample_hmc(tgt, init[c], num_samples=S, num_steps_per_sample=L, step_size=0.2, inv_mass=mass,
+                                 normals=z[:, c], log_uniforms=logu[:, c])
+                assert res.accepted[c].cpu().bool().tolist() == o['accepted']
+                assert torch.allclose(res.samples[c].cpu(), torch.stack(o['samples']), rtol=2e-4, atol=2e-4)
+    # one iteration, nothing retained but params_init
+    r1 = engine.hmc_run(_corr_gaussian(20, 1), torch.zeros(2, 20), 1, 3, 0.1, inv_mass=_spd(20, 2), seed=3)
+    torch.cuda.synchronize()
+    assert r1.samples.shape == (2, 1, 20) and torch.equal(r1.samples[:, 0].cpu(), torch.zeros(2, 20))
