@@ -36,11 +36,25 @@ def _deps():
         glob.glob(os.path.join(os.path.dirname(HERE), 'include', '*.h')) + [os.path.abspath(__file__)]
 
 
+def _obj_of(src):
+    return os.path.join(LIB_DIR, 'obj', os.path.basename(src)[:-3] + '.o')
+
+
 def up_to_date():
+    """The library is newer than every object, and every object is newer than its source and the shared headers
+    (a source edited while a build was running is therefore rebuilt next time; a fresh checkout with only the .so
+    -- the GPU box -- counts as up to date)."""
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(f) <= t for f in _deps())
+    if not all(os.path.getmtime(f) <= t for f in _deps()):
+        return False
+    common = [f for f in _deps() if not f.endswith('.cu')]
+    for src in sources():
+        obj = _obj_of(src)
+        if os.path.exists(obj) and any(os.path.getmtime(f) > os.path.getmtime(obj) for f in [src] + common):
+            return False
+    return True
 
 
 def build(force=False, verbose=False):

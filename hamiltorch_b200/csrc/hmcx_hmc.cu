@@ -27,6 +27,8 @@ struct ElemTarget {           // element-wise target + mass description, passed 
     const float* im;          // inv_mass [D]
     const float* sd;          // sqrt(mass) [D]
     float log_norm;
+    uint32_t vpr_magic;       // ceil(2^vpr_shift / (ld/4)): row = (v * magic) >> shift for v < 2^31 (Granlund-Montgomery)
+    int vpr_shift;
 };
 
 // per-group constants kept in registers (dead members are eliminated for ISO / MASS_NONE)
@@ -288,6 +290,13 @@ hmc_run_kernel(const RunArgs a) {
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
         const float half = mul(0.5f, eps);
+        if (a.nuts && tid == 0 && n <= a.burn) {
+            // dual averaging is a serial scalar recurrence on the critical path (all other threads wait for the new step
+            // size): pull this iteration's five table constants towards the SM now, a whole trajectory ahead of their use
+            const double* T = a.table + 5 * (size_t)n;
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(T));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(T + 4));
+        }
         // the iteration's log-uniform (warp 0; rides the reduction's shared buffer)
         float logu = 0.0f;
         if (warp0) {
@@ -587,8 +596,12 @@ leapfrog_kernel(const ElemTarget t, const float* __restrict__ q_in, const float*
     const int vpr = t.ld >> 2;                                  // float4 vectors per row
     const size_t nvec = (size_t)t.C * vpr;
     const size_t traj_stride = (size_t)t.C * t.ld;
+    // row of a vector: one multiply-high by a host-computed reciprocal (exact for v < 2^31) instead of a 64-bit division --
+    // the division alone was ~45 of the ~70 instructions per float4 and kept this kernel issue-bound below the HBM roofline
+    const bool fast = nvec < (1ull << 31);
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(v / vpr), e0 = 4 * (int)(v - (size_t)c * vpr);
+        const int c = fast ? (int)(((uint64_t)(uint32_t)v * t.vpr_magic) >> t.vpr_shift) : (int)(v / vpr);
+        const int e0 = 4 * (int)(v - (size_t)c * vpr);
         VecConst<4> vc;
         load_consts<TK, MK, 4>(t, e0, vc);
         float q[4], p[4];
@@ -665,6 +678,13 @@ static int fill_elem_target(const hmcx_target_t* target, const hmcx_mass_t* mass
     if (target->kind == HMCX_TARGET_GAUSS_DIAG && !target->inv_var) return HMCX_ERR_INVALID_ARG;
     if (mk == HMCX_MASS_DIAG && (!mass->inv_mass || !mass->mass_factor)) return HMCX_ERR_INVALID_ARG;
     t.tk = target->kind; t.mk = mk; t.D = target->dim; t.ld = ld; t.C = C;
+    {
+        const uint32_t d = (uint32_t)(ld >> 2);                 // vectors per row, d >= 1
+        int s = 0;
+        while ((1u << s) < d) ++s;                              // s = ceil(log2 d)
+        t.vpr_shift = 31 + s;
+        t.vpr_magic = (uint32_t)((((uint64_t)1 << t.vpr_shift) + d - 1) / d);      // < 2^32 because 2^s < 2 d
+    }
     t.mean = target->mean; t.ivar = target->inv_var; t.log_norm = target->log_norm;
     t.im = mass ? mass->inv_mass : nullptr; t.sd = mass ? mass->mass_factor : nullptr;
     return HMCX_OK;
@@ -742,14 +762,16 @@ int elem_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int D, int C, int
 }
 
 // Register-resident geometry (one CTA per chain): each thread owns K groups of E contiguous elements.
-//   tuning 0 / 1 (auto): one float4 per thread (E=4,K=1), D <= 4096.  Measured best on B200 for BASELINE config 2
-//                    (profiles/README.md): the per-warp fixed cost of an iteration (reduction, loop, RNG for the MH test)
-//                    makes both thinner threads (E=2: 2.25 ms) and fatter threads (K=2: 2.14, K=4: 3.6 ms) slower
-//                    than float4 (1.94 ms).
+//   tuning 0 (auto): one float4 per thread (E=4,K=1) for D <= 2560, two (K=2) above.  Measured on B200: at BASELINE
+//                    config 2 (D=1024) the per-warp fixed cost of an iteration (reduction, loop, RNG for the MH test)
+//                    makes both thinner threads (E=2: 2.25 ms) and fatter threads (K=2: 2.14, K=4: 3.6 ms) slower than
+//                    float4 (1.94 ms); at D >= 3072 (config 5: D=4096) CTAs of 768-1024 threads lose 5-9 % to 512 x 2.
+//   tuning 1: E=4, K=1 forced.
 //   tuning 2 / 4: E=4 with K = 2 / 4 groups per thread;  21: E=2,K=1 (D <= 2048);  22: E=2,K=2.
 static bool pick_geometry(int ld, int tuning, int& E, int& K, int& G) {
     if (ld > 4096) return false;
-    if (tuning == 0 || tuning == 1) { E = 4; K = 1; }
+    if (tuning == 0) { E = 4; K = ld > 2560 ? 2 : 1; }       // measured (scripts/sweep_nuts.py): D >= 3072 runs 5-9 % faster
+    else if (tuning == 1) { E = 4; K = 1; }                  // with 512 threads x 2 float4 than with 768-1024 x 1
     else if (tuning == 21) { E = 2; K = 1; }
     else if (tuning == 2 || tuning == 4) { E = 4; K = tuning; }
     else if (tuning == 22) { E = 2; K = 2; }
@@ -790,7 +812,7 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     if (sink) {                                            // thinning / moments: float4-per-thread geometry only
         if (ld > 4096 || (tuning != 0 && tuning != 1)) return HMCX_ERR_UNSUPPORTED;
         a.thin = sink->thin; a.msum = sink->sum; a.msumsq = sink->sumsq;
-        pick_geometry(ld, 0, E, K, G);
+        pick_geometry(ld, 1, E, K, G);
 #define CALLSINK(TK, MK)                                                                                \
         if (G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256, true><<<C, G, 0, st>>>(a);                      \
         else hmc_run_kernel<TK, MK, 4, 1, 1024, true><<<C, G, 0, st>>>(a)
@@ -814,6 +836,7 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     else if (K == 1 && G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256><<<C, G, 0, st>>>(a);                 \
     else if (K == 1 && philox) hmc_run_kernel<TK, MK, 4, 1, 1024, false, true><<<C, G, 0, st>>>(a);     \
     else if (K == 1) hmc_run_kernel<TK, MK, 4, 1, 1024><<<C, G, 0, st>>>(a);                            \
+    else if (K == 2 && philox) hmc_run_kernel<TK, MK, 4, 2, 512, false, true><<<C, G, 0, st>>>(a);      \
     else if (K == 2) hmc_run_kernel<TK, MK, 4, 2, 512><<<C, G, 0, st>>>(a);                             \
     else hmc_run_kernel<TK, MK, 4, 4, 256><<<C, G, 0, st>>>(a)
     DISPATCH_TK_MK(a.t, CALL);

@@ -164,7 +164,8 @@ int hmcx_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass,
                   float* q_out, float* p_out, float* q_traj, float* p_traj, void* stream);
 
 /*
- * hmcx_hamiltonian == samplers.hamiltonian, sampler=HMC (samplers.py:779-815).
+ * hmcx_hamiltonian == samplers.hamiltonian, sampler=HMC (samplers.py:779-815); same target / mass coverage as
+ * hmcx_leapfrog.
  *   H_out [C]; flags_out [C] (optional) = 1 where log p is non-finite (the reference raises LogProbError, :783-785)
  */
 int hmcx_hamiltonian(const hmcx_target_t* target, const hmcx_mass_t* mass,
@@ -189,8 +190,9 @@ int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_
  *   accept_out / diverged_out  optional [C, num_samples] (uint8); ham_out optional [C, num_samples, 2] = (H_old, H_new)
  *   num_rejected optional [C] int32 in/out counter (:961, :1016, :1046)
  *   workspace    hmcx_hmc_workspace_bytes() bytes of device scratch (NULL when that is 0)
- *   tuning       0 = automatic register geometry (= 1, one float4 per thread); 2 / 4 = that many float4 groups per
- *                thread; 21 / 22 = one / two float2 groups per thread (tests and tuning sweeps; results never depend on it)
+ *   tuning       0 = automatic register geometry (one float4 per thread for D <= 2560, two above); 1 = one float4 per
+ *                thread; 2 / 4 = that many float4 groups per thread; 21 / 22 = one / two float2 groups per thread
+ *                (tests and tuning sweeps; element-wise state and the random stream never depend on it)
  */
 int hmcx_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,
                  const hmcx_nuts_t* nuts,
