@@ -352,7 +352,7 @@ def run_b200_arm(args, rank, world, local_rank):
                              'hb.sample_chains(out=<device block>) + D2H copy of the samples'),
                     'ms_per_step_copy_path': t_e2e_copy_ms, 'ms_per_step_stream_path': t_e2e_stream_ms},
             'gpu_launches': args.steps,
-            'accept_rate': 1.0 - rejected / (world * C * S),
+            'accept_rate': 1.0 - rejected / (world * C * S * args.steps),
             'clocks': clk,
         }
         if allgather_ms is not None:

@@ -179,6 +179,61 @@ __device__ __forceinline__ void block_sum3_small(float& a, float& b, float& c, f
     extra = sbuf[32];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Thread-block clusters: one chain spread over CS CTAs (SMs) -- finer-grained work units for launches with few chains
+// (BASELINE config 2: 256 chains on 148 SMs), so that every SM holds several independent CTAs whose latencies overlap.
+// MEASURED on B200 (config 2, profiles/README.md r1h): the cluster barrier + DSMEM round trip per iteration costs more
+// than the finer granularity buys -- 2.08 ms (CS=2) and 2.7-3.5 ms (CS=4) against 1.63 ms for one CTA per chain -- so this
+// form is opt-in (tuning 41 / 42), kept as the tested starting point for single-chain / few-chain launches where one
+// SM per chain leaves the GPU idle.
+// The chain's only cross-thread traffic, the per-iteration reduction, goes through DISTRIBUTED SHARED MEMORY: every
+// warp publishes its partial sums in its CTA's slot, one cluster barrier (arrive ... independent work ... wait), then
+// every thread adds all CS x nwarp partials in rank / warp order -- identical bits, hence identical decisions, in every
+// CTA of the cluster.  Slots are double-buffered by iteration parity: one cluster barrier per iteration.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 ld_dsmem_f4(const void* smem_ptr, uint32_t rank) {
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
+}
+// phase 1: warp-level sums -> this CTA's slot; signal the cluster
+__device__ __forceinline__ void cluster_sum3_publish(float a, float b, float c, float extra, float4* slot) {
+    warp_sum3(a, b, c, true);
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = make_float4(a, b, c, extra);
+    cluster_arrive();
+}
+// phase 2: wait for every CTA's slot, add all partials in (rank, warp) order; `extra` is rank 0 / warp 0's
+template <int CS>
+__device__ __forceinline__ void cluster_sum3_collect(float& a, float& b, float& c, float& extra, const float4* slot) {
+    cluster_wait();
+    const int nwarp = (blockDim.x + 31) >> 5;
+    a = 0.0f; b = 0.0f; c = 0.0f;
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {
+        for (int w = 0; w < nwarp; ++w) {
+            const float4 v = ld_dsmem_f4(slot + w, (uint32_t)r);
+            if (r == 0 && w == 0) { a = v.x; b = v.y; c = v.z; extra = v.w; }
+            else { a = add(a, v.x); b = add(b, v.y); c = add(c, v.z); }
+        }
+    }
+}
+// one value, off the hot loop (initial log p, the :1018 quirk): full barrier on both sides
+template <int CS>
+__device__ __forceinline__ float cluster_sum1(float v, float4* slot) {
+    float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f;
+    cluster_sum3_publish(v, z0, z1, 0.0f, slot);
+    cluster_sum3_collect<CS>(v, z0, z1, z2, slot);
+    cluster_arrive();
+    cluster_wait();                        // everyone has read: the slot may be reused
+    return v;
+}
+
 constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * K <= 8 ? 512 : 256); }
 
 // MAXT = CTA size the instantiation is compiled for (register budget 64K/MAXT): chains of D <= 1024 run with <= 256
@@ -188,13 +243,18 @@ constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * 
 // PHILOX = true compiles the in-kernel counter RNG branch-free (no memory access, so dead lanes just compute and are
 // masked): the Philox / Box-Muller arithmetic of iteration n+1 and the shuffle chain of iteration n's reduction then
 // sit in one basic block and the scheduler interleaves them.
-template <int TK, int MK, int E, int K, int MAXT, bool SINK = false, bool PHILOX = false>
+// CS > 1: the chain is owned by a cluster of CS CTAs (see above); CTA `rank` holds float4 groups [rank*G, (rank+1)*G).
+template <int TK, int MK, int E, int K, int MAXT, bool SINK = false, bool PHILOX = false, int CS = 1>
 __global__ void __launch_bounds__(MAXT)
 hmc_run_kernel(const RunArgs a) {
+    static_assert(CS == 1 || (K == 1 && !SINK), "cluster form: one group per thread, no sink");
     __shared__ __align__(16) float s_red[2][100];
+    __shared__ __align__(16) float4 s_part[3][8];           // CS > 1: per-warp partials (two iteration parities + misc)
     __shared__ float s_eps[2];
 
-    const int c = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
+    const int c = blockIdx.x / CS, rank = blockIdx.x % CS, G = blockDim.x;
+    const int tid = threadIdx.x, gt = rank * G + tid;       // thread index within the CTA / within the chain
+    const bool lead = tid == 0 && rank == 0;                // writes the chain's scalar outputs
     const ElemTarget& t = a.t;
     const int ld = t.ld, D = t.D;
     const size_t row = (size_t)c * ld;
@@ -205,7 +265,7 @@ hmc_run_kernel(const RunArgs a) {
     bool live[K];                 // group lies inside the padded row
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int e0 = E * (tid + k * G);
+        const int e0 = E * (gt + k * G);
         live[k] = e0 < ld;
         load_consts<TK, MK, E>(t, e0, vc[k]);
         if (live[k]) ldE<E>(a.q_cur + row + e0, qc[k]);
@@ -222,7 +282,8 @@ hmc_run_kernel(const RunArgs a) {
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int j = 0; j < E; ++j) r[0] = add(r[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
-        block_sum<1>(r, s_red[1]);
+        if (CS > 1) r[0] = cluster_sum1<CS>(r[0], s_part[2]);
+        else block_sum<1>(r, s_red[1]);
         lp_cur = log_prob_from_sum(r[0], t.log_norm);
         __syncthreads();
     }
@@ -240,8 +301,8 @@ hmc_run_kernel(const RunArgs a) {
         for (int k = 0; k < K; ++k) {
 #pragma unroll
             for (int j = 0; j < E; ++j) { msum[k][j] = 0.0f; msq[k][j] = 0.0f; }
-            if (live[k] && a.msum) ldE<E>(a.msum + row + E * (tid + k * G), msum[k]);
-            if (live[k] && a.msumsq) ldE<E>(a.msumsq + row + E * (tid + k * G), msq[k]);
+            if (live[k] && a.msum) ldE<E>(a.msum + row + E * (gt + k * G), msum[k]);
+            if (live[k] && a.msumsq) ldE<E>(a.msumsq + row + E * (gt + k * G), msq[k]);
         }
     }
 
@@ -250,13 +311,13 @@ hmc_run_kernel(const RunArgs a) {
     float* row_ptr = nullptr;
     if (!SINK && my_samples) {
         const int first = (a.it0 > a.burn + 1 ? a.it0 : a.burn + 1) - a.burn;
-        row_ptr = my_samples + (size_t)first * ld + E * tid;
+        row_ptr = my_samples + (size_t)first * ld + E * gt;
     }
 
     if (a.it0 == 0 && my_samples) {                // ret_params = [params_init] (:959)
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            if (live[k]) stE_stream<E>(my_samples + E * (tid + k * G), qc[k]);
+            if (live[k]) stE_stream<E>(my_samples + E * (gt + k * G), qc[k]);
     }
 
     // the standard normals of iteration n: produced one iteration AHEAD (they do not depend on the MH decision), so
@@ -265,7 +326,7 @@ hmc_run_kernel(const RunArgs a) {
     auto draw = [&](int n) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int grp = tid + k * G, e0 = E * grp;
+            const int grp = gt + k * G, e0 = E * grp;
 #pragma unroll
             for (int j = 0; j < E; ++j) zn[k][j] = 0.0f;
             if (PHILOX) {
@@ -285,7 +346,7 @@ hmc_run_kernel(const RunArgs a) {
     // dependent instructions of Philox + logf leave the per-iteration critical path (every other warp waits for warp 0 at
     // the reduction's barrier) and cost 1/32 of the issue slots
     float logu_lanes = 0.0f;
-    const bool warp0 = tid < 32;
+    const bool warp0 = tid < 32 && rank == 0;
 
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
@@ -334,8 +395,10 @@ hmc_run_kernel(const RunArgs a) {
             }
         // next iteration's normals: independent work.  In Philox mode the draw is branch-free and unconditional (one
         // unused draw after the last iteration) so that it shares a basic block with the reduction's shuffle chain.
+        if (CS > 1) cluster_sum3_publish(r0, r1, r2, logu, s_part[n & 1]);      // ... the draw below overlaps the barrier
         if (PHILOX || n + 1 < a.it1) draw(n + 1);
-        if (MAXT <= 256) block_sum3_small(r0, r1, r2, logu, s_red[n & 1]);
+        if (CS > 1) cluster_sum3_collect<CS>(r0, r1, r2, logu, s_part[n & 1]);
+        else if (MAXT <= 256) block_sum3_small(r0, r1, r2, logu, s_red[n & 1]);
         else block_sum3(r0, r1, r2, logu, s_red[n & 1]);
         const float lp_new = log_prob_from_sum(r1, t.log_norm);
         const float h_old = add(-lp_cur, mul(0.5f, r0));                     // potential + kinetic (:815)
@@ -359,7 +422,7 @@ hmc_run_kernel(const RunArgs a) {
                 float s[1] = {0.0f};
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const int e0 = E * (tid + k * G);
+                    const int e0 = E * (gt + k * G);
                     if (live[k]) ldE<E>(a.q_init + row + e0, qc[k]);
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
@@ -367,7 +430,8 @@ hmc_run_kernel(const RunArgs a) {
                         s[0] = add(s[0], uterm1<TK>(qc[k][j], vc[k].mean[j], vc[k].ivar[j]));
                     }
                 }
-                block_sum<1>(s, s_red[(n & 1) ^ 1]);
+                if (CS > 1) s[0] = cluster_sum1<CS>(s[0], s_part[2]);       // every CTA of the cluster takes this branch
+                else block_sum<1>(s, s_red[(n & 1) ^ 1]);
                 lp_cur = log_prob_from_sum(s[0], t.log_norm);
                 __syncthreads();          // the next iteration reduces through the same buffer
             }
@@ -386,7 +450,7 @@ hmc_run_kernel(const RunArgs a) {
                     float* dst = my_samples + (size_t)((n - a.burn) / thin) * ld;
 #pragma unroll
                     for (int k = 0; k < K; ++k)
-                        if (live[k]) stE_stream<E>(dst + E * (tid + k * G), qc[k]);
+                        if (live[k]) stE_stream<E>(dst + E * (gt + k * G), qc[k]);
                 }
             }
         } else if (n > a.burn && my_samples) {
@@ -395,7 +459,7 @@ hmc_run_kernel(const RunArgs a) {
                 if (live[k]) stE_stream<E>(row_ptr + E * k * G, qc[k]);
             row_ptr += ld;
         }
-        if (tid == 0) {
+        if (lead) {
             const size_t o = (size_t)c * a.S + n;
             if (a.accept) a.accept[o] = acc ? 1 : 0;
             if (a.diverged) a.diverged[o] = bad ? 1 : 0;
@@ -416,27 +480,28 @@ hmc_run_kernel(const RunArgs a) {
                 }
                 if (n == a.burn) e = (float)eps_bar;                          // freeze (:1033-1034)
                 s_eps[n & 1] = e;
-                if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = e;
+                if (a.eps_trace && lead) a.eps_trace[(size_t)c * a.S + n] = e;
             }
             __syncthreads();
             eps = s_eps[n & 1];
-        } else if (a.eps_trace && tid == 0) {
+        } else if (a.eps_trace && lead) {
             a.eps_trace[(size_t)c * a.S + n] = eps;
         }
     }
+    if (CS > 1) { cluster_arrive(); cluster_wait(); }       // no CTA leaves while a peer may still read its slots
 
     // final state for resumption
 #pragma unroll
     for (int k = 0; k < K; ++k)
-        if (live[k]) stE<E>(a.q_cur + row + E * (tid + k * G), qc[k]);
+        if (live[k]) stE<E>(a.q_cur + row + E * (gt + k * G), qc[k]);
     if (SINK) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if (live[k] && a.msum) stE<E>(a.msum + row + E * (tid + k * G), msum[k]);
-            if (live[k] && a.msumsq) stE<E>(a.msumsq + row + E * (tid + k * G), msq[k]);
+            if (live[k] && a.msum) stE<E>(a.msum + row + E * (gt + k * G), msum[k]);
+            if (live[k] && a.msumsq) stE<E>(a.msumsq + row + E * (gt + k * G), msq[k]);
         }
     }
-    if (tid == 0) {
+    if (lead) {
         a.eps[c] = eps;
         if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
         if (a.num_rejected) a.num_rejected[c] += rejected;
@@ -570,7 +635,7 @@ hmc_run_big_kernel(const RunArgs a, float* __restrict__ work) {
                 }
                 if (n == a.burn) e = (float)eps_bar;
                 s_eps[n & 1] = e;
-                if (a.eps_trace) a.eps_trace[(size_t)c * a.S + n] = e;
+                if (a.eps_trace && tid == 0) a.eps_trace[(size_t)c * a.S + n] = e;
             }
             __syncthreads();
             eps = s_eps[n & 1];
@@ -809,6 +874,28 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
 
     int E, K, G;
+    if (tuning == 41 || tuning == 42) {                    // one chain per cluster of 4 / 2 CTAs (DSMEM reduction)
+        if (sink) return HMCX_ERR_UNSUPPORTED;
+        const int CS = tuning == 41 ? 4 : 2;
+        const int groups = (ld / 4 + CS - 1) / CS;
+        G = (groups + 31) / 32 * 32;
+        if (G > 256) return HMCX_ERR_UNSUPPORTED;
+        const bool philox = a.rng_mode == HMCX_RNG_PHILOX;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(C * CS)); cfg.blockDim = dim3((unsigned)G); cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+#define CALLCL(TK, MK)                                                                                  \
+        if (CS == 4 && philox) cudaLaunchKernelEx(&cfg, hmc_run_kernel<TK, MK, 4, 1, 256, false, true, 4>, a);   \
+        else if (CS == 4) cudaLaunchKernelEx(&cfg, hmc_run_kernel<TK, MK, 4, 1, 256, false, false, 4>, a);       \
+        else if (philox) cudaLaunchKernelEx(&cfg, hmc_run_kernel<TK, MK, 4, 1, 256, false, true, 2>, a);         \
+        else cudaLaunchKernelEx(&cfg, hmc_run_kernel<TK, MK, 4, 1, 256, false, false, 2>, a)
+        DISPATCH_TK_MK(a.t, CALLCL);
+#undef CALLCL
+        return cuda_status();
+    }
     if (sink) {                                            // thinning / moments: float4-per-thread geometry only
         if (ld > 4096 || (tuning != 0 && tuning != 1)) return HMCX_ERR_UNSUPPORTED;
         a.thin = sink->thin; a.msum = sink->sum; a.msumsq = sink->sumsq;

@@ -68,10 +68,11 @@ def test_golden_chain_parity(name):
             assert float(res.step_size[c]) == np.float32(case['kw']['step_size'])
 
 
-@pytest.mark.parametrize('tuning', [2, 4, 21, 22])
+@pytest.mark.parametrize('tuning', [1, 2, 4, 21, 22, 41, 42])
 def test_register_geometry_variants_agree(tuning):
-    """The register geometry (float2 / float4 groups, 1-4 groups per thread) only changes the reduction tree, never the
-    element-wise state -- and, in Philox mode, not the random stream either."""
+    """The register geometry (float2 / float4 groups, 1-4 groups per thread; 41 / 42: the chain spread over a thread-block
+    cluster of 4 / 2 CTAs with the reduction through distributed shared memory) only changes the reduction tree, never
+    the element-wise state -- and, in Philox mode, not the random stream either."""
     for name in ('iso256', 'diag48_mass'):
         case = cases.plain_cases()[name]
         d = np.load(os.path.join(GOLD, name + '.npz'))
