@@ -25,8 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, C_PER_GPU, S, L, EPS = 1024, 256, 1000, 10, 0.05
-WARP_INST_PER_LAUNCH = 1088380528          # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
-                                           # (profiles/r1h_prof_hmc_run.summary.txt)
+WARP_INST_PER_LAUNCH = 1076063104          # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
+                                           # (profiles/r1i_prof_hmc_run.summary.txt)
 METRIC = 'leapfrog-steps x chains / sec'
 UNIT = 'chain-steps/s'
 
@@ -98,21 +98,67 @@ def run_reference_arm(args, rank, world):
 # clocks
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled every 20 ms while the timed regions run.  In-process NVML (nvidia_ml_py) on a
+    daemon thread: one nvmlInit before the warm-up, then ~50 us queries -- no subprocess attaching to the driver while
+    kernels are being launched (an `nvidia-smi -lms` loop did stall launches for milliseconds now and then).  Falls back
+    to that loop only if NVML cannot be imported."""
+    REASONS = (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown'),
+               ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown'),
+               ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown'),
+               ('sw_power_cap', 'nvmlClocksEventReasonSwPowerCap'))
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.thread = index, None, None
+        self.sm, self.mx, self.reasons, self.stop_flag = [], [], set(), False
+
+    def _visible_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _loop(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, const in self.REASONS:
+                    if r & getattr(nv, const):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '20'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -122,7 +168,7 @@ class ClockSampler:
             self.proc.kill()
             out = ''
         sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        names = [n for n, _ in self.REASONS]
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 6:
@@ -136,7 +182,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -192,18 +238,35 @@ def run_b200_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ----
+    # The clock sampler is started BEFORE the warm-up (NVML initialisation must not land inside a timed region); its
+    # 20 ms polls then run through the warm-up and all timed regions.
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.2)
+    barrier()
+
+    # ---- warm-up: the W requested steps, then (still untimed) until the step time has settled ----
+    # A fresh box runs its first launches several times slower for up to a few seconds (observed on B200 boxes right
+    # after start-up: 5-9 ms instead of 1.5 ms per step, clocks already at maximum); W = 3 steps do not outlast that.
     for w in range(args.warmup):
         keep_stats(w, step(w))
     gather_stats()
     barrier()
+    extra_warmup, best, stable, t_w = 0, float('inf'), 0, time.time()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while extra_warmup < 400 and time.time() - t_w < 4.0 and stable < 8:
+        w0.record()
+        step(1000 + extra_warmup)
+        w1.record()
+        torch.cuda.synchronize()
+        ms = w0.elapsed_time(w1)
+        extra_warmup += 1
+        best = min(best, ms)
+        stable = stable + 1 if ms <= 1.1 * best else 0
+    barrier()
 
     # ---- device-timed region: EXACTLY K steps, inputs resident in HBM ----
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.15)
-    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     ev[0].record()
     for k in range(args.steps):
@@ -324,17 +387,18 @@ def run_b200_arm(args, rank, world, local_rank):
                                    'eps=0.05, S=1000 iterations per step, in-kernel Philox RNG',
                        'chains_per_gpu': C, 'dim': D, 'L': L, 'iterations_per_step': S,
                        'l2_policy': 'each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
+                       'extra_untimed_warmup_steps': extra_warmup,
                        'parallelism': 'chains sharded over %d GPU(s), no data-path collective' % world},
-            'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1,PHILOX,NUTS=0>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
-                         # profiles/r1h_prof_hmc_run.summary.txt (1.15 MB read + 990.76 MB written)
-                         'traffic': 991.9e6, 'peak_source': peak_src,
+                         # profiles/r1i_prof_hmc_run.summary.txt (1.14 MB read + 990.40 MB written)
+                         'traffic': 991.5e6, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': t_kernel_ms,
                          'note': 'fused trajectory kernel: L=10 steps per 4*D bytes written, fp32-issue bound by design; '
                                  'see roofline_streaming for the HBM-bound form'},
             # what actually bounds the fused kernel: warp-instruction issue.  Instructions per launch are static for this
-            # geometry (ncu smsp__inst_executed.sum, profiles/r1h_prof_hmc_run.summary.txt); time is measured live.
+            # geometry (ncu smsp__inst_executed.sum, profiles/r1i_prof_hmc_run.summary.txt); time is measured live.
             'roofline_issue': {'bound': 'issue', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>',
                                'warp_instructions_per_launch': WARP_INST_PER_LAUNCH,
                                'achieved': WARP_INST_PER_LAUNCH / (t_kernel_ms * 1e-3) / 1e9,

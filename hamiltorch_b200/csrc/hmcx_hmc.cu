@@ -244,7 +244,8 @@ constexpr int run_max_threads(int E, int K) { return (E * K <= 4) ? 1024 : (E * 
 // masked): the Philox / Box-Muller arithmetic of iteration n+1 and the shuffle chain of iteration n's reduction then
 // sit in one basic block and the scheduler interleaves them.
 // CS > 1: the chain is owned by a cluster of CS CTAs (see above); CTA `rank` holds float4 groups [rank*G, (rank+1)*G).
-template <int TK, int MK, int E, int K, int MAXT, bool SINK = false, bool PHILOX = false, int CS = 1>
+// NUTS = false compiles the dual-averaging path out (the plain sample() loop then carries no trace of it).
+template <int TK, int MK, int E, int K, int MAXT, bool SINK = false, bool PHILOX = false, int CS = 1, bool NUTS = true>
 __global__ void __launch_bounds__(MAXT)
 hmc_run_kernel(const RunArgs a) {
     static_assert(CS == 1 || (K == 1 && !SINK), "cluster form: one group per thread, no sink");
@@ -255,6 +256,7 @@ hmc_run_kernel(const RunArgs a) {
     const int c = blockIdx.x / CS, rank = blockIdx.x % CS, G = blockDim.x;
     const int tid = threadIdx.x, gt = rank * G + tid;       // thread index within the CTA / within the chain
     const bool lead = tid == 0 && rank == 0;                // writes the chain's scalar outputs
+    const bool nuts = NUTS && a.nuts;
     const ElemTarget& t = a.t;
     const int ld = t.ld, D = t.D;
     const size_t row = (size_t)c * ld;
@@ -290,7 +292,7 @@ hmc_run_kernel(const RunArgs a) {
 
     float eps = a.eps[c];
     double h_bar = 0.0, eps_bar = 1.0;
-    if (a.nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
+    if (nuts && tid == 0) { h_bar = a.h_bar[c]; eps_bar = a.eps_bar[c]; }
     int rejected = 0;
     const int thin = SINK ? a.thin : 1;
     const int keep = SINK ? 1 + (a.S - a.burn - 1) / thin : a.S - a.burn;    // slots per chain in samples_out
@@ -351,7 +353,7 @@ hmc_run_kernel(const RunArgs a) {
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * t.C + c];
         const float half = mul(0.5f, eps);
-        if (a.nuts && tid == 0 && n <= a.burn) {
+        if (nuts && tid == 0 && n <= a.burn) {
             // dual averaging is a serial scalar recurrence on the critical path (all other threads wait for the new step
             // size): pull this iteration's five table constants towards the SM now, a whole trajectory ahead of their use
             const double* T = a.table + 5 * (size_t)n;
@@ -466,7 +468,7 @@ hmc_run_kernel(const RunArgs a) {
             if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
         }
         // ---- dual averaging (:1030-1035, exception path :1060-1067) ----
-        if (a.nuts && n <= a.burn) {
+        if (nuts && n <= a.burn) {
             if (tid == 0) {
                 float e = eps;
                 if (n < a.burn || bad) {
@@ -503,7 +505,7 @@ hmc_run_kernel(const RunArgs a) {
     }
     if (lead) {
         a.eps[c] = eps;
-        if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
+        if (nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
         if (a.num_rejected) a.num_rejected[c] += rejected;
     }
 }
@@ -919,6 +921,8 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
 #define CALL(TK, MK)                                                                                    \
     if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1, 1024><<<C, G, 0, st>>>(a);                       \
     else if (E == 2) hmc_run_kernel<TK, MK, 2, 2, 1024><<<C, G, 0, st>>>(a);                            \
+    else if (K == 1 && G <= 256 && philox && !a.nuts)                                                   \
+        hmc_run_kernel<TK, MK, 4, 1, 256, false, true, 1, false><<<C, G, 0, st>>>(a);                   \
     else if (K == 1 && G <= 256 && philox) hmc_run_kernel<TK, MK, 4, 1, 256, false, true><<<C, G, 0, st>>>(a); \
     else if (K == 1 && G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256><<<C, G, 0, st>>>(a);                 \
     else if (K == 1 && philox) hmc_run_kernel<TK, MK, 4, 1, 1024, false, true><<<C, G, 0, st>>>(a);     \
