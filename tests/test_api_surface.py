@@ -87,3 +87,39 @@ def test_nuts_table_matches_python_doubles():
         assert tab[n, 2].item() == (t ** 0.5) / 0.05
         assert tab[n, 3].item() == t ** -0.75
         assert tab[n, 4].item() == 1 - t ** -0.75
+
+
+def test_sink_and_rmhmc_routing_errors_are_raised_on_the_host():
+    """Argument checks that must fire before any CUDA work (so they are testable without a GPU): the sample sink is only
+    wired into the element-wise persistent kernel; RMHMC at D > 16 needs a constant metric."""
+    import pytest
+    import torch
+    import hamiltorch_b200 as hb
+    from hamiltorch_b200 import targets as T
+    D = 24
+    full = T.GaussianFull(torch.zeros(D), cov=torch.eye(D, dtype=torch.float64) * 2)
+    for kw in (dict(thin=2), dict(moments=True), dict(keep_samples=False), dict(store_on_GPU=False)):
+        with pytest.raises(NotImplementedError):
+            hb.sample_chains(full, torch.zeros(2, D), num_samples=5, **kw)
+    with pytest.raises(NotImplementedError):                       # position-dependent metric at D > 16
+        hb.sample_chains(T.Funnel(D), torch.zeros(2, D), num_samples=5, sampler=hb.Sampler.RMHMC,
+                         integrator=hb.Integrator.EXPLICIT)
+    with pytest.raises(NotImplementedError):                       # jitter makes the metric a per-call random matrix
+        hb.sample_chains(full, torch.zeros(2, D), num_samples=5, jitter=1e-3, sampler=hb.Sampler.RMHMC,
+                         integrator=hb.Integrator.EXPLICIT)
+    with pytest.raises(RuntimeError):                              # burn >= num_samples (samplers.py:928-929)
+        hb.sample_chains(T.GaussianIso(8), torch.zeros(2, 8), num_samples=5, burn=5)
+
+
+def test_bench_clock_sampler_degrades_without_a_gpu():
+    """bench.py's clock sampler never raises: without NVML / nvidia-smi it reports that instead of clocks."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    s = mod.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
