@@ -71,7 +71,27 @@ def plain_cases():
         target=T.GaussianDiag(torch.linspace(-1, 1, 5), _rand_var(5, 11)),
         kw=dict(num_samples=50, num_steps_per_sample=6, step_size=0.25, burn=5, inv_mass=im_full),
         seeds=[31, 32], init='randn0.1', rtol=2e-5)
+    # ---- D > 16: the tensor-core paths (3xTF32 GEMMs over all chains vs the reference's fp32 mv / matmul): rtol 2e-4
+    cases['full48_dense'] = dict(                      # dense precision, no mass: dense_step_kernel
+        target=T.GaussianFull(0.3 * torch.randn(48, generator=g), cov=_spd64(48, 61)),
+        kw=dict(num_samples=14, num_steps_per_sample=6, step_size=0.25, burn=2),
+        seeds=[43, 44], init='randn0.1', rtol=2e-4)
+    cases['full40_fullmass'] = dict(                   # dense precision AND 2-D inv_mass: dense_lin_kernel, 2L+4 GEMMs
+        target=T.GaussianFull(0.3 * torch.randn(40, generator=g), cov=_spd64(40, 62)),
+        kw=dict(num_samples=12, num_steps_per_sample=5, step_size=0.2, burn=3, inv_mass=_spd64(40, 63).float()),
+        seeds=[41, 42], init='randn0.1', rtol=2e-4)
+    cases['iso40_fullmass_nuts'] = dict(               # element-wise target, 2-D inv_mass, step-size adaptation
+        target=T.GaussianIso(40),
+        kw=dict(num_samples=14, num_steps_per_sample=5, step_size=0.1, burn=8, nuts=True, desired_accept_rate=0.8,
+                inv_mass=_spd64(40, 64).float()),
+        seeds=[45], init='randn0.1', rtol=2e-4)
     return cases
+
+
+def _spd64(dim, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(dim, dim, generator=g, dtype=torch.float64) / dim ** 0.5
+    return A @ A.t() + 0.6 * torch.eye(dim, dtype=torch.float64)
 
 
 def make_init(kind, dim, seed):
@@ -165,5 +185,16 @@ def rmhmc_cases():
                                       init=[0.2, 0.8, -1.5], integrator='EXPLICIT', num_samples=10,
                                       num_steps_per_sample=4, step_size=0.15, burn=0, explicit_binding_const=5,
                                       metric='HESSIAN', jitter=None, softabs_const=None, seeds=[6]),
+        # ---- constant-metric tensor-core path (hmcx_rmhmc_dense_run): Gaussian targets without jitter
+        'rmhmc_exp_hess_full24': dict(target=T.GaussianFull(torch.linspace(-0.5, 0.5, 24), cov=_spd64(24, 71)),
+                                      init=[0.1 * ((i * 7) % 5 - 2) for i in range(24)], integrator='EXPLICIT',
+                                      num_samples=6, num_steps_per_sample=3, step_size=0.6, burn=1,
+                                      explicit_binding_const=10, metric='HESSIAN', jitter=None, softabs_const=None,
+                                      seeds=[7, 8]),
+        'rmhmc_imp_softabs_diag20': dict(target=T.GaussianDiag(torch.linspace(-1, 1, 20), _rand_var(20, 72)),
+                                         init=[0.2 * ((i * 3) % 7 - 3) for i in range(20)], integrator='IMPLICIT',
+                                         num_samples=6, num_steps_per_sample=3, step_size=0.5, burn=1,
+                                         softabs_const=1.0, metric='SOFTABS', jitter=None, fixed_point_threshold=1e-5,
+                                         fixed_point_max_iterations=1000, seeds=[9]),
     }
     return cases

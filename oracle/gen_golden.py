@@ -262,17 +262,23 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = import_reference()
-    run_reversibility(ref)
-    which = sys.argv[1:] or ['plain', 'mlp', 'rmhmc']
+    args = sys.argv[1:]
+    only = {a[5:] for a in args if a.startswith('only:')}          # only:<case name> regenerates just those fixtures
+    which = [a for a in args if not a.startswith('only:')] or ['plain', 'mlp', 'rmhmc']
+    if not only:
+        run_reversibility(ref)
     if 'plain' in which:
         for name, case in cases.plain_cases().items():
-            run_plain_case(ref, name, case)
+            if not only or name in only:
+                run_plain_case(ref, name, case)
     if 'mlp' in which:
         for name, case in cases.mlp_cases().items():
-            run_mlp_case(ref, name, case)
+            if not only or name in only:
+                run_mlp_case(ref, name, case)
     if 'rmhmc' in which:
         for name, case in cases.rmhmc_cases().items():
-            run_rmhmc_case(ref, name, case)
+            if not only or name in only:
+                run_rmhmc_case(ref, name, case)
 
 
 if __name__ == '__main__':
