@@ -687,7 +687,7 @@ int small_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     const int D = target->dim;
     if (D < 1 || C < 1 || ld < D || (ld & 3) || L < 1 || S < 1 || burn < 0 || burn >= S || it0 < 0 || it1 > S || it0 > it1)
         return HMCX_ERR_INVALID_ARG;
-    if (D > 16) return HMCX_ERR_UNSUPPORTED;      // large dense targets / mass matrices: tensor-core path, next round
+    if (D > 16) return HMCX_ERR_UNSUPPORTED;      // large dense targets / mass matrices run on the tensor cores (hmcx_tc.cu)
     SmallRunArgs a = {};
     a.t.kind = target->kind; a.t.D = D; a.t.log_norm = target->log_norm; a.t.inv_var_v = target->funnel_inv_var_v;
     a.t.mean = target->mean; a.t.ivar = target->inv_var; a.t.prec = target->prec;
