@@ -31,6 +31,14 @@ METRIC = 'leapfrog-steps x chains / sec'
 UNIT = 'chain-steps/s'
 
 
+def workload_config(world):
+    """The `config` object both arms report: BASELINE config 2."""
+    return {'workload': 'BASELINE config 2: D=1024 isotropic Gaussian, plain HMC, 256 chains/GPU, L=10, '
+                        'eps=0.05, S=1000 iterations per step',
+            'chains_per_gpu': C_PER_GPU, 'dim': D, 'L': L, 'iterations_per_step': S,
+            'parallelism': 'chains sharded over %d GPU(s), no data-path collective' % world}
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -86,8 +94,10 @@ def run_reference_arm(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE config 2: D=1024 isotropic Gaussian, plain HMC, L=10, eps=0.05',
-                   'sample': sample},
+        # same workload as the B200 arm; each reference step is the bounded sample named in `sample` (independent chains
+        # of config 2 through the reference's per-chain Python loop; the rate is per chain-step, so it extrapolates
+        # linearly to the full 256 x 1000 job)
+        'config': dict(workload_config(args.gpus), sample=sample),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -383,12 +393,9 @@ def run_b200_arm(args, rank, world, local_rank):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE config 2: D=1024 isotropic Gaussian, plain HMC, 256 chains/GPU, L=10, '
-                                   'eps=0.05, S=1000 iterations per step, in-kernel Philox RNG',
-                       'chains_per_gpu': C, 'dim': D, 'L': L, 'iterations_per_step': S,
-                       'l2_policy': 'each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
-                       'extra_untimed_warmup_steps': extra_warmup,
-                       'parallelism': 'chains sharded over %d GPU(s), no data-path collective' % world},
+            'config': dict(workload_config(world), rng='in-kernel Philox4x32-10',
+                           l2_policy='each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
+                           extra_untimed_warmup_steps=extra_warmup),
             'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1,PHILOX,NUTS=0>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
