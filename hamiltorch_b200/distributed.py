@@ -44,13 +44,36 @@ def all_gather_rows(local, num_chains, group=None):
     return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
 
 
+def pooled_moments(moment_sum, moment_sumsq, count_per_chain, group=None):
+    """Posterior mean and variance pooled over ALL chains of ALL ranks from the sample sink's per-chain running sums
+    (``sample_chains(..., moments=True)``: ``moment_sum`` / ``moment_sumsq`` (C_local, D), ``moment_count`` states per
+    chain) with ONE all-reduce of a (2D+1,) fp64 vector -- the multi-GPU consumer that needs no sample gather at all
+    (O(D) bytes over NVLink instead of O(C*S*D)).  Returns (mean (D,), var (D,), n) as fp64, identical on every rank;
+    var is the population variance of the pooled draws."""
+    s = moment_sum.double().sum(0)
+    sq = moment_sumsq.double().sum(0)
+    n = torch.tensor([float(moment_sum.shape[0]) * float(count_per_chain)], dtype=torch.float64, device=s.device)
+    buf = torch.cat([s, sq, n])
+    rank, world = _world()
+    if world > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    Dd = s.numel()
+    total = float(buf[-1])
+    if total <= 0:
+        raise RuntimeError('pooled_moments: no post-burn states were accumulated')
+    mean = buf[:Dd] / total
+    var = buf[Dd:2 * Dd] / total - mean * mean
+    return mean, var.clamp_min(0.0), total
+
+
 def sample_chains_sharded(log_prob_func, params_init, gather_samples=False, runner=None, **kwargs):
     """``sample_chains`` over all ranks.  ``params_init`` is the FULL (C, D) batch on every rank (it is tiny next to
     the samples); each rank advances its block of chains on its own GPU.
 
     Returns a dict on every rank: ``num_rejected`` (C,), ``step_size`` (C,), ``bounds`` (this rank's [lo, hi)),
     ``local`` (this rank's HMCResult) and, when ``gather_samples``, ``samples`` (C, S-burn, D) collected with one
-    all-gather.  Injected-stream arguments ``normals`` (S, C, D) / ``log_uniforms`` (S, C) are sliced per rank.
+    all-gather.  With the sample sink's ``moments=True`` the per-chain running sums are pooled over all ranks by one
+    O(D) all-reduce: ``posterior_mean`` / ``posterior_var`` (D,) fp64, ``posterior_n`` -- no sample ever leaves its GPU.  Injected-stream arguments ``normals`` (S, C, D) / ``log_uniforms`` (S, C) are sliced per rank.
     ``runner`` replaces ``samplers.sample_chains`` (used by the CPU tests of this host logic).
     """
     from . import samplers
@@ -69,4 +92,7 @@ def sample_chains_sharded(log_prob_func, params_init, gather_samples=False, runn
            'step_size': all_gather_rows(local.step_size, C)}
     if gather_samples:
         out['samples'] = all_gather_rows(local.samples_padded, C)[..., :local.dim]
+    if getattr(local, 'moment_sum', None) is not None:          # sink moments requested: pool them over all ranks
+        out['posterior_mean'], out['posterior_var'], out['posterior_n'] = pooled_moments(
+            local.moment_sum, local.moment_sumsq, local.moment_count)
     return out

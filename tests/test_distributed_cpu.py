@@ -71,3 +71,34 @@ def test_shard_bounds_cover_all_chains():
             assert b[0][0] == 0 and b[-1][1] == C
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def _moments_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        draws = torch.randn(6, 9, 4, generator=g) * 2 + 1          # 6 chains x 9 post-burn states x D=4, same on all ranks
+        lo, hi = D.shard_bounds(6, rank, world)
+        mine = draws[lo:hi]
+        mean, var, n = D.pooled_moments(mine.sum(1), (mine * mine).sum(1), 9)
+        flat = draws.reshape(-1, 4).double()
+        ok = n == 54 and torch.allclose(mean, flat.mean(0), atol=1e-6) and \
+            torch.allclose(var, flat.var(0, unbiased=False), atol=1e-5)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pooled_moments_all_reduce_gloo_world2():
+    """The sink's per-chain running sums pooled over ranks by one O(D) all-reduce == moments of all draws."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_moments_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    got = dict(q.get(timeout=10) for _ in range(2))
+    assert got == {0: True, 1: True}
