@@ -12,9 +12,10 @@
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
+import ctypes
 import json
-import math
 import os
+import signal
 import subprocess
 import sys
 import time
@@ -29,22 +30,131 @@ WARP_INST_PER_LAUNCH = 1076063104          # config 2, E=4 K=1 geometry: ncu sms
                                            # (profiles/r1i_prof_hmc_run.summary.txt)
 METRIC = 'leapfrog-steps x chains / sec'
 UNIT = 'chain-steps/s'
+REFERENCE_ARM_BUDGET_S = 75.0              # wall-clock bound of `--impl reference` whatever --steps says
 
 
 def workload_config(world):
-    """The `config` object both arms report: BASELINE config 2."""
+    """The `config` object BOTH arms report, key for key: BASELINE config 2."""
     return {'workload': 'BASELINE config 2: D=1024 isotropic Gaussian, plain HMC, 256 chains/GPU, L=10, '
                         'eps=0.05, S=1000 iterations per step',
             'chains_per_gpu': C_PER_GPU, 'dim': D, 'L': L, 'iterations_per_step': S,
-            'parallelism': 'chains sharded over %d GPU(s), no data-path collective' % world}
+            'parallelism': 'chains sharded over %d GPU(s), no data-path collective; one all-gather collects the samples'
+                           % world}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def measured_peak_hbm():
+    p = measured_peaks()
+    if 'hbm_gbs' in p:
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ----------------------------------------------------------------------------------------------------------
+# host topology: usable logical CPUs, physical cores, cgroup quota, NUMA node of a GPU
+# ----------------------------------------------------------------------------------------------------------
+def host_cpus():
+    """{'logical': CPUs this process may run on, 'physical_cores': distinct (socket, core) pairs among them,
+    'cgroup_quota': CPUs' worth of cgroup cpu.max quota or None, 'workers': processes the CPU arm starts}."""
     try:
-        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        usable = sorted(os.sched_getaffinity(0))
     except Exception:
-        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+        usable = list(range(os.cpu_count() or 1))
+    phys = set()
+    try:
+        cpu = pid = cid = None
+        with open('/proc/cpuinfo') as f:
+            for ln in f.read().splitlines() + ['']:
+                if ln.startswith('processor'):
+                    cpu = int(ln.split(':')[1])
+                elif ln.startswith('physical id'):
+                    pid = int(ln.split(':')[1])
+                elif ln.startswith('core id'):
+                    cid = int(ln.split(':')[1])
+                elif not ln.strip():
+                    if cpu is not None and cpu in usable and pid is not None and cid is not None:
+                        phys.add((pid, cid))
+                    cpu = pid = cid = None
+    except Exception:
+        pass
+    quota = None
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, per = f.read().split()
+            if q != 'max':
+                quota = float(q) / float(per)
+    except Exception:
+        pass
+    workers = len(usable)
+    if quota:
+        workers = max(1, min(workers, int(quota + 0.5)))
+    return {'logical': len(usable), 'physical_cores': len(phys) or None, 'cgroup_quota': quota, 'workers': workers}
+
+
+def _parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(','):
+        if not part:
+            continue
+        if '-' in part:
+            a, b = part.split('-')
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore every page it first-touches, pinned host blocks included) to the NUMA node its
+    GPU hangs off: CPU affinity = the node's cpulist, memory policy = MPOL_PREFERRED that node.  Must run BEFORE the
+    first pinned allocation.  Returns a small dict for the bench line; never raises."""
+    info = {'bound': False}
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        bdf = nv.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(':')[0]) == 8:                       # NVML prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read())
+        info['pci'] = bdf
+        if node < 0:
+            info['node'] = None
+            return info
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        info.update(node=node, cpus=len(allowed), bound=bool(allowed))
+        # set_mempolicy(MPOL_PREFERRED, {node}): x86_64 syscall 238; harmless if refused (first touch under the CPU
+        # affinity above already allocates locally)
+        try:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(16 * 64))
+            info['mempolicy'] = 'preferred' if rc == 0 else 'refused (errno %d)' % ctypes.get_errno()
+        except Exception as e:                                # pragma: no cover
+            info['mempolicy'] = 'unavailable: %s' % e
+    except Exception as e:
+        info['error'] = str(e)[:120]
+    return info
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -64,54 +174,127 @@ def _cpu_chain(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(n_iter, procs):
-    """`procs` independent chains (one process per host core, 1 torch thread each -- intra-op threads do not help at
-    D=1024), each running n_iter iterations of config 2.  Returns chain-steps/s and wall."""
-    import multiprocessing as mp
-    ctx = mp.get_context('fork')
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_chain, [(1000 + i, n_iter) for i in range(procs)])
-    wall = time.perf_counter() - t0
-    return procs * n_iter * L / wall, wall
+class CpuArm:
+    """One pool of worker processes (one per usable CPU, 1 torch thread each -- intra-op threads do not help at D=1024,
+    BASELINE.md section 3), created ONCE and reused for every step.  A step = every worker runs `n_iter` iterations of
+    one independent config-2 chain through the reference's per-chain Python loop."""
+
+    def __init__(self, workers):
+        import multiprocessing as mp
+        self.workers = workers
+        self.pool = mp.get_context('fork').Pool(workers)
+        self.k = 0
+
+    def step(self, n_iter):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_chain, [(1000 + self.k * self.workers + i, n_iter) for i in range(self.workers)], chunksize=1)
+        self.k += 1
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.terminate()
+        self.pool.join()
+
+
+def cpu_sample_text(host, n_iter, steps_done):
+    return ('%d independent chains (1 per usable CPU; %s physical cores, %d logical%s) x %d iterations x L=%d of '
+            'config 2 per step, %d step(s)' % (host['workers'], host['physical_cores'] or '?', host['logical'],
+                                               (', cgroup quota %.1f' % host['cgroup_quota']) if host['cgroup_quota'] else '',
+                                               n_iter, L, steps_done))
+
+
+def cpu_baseline_quick(budget_s=12.0):
+    """The cpu_baseline leg of the B200 arm: a bounded sample, forked BEFORE this process touches CUDA."""
+    host = host_cpus()
+    arm = CpuArm(host['workers'])
+    try:
+        arm.step(2)                                           # page the workers in
+        t_cal = arm.step(20)                                  # calibration
+        n_iter = int(max(50, min(2000, 20 * (budget_s / max(t_cal, 1e-3)))))
+        wall = arm.step(n_iter)
+    finally:
+        arm.close()
+    rate = host['workers'] * n_iter * L / wall
+    return {'value': rate, 'unit': UNIT, 'cores': host['workers'], 'physical_cores': host['physical_cores'],
+            'logical_cpus': host['logical'], 'cgroup_quota': host['cgroup_quota'], 'kind': 'port',
+            'sample': cpu_sample_text(host, n_iter, 1) + ', %.1f s wall' % wall}
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the oracle port on all usable host CPUs, bounded to REFERENCE_ARM_BUDGET_S of wall clock
+    whatever --steps / --warmup say (the driver gives this arm a per-N time slot): the per-step sample size is chosen
+    from a calibration step so that warm-up + K steps fit, the JSON line is also printed if the run is cut short
+    (SIGTERM / SIGINT) with the steps completed so far."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    n_iter = args.cpu_iters
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_rate(max(2, n_iter // 10), cores)
-    t_tot, steps_tot = 0.0, 0
-    for _ in range(args.steps):
-        rate, wall = cpu_reference_rate(n_iter, cores)
-        t_tot += wall
-        steps_tot += cores * n_iter * L
-    value = steps_tot / t_tot
-    sample = '%d chains (1 per core) x %d iterations x L=%d of config 2 per step' % (cores, n_iter, L)
-    line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        # same workload as the B200 arm; each reference step is the bounded sample named in `sample` (independent chains
-        # of config 2 through the reference's per-chain Python loop; the rate is per chain-step, so it extrapolates
-        # linearly to the full 256 x 1000 job)
-        'config': dict(workload_config(args.gpus), sample=sample),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }
-    print(json.dumps(line), flush=True)
+    t_start = time.perf_counter()
+    host = host_cpus()
+    arm = CpuArm(host['workers'])
+    state = {'t': 0.0, 'steps': 0, 'n_iter': 0, 'printed': False}
+
+    def emit(cut_short=False):
+        if state['printed']:
+            return
+        state['printed'] = True
+        steps_done = max(state['steps'], 1)
+        n_iter = max(state['n_iter'], 1)
+        t_tot = state['t'] if state['steps'] else max(time.perf_counter() - t_start, 1e-9)
+        value = (host['workers'] * n_iter * L * state['steps'] / t_tot) if state['steps'] else 0.0
+        sample = cpu_sample_text(host, n_iter, state['steps'])
+        cfg = workload_config(args.gpus)
+        line = {
+            'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / steps_done,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            # identical to the B200 arm's `config`; what a reference step is lives in cpu_baseline.sample (independent
+            # chains of config 2 through the reference's per-chain Python loop; the rate is per chain-step, so it
+            # extrapolates linearly to the full 256 x 1000 job)
+            'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': host['workers'],
+                             'physical_cores': host['physical_cores'], 'logical_cpus': host['logical'],
+                             'cgroup_quota': host['cgroup_quota'], 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'steps_completed': state['steps'], 'cut_short': bool(cut_short),
+            'wall_s': time.perf_counter() - t_start,
+        }
+        print(json.dumps(line), flush=True)
+
+    def on_term(signum, frame):
+        emit(cut_short=True)
+        try:
+            arm.pool.terminate()
+        finally:
+            os._exit(0)
+
+    signal.signal(signal.SIGTERM, on_term)
+    signal.signal(signal.SIGINT, on_term)
+    try:
+        arm.step(2)                                           # page the workers in (imports, first autograd call)
+        t_cal = arm.step(10)                                  # calibration
+        budget = max(5.0, REFERENCE_ARM_BUDGET_S - (time.perf_counter() - t_start) - 3.0)
+        per_step = budget / (args.steps + (1 if args.warmup > 0 else 0))
+        n_iter = args.cpu_iters if args.cpu_iters > 0 else int(max(4, min(2000, 10 * per_step / max(t_cal, 1e-3))))
+        state['n_iter'] = n_iter
+        if args.warmup > 0:
+            arm.step(n_iter)
+        for _ in range(args.steps):
+            state['t'] += arm.step(n_iter)
+            state['steps'] += 1
+            if time.perf_counter() - t_start > REFERENCE_ARM_BUDGET_S + 15.0:
+                break                                         # a box slower than its calibration step: stop early
+        emit(cut_short=state['steps'] < args.steps)
+    finally:
+        arm.close()
 
 
 # ----------------------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons sampled every 20 ms while the timed regions run.  In-process NVML (nvidia_ml_py) on a
-    daemon thread: one nvmlInit before the warm-up, then ~50 us queries -- no subprocess attaching to the driver while
-    kernels are being launched (an `nvidia-smi -lms` loop did stall launches for milliseconds now and then).  Falls back
-    to that loop only if NVML cannot be imported."""
+    """SM / memory clock + throttle reasons sampled every 20 ms while the timed regions run.  In-process NVML
+    (nvidia_ml_py) on a daemon thread: one nvmlInit before the warm-up, then ~50 us queries -- no subprocess attaching to
+    the driver while kernels are being launched (an `nvidia-smi -lms` loop did stall launches for milliseconds now and
+    then).  Falls back to that loop only if NVML cannot be imported."""
     REASONS = (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown'),
                ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown'),
                ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown'),
@@ -121,7 +304,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.thread = index, None, None
-        self.sm, self.mx, self.reasons, self.stop_flag = [], [], set(), False
+        self.sm, self.mem, self.mx, self.reasons, self.stop_flag = [], [], [], set(), False
 
     def _visible_index(self):
         vis = os.environ.get('CUDA_VISIBLE_DEVICES')
@@ -135,6 +318,7 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mem.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_MEM)))
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 for name, const in self.REASONS:
                     if r & getattr(nv, const):
@@ -166,8 +350,9 @@ class ClockSampler:
         if self.thread is not None:
             self.stop_flag = True
             self.thread.join(timeout=2)
-            sm = sorted(self.sm)
+            sm, mem = sorted(self.sm), sorted(self.mem)
             return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                    'mem_mhz': mem[len(mem) // 2] if mem else None,
                     'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
@@ -196,6 +381,86 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4, 5 on this rank's GPU (reported under `other_configs`; config 2 is the headline)
+# ----------------------------------------------------------------------------------------------------------
+def _event_timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = None
+    for _ in range(reps):
+        r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, r
+
+
+def other_configs(dev, rank, world):
+    """One device-timed launch (after one warm-up launch) of BASELINE configs 3, 4 and 5 with this rank's share of the
+    chains, in-kernel Philox, inputs resident in HBM.  Returns {name: {...}} with per-rank chain-steps/s; the caller
+    sums over ranks.  Each entry names its kernel and the roofline that bounds it."""
+    import torch.nn as nn
+    import hamiltorch_b200 as hb
+    from hamiltorch_b200 import targets as T
+    out = {}
+    peaks = measured_peaks()
+    # ---- config 3: explicit RMHMC, 2-D funnel, softabs 1e6, omega 10, 512 chains per GPU, L=10, eps=.05, S=200 ----
+    C3, S3 = 512, 200
+    init3 = torch.tensor([0., 1.], device=dev).repeat(C3, 1)
+    ms, res = _event_timed(lambda: hb.sample_chains(
+        T.Funnel(2), init3, num_samples=S3, num_steps_per_sample=10, step_size=0.05, jitter=1e-3, softabs_const=1e6,
+        explicit_binding_const=10, sampler=hb.Sampler.RMHMC, integrator=hb.Integrator.EXPLICIT,
+        metric=hb.Metric.SOFTABS, rng='philox', seed=2, chain_offset=rank * C3), reps=3)
+    out['config3'] = {'workload': 'explicit RMHMC, 2-D funnel, softabs 1e6, omega=10, jitter 1e-3, 512 chains/GPU, '
+                                  'L=10, eps=0.05, S=200', 'kernel': 'rmhmc_run_kernel<2>', 'bound': 'latency/SFU',
+                      'kernel_ms': ms, 'value': C3 * S3 * 10 / (ms * 1e-3), 'unit': UNIT,
+                      'accept_rate': float(res.accepted.float().mean()),
+                      'log_prob_error_rate': float(res.diverged.float().mean())}
+    # ---- config 4: Linear(64,128)-ReLU-Linear(128,1) BNN (D=8449), N=1024 in M=4 splits, symmetric split HMC,
+    #      64 chains over 8 GPUs = 8 per GPU (all 64 on one GPU when world == 1), L=10, eps=5e-4, S=300 ----
+    C4 = 64 if world == 1 else max(1, 64 // world)
+    S4 = 300
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(1024, 64, generator=g)
+    w = torch.randn(64, 1, generator=g)
+    y = torch.sin(X @ w / 8) + 0.1 * torch.randn(1024, 1, generator=g)
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 1))
+    descs = [T.MLPRegression.from_model(model, X[m * 256:(m + 1) * 256], y[m * 256:(m + 1) * 256], None, 100.,
+                                        prior_scale=4) for m in range(4)]
+    D4 = descs[0].dim
+    init4 = (hb.util.flatten(model).detach()[None] + 0.01 * torch.randn(C4, D4, generator=g)).to(dev)
+    ones = torch.ones(D4)
+    ms, res = _event_timed(lambda: hb.sample_chains(
+        descs, init4, num_samples=S4, num_steps_per_sample=10, step_size=5e-4, inv_mass=ones,
+        integrator=hb.Integrator.SPLITTING, rng='philox', seed=3, chain_offset=rank * C4), reps=1)
+    flops = 68.7e6 * C4 * S4 * 10                        # SURVEY 8d: 68.7 MFLOP per chain-step
+    tf = flops / (ms * 1e-3) / 1e12
+    peak_tc = float(peaks.get('bf16_tflops_sustained', 2250.0)) / 6.0      # tf32 = bf16/2, 3 UMMAs per product
+    out['config4'] = {'workload': 'BNN 64-128-1 (D=8449) regression, N=1024, M=4 symmetric split HMC, %d chains/GPU, '
+                                  'L=10, eps=5e-4, S=300' % C4, 'kernel': 'mlp_run_kernel (tcgen05 3xTF32)',
+                      'bound': 'tensor', 'kernel_ms': ms, 'value': C4 * S4 * 10 / (ms * 1e-3), 'unit': UNIT,
+                      'algorithmic_tflops': tf, 'roofline_frac': tf / peak_tc, 'roofline_peak_tflops': peak_tc,
+                      'accept_rate': float(res.accepted.float().mean())}
+    # ---- config 5: HMC_NUTS step-size adaptation, D=4096 isotropic Gaussian, 1024 chains over 8 GPUs = 128 per GPU,
+    #      L=10, eps0=0.1, burn=100, S=150 ----
+    C5, D5, S5, B5 = 128, 4096, 150, 100
+    init5 = (0.1 * torch.randn(C5, D5, generator=g)).to(dev)
+    ms, res = _event_timed(lambda: hb.sample_chains(
+        T.GaussianIso(D5), init5, num_samples=S5, num_steps_per_sample=10, step_size=0.1, burn=B5,
+        sampler=hb.Sampler.HMC_NUTS, rng='philox', seed=1, chain_offset=rank * C5), reps=3)
+    out['config5'] = {'workload': 'HMC_NUTS (dual averaging), D=4096 isotropic Gaussian, 128 chains/GPU, L=10, '
+                                  'eps0=0.1, burn=100, S=150', 'kernel': 'hmc_run_kernel<ISO,NONE,NUTS=1>',
+                      'bound': 'issue/latency (HBM traffic = retained samples only)', 'kernel_ms': ms,
+                      'note': 'kernel_ms is the whole public-API call (allocations + launch), not the kernel alone',
+                      'value': C5 * S5 * 10 / (ms * 1e-3), 'unit': UNIT,
+                      'median_adapted_step_size': float(res.step_size.median()),
+                      'post_burn_accept_rate': float(res.accepted[:, B5 + 1:].float().mean())}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------
 def run_b200_arm(args, rank, world, local_rank):
@@ -206,12 +471,10 @@ def run_b200_arm(args, rank, world, local_rank):
     N.require_cuda()
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        # fork the CPU workers BEFORE this process touches CUDA or spins up torch's intra-op pool
-        cores = os.cpu_count() or 1
-        rate, wall = cpu_reference_rate(args.cpu_iters, cores)
-        cpu_base = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                    'sample': '%d chains (1 per core) x %d iterations x L=%d of config 2, %.1f s wall'
-                              % (cores, args.cpu_iters, L, wall)}
+        # fork the CPU workers BEFORE this process touches CUDA / NVML, spins up torch's intra-op pool or narrows its
+        # CPU affinity to the GPU's NUMA node
+        cpu_base = cpu_baseline_quick()
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {'bound': False, 'skipped': True}
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1 and not dist.is_initialized():
@@ -221,27 +484,35 @@ def run_b200_arm(args, rank, world, local_rank):
     chain_offset = rank * C
     tgt = engine.NativeTarget(T.GaussianIso(D), dev)
     ld = N.padded_ld(D)
-    g = torch.Generator().manual_seed(1234 + rank)
-    q0_host = (0.1 * torch.randn(C, D, generator=g)).pin_memory()
+
+    def init_of(r):                                 # rank r's params_init (any rank can rebuild any shard's inputs)
+        return 0.1 * torch.randn(C, D, generator=torch.Generator().manual_seed(1234 + r))
+
+    q0_host = init_of(rank).pin_memory()
     q0 = q0_host.to(dev)
     out = torch.empty((C, S, ld), dtype=torch.float32, device=dev)           # 1 GiB: 8x the 126 MB L2
     host_out = torch.empty((C, S, ld), dtype=torch.float32).pin_memory()
     stats_local = torch.zeros((max(args.steps, args.warmup, 1), C, 2), dtype=torch.float32, device=dev)
     stats = torch.empty((world,) + tuple(stats_local.shape), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, C, S, ld), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def step(seed):
-        return engine.hmc_run(tgt, q0, S, L, EPS, seed=seed, chain_offset=chain_offset, out=out, device=dev,
-                              tuning=int(os.environ.get('HMCX_TUNING', '0')))
+    def step(seed, q=None, offset=None, dst=None):
+        return engine.hmc_run(tgt, q0 if q is None else q, S, L, EPS, seed=seed,
+                              chain_offset=chain_offset if offset is None else offset, out=out if dst is None else dst,
+                              device=dev, tuning=int(os.environ.get('HMCX_TUNING', '0')))
 
     def keep_stats(k, res):               # per-chain summary of step k (reject count, final step size), device side
         stats_local[k, :, 0].copy_(res.num_rejected)
         stats_local[k, :, 1].copy_(res.step_size)
 
-    def gather_stats():                   # the run's single (tiny) collective: every rank's per-chain summaries
+    def gather_stats():                   # every rank's per-chain summaries (tiny)
         if world > 1:
             dist.all_gather_into_tensor(stats.view(-1), stats_local.view(-1))
         else:
             stats[0].copy_(stats_local)
+
+    def gather_samples():                 # the run's one real collective -- every rank's sample block
+        dist.all_gather_into_tensor(gathered.view(-1), out.view(-1))
 
     def barrier():
         if world > 1:
@@ -256,24 +527,32 @@ def run_b200_arm(args, rank, world, local_rank):
         time.sleep(0.2)
     barrier()
 
-    # ---- warm-up: the W requested steps, then (still untimed) until the step time has settled ----
-    # A fresh box runs its first launches several times slower for up to a few seconds (observed on B200 boxes right
-    # after start-up: 5-9 ms instead of 1.5 ms per step, clocks already at maximum); W = 3 steps do not outlast that.
+    # ---- warm-up: the W requested steps, then (still untimed) until the GPU has been busy for >= 1.5 s AND the last
+    #      16 steps are within 3 % of the fastest seen.  A freshly leased box ran the first ~second of launches up to
+    #      several times slower with the SM clock already reported at maximum (round-1 notes) and a 13-step warm-up (25 ms
+    #      of GPU time) left round 1's SCALE N=1 point 18 % slow; the warm-up is now bounded by GPU-busy time, not by a
+    #      step count.  Hard limits: 6 s / 4000 steps.
     for w in range(args.warmup):
         keep_stats(w, step(w))
+        if world > 1:
+            gather_samples()
     gather_stats()
     barrier()
-    extra_warmup, best, stable, t_w = 0, float('inf'), 0, time.time()
+    extra_warmup, best, stable, busy_ms, t_w = 0, float('inf'), 0, 0.0, time.time()
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    while extra_warmup < 400 and time.time() - t_w < 4.0 and stable < 8:
+    warm_trace = []
+    while extra_warmup < 4000 and time.time() - t_w < 6.0 and (stable < 16 or busy_ms < 1500.0):
         w0.record()
         step(1000 + extra_warmup)
         w1.record()
         torch.cuda.synchronize()
         ms = w0.elapsed_time(w1)
+        if extra_warmup < 4 or extra_warmup % 100 == 0:
+            warm_trace.append(round(ms, 4))
         extra_warmup += 1
+        busy_ms += ms
         best = min(best, ms)
-        stable = stable + 1 if ms <= 1.1 * best else 0
+        stable = stable + 1 if ms <= 1.03 * best else 0
     barrier()
 
     # ---- device-timed region: EXACTLY K steps, inputs resident in HBM ----
@@ -288,8 +567,45 @@ def run_b200_arm(args, rank, world, local_rank):
     ev[-1].record()
     barrier()
     t_total_ms = ev[0].elapsed_time(ev[-1])
-    t_kernel_ms = sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(args.steps)) / args.steps
+    step_ms = [ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(args.steps)]
+    t_kernel_ms = sum(step_ms) / args.steps
     rejected = stats[:, :args.steps, :, 0].sum().item()
+
+    # ---- the same K steps, each followed by the all-gather of its samples (SURVEY 8e / north_star: "a single NCCL
+    #      all-gather over NVLink to collect samples"), device-timed: value_with_gather ----
+    t_gather_total_ms = t_allgather_ms = None
+    gather_check = None
+    if world > 1 and not args.no_gather_samples:
+        gather_samples()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+        g0.record()
+        for k in range(args.steps):
+            step(100 + k)
+            a_ev[2 * k].record()
+            gather_samples()
+            a_ev[2 * k + 1].record()
+        g1.record()
+        barrier()
+        t_gather_total_ms = g0.elapsed_time(g1)
+        t_allgather_ms = sum(a_ev[2 * k].elapsed_time(a_ev[2 * k + 1]) for k in range(args.steps)) / args.steps
+        # cross-rank check ON HARDWARE: `gathered` holds the last step (seed 100+K-1) of every rank; this rank
+        # recomputes EVERY shard alone (that shard's params_init and chain_offset, same seed) and compares bit for bit:
+        # G GPUs == one GPU.
+        scratch = torch.empty_like(out)
+        seed_last = 100 + args.steps - 1
+        equal = True
+        for r in range(world):
+            step(seed_last, q=init_of(r).to(dev), offset=r * C, dst=scratch)
+            equal = equal and bool(torch.equal(scratch, gathered[r]))
+        flag = torch.tensor([1 if equal else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        # order-independent checksum of the gathered block (identical on every rank, and to a 1-GPU run of all shards)
+        csum = int(gathered.view(torch.int32).to(torch.int64).sum().item()) & 0xFFFFFFFFFFFF
+        gather_check = {'shards_recomputed_on_every_rank': world, 'bitwise_equal_to_single_gpu_runs': bool(flag.item()),
+                        'checksum48': csum}
+        del scratch
 
     # ---- e2e: public API, HOST buffers, H2D of the inputs and D2H of the result inside the timed region ----
     def e2e_step(seed):
@@ -325,21 +641,6 @@ def run_b200_arm(args, rank, world, local_rank):
     e2e_stream_step(999)
     torch.cuda.synchronize()
     assert torch.equal(ref_rows, host_out[:, -1]), 'streamed samples differ from the copied ones'
-    t_e2e_ms = min(t_e2e_copy_ms, t_e2e_stream_ms)
-
-    # ---- optional: cost of collecting every rank's samples with one NCCL all-gather (reported, not in `value`) ----
-    allgather_ms = None
-    if world > 1 and args.gather_samples:
-        big = torch.empty((world, C, S, ld), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(big.view(-1), out.view(-1))
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        dist.all_gather_into_tensor(big.view(-1), out.view(-1))
-        a1.record()
-        barrier()
-        allgather_ms = a0.elapsed_time(a1)
-        del big
 
     # ---- streaming leapfrog kernel (the HBM-roofline form of samplers.leapfrog): state >> L2, L=1 ----
     Cs = 32768                                           # 32768 x 1024 fp32 = 128 MiB per array, 4 arrays
@@ -366,14 +667,29 @@ def run_b200_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     t_stream_ms = s0.elapsed_time(s1) / n_s
     del qs, ps, qo, po
-    clk = clocks.stop() if rank == 0 else None        # sampled across all three timed regions (all under load)
+    clk = clocks.stop() if rank == 0 else None        # sampled across all timed regions above (all under load)
 
-    # max over ranks of every timing
-    t = torch.tensor([t_total_ms, t_kernel_ms, t_e2e_copy_ms, t_stream_ms, t_e2e_stream_ms], dtype=torch.float64,
-                     device=dev)
+    # ---- BASELINE configs 3 / 4 / 5 with this rank's share of their chains ----
+    others = None
+    if not args.no_other_configs:
+        del out, gathered
+        torch.cuda.empty_cache()
+        others = other_configs(dev, rank, world)
+
+    # max over ranks of every timing; sum over ranks of the other configs' rates
+    names = ['total', 'kernel', 'e2e_copy', 'stream', 'e2e_stream', 'gather_total', 'allgather']
+    vals = [t_total_ms, t_kernel_ms, t_e2e_copy_ms, t_stream_ms, t_e2e_stream_ms, t_gather_total_ms or 0.0,
+            t_allgather_ms or 0.0]
+    if others:
+        for k in sorted(others):
+            names.append('o_' + k)
+            vals.append(others[k]['kernel_ms'])
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_total_ms, t_kernel_ms, t_e2e_copy_ms, t_stream_ms, t_e2e_stream_ms = t.tolist()
+    tm = dict(zip(names, t.tolist()))
+    t_total_ms, t_kernel_ms, t_stream_ms = tm['total'], tm['kernel'], tm['stream']
+    t_e2e_copy_ms, t_e2e_stream_ms = tm['e2e_copy'], tm['e2e_stream']
     t_e2e_ms = min(t_e2e_copy_ms, t_e2e_stream_ms)
 
     if rank == 0:
@@ -389,13 +705,22 @@ def run_b200_arm(args, rank, world, local_rank):
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         sm_mhz = float((clk or {}).get('sm_mhz') or 1965.0)
         issue_peak = n_sm * 4 * sm_mhz * 1e6 / 1e9
+        sorted_ms = sorted(step_ms)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(world), rng='in-kernel Philox4x32-10',
-                           l2_policy='each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
-                           extra_untimed_warmup_steps=extra_warmup),
+            'config': workload_config(world),
+            'run_notes': {'rng': 'in-kernel Philox4x32-10',
+                          'l2_policy': 'each step streams 1.0 GiB of samples (8x the 126 MB L2); no explicit flush',
+                          'extra_untimed_warmup_steps': extra_warmup, 'warmup_gpu_busy_ms': busy_ms,
+                          'warmup_step_ms_trace': warm_trace,
+                          'timed_step_ms': {'min': sorted_ms[0], 'median': sorted_ms[len(sorted_ms) // 2],
+                                            'max': sorted_ms[-1]},
+                          'numa': numa,
+                          'parity': 'config 2: samples bit-exact vs the reference (tests/test_hmc_gpu.py); config 5 (NUTS): '
+                                    'bit-exact under the reference step-size schedule (teacher forcing); configs 3/4: see '
+                                    'DESIGN.md section 4 for the measured tolerances'},
             'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1,PHILOX,NUTS=0>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
@@ -418,6 +743,7 @@ def run_b200_arm(args, rank, world, local_rank):
                                    'chain_steps_per_s': Cs / (t_stream_ms * 1e-3)},
             'e2e': {'value': units_per_step / (t_e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': t_e2e_ms,
+                    'pcie_gbs_per_rank': (h2d + d2h) / (t_e2e_ms * 1e-3) / 1e9,
                     'path': ('hb.sample_chains(out=<pinned host block>): kernel streams the samples to the host'
                              if t_e2e_stream_ms <= t_e2e_copy_ms else
                              'hb.sample_chains(out=<device block>) + D2H copy of the samples'),
@@ -426,8 +752,26 @@ def run_b200_arm(args, rank, world, local_rank):
             'accept_rate': 1.0 - rejected / (world * C * S * args.steps),
             'clocks': clk,
         }
-        if allgather_ms is not None:
-            line['allgather_samples_ms'] = allgather_ms
+        if t_gather_total_ms is not None:
+            ms_g = tm['gather_total'] / args.steps
+            line['allgather_samples_ms'] = tm['allgather']
+            line['ms_per_step_with_gather'] = ms_g
+            line['value_with_gather'] = units_per_step / (ms_g * 1e-3)
+            line['allgather_gbs_per_rank'] = (world - 1) * C * S * ld * 4 / (tm['allgather'] * 1e-3) / 1e9
+            line['gather_check'] = gather_check
+        if others:
+            oc = {}
+            for k in sorted(others):
+                e = dict(others[k])
+                e['kernel_ms'] = tm['o_' + k]                           # max over ranks
+                units = e['value'] * others[k]['kernel_ms'] * 1e-3      # this rank's chain-steps per launch
+                e['value'] = world * units / (e['kernel_ms'] * 1e-3)    # whole job: every rank runs the same share
+                if 'algorithmic_tflops' in e:
+                    e['algorithmic_tflops_per_gpu'] = e.pop('algorithmic_tflops') * others[k]['kernel_ms'] / e['kernel_ms']
+                    e['roofline_frac'] = e['algorithmic_tflops_per_gpu'] / e['roofline_peak_tflops']
+                e['n_gpus'] = world
+                oc[k] = e
+            line['other_configs'] = oc
         if cpu_base is not None:
             line['cpu_baseline'] = cpu_base
         print(json.dumps(line), flush=True)
@@ -442,9 +786,14 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--cpu-iters', type=int, default=2000, help='iterations per chain of the bounded CPU sample')
+    ap.add_argument('--cpu-iters', type=int, default=0,
+                    help='reference arm: iterations per chain and step (0 = sized from a calibration step so that the '
+                         'whole run fits the %d s budget)' % REFERENCE_ARM_BUDGET_S)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--gather-samples', action='store_true', help='also time one NCCL all-gather of all samples')
+    ap.add_argument('--no-gather-samples', action='store_true',
+                    help='N > 1: skip the timed all-gather of every step\'s samples (value_with_gather)')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip BASELINE configs 3 / 4 / 5')
+    ap.add_argument('--no-numa-bind', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -576,6 +576,7 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
             N.check(rc, 'hmcx_rmhmc_run')
     res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
     res.eps_trace = None
+    res.final_state = q_cur[:, :D]
     res._keep_alive = keep_alive
     return res
 

@@ -24,12 +24,14 @@ class JitterSource:
     """torch.rand(D) by default (the reference's draw, :115); or successive rows of an injected (J, D) tensor."""
 
     def __init__(self, rows=None):
-        self.rows, self.i = rows, 0
+        self.rows, self.i, self.retries = rows, 0, 0        # retries: NaN-gradient re-evaluations (:402-410)
 
     def __call__(self, d):
         if self.rows is None:
+            self.i += 1
             return torch.rand(d)
-        r = self.rows[self.i]
+        # more draws than rows (NaN-retry loop, :402-410): re-use the last row -- the CUDA kernel's convention
+        r = self.rows[min(self.i, len(self.rows) - 1)]
         self.i += 1
         return r
 
@@ -82,15 +84,19 @@ def rm_hamiltonian(q, p, log_prob, jitter, alpha, metric, jit):
 def _grad_wrt_params(q, p, args, max_tries):
     """hamAB_grad_params (:395-414) / the implicit integrator's dH/dtheta (:317-331): NaN gradients are retried with a
     fresh jitter draw up to jitter_max_tries."""
-    tries = 0
-    while True:
+    def evaluate():
         x = q.detach().requires_grad_()
-        g = torch.autograd.grad(rm_hamiltonian(x, p.detach(), *args), x)[0]
-        if not nonfinite(g):
-            return g
+        return torch.autograd.grad(rm_hamiltonian(x, p.detach(), *args), x)[0]
+
+    g = evaluate()
+    tries = 0
+    while nonfinite(g):                  # :402-410 verbatim: re-evaluate FIRST, then count -- the evaluation that
+        g = evaluate()                   # exhausts the budget still happens (and still draws its jitter)
+        args[-1].retries += 1
         tries += 1
         if tries > max_tries:
             raise OracleLogProbError()
+    return g
 
 
 def _grad_wrt_momentum(q, p, args):
@@ -162,11 +168,14 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
     burn_prev = params_init.clone()
     kept = [params_init.clone()]
     accepted, ham_old, ham_new, diverged = [], [], [], []
+    state_in, proposal, jitter_draws, nan_retries = [], [], [], []          # diagnostics for the teacher-forced parity tests
     rejected = 0
     for n in range(num_samples):
         jit = JitterSource(None if uniforms is None else uniforms[n])
         args = (log_prob, jitter, softabs_const, metric, jit)
         h0 = h1 = float('nan')
+        state_in.append(q.detach().clone())
+        prop = torch.full_like(params_init, float('nan'))
         try:
             G = fisher(q, log_prob, jitter, softabs_const, metric, jit)[0]                    # gibbs :183-184
             if normals is None:
@@ -185,6 +194,7 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
                                            fixed_point_max_iterations, jitter_max_tries)
             h0 = float(H0)
             q = qs[-1].detach()
+            prop = q.clone()
             H1 = rm_hamiltonian(q, ps[-1].detach(), *args)                                    # :989 / :995
             h1 = float(H1)
             rho = log_accept_ratio(H0, H1)
@@ -215,5 +225,9 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
                 q = burn_prev.clone()
         ham_old.append(h0)
         ham_new.append(h1)
+        proposal.append(prop)
+        jitter_draws.append(jit.i)
+        nan_retries.append(jit.retries)
     return dict(samples=[t.detach() for t in kept], accepted=accepted, ham_old=ham_old, ham_new=ham_new,
-                num_rejected=rejected, diverged=diverged)
+                num_rejected=rejected, diverged=diverged, state_in=state_in, proposal=proposal,
+                jitter_draws=jitter_draws, nan_retries=nan_retries)

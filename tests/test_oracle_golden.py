@@ -95,3 +95,74 @@ def test_oracle_equals_reference_live():
         assert torch.equal(torch.stack(r[0]), torch.stack(o['samples']))
         if nuts:
             assert r[1] == o['step_size']
+
+
+# ---- sampler=RMHMC: oracle/rmhmc_oracle.py ---------------------------------------------------------------------
+@pytest.mark.parametrize('name', sorted(cases.rmhmc_cases()))
+def test_rmhmc_oracle_reproduces_reference_fixture(name):
+    """The RMHMC oracle driven by the stored stream returns the reference's chain (explicit / implicit, both metrics)."""
+    from oracle import rmhmc_oracle as R
+    torch.set_num_threads(1)
+    case = cases.rmhmc_cases()[name]
+    d = np.load(os.path.join(GOLD, name + '.npz'))
+    explicit = case['integrator'] == 'EXPLICIT'
+    kw = dict(num_samples=case['num_samples'], num_steps_per_sample=case['num_steps_per_sample'],
+              step_size=case['step_size'], burn=case['burn'], jitter=case['jitter'], softabs_const=case['softabs_const'],
+              integrator=R.EXPLICIT if explicit else R.IMPLICIT,
+              metric=R.SOFTABS if case['metric'] == 'SOFTABS' else R.HESSIAN)
+    if explicit:
+        kw['explicit_binding_const'] = case['explicit_binding_const']
+    else:
+        kw.update(fixed_point_threshold=case['fixed_point_threshold'],
+                  fixed_point_max_iterations=case['fixed_point_max_iterations'])
+    ci = 0
+    res = R.sample_rmhmc(case['target'], torch.tensor(case['init']), normals=torch.from_numpy(d['z_%d' % ci]),
+                         log_uniforms=torch.from_numpy(d['logu_%d' % ci]),
+                         uniforms=torch.from_numpy(d['uniforms_%d' % ci]) if case['jitter'] is not None else None, **kw)
+    assert list(np.array(res['accepted'], dtype=np.uint8)) == list(d['accepted_%d' % ci])
+    np.testing.assert_allclose(torch.stack(res['samples']).numpy(), d['samples_%d' % ci], rtol=1e-5, atol=1e-5)
+
+
+def test_cfg3_pin_fixture_rejects_logprob_errors_and_nan_retries():
+    """tests/golden/cfg3_rmhmc_pin.npz: BASELINE config 3 chains of the UNMODIFIED reference (torch global RNG) that
+    reject, raise LogProbError and run the NaN-retry loop of samplers.py:402-410; the oracle under the same seed must
+    return the same chain -- this is what pins those paths (and what caught the oracle's off-by-one in the retry
+    loop).  Exact on this torch build; decisions + 1e-5 elsewhere."""
+    from oracle import gen_cfg3 as G, rmhmc_oracle as R
+    torch.set_num_threads(1)
+    d = np.load(os.path.join(GOLD, 'cfg3_rmhmc_pin.npz'))
+    assert sum(int(d['diverged_%d' % c].sum()) for c in range(len(d['seeds']))) > 0
+    assert sum(int(d['nan_retries_%d' % c].sum()) for c in range(len(d['seeds']))) > 0
+    from hamiltorch_b200 import targets as T
+    import contextlib
+    import io
+    ci = 0
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(int(d['seeds'][ci]))
+        res = R.sample_rmhmc(T.Funnel(2), torch.tensor(G.INIT), num_samples=25, burn=3, **G.KW)
+    assert list(np.array(res['accepted'], dtype=np.uint8)) == list(d['accepted_%d' % ci])
+    assert list(np.array(res['diverged'], dtype=np.uint8)) == list(d['diverged_%d' % ci])
+    assert list(res['nan_retries']) == list(d['nan_retries_%d' % ci])
+    np.testing.assert_allclose(torch.stack(res['samples']).numpy(), d['samples_%d' % ci], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference only exists in the build container')
+def test_cfg4_oracle_equals_reference_live():
+    """BASELINE config 4 exactly (oracle/cfg4.py): hamiltorch.sample_split_model == the oracle, bit for bit."""
+    import torch.utils.data as tud
+    from oracle import cfg4
+    torch.set_num_threads(1)
+    ref = import_reference()
+    model, X, y = cfg4.problem()
+    descs = cfg4.descriptors(model, X, y)
+    D = descs[0].dim
+    init = ref.util.flatten(model).detach().clone()
+    loader = tud.DataLoader(tud.TensorDataset(X, y), batch_size=cfg4.N_ROWS // cfg4.M, shuffle=False)
+    kw = dict(num_samples=4, num_steps_per_sample=cfg4.L, step_size=cfg4.EPS, inv_mass=torch.ones(D))
+    torch.manual_seed(5)
+    r = ref.sample_split_model(model, loader, params_init=init, num_splits=cfg4.M, model_loss='regression',
+                               tau_out=cfg4.TAU_OUT, integrator=ref.Integrator.SPLITTING, verbose=False, **kw)
+    torch.manual_seed(5)
+    next(iter(loader))                       # the DataLoader's base-seed draw (see oracle/gen_golden.py)
+    o = O.sample_hmc(descs, init, split_scheme=O.SPLIT_SYM, **kw)
+    assert torch.equal(torch.stack(r), torch.stack(o['samples']))
