@@ -150,7 +150,19 @@ struct RunArgs {
     int thin;
     float* msum;
     float* msumsq;
+    float* msum_lo;           // optional: the compensation terms of the running sums (true sum = hi + lo)
+    float* msumsq_lo;
 };
+
+// Neumaier's compensated accumulation: s + c carries the running sum to ~2^-46 relative whatever the number of terms
+// (the sink exists for LONG runs: a naive fp32 running sum of x^2 loses the variance once |mean| >> std).  Plain fp32
+// adds, never contracted or re-associated.
+__device__ __forceinline__ void comp_add(float& s, float& c, float x) {
+    const float t = add(s, x);
+    const float e = (fabsf(s) >= fabsf(x)) ? add(sub(s, t), x) : add(sub(x, t), s);
+    c = add(c, e);
+    s = t;
+}
 
 // block_sum3 for CTAs of at most 8 warps: the second level reads the warps' partials with broadcast LDS.128 and adds them
 // in warp order (3 independent 8-term chains) instead of a second shuffle butterfly: ~90 cycles less latency on the
@@ -297,14 +309,16 @@ hmc_run_kernel(const RunArgs a) {
     const int thin = SINK ? a.thin : 1;
     const int keep = SINK ? 1 + (a.S - a.burn - 1) / thin : a.S - a.burn;    // slots per chain in samples_out
     float* const my_samples = a.samples ? a.samples + (size_t)c * keep * ld : nullptr;
-    float msum[K][E], msq[K][E];
+    float msum[K][E], msq[K][E], csum[K][E], csq[K][E];
     if (SINK) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
 #pragma unroll
-            for (int j = 0; j < E; ++j) { msum[k][j] = 0.0f; msq[k][j] = 0.0f; }
+            for (int j = 0; j < E; ++j) { msum[k][j] = 0.0f; msq[k][j] = 0.0f; csum[k][j] = 0.0f; csq[k][j] = 0.0f; }
             if (live[k] && a.msum) ldE<E>(a.msum + row + E * (gt + k * G), msum[k]);
             if (live[k] && a.msumsq) ldE<E>(a.msumsq + row + E * (gt + k * G), msq[k]);
+            if (live[k] && a.msum && a.msum_lo) ldE<E>(a.msum_lo + row + E * (gt + k * G), csum[k]);
+            if (live[k] && a.msumsq && a.msumsq_lo) ldE<E>(a.msumsq_lo + row + E * (gt + k * G), csq[k]);
         }
     }
 
@@ -445,8 +459,10 @@ hmc_run_kernel(const RunArgs a) {
                 for (int k = 0; k < K; ++k)
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
-                        msum[k][j] = add(msum[k][j], qc[k][j]);
-                        msq[k][j] = add(msq[k][j], mul(qc[k][j], qc[k][j]));
+                        const float x = qc[k][j], xx = mul(x, x);
+                        comp_add(msum[k][j], csum[k][j], x);
+                        comp_add(msq[k][j], csq[k][j], xx);
+                        csq[k][j] = add(csq[k][j], fmaf(x, x, -xx));      // the rounding error of x*x itself (exact)
                     }
                 if (my_samples && (n - a.burn) % thin == 0) {
                     float* dst = my_samples + (size_t)((n - a.burn) / thin) * ld;
@@ -499,8 +515,18 @@ hmc_run_kernel(const RunArgs a) {
     if (SINK) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
+            if (!a.msum_lo) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) msum[k][j] = add(msum[k][j], csum[k][j]);
+            }
+            if (!a.msumsq_lo) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) msq[k][j] = add(msq[k][j], csq[k][j]);
+            }
             if (live[k] && a.msum) stE<E>(a.msum + row + E * (gt + k * G), msum[k]);
             if (live[k] && a.msumsq) stE<E>(a.msumsq + row + E * (gt + k * G), msq[k]);
+            if (live[k] && a.msum && a.msum_lo) stE<E>(a.msum_lo + row + E * (gt + k * G), csum[k]);
+            if (live[k] && a.msumsq && a.msumsq_lo) stE<E>(a.msumsq_lo + row + E * (gt + k * G), csq[k]);
         }
     }
     if (lead) {
@@ -901,6 +927,7 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
     if (sink) {                                            // thinning / moments: float4-per-thread geometry only
         if (ld > 4096 || (tuning != 0 && tuning != 1)) return HMCX_ERR_UNSUPPORTED;
         a.thin = sink->thin; a.msum = sink->sum; a.msumsq = sink->sumsq;
+        a.msum_lo = sink->sum_lo; a.msumsq_lo = sink->sumsq_lo;
         pick_geometry(ld, 1, E, K, G);
 #define CALLSINK(TK, MK)                                                                                \
         if (G <= 256) hmc_run_kernel<TK, MK, 4, 1, 256, true><<<C, G, 0, st>>>(a);                      \

@@ -988,6 +988,7 @@ struct MlpRunArgs {
     double* h_bar;
     double* eps_bar;
     const float* eps_schedule;
+    double eps0;                  // hmcx_nuts_t.step_size_init (0 = not given)
     float* eps_trace;
     const float* q_init;
     float* q_cur;
@@ -1055,6 +1056,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         __syncthreads();
     };
 
+    // split drifts divide the step size as a DOUBLE (step_size/K_div, samplers.py:513, :558): the run's initial Python
+    // double while the chain still uses it, the fp32 value once dual averaging produced one (:668)
+    auto eps_double = [&](float e) { return (a.eps0 != 0.0 && e == (float)a.eps0) ? a.eps0 : (double)e; };
+
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * a.C + c];
         const float half = mul(0.5f, eps);
@@ -1094,7 +1099,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             }
             kick(-half);                                                  // p - half*g == p + (-half)*g exactly
         } else if (a.scheme == HMCX_SCHEME_SPLIT_SYM) {                   // :499-540
-            const float cd = (float)((double)eps / (double)((M - 1) * 2));
+            const float cd = (float)(eps_double(eps) / (double)((M - 1) * 2));
             for (int l = 0; l < a.L; ++l) {
                 for (int s = 0; s < M; ++s) {
                     mlp_grad_split<CS>(m, q, g, tile, s, cc, tc);
@@ -1108,7 +1113,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                 }
             }
         } else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) {                  // :551-568
-            const float cd = (float)((double)eps / (double)M);
+            const float cd = (float)(eps_double(eps) / (double)M);
             for (int l = 0; l < a.L; ++l)
                 for (int s = 0; s < M; ++s) {
                     mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc, tc);
@@ -1377,6 +1382,7 @@ int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     a.rng_mode = rng->mode; a.seed = rng->seed; a.chain_offset = rng->chain_offset;
     a.normals = rng->normals; a.logu = rng->log_uniforms; a.perms = rng->perms;
     a.nuts = (nuts && nuts->enabled) ? 1 : 0;
+    a.eps0 = nuts ? nuts->step_size_init : 0.0;
     if (a.nuts) {
         if (!nuts->table || !nuts->h_bar || !nuts->eps_bar || burn < 1) return HMCX_ERR_INVALID_ARG;
         a.delta = nuts->desired_accept_rate; a.mu = nuts->mu; a.table = nuts->table;

@@ -527,6 +527,202 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
 
 
 // ---------------------------------------------------------------------------------------------------------
+// BASELINE config 3 form: D == 2, explicit integrator.  A chain is a serial recurrence of 8L+3 metric evaluations per
+// iteration, ~1e3 dependent instructions each, so the run time is the LATENCY of that recurrence, not throughput.  The
+// two evaluations of every A / B flow of the explicit step (samplers.py:429-430, :432-433, :454-455, :457-458) take the
+// SAME arguments and differ only in the jitter row and in what is differentiated (dH/dtheta vs dH/dp): they are
+// independent.  So a chain is owned by a PAIR of threads in two different warps (= two schedulers of the SM): warp 0
+// evaluates every dH/dtheta, warp 1 every dH/dp, at the same time; results cross through a double-buffered shared
+// mailbox with one barrier per flow, and both threads apply both updates to their replica of (theta, p, theta~, p~)
+// with the reference's roundings, so they stay bit-identical and every scalar decision is taken twice, identically.
+// Critical path per iteration: 4L+3 evaluations instead of 8L+3.  32 chains per CTA -> 512 chains = 16 CTAs on 16 SMs.
+//
+// Jitter rows (fisher's torch.rand(D), :115) are consumed in the reference's order.  In an A flow dH/dtheta comes first
+// and its NaN-retry loop (:402-410) may take extra rows, shifting the row of the dH/dp that follows: warp 1 assumes no
+// retry and is re-run for the (rare) chains where warp 0 reports some.
+// ---------------------------------------------------------------------------------------------------------
+struct PairMail { float g0, g1; int ok, retries; };
+
+__device__ __forceinline__ const float* rm2_jitter_row(const RmRunArgs& a, int c, int n, uint64_t chain_id, int idx,
+                                                       float* buf) {
+    if (a.cfg.jitter < 0.0f) return nullptr;
+    if (a.rng_mode == HMCX_RNG_INJECTED) {
+        const int j = idx < a.J ? idx : a.J - 1;              // overflow (NaN retries) re-uses the last row
+        const float* src = a.uniforms + (((size_t)(n - a.it0) * a.C + c) * a.J + j) * a.ld;
+        buf[0] = src[0]; buf[1] = src[1];
+    } else {
+        const uint4 r = philox_draw(a.seed, chain_id, (uint64_t)n, (uint32_t)(idx * 8), STREAM_JITTER);
+        buf[0] = (float)(r.x >> 8) * 5.9604645e-8f;
+        buf[1] = (float)(r.y >> 8) * 5.9604645e-8f;
+    }
+    return buf;
+}
+
+__global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
+    __shared__ PairMail mailQ[2][32], mailP[2][32];
+    const int lane = threadIdx.x & 31;
+    const bool roleP = threadIdx.x >= 32;                     // warp 1: dH/dp evaluations; warp 0: dH/dtheta + all stores
+    const int c = blockIdx.x * 32 + lane;
+    const bool live = c < a.C;
+    const int cc = live ? c : a.C - 1;                        // idle lanes shadow the last chain (no stores)
+    const RmTarget& t = a.t;
+    const size_t row = (size_t)cc * a.ld;
+    const uint64_t chain_id = a.chain_offset + (uint64_t)cc;
+    const bool writer = live && !roleP;
+
+    float qc[2], q[2], p[2], qt[2], pt[2], g[2], w[2], ub[2];
+    qc[0] = a.q_cur[row]; qc[1] = a.q_cur[row + 1];
+    const float eps = a.eps[cc];
+    const float half = mul(0.5f, eps);
+    int rejected = 0;
+    const int keep = a.S - a.burn;
+    float* const my_samples = (a.samples && writer) ? a.samples + (size_t)cc * keep * a.ld : nullptr;
+    if (a.it0 == 0 && my_samples)
+        for (int i = 0; i < a.ld; ++i) my_samples[i] = i < 2 ? qc[i] : 0.0f;
+    const bool jit_on = a.cfg.jitter >= 0.0f;
+    int phase = 0;
+    Metric<2> M;
+
+    for (int n = a.it0; n < a.it1; ++n) {
+        int idx = 0;                                          // jitter rows consumed so far in this iteration
+        bool ok = true;
+        float h_old = nanf(""), h_new = nanf("");
+        // one dH/dtheta with the reference's NaN-retry loop; returns the number of extra rows it consumed
+        auto dHdq = [&](const float* th, const float* pp, int first_row, float* out, bool& good) -> int {
+            int tries = 0;
+            for (;; ++tries) {
+                if (!eval_metric<2>(t, a.cfg, th, rm2_jitter_row(a, cc, n, chain_id, first_row + tries, ub), M)) { good = false; break; }
+                bool okh = true;
+                rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
+                if (!okh) { good = false; break; }
+                grad_params<2>(t, th, M, pp, out);
+                if (finite_f(out[0]) && finite_f(out[1])) break;
+                if (tries + 1 > a.jitter_max_tries) { good = false; break; }
+            }
+            return tries;
+        };
+        auto dHdp = [&](const float* th, const float* pp, int rowi, float* out, bool& good) {
+            if (!eval_metric<2>(t, a.cfg, th, rm2_jitter_row(a, cc, n, chain_id, rowi, ub), M)) { good = false; return; }
+            bool okh = true;
+            rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
+            if (!okh) { good = false; return; }
+            grad_momentum<2>(t, M, pp, out);
+        };
+        // One flow: warp 0 evaluates dH/dtheta(th, pp), warp 1 dH/dp(th, pp).  q_first: the reference calls dH/dtheta
+        // first (A flows) -- else dH/dp first (B flows).  On return gq / gp hold both gradients in BOTH threads.
+        auto flow = [&](const float* th, const float* pp, bool q_first, float* gq, float* gp) {
+            const int b = phase & 1;
+            ++phase;
+            const int rowQ = q_first ? idx : idx + 1, rowP = q_first ? idx + 1 : idx;
+            bool good = true;
+            if (ok) {
+                if (!roleP) {
+                    const int r = dHdq(th, pp, rowQ, g, good);
+                    mailQ[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, r};
+                } else {
+                    dHdp(th, pp, rowP, g, good);
+                    mailP[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, 0};
+                }
+            }
+            __syncthreads();
+            PairMail mq = mailQ[b][lane], mp = mailP[b][lane];
+            if (jit_on && q_first) {                          // retries of dH/dtheta shift the row of the dH/dp after it
+                const bool redo = ok && mq.ok && mq.retries > 0;
+                if (__syncthreads_or(redo)) {
+                    if (redo && roleP) {
+                        good = true;
+                        dHdp(th, pp, rowP + mq.retries, g, good);
+                        mailP[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, 0};
+                    }
+                    __syncthreads();
+                    mp = mailP[b][lane];
+                }
+            }
+            if (ok) {
+                // reference order: the first call's LogProbError aborts before the second call is made
+                ok = mq.ok && mp.ok;
+                gq[0] = mq.g0; gq[1] = mq.g1; gp[0] = mp.g0; gp[1] = mp.g1;
+                idx += 2 + mq.retries;
+            }
+        };
+
+        // ---- gibbs (:969 -> :183-184); both threads of the pair do it (identical bits) ----
+        ok = eval_metric<2>(t, a.cfg, qc, rm2_jitter_row(a, cc, n, chain_id, idx++, ub), M);
+        {
+            float z[2];
+            if (a.rng_mode == HMCX_RNG_INJECTED) {
+                const float* zp = a.normals + ((size_t)(n - a.it0) * a.C + cc) * a.ld;
+                z[0] = zp[0]; z[1] = zp[1];
+            } else {
+                float z4[4];
+                philox_normal4(a.seed, chain_id, (uint64_t)n, 0u, z4);
+                z[0] = z4[0]; z[1] = z4[1];
+            }
+            if (ok) ok = gibbs_rm<2>(t, M, z, p);
+        }
+        q[0] = qc[0]; q[1] = qc[1];
+        // ---- H(theta, p) (:971) ----
+        if (ok && eval_metric<2>(t, a.cfg, q, rm2_jitter_row(a, cc, n, chain_id, idx++, ub), M))
+            h_old = rm_hamiltonian<2>(t, a.cfg, q, p, M, w, ok);
+        else ok = false;
+        // ---- explicit trajectory (:423-461): every thread of the CTA runs all L steps' barriers ----
+        qt[0] = q[0]; qt[1] = q[1]; pt[0] = p[0]; pt[1] = p[1];
+        float gq[2], gp[2];
+        for (int l = 0; l < a.L; ++l) {
+            flow(q, pt, true, gq, gp);                                                                  // A
+            if (ok) for (int i = 0; i < 2; ++i) { p[i] = sub(p[i], mul(half, gq[i])); qt[i] = add(qt[i], mul(half, gp[i])); }
+            flow(qt, p, false, gq, gp);                                                                 // B
+            if (ok) {
+                for (int i = 0; i < 2; ++i) { q[i] = add(q[i], mul(half, gp[i])); pt[i] = sub(pt[i], mul(half, gq[i])); }
+                for (int i = 0; i < 2; ++i) {                                                           // C, sequential
+                    const float cw = a.cosw, sw = a.sinw;
+                    const float qn = mul(0.5f, add(add(add(q[i], qt[i]), mul(cw, sub(q[i], qt[i]))), mul(sw, sub(p[i], pt[i]))));
+                    const float pn = mul(0.5f, add(sub(add(p[i], pt[i]), mul(sw, sub(qn, qt[i]))), mul(cw, sub(p[i], pt[i]))));
+                    const float qtn = mul(0.5f, sub(sub(add(qn, qt[i]), mul(cw, sub(qn, qt[i]))), mul(sw, sub(pn, pt[i]))));
+                    const float ptn = mul(0.5f, sub(add(add(pn, pt[i]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[i]))));
+                    q[i] = qn; p[i] = pn; qt[i] = qtn; pt[i] = ptn;
+                }
+            }
+            flow(qt, p, false, gq, gp);                                                                 // B
+            if (ok) for (int i = 0; i < 2; ++i) { q[i] = add(q[i], mul(half, gp[i])); pt[i] = sub(pt[i], mul(half, gq[i])); }
+            flow(q, pt, true, gq, gp);                                                                  // A
+            if (ok) for (int i = 0; i < 2; ++i) { p[i] = sub(p[i], mul(half, gq[i])); qt[i] = add(qt[i], mul(half, gp[i])); }
+        }
+        // ---- H(theta_L, p_L) on the un-augmented Hamiltonian (:989) ----
+        if (ok && eval_metric<2>(t, a.cfg, q, rm2_jitter_row(a, cc, n, chain_id, idx++, ub), M))
+            h_new = rm_hamiltonian<2>(t, a.cfg, q, p, M, w, ok);
+        else ok = false;
+        // ---- MH + bookkeeping (both threads decide identically; warp 0 stores) ----
+        const float x = add(-h_new, h_old);
+        const float rho = (x < 0.0f) ? x : 0.0f;
+        const float logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * a.C + cc]
+                                                             : philox_log_uniform(a.seed, chain_id, (uint64_t)n);
+        const bool acc = ok && (rho >= logu);
+        if (acc) {
+            qc[0] = q[0]; qc[1] = q[1];
+        } else {
+            ++rejected;
+            if (n == a.burn + 1) { qc[0] = a.q_init[row]; qc[1] = a.q_init[row + 1]; }                 // :1018 quirk
+        }
+        if (writer) {
+            if (n > a.burn && my_samples) {
+                float* dst = my_samples + (size_t)(n - a.burn) * a.ld;
+                for (int i = 0; i < a.ld; ++i) dst[i] = i < 2 ? qc[i] : 0.0f;
+            }
+            const size_t o = (size_t)cc * a.S + n;
+            if (a.accept) a.accept[o] = acc ? 1 : 0;
+            if (a.diverged) a.diverged[o] = ok ? 0 : 1;
+            if (a.ham) { a.ham[2 * o] = h_old; a.ham[2 * o + 1] = h_new; }
+        }
+    }
+    if (writer) {
+        a.q_cur[row] = qc[0]; a.q_cur[row + 1] = qc[1];
+        if (a.num_rejected) a.num_rejected[cc] += rejected;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
 // plain HMC / HMC_NUTS for small coupled problems (D <= 16): one thread per chain
 //   targets GAUSS_FULL and FUNNEL (whose gradients couple the coordinates) and the full (2-D) inv_mass of
 //   samplers.py:293-294 (drift), :811-812 (kinetic), :198-199 (gibbs: MultivariateNormal(0, inverse(inv_mass)))
@@ -757,7 +953,8 @@ int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_r
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
     const int block = 128, grid = (C + block - 1) / block;
-    if (D == 2) rmhmc_run_kernel<2><<<grid, block, 0, st>>>(a);
+    if (D == 2 && cfg->integrator == 1) rmhmc2_pair_kernel<<<(C + 31) / 32, 64, 0, st>>>(a);       // BASELINE config 3
+    else if (D == 2) rmhmc_run_kernel<2><<<grid, block, 0, st>>>(a);
     else if (D <= 6) rmhmc_run_kernel<6><<<grid, block, 0, st>>>(a);
     else rmhmc_run_kernel<16><<<grid, block, 0, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? HMCX_OK : HMCX_ERR_CUDA;

@@ -81,9 +81,14 @@ def sample_chains_sharded(log_prob_func, params_init, gather_samples=False, runn
     C = params_init.shape[0]
     lo, hi = shard_bounds(C, rank, world)
     kw = dict(kwargs)
-    if kw.get('normals') is not None:
-        kw['normals'] = kw['normals'][:, lo:hi]
-        kw['log_uniforms'] = kw['log_uniforms'][:, lo:hi]
+    if hi == lo:
+        raise RuntimeError('sample_chains_sharded: rank %d of %d would own no chain (C=%d < world); use fewer ranks'
+                           % (rank, world, C))
+    for name in ('normals', 'log_uniforms', 'perms', 'uniforms'):          # every injected stream is (S, C, ...)
+        if kw.get(name) is not None:
+            if kw[name].shape[1] != C:
+                raise RuntimeError('%s must be (S, C=%d, ...), got %s' % (name, C, tuple(kw[name].shape)))
+            kw[name] = kw[name][:, lo:hi]
     kw['chain_offset'] = kw.get('chain_offset', 0) + lo
     run = runner if runner is not None else samplers.sample_chains
     local = run(log_prob_func, params_init[lo:hi], **kw)
@@ -91,7 +96,11 @@ def sample_chains_sharded(log_prob_func, params_init, gather_samples=False, runn
            'num_rejected': all_gather_rows(local.num_rejected, C),
            'step_size': all_gather_rows(local.step_size, C)}
     if gather_samples:
-        out['samples'] = all_gather_rows(local.samples_padded, C)[..., :local.dim]
+        blk = local.samples_padded
+        if not blk.is_cuda and dist.is_initialized() and dist.get_backend() == 'nccl':
+            raise RuntimeError('gather_samples with store_on_GPU=False: the samples live in pinned host memory, which '
+                               'NCCL cannot gather -- keep them on the GPU or gather on the host')
+        out['samples'] = all_gather_rows(blk, C)[..., :local.dim]
     if getattr(local, 'moment_sum', None) is not None:          # sink moments requested: pool them over all ranks
         out['posterior_mean'], out['posterior_var'], out['posterior_n'] = pooled_moments(
             local.moment_sum, local.moment_sumsq, local.moment_count)

@@ -290,7 +290,8 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     schedule); ``record_eps`` returns the kernel's own adapted step sizes in ``result.eps_trace`` (C, S).
     Sample sink (include/hmcx.h hmcx_sink_t; element-wise targets): ``thin`` keeps every thin-th post-burn state,
     ``moments`` accumulates per-chain running sum / sum of squares over every post-burn iteration in the kernel's
-    registers (``result.moment_sum``, ``result.moment_sumsq``, ``result.moment_count``), ``keep_samples=False`` stores no
+    registers with compensated (Neumaier) summation (``result.moment_sum``, ``result.moment_sumsq``: fp64 tensors
+    relative error ~ n*eps^2 instead of the naive n*eps; ``result.moment_count``), ``keep_samples=False`` stores no
     samples at all, ``host_samples=True`` makes the kernel stream the retained rows straight into pinned host memory
     (the reference's ``store_on_GPU=False``, samplers.py:1008-1012) -- ``result.samples`` is then a CPU tensor, valid
     after a stream synchronisation.
@@ -352,7 +353,10 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
         rng.normals, rng.log_uniforms = z.data_ptr(), lu.data_ptr()
         keep_alive += [z, lu]
         if perms is not None:
-            pm = perms.detach().to(device=device, dtype=torch.int32).reshape(S, Cn, -1).contiguous()
+            if perms.dim() != 3 or tuple(perms.shape[:2]) != (S, Cn) or perms.shape[2] != nt.num_splits:
+                raise RuntimeError('perms must be (S, C, M) = (%d, %d, %d), got %s'
+                                   % (S, Cn, nt.num_splits, tuple(perms.shape)))
+            pm = perms.detach().to(device=device, dtype=torch.int32).contiguous()
             rng.perms = pm.data_ptr()
             keep_alive.append(pm)
     else:
@@ -360,6 +364,8 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
 
     nuts_s = N.NutsStruct()
     eps_trace = None
+    if not torch.is_tensor(step_size):
+        nuts_s.step_size_init = float(step_size)           # the double the reference divides in its split drifts
     if nuts:
         table = nuts_table(burn).to(device)
         h_bar = torch.zeros(Cn, dtype=torch.float64, device=device)
@@ -377,7 +383,7 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
             eps_trace = torch.zeros((Cn, S), dtype=torch.float32, device=device)
             nuts_s.eps_trace = eps_trace.data_ptr()
 
-    msum = msq = None
+    msum = msq = msum_lo = msq_lo = None
     with torch.cuda.device(device):
         if scheme is None:
             ws_bytes = lib.hmcx_hmc_workspace_bytes(nt.ref(), nm.ref(), Cn, ld)
@@ -386,9 +392,10 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
                 sink = N.SinkStruct()
                 sink.thin = thin
                 if moments:
-                    msum = torch.zeros((Cn, ld), dtype=torch.float32, device=device)
-                    msq = torch.zeros((Cn, ld), dtype=torch.float32, device=device)
+                    msum, msq, msum_lo, msq_lo = (torch.zeros((Cn, ld), dtype=torch.float32, device=device)
+                                                  for _ in range(4))
                     sink.sum, sink.sumsq = msum.data_ptr(), msq.data_ptr()
+                    sink.sum_lo, sink.sumsq_lo = msum_lo.data_ptr(), msq_lo.data_ptr()
                 rc = lib.hmcx_hmc_run_sink(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init),
                                            N.ptr(q_cur), N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples),
                                            N.ptr(accepted), N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected),
@@ -409,8 +416,9 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     res = HMCResult(samples, accepted, diverged, ham, eps, num_rejected, D, S)
     res.eps_trace = eps_trace
     res.thin = thin
-    res.moment_sum = None if msum is None else msum[:, :D]
-    res.moment_sumsq = None if msq is None else msq[:, :D]
+    # compensated running sums: hi + lo combined in fp64 (relative error ~2^-46 whatever the run length)
+    res.moment_sum = None if msum is None else (msum.double() + msum_lo.double())[:, :D]
+    res.moment_sumsq = None if msq is None else (msq.double() + msq_lo.double())[:, :D]
     res.moment_count = S - burn - 1
     res.final_state = q_cur[:, :D]
     if nuts:
@@ -541,6 +549,8 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
         z = normals.detach().to(device=device, dtype=torch.float32)
         if z.dim() == 2:
             z = z.unsqueeze(1)
+        if tuple(z.shape) != (S, Cn, D):
+            raise RuntimeError('normals must be (S, C, D) = (%d, %d, %d), got %s' % (S, Cn, D, tuple(z.shape)))
         z = N.pad_rows(z.contiguous(), ld)
         lu = log_uniforms.detach().to(device=device, dtype=torch.float32).reshape(S, Cn).contiguous()
         rng.mode, rng.normals, rng.log_uniforms = N.RNG_INJECTED, z.data_ptr(), lu.data_ptr()
@@ -551,6 +561,9 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
             u = uniforms.detach().to(device=device, dtype=torch.float32)
             if u.dim() == 3:
                 u = u.unsqueeze(1)
+            if u.dim() != 4 or tuple(u.shape[:2]) != (S, Cn) or u.shape[3] != D:
+                raise RuntimeError('uniforms must be (S, C, J, D) = (%d, %d, J, %d), got %s'
+                                   % (S, Cn, D, tuple(u.shape)))
             u = N.pad_rows(u.contiguous(), ld)
             rng.uniforms, rng.uniforms_per_iter = u.data_ptr(), u.shape[2]
             keep_alive.append(u)

@@ -278,8 +278,11 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
     if (sink.get('thin', 1) != 1 or sink.get('moments') or not sink.get('keep_samples', True) or
             sink.get('host_samples')) and not (sampler in (Sampler.HMC, Sampler.HMC_NUTS) and
                                                isinstance(log_prob_func, (T.GaussianIso, T.GaussianDiag)) and
-                                               integrator not in _SPLIT_INTEGRATORS):
-        raise NotImplementedError('thin / moments / keep_samples / store_on_GPU=False: plain HMC on element-wise targets')
+                                               integrator not in _SPLIT_INTEGRATORS and
+                                               not (torch.is_tensor(inv_mass) and inv_mass.dim() == 2) and
+                                               not isinstance(inv_mass, list)):
+        raise NotImplementedError('thin / moments / keep_samples / store_on_GPU=False: plain HMC on element-wise targets '
+                                  'with inv_mass None or 1-D')
     if nuts:
         sampler = Sampler.HMC                                                     # :932-936
     if sampler == Sampler.HMC and integrator not in _SPLIT_INTEGRATORS:

@@ -88,6 +88,16 @@ def multi_chain(chain, num_workers, seeds, parallel=False):
         return [chain(s) for s in seeds]
     _, prior, kw = meta
     kw = dict(kw)
+    if kw.get('pass_grad') is not None:
+        raise NotImplementedError('pass_grad: gradients are analytic inside the kernel')
+    # the one-launch form pre-draws randn(D) + rand(1) per iteration: exactly the stream of plain HMC / HMC_NUTS with the
+    # plain integrator.  SPLITTING_RAND (randperm per trajectory) and RMHMC (jitter draws) consume more: those chains run
+    # one by one through sample(), which draws their stream itself.
+    batched = kw.get('sampler', samplers.Sampler.HMC) in (samplers.Sampler.HMC, samplers.Sampler.HMC_NUTS) and \
+        kw.get('integrator', samplers.Integrator.IMPLICIT) not in samplers._SPLIT_INTEGRATORS and \
+        not isinstance(kw.get('log_prob_func'), list)
+    if not batched:
+        return [chain(s) for s in seeds]
     verbose = kw.pop('verbose', True)
     debug = kw.pop('debug', False)
     store_on_GPU = kw.pop('store_on_GPU', True)

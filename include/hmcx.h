@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HMCX_ABI_VERSION 4
+#define HMCX_ABI_VERSION 5
 
 #define HMCX_MLP_TC_AUTO 0
 #define HMCX_MLP_TC_OFF  1
@@ -143,6 +143,12 @@ typedef struct hmcx_nuts {
                                        schedule because adaptation amplifies fp32 summation-order noise)       */
     float* eps_trace;               /* optional [C, num_samples]: the step size the kernel's own adaptation
                                        yields after iteration n (i.e. for iteration n+1)                       */
+    double step_size_init;          /* the Python-double step size the run starts from (0 = not given; read even when
+                                       enabled == 0).  The splitting integrators divide the DOUBLE step size before the
+                                       product with the fp32 tensor rounds it (step_size/K_div, samplers.py:513, :558):
+                                       while a chain's fp32 step size still equals (float)step_size_init the drift
+                                       coefficient is (float)(step_size_init / K); an adapted step size is an fp32
+                                       value in the reference too (:668) and is divided as such.                   */
 } hmcx_nuts_t;
 
 int         hmcx_abi_version(void);
@@ -311,8 +317,12 @@ int hmcx_rmhmc_dense_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, c
  *          params_init, slot j = the chain state after iteration burn + j*thin  (thin = 1: the reference's list)
  *   sum, sumsq   optional [C, ld] in/out accumulators: running sum / sum of squares of the chain state over EVERY
  *          iteration n > burn (= elements 1.. of the reference's returned list), so posterior means and variances
- *          need no sample storage at all (samples_out may then be NULL).  fp32; accumulate windows of iterations
- *          (iter_begin/iter_end) and combine in higher precision for very long runs.
+ *          need no sample storage at all (samples_out may then be NULL).  Accumulated in registers with Neumaier
+ *          compensation (the rounding of x*x included): relative error ~ n*eps^2 after n iterations (eps = 2^-24)
+ *          instead of the ~ n*eps of a plain fp32 running sum:
+ *   sum_lo, sumsq_lo   optional [C, ld] in/out: the compensation terms; the sums are hi + lo (combine in fp64: var =
+ *          E[x^2] - mean^2 then holds for |mean| >> std; measured 1.6e-7 on a variance of 1 at mean 100, n = 2e4, where
+ *          the plain sum is off by percents).  Without them the fp32 rounding of hi + lo is stored in sum / sumsq.
  * samples_out may point to device-mapped pinned HOST memory: the kernel's retained-row stores are coalesced 16-byte
  * streaming stores (st.global.cs), which is how samples leave the GPU while the chains keep running.
  */
@@ -320,9 +330,11 @@ typedef struct hmcx_sink {
     int32_t thin;
     float*  sum;
     float*  sumsq;
+    float*  sum_lo;
+    float*  sumsq_lo;
 } hmcx_sink_t;
 
-/* hmcx_hmc_run with a sample sink (sink == NULL or {1, NULL, NULL}: identical to hmcx_hmc_run).  Element-wise
+/* hmcx_hmc_run with a sample sink (sink == NULL or {1, NULL, NULL, NULL, NULL}: identical to hmcx_hmc_run).  Element-wise
  * targets (GAUSS_ISO / GAUSS_DIAG, mass none / diagonal, ld <= 4096); other combinations return HMCX_ERR_UNSUPPORTED
  * when the sink asks for thinning or moments. */
 int hmcx_hmc_run_sink(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng,

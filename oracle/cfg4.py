@@ -41,8 +41,9 @@ def stream(seed, S, D, flat):
 
 
 def run_chain(args):
-    """One chain through the oracle; returns numpy arrays (samples (S,D), accepted (S,), ham (S,2))."""
-    seed, S = args
+    """One chain through the oracle; returns numpy arrays (samples (S,D), accepted (S,), ham (S,2)).  perturb=1 moves
+    params_init by one ulp per element (random sign): how far the REFERENCE itself drifts under fp32 round-off."""
+    seed, S, perturb = (tuple(args) + (0,))[:3]
     import numpy as np
     torch.set_num_threads(1)
     from hamiltorch_b200 import util
@@ -51,6 +52,9 @@ def run_chain(args):
     descs = descriptors(model, X, y)
     D = descs[0].dim
     init, z, logu = stream(seed, S, D, util.flatten(model).detach().clone())
+    if perturb:
+        sign = torch.sign(torch.randn(D, generator=torch.Generator().manual_seed(99 + seed)))
+        init = init * (1 + 1.1920929e-07 * sign)
     r = O.sample_hmc(descs, init, num_samples=S, num_steps_per_sample=L, step_size=EPS, inv_mass=torch.ones(D),
                      split_scheme=O.SPLIT_SYM, normals=z, log_uniforms=logu)
     return (torch.stack(r['samples']).numpy(), np.array(r['accepted'], np.uint8),

@@ -31,15 +31,14 @@ def test_thinning_and_moments_equal_the_plain_run(nuts):
     assert torch.equal(thin.accepted, full.accepted) and torch.equal(thin.step_size, full.step_size)
     assert thin.samples.shape[1] == 1 + (50 - 7 - 1) // 4
     assert torch.equal(thin.samples, full.samples[:, ::4])
-    # moments: sequential fp32 sums over the reference's returned list minus element 0 (params_init)
-    s = torch.zeros_like(full.samples[:, 0])
-    sq = torch.zeros_like(s)
-    for j in range(1, full.samples.shape[1]):
-        s = s + full.samples[:, j]
-        sq = sq + full.samples[:, j] * full.samples[:, j]
+    # moments: compensated in-kernel sums (hi + lo) == fp64 sums over the reference's returned list minus element 0
+    x = full.samples[:, 1:].double()
+    s, sq = x.sum(1), (x * x).sum(1)
     assert thin.moment_count == full.samples.shape[1] - 1
-    assert torch.equal(thin.moment_sum, s) and torch.equal(thin.moment_sumsq, sq)
-    assert torch.equal(none.moment_sum, s) and torch.equal(none.moment_sumsq, sq)
+    assert thin.moment_sum.dtype == torch.float64
+    assert torch.allclose(thin.moment_sum, s, rtol=1e-10, atol=1e-10)
+    assert torch.allclose(thin.moment_sumsq, sq, rtol=1e-10, atol=1e-10)
+    assert torch.equal(none.moment_sum, thin.moment_sum) and torch.equal(none.moment_sumsq, thin.moment_sumsq)
     assert torch.equal(none.final_state, full.samples[:, -1])
     with pytest.raises(RuntimeError):
         none.samples
@@ -80,6 +79,41 @@ def test_sink_edge_cases():
                             moments=True)
     torch.cuda.synchronize()
     assert thin.samples.shape == (C, 1, D) and torch.equal(thin.samples[:, 0], full.samples[:, 0])
-    assert torch.allclose(thin.moment_sum, full.samples[:, 1:].sum(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(thin.moment_sum, full.samples[:, 1:].double().sum(1), rtol=1e-12, atol=1e-12)
     with pytest.raises(RuntimeError):
         hb.sample_chains(tgt, init, num_samples=5, thin=0)
+
+
+def test_moments_of_a_long_run_far_from_zero():
+    """|mean| = 100 std over 20000 post-burn iterations.  A naive fp32 running sum of x^2 loses
+    percents of the variance here (error ~ n*eps); the compensated sums carry ~ n*eps^2 (measured 1.6e-7 on the variance at
+    n = 2e4, mean^2/var = 1e4), i.e. the posterior variance of every chain to 2e-6 of what fp64 arithmetic over the stored
+    samples gives -- and pooled_moments (var = E[x^2] - mean^2 in fp64) must agree."""
+    from hamiltorch_b200 import distributed
+    D, C, S = 16, 4, 20001
+    tgt = T.GaussianDiag(torch.full((D,), 100.0), torch.ones(D))
+    init = tgt.mean[None] + torch.randn(C, D, generator=torch.Generator().manual_seed(1))
+    kw = dict(num_samples=S, num_steps_per_sample=3, step_size=0.4, rng='philox', seed=5)
+    full = hb.sample_chains(tgt, init, **kw)
+    mom = hb.sample_chains(tgt, init, keep_samples=False, moments=True, **kw)
+    torch.cuda.synchronize()
+    x = full.samples[:, 1:].double()
+    n = x.shape[1]
+    assert mom.moment_count == n
+    mean64, var64 = x.mean(1), x.var(1, unbiased=False)
+    mean = mom.moment_sum / n
+    var = mom.moment_sumsq / n - mean * mean
+    assert torch.allclose(mean, mean64, rtol=1e-9)
+    assert torch.allclose(var, var64, rtol=2e-6), (var - var64).abs().max()
+    assert 0.8 < float(var64.mean()) < 1.25                   # the chain did sample N(100, 1)
+    # the naive fp32 recurrence the kernel used in round 1, for the record: off by > 1e-3 here
+    s32 = torch.zeros_like(full.samples[:, 0]); q32 = torch.zeros_like(s32)
+    for j in range(1, 2001):
+        s32 = s32 + full.samples[:, j]; q32 = q32 + full.samples[:, j] * full.samples[:, j]
+    naive = q32.double() / 2000 - (s32.double() / 2000) ** 2
+    exact = full.samples[:, 1:2001].double().var(1, unbiased=False)
+    assert float((naive - exact).abs().max()) > 10 * float((var - var64).abs().max())
+    pm, pv, pn = distributed.pooled_moments(mom.moment_sum, mom.moment_sumsq, mom.moment_count)
+    allx = x.reshape(-1, D)
+    assert pn == C * n and torch.allclose(pm, allx.mean(0), rtol=1e-9)
+    assert torch.allclose(pv, allx.var(0, unbiased=False), rtol=2e-6)
