@@ -556,7 +556,18 @@ def run_b200_arm(args, rank, world, local_rank):
     barrier()
 
     # ---- device-timed region: EXACTLY K steps, inputs resident in HBM ----
+    # The stream is first given ~25 ms of head start (a spin kernel) so that the host has queued all K launches before
+    # the first timed event executes: the events then bracket K kernels running back to back on the device and a host
+    # hiccup (allocator, GC, a CFS throttle of the container's CPU quota -- one 20 ms stall in one of 20 steps was seen
+    # on a 2-GPU box) cannot leak into a device-side timestamp.
+    def head_start():
+        torch.cuda._sleep(int(25e-3 * 1.9e9))
+
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    for e_ in ev:                                  # create the CUDA events now, not lazily inside the timed region
+        e_.record()
+    barrier()
+    head_start()
     ev[0].record()
     for k in range(args.steps):
         ev[1 + 2 * k].record()
@@ -580,6 +591,10 @@ def run_b200_arm(args, rank, world, local_rank):
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+        for e_ in a_ev + [g0, g1]:
+            e_.record()
+        barrier()
+        head_start()
         g0.record()
         for k in range(args.steps):
             step(100 + k)

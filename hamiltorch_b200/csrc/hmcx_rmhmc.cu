@@ -171,6 +171,7 @@ struct Metric {
 
 struct RmCfg {
     int softabs;          // Metric.SOFTABS (1) or Metric.HESSIAN (0)
+    int jacdiag;          // Metric.JACOBIAN_DIAG (:100-106): G = diag((d log p / d theta_i)^2), no eigen-decomposition
     float alpha, jitter;  // softabs_const, jitter scale (jitter < 0: none)
     float pi_term;        // D*log(2*pi) in fp32 as samplers.py:712
 };
@@ -180,6 +181,20 @@ template <int DM>
 __device__ __forceinline__ bool eval_metric(const RmTarget& t, const RmCfg& cfg, const float* th, const float* u,
                                             Metric<DM>& M) {
     const int d = rm_dim<DM>(t);
+    if (cfg.jacdiag) {
+        // fish = (jac jac^T).diag().diag() (:104-106) + diag(u * jitter): already diagonal -> Q = I, lam~ = lam
+        float g[DM];
+        rm_grad_log_prob<DM>(t, th, g);
+        bool okd = true;
+        for (int a = 0; a < d; ++a) {
+            for (int b = 0; b < d; ++b) M.Q[a][b] = (a == b) ? 1.0f : 0.0f;
+            float v = mul(g[a], g[a]);
+            if (u) v = add(v, mul(u[a], cfg.jitter));
+            M.lam[a] = v; M.lt[a] = v; M.dlt[a] = 1.0f;
+            okd = okd && finite_f(v);
+        }
+        return okd;
+    }
     float G[DM][DM];
     rm_fill_metric<DM>(t, th, G);
     bool ok = true;
@@ -192,11 +207,21 @@ __device__ __forceinline__ bool eval_metric(const RmTarget& t, const RmCfg& cfg,
     for (int i = 0; i < d; ++i) {
         const float l = M.lam[i];
         if (cfg.softabs) {
-            const float x = cfg.alpha * l, th_ = tanhf(x);
-            M.lt[i] = (1.0f / th_) * l;                                   // (1./tanh(alpha*lam))*lam   (:120)
-            const float sh = sinhf(x);
-            M.dlt[i] = 1.0f / th_ - x / (sh * sh);
-            if (!finite_f(M.dlt[i])) M.dlt[i] = (l >= 0.0f) ? 1.0f : -1.0f;   // saturated: |lam|' = sign
+            const float x = cfg.alpha * l;
+            if (fabsf(x) >= 20.0f && finite_f(x)) {
+                // saturated softabs (alpha = 1e6: practically always).  tanhf(x) is exactly +-1 in fp32 beyond |x| = 9.1,
+                // and x/sinh(x)^2 < 4e-16 vanishes against 1/tanh: the general branch below returns exactly these
+                // bits, after ~110 more dependent instructions (tanhf, sinhf, two divisions) on the critical path.
+                const float sg = x > 0.0f ? 1.0f : -1.0f;
+                M.lt[i] = sg * l;                                             // (1/+-1) * lam
+                M.dlt[i] = sg;
+            } else {
+                const float th_ = tanhf(x);
+                M.lt[i] = (1.0f / th_) * l;                               // (1./tanh(alpha*lam))*lam   (:120)
+                const float sh = sinhf(x);
+                M.dlt[i] = 1.0f / th_ - x / (sh * sh);
+                if (!finite_f(M.dlt[i])) M.dlt[i] = (l >= 0.0f) ? 1.0f : -1.0f;   // saturated: |lam|' = sign
+            }
         } else {
             M.lt[i] = l;
             M.dlt[i] = 1.0f;
@@ -241,6 +266,27 @@ __device__ __forceinline__ void grad_momentum(const RmTarget& t, const Metric<DM
         float s = 0.0f;
         for (int i = 0; i < d; ++i) s += M.Q[a][i] * u[i];
         out[a] = s;
+    }
+}
+
+// dH/dtheta for Metric.JACOBIAN_DIAG: G = diag(g_i^2 (+ jitter)), g = grad log p, so
+//   dH/dtheta_k = -g_k + sum_i Z_ii * d(g_i^2)/dtheta_k = -g_k + sum_i (1/(2 d_i) - p_i^2/(2 d_i^2)) * 2 g_i * Hess_ik
+// with Hess = Hessian(log p) = -(the matrix rm_fill_metric returns).  (autograd through .diag().diag(), :104-106)
+template <int DM>
+__device__ __forceinline__ void grad_params_jacdiag(const RmTarget& t, const float* th, const Metric<DM>& M,
+                                                    const float* p, float* out) {
+    const int d = rm_dim<DM>(t);
+    float g[DM], zz[DM], Gh[DM][DM];
+    rm_grad_log_prob<DM>(t, th, g);
+    rm_fill_metric<DM>(t, th, Gh);
+    for (int i = 0; i < d; ++i) {
+        const float ui = p[i] / M.lt[i];
+        zz[i] = (0.5f / M.lt[i] - 0.5f * ui * ui) * 2.0f * g[i];
+    }
+    for (int k = 0; k < d; ++k) {
+        float s = 0.0f;
+        for (int i = 0; i < d; ++i) s += zz[i] * (-Gh[i][k]);
+        out[k] = s - g[k];
     }
 }
 
@@ -404,7 +450,7 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
                 bool okh = true;
                 rm_hamiltonian<DM>(t, a.cfg, th, pp, M, w, okh);
                 if (!okh) { ok = false; break; }
-                grad_params<DM>(t, th, M, pp, out);
+                if (a.cfg.jacdiag) grad_params_jacdiag<DM>(t, th, M, pp, out); else grad_params<DM>(t, th, M, pp, out);
                 bool fin = true;
                 for (int i = 0; i < d; ++i) fin = fin && finite_f(out[i]);
                 if (fin) break;
@@ -595,7 +641,7 @@ __global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
                 bool okh = true;
                 rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
                 if (!okh) { good = false; break; }
-                grad_params<2>(t, th, M, pp, out);
+                if (a.cfg.jacdiag) grad_params_jacdiag<2>(t, th, M, pp, out); else grad_params<2>(t, th, M, pp, out);
                 if (finite_f(out[0]) && finite_f(out[1])) break;
                 if (tries + 1 > a.jitter_max_tries) { good = false; break; }
             }
@@ -932,11 +978,12 @@ int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_r
     if (target->kind == HMCX_TARGET_FUNNEL && D < 2) return HMCX_ERR_INVALID_ARG;
     if (target->kind == HMCX_TARGET_GAUSS_DIAG && !target->inv_var) return HMCX_ERR_INVALID_ARG;
     if (cfg->integrator != 1 && cfg->integrator != 2) return HMCX_ERR_UNSUPPORTED;      // S3: out of scope
-    if (cfg->metric != 1 && cfg->metric != 2) return HMCX_ERR_UNSUPPORTED;              // JACOBIAN_DIAG: out of scope
+    if (cfg->metric != 1 && cfg->metric != 2 && cfg->metric != 3) return HMCX_ERR_UNSUPPORTED;
     RmRunArgs a = {};
     a.t.kind = target->kind; a.t.D = D; a.t.log_norm = target->log_norm; a.t.inv_var_v = target->funnel_inv_var_v;
     a.t.mean = target->mean; a.t.ivar = target->inv_var; a.t.prec = target->prec;
-    a.cfg.softabs = cfg->metric == 2; a.cfg.alpha = cfg->softabs_const; a.cfg.jitter = cfg->jitter;
+    a.cfg.softabs = cfg->metric == 2; a.cfg.jacdiag = cfg->metric == 3; a.cfg.alpha = cfg->softabs_const;
+    a.cfg.jitter = cfg->jitter;
     a.cfg.pi_term = cfg->pi_term;
     a.integrator = cfg->integrator; a.cosw = cfg->cos_2we; a.sinw = cfg->sin_2we;
     a.fp_threshold = cfg->fixed_point_threshold; a.fp_max_iter = cfg->fixed_point_max_iterations;

@@ -120,7 +120,19 @@ class NativeMass:
         if inv_mass is None:
             s.kind = N.MASS_NONE
         elif isinstance(inv_mass, list):
-            raise NotImplementedError('block-list inv_mass (samplers.py:287-292) is not supported by the B200 engine')
+            # block list (samplers.py:188-197, :287-292, :803-809, :944-947) == the block-diagonal 2-D inv_mass: every
+            # block inverted and Cholesky-factorised on its own with the reference's torch ops, then laid out as ONE
+            # (D, D) operand pair for the full-mass kernels (thread-per-chain for D <= 16, tcgen05 dense_lin above)
+            blocks = [b.detach().to(torch.float32) for b in inv_mass]
+            if any(b.dim() != 2 or b.shape[0] != b.shape[1] for b in blocks) or sum(b.shape[0] for b in blocks) != dim:
+                raise RuntimeError('block-list inv_mass: square blocks whose sizes add up to %d' % dim)
+            im = torch.block_diag(*blocks)
+            tril = torch.block_diag(*[torch.linalg.cholesky(torch.inverse(b)) for b in blocks])
+            s.kind = N.MASS_FULL
+            self._keep['im'] = im.to(self.device).contiguous()
+            self._keep['tril'] = tril.to(self.device).contiguous()
+            s.inv_mass = self._keep['im'].data_ptr()
+            s.mass_factor = self._keep['tril'].data_ptr()
         elif inv_mass.dim() == 1:
             if inv_mass.numel() != dim:
                 raise RuntimeError('inv_mass must have %d entries' % dim)
@@ -491,10 +503,11 @@ def const_metric(target, softabs, softabs_const):
     return ginv.contiguous(), lower.contiguous(), log_det
 
 
-def _rmhmc_is_dense(target, jitter):
+def _rmhmc_is_dense(target, jitter, jacdiag=False):
     """Gaussian targets without jitter have a constant metric: the tensor-core path (any D).  GaussianIso / GaussianDiag
-    at D <= 16 stay on the thread-per-chain kernel (which also handles jitter)."""
-    if jitter is not None:
+    at D <= 16 stay on the thread-per-chain kernel (which also handles jitter).  Metric.JACOBIAN_DIAG depends on the
+    gradient, i.e. on the position, for every target: never constant."""
+    if jitter is not None or jacdiag:
         return False
     if isinstance(target, T.GaussianFull):
         return True
@@ -503,7 +516,7 @@ def _rmhmc_is_dense(target, jitter):
 
 def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, jitter=None,
               softabs_const=None, explicit_binding_const=100, fixed_point_threshold=1e-5,
-              fixed_point_max_iterations=1000, jitter_max_tries=10, explicit=True, softabs=False, seed=0,
+              fixed_point_max_iterations=1000, jitter_max_tries=10, explicit=True, softabs=False, jacdiag=False, seed=0,
               chain_offset=0, normals=None, log_uniforms=None, uniforms=None, record_ham=False, device=None):
     """The reference's sample() loop for sampler=RMHMC over C chains (one thread per chain).
 
@@ -532,7 +545,7 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
 
     cfg = N.RmhmcStruct()
     cfg.integrator = 1 if explicit else 2
-    cfg.metric = 2 if softabs else 1
+    cfg.metric = 3 if jacdiag else (2 if softabs else 1)          # Metric enum values (samplers.py:28-31)
     cfg.softabs_const = float(softabs_const) if softabs_const is not None else 0.0
     cfg.jitter = float(jitter) if jitter is not None else -1.0
     cfg.pi_term = float(D * torch.log(2. * torch.tensor(math.pi)))                              # samplers.py:711-712
@@ -570,7 +583,7 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
     else:
         rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
     with torch.cuda.device(device):
-        if _rmhmc_is_dense(nt.target, jitter):
+        if _rmhmc_is_dense(nt.target, jitter, jacdiag):
             ginv, lower, log_det = const_metric(nt.target, softabs, softabs_const)
             gm = N.ConstMetricStruct()
             ginv_d, lower_d = ginv.to(device), lower.to(device)

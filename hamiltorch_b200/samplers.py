@@ -94,8 +94,14 @@ def gibbs(params, sampler=Sampler.HMC, log_prob_func=None, jitter=None, normaliz
         raise NotImplementedError('RMHMC momentum refresh happens inside the RMHMC kernel')
     if mass is None:
         return torch.randn(params.shape, dtype=params.dtype, device=params.device)
-    if isinstance(mass, list):
-        raise NotImplementedError('block-list mass is not supported by the B200 engine')
+    if isinstance(mass, list):                                          # :188-197
+        samples = torch.zeros_like(params)
+        i = 0
+        for block in mass:
+            it = block[0].shape[0]
+            samples[i:it + i] = torch.distributions.MultivariateNormal(torch.zeros_like(block[0]), block).sample()
+            i += it
+        return samples
     if mass.dim() == 2:
         return torch.distributions.MultivariateNormal(torch.zeros_like(params), mass).sample()
     return torch.normal(torch.zeros_like(params), mass ** 0.5)
@@ -158,7 +164,7 @@ def _check_sample_args(params_init_dim_ok, num_samples, burn, sampler):
         raise RuntimeError('burn must be greater than 0 for NUTS.')             # :933-934
 
 
-def _draw_reference_stream(dim, num_samples, device, num_perm=0):
+def _draw_reference_stream(dim, num_samples, device, num_perm=0, blocks=None):
     """Pre-draw one chain's randoms from torch's GLOBAL generators in exactly the order the reference consumes
     them: per iteration the momentum normals -- ``Normal(zeros_like(params),
     ones_like(params)).sample()`` (:186, :202), i.e. the generator of params' device -- then ``torch.rand(1)`` on
@@ -167,7 +173,10 @@ def _draw_reference_stream(dim, num_samples, device, num_perm=0):
     logu = torch.empty(num_samples, dtype=torch.float32)
     perms = torch.empty((num_samples, num_perm), dtype=torch.int32) if num_perm else None
     for n in range(num_samples):
-        z[n] = torch.randn(dim, dtype=torch.float32, device=device)
+        if blocks:                                          # block-list mass: one draw per block (:188-197)
+            z[n] = torch.cat([torch.randn(b, dtype=torch.float32, device=device) for b in blocks])
+        else:
+            z[n] = torch.randn(dim, dtype=torch.float32, device=device)
         if num_perm:
             perms[n] = torch.randperm(num_perm)             # SPLITTING_RAND: once per trajectory (:550)
         logu[n] = torch.log(torch.rand(1))[0]
@@ -294,7 +303,8 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
         if rng == 'reference':
             if q0.shape[0] != 1:
                 raise RuntimeError("rng='reference' replays torch's global stream and is defined for one chain")
-            z, logu = _draw_reference_stream(D, num_samples, q0.device)
+            z, logu = _draw_reference_stream(D, num_samples, q0.device,
+                                             blocks=[b.shape[0] for b in inv_mass] if isinstance(inv_mass, list) else None)
             normals, log_uniforms = z.unsqueeze(1), logu.unsqueeze(1)
         elif rng == 'injected':
             if normals is None or log_uniforms is None:
@@ -316,6 +326,9 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
         if M == 1 and integrator in (Integrator.SPLITTING, Integrator.SPLITTING_KMID):
             raise RuntimeError('For symmetric splitting log_prob_func must be list of functions greater than '
                                'length 1')                                                          # :497-498, :577-578
+        if isinstance(inv_mass, list):
+            raise NotImplementedError('block-list inv_mass with a splitting integrator: the reference ignores the blocks in '
+                                      'the drift (samplers.py:514-515); pass the block-diagonal matrix or a 1-D inv_mass')
         scheme = {Integrator.SPLITTING: N.SCHEME_SPLIT_SYM, Integrator.SPLITTING_RAND: N.SCHEME_SPLIT_RAND,
                   Integrator.SPLITTING_KMID: N.SCHEME_SPLIT_KMID}[integrator]
         D = log_prob_func[0].dim
@@ -348,13 +361,16 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
         if isinstance(log_prob_func, list) or not isinstance(log_prob_func, (T.Funnel, T.GaussianIso, T.GaussianDiag,
                                                                              T.GaussianFull)):
             raise NotImplementedError('RMHMC needs closed-form third derivatives: Funnel / Gaussian descriptors')
-        if isinstance(log_prob_func, T.GaussianFull) and jitter is not None:
-            raise NotImplementedError('GaussianFull under RMHMC runs on the constant-metric tensor-core path: jitter=None')
-        if not isinstance(log_prob_func, T.GaussianFull) and log_prob_func.dim > 16 and \
-                (isinstance(log_prob_func, T.Funnel) or jitter is not None):
+        jacdiag = metric == Metric.JACOBIAN_DIAG
+        if metric not in (Metric.HESSIAN, Metric.SOFTABS, Metric.JACOBIAN_DIAG):
+            raise NotImplementedError()
+        small = log_prob_func.dim <= 16
+        if isinstance(log_prob_func, T.GaussianFull) and not small and (jitter is not None or jacdiag):
+            raise NotImplementedError('GaussianFull under RMHMC at D > 16 runs on the constant-metric tensor-core path: '
+                                      'jitter=None, HESSIAN / SOFTABS')
+        if not isinstance(log_prob_func, T.GaussianFull) and not small and \
+                (isinstance(log_prob_func, T.Funnel) or jitter is not None or jacdiag):
             raise NotImplementedError('RMHMC at D > 16: Gaussian targets with jitter=None (constant metric, tensor cores)')
-        if metric not in (Metric.HESSIAN, Metric.SOFTABS):
-            raise NotImplementedError('Metric.JACOBIAN_DIAG is out of scope (experimental in the reference)')
         if inv_mass is not None:
             pass                                            # the reference ignores inv_mass for RMHMC (:989 comment)
         D = log_prob_func.dim
@@ -397,7 +413,8 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
                                 fixed_point_threshold=fixed_point_threshold,
                                 fixed_point_max_iterations=fixed_point_max_iterations,
                                 jitter_max_tries=jitter_max_tries, explicit=explicit,
-                                softabs=(metric == Metric.SOFTABS), seed=seed or 0, chain_offset=chain_offset,
+                                softabs=(metric == Metric.SOFTABS), jacdiag=jacdiag, seed=seed or 0,
+                                chain_offset=chain_offset,
                                 normals=normals, log_uniforms=log_uniforms, uniforms=uniforms, record_ham=record_ham)
     raise NotImplementedError()                                                                     # :606, :844
 

@@ -215,7 +215,8 @@ size_t hmcx_hmc_workspace_bytes(const hmcx_target_t* target, const hmcx_mass_t* 
 /* sampler=RMHMC configuration (samplers.py:850 arguments that only this sampler reads) */
 typedef struct hmcx_rmhmc {
     int32_t integrator;             /* Integrator enum value: 1 EXPLICIT (:389-462), 2 IMPLICIT (:305-387)         */
-    int32_t metric;                 /* Metric enum value: 1 HESSIAN, 2 SOFTABS (:116-122)                          */
+    int32_t metric;                 /* Metric enum value: 1 HESSIAN, 2 SOFTABS (:116-122), 3 JACOBIAN_DIAG (:100-106,
+                                       hmcx_rmhmc_run only: the metric diag((d log p/d theta_i)^2) is never constant)  */
     float   softabs_const;          /* alpha                                                                      */
     float   jitter;                 /* scale of the uniform diagonal jitter (:113-115); < 0 = None                */
     float   pi_term;                /* D*log(2*pi) evaluated in fp32 as :712                                      */

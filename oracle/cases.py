@@ -85,6 +85,18 @@ def plain_cases():
         kw=dict(num_samples=14, num_steps_per_sample=5, step_size=0.1, burn=8, nuts=True, desired_accept_rate=0.8,
                 inv_mass=_spd64(40, 64).float()),
         seeds=[45], init='randn0.1', rtol=2e-4)
+    # ---- block-list inv_mass (samplers.py:188-197, :287-292, :803-809): blocks of 2 + 3 + 1 on the thread-per-chain
+    #      kernel, 16 + 24 on the tensor-core path; the kernels see the block-diagonal matrix
+    cases['diag6_blockmass'] = dict(
+        target=T.GaussianDiag(torch.linspace(-1, 1, 6), _rand_var(6, 12)),
+        kw=dict(num_samples=40, num_steps_per_sample=5, step_size=0.3, burn=4,
+                inv_mass=[_spd64(2, 81).float(), _spd64(3, 82).float(), _spd64(1, 83).float()]),
+        seeds=[51, 52], init='randn0.1', rtol=2e-5)
+    cases['iso40_blockmass'] = dict(
+        target=T.GaussianIso(40),
+        kw=dict(num_samples=12, num_steps_per_sample=5, step_size=0.15, burn=2,
+                inv_mass=[_spd64(16, 84).float(), _spd64(24, 85).float()]),
+        seeds=[53], init='randn0.1', rtol=2e-4)
     return cases
 
 
@@ -191,6 +203,24 @@ def rmhmc_cases():
                                       num_samples=6, num_steps_per_sample=3, step_size=0.6, burn=1,
                                       explicit_binding_const=10, metric='HESSIAN', jitter=None, softabs_const=None,
                                       seeds=[7, 8]),
+        # Metric.JACOBIAN_DIAG (:100-106): G = diag((d log p / d theta_i)^2) + jitter
+        'rmhmc_exp_jacdiag_funnel3': dict(target=T.Funnel(3), init=[0.5, 1., -1.], integrator='EXPLICIT', num_samples=8,
+                                          num_steps_per_sample=3, step_size=0.05, burn=0, explicit_binding_const=10,
+                                          metric='JACOBIAN_DIAG', jitter=1e-2, softabs_const=None,
+                                          seeds=[10, 16]),      # seeds whose first iteration accepts: the reference
+                                          # crashes (RuntimeError) after a reject at n <= burn with this metric
+        'rmhmc_imp_jacdiag_gauss3': dict(target=T.GaussianDiag(torch.tensor([0., 1., -1.]),
+                                                               torch.tensor([.5, 1., 2.]) ** 2),
+                                         init=[0.6, 0.2, -2.5], integrator='IMPLICIT', num_samples=8,
+                                         num_steps_per_sample=3, step_size=0.05, burn=0, metric='JACOBIAN_DIAG',
+                                         jitter=None, softabs_const=None, fixed_point_threshold=1e-5,
+                                         fixed_point_max_iterations=1000, seeds=[16]),
+        # the thread-per-chain kernel on a dense precision WITH jitter (D <= 16: position-independent but per-call random metric)
+        'rmhmc_exp_softabs_full5_jitter': dict(target=T.GaussianFull(torch.linspace(-0.5, 0.5, 5), cov=_spd64(5, 73)),
+                                               init=[0.3, -0.2, 0.1, 0.4, -0.3], integrator='EXPLICIT', num_samples=8,
+                                               num_steps_per_sample=3, step_size=0.2, burn=1,
+                                               explicit_binding_const=10, metric='SOFTABS', jitter=1e-2,
+                                               softabs_const=1e3, seeds=[14]),
         'rmhmc_imp_softabs_diag20': dict(target=T.GaussianDiag(torch.linspace(-1, 1, 20), _rand_var(20, 72)),
                                          init=[0.2 * ((i * 3) % 7 - 3) for i in range(20)], integrator='IMPLICIT',
                                          num_samples=6, num_steps_per_sample=3, step_size=0.5, burn=1,

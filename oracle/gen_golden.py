@@ -56,8 +56,9 @@ def run_plain_case(ref, name, case):
         cases.make_init(case['init'], dim, seed)
         z = torch.empty(S, dim)
         logu = torch.empty(S)
+        blocks = [b.shape[0] for b in kw['inv_mass']] if isinstance(kw.get('inv_mass'), list) else None
         for n in range(S):
-            z[n] = torch.randn(dim)
+            z[n] = torch.cat([torch.randn(b) for b in blocks]) if blocks else torch.randn(dim)
             if res['diverged'][n]:
                 logu[n] = 0.0          # a LogProbError iteration never reaches torch.rand(1) (samplers.py:1004 vs :1045)
             else:
@@ -225,25 +226,31 @@ def run_rmhmc_case(ref, name, case):
                              metric=getattr(ref.Metric, case['metric']), verbose=False, **kw)
         samples = torch.stack(samples)
         okw = dict(kw, integrator=R.EXPLICIT if explicit else R.IMPLICIT,
-                   metric=R.SOFTABS if case['metric'] == 'SOFTABS' else R.HESSIAN)
+                   metric={'SOFTABS': R.SOFTABS, 'HESSIAN': R.HESSIAN, 'JACOBIAN_DIAG': R.JACOBIAN_DIAG}[case['metric']])
         torch.manual_seed(seed)
         res = R.sample_rmhmc(tgt, init, **okw)
         assert torch.equal(torch.stack(res['samples']), samples), name
         # the consumed stream: per iteration jitter(gibbs), normals, jitter(ham), 8L jitters (explicit), jitter(new_ham),
-        # rand(1) -- only recorded when the count per iteration is fixed (explicit, or no jitter at all)
-        J = (8 * L + 3) if (explicit and case['jitter'] is not None) else 0
-        assert not any(res['diverged'])
+        # rand(1).  A LogProbError cuts the iteration short (fewer jitter draws, no rand(1)), NaN-gradient retries add
+        # draws: the oracle's per-iteration counters say how many of each the reference consumed.  Recorded when the
+        # count is knowable: explicit integrator, or no jitter at all.
+        jittered = case['jitter'] is not None
+        assert explicit or not jittered
+        J = max(max(res['jitter_draws']), 8 * L + 3) if jittered else 0
         torch.manual_seed(seed)
-        z = torch.empty(S, D)
-        logu = torch.empty(S)
+        z = torch.zeros(S, D)
+        logu = torch.zeros(S)
         uni = torch.zeros(S, max(J, 1), D)
         for n in range(S):
-            if J:
+            k = res['jitter_draws'][n] if jittered else 0
+            if k >= 1:
                 uni[n, 0] = torch.rand(D)
-            z[n] = torch.randn(D)
-            for j in range(1, J):
+            if res['gibbs_done'][n]:
+                z[n] = torch.randn(D)
+            for j in range(1, k):
                 uni[n, j] = torch.rand(D)
-            logu[n] = torch.log(torch.rand(1))[0]
+            if not res['diverged'][n]:
+                logu[n] = torch.log(torch.rand(1))[0]
         res2 = R.sample_rmhmc(tgt, init, normals=z, log_uniforms=logu, uniforms=uni if J else None, **okw)
         assert torch.equal(torch.stack(res2['samples']), samples), name + ' (injected)'
         out['samples_%d' % ci] = samples.numpy()
@@ -253,9 +260,11 @@ def run_rmhmc_case(ref, name, case):
         out['accepted_%d' % ci] = np.array(res['accepted'], dtype=np.uint8)
         out['ham_old_%d' % ci] = np.array(res['ham_old'], dtype=np.float64)
         out['ham_new_%d' % ci] = np.array(res['ham_new'], dtype=np.float64)
+        out['diverged_%d' % ci] = np.array(res['diverged'], dtype=np.uint8)
     out['seeds'] = np.array(case['seeds'])
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
-    print('wrote', name, out['samples_0'].shape, 'acc', [float(out['accepted_%d' % c].mean()) for c in range(len(case['seeds']))])
+    print('wrote', name, out['samples_0'].shape, 'acc', [float(out['accepted_%d' % c].mean()) for c in range(len(case['seeds']))],
+          'LogProbError', [int(out['diverged_%d' % c].sum()) for c in range(len(case['seeds']))])
 
 
 def main():

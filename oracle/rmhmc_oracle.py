@@ -16,7 +16,7 @@ import torch
 
 from .hmc_oracle import OracleLogProbError, nonfinite, log_accept_ratio
 
-HESSIAN, SOFTABS = 1, 2
+HESSIAN, SOFTABS, JACOBIAN_DIAG = 1, 2, 3
 EXPLICIT, IMPLICIT = 1, 2
 
 
@@ -41,14 +41,23 @@ def fisher(q, log_prob, jitter, alpha, metric, jit):
     lp = log_prob(q)
     if nonfinite(lp):
         raise OracleLogProbError()
-    hess = torch.autograd.functional.hessian(log_prob, q, create_graph=True)
-    fish = -hess
+    if metric == JACOBIAN_DIAG:                                     # :100-106 (util.jacobian of the scalar log p)
+        # NB the reference needs `params` to require grad here; after a reject at n <= burn it passes
+        # param_burn_prev.clone() (no grad) and crashes with a RuntimeError -- the oracle just re-attaches the graph
+        x = q if q.requires_grad else q.detach().requires_grad_()
+        out = (lp if q.requires_grad else log_prob(x)).view(-1)
+        jac = torch.autograd.grad(out, [x], torch.ones_like(out), allow_unused=True, retain_graph=True,
+                                  create_graph=True)[0].contiguous().view(-1)
+        fish = torch.matmul(jac.view(-1, 1), jac.view(1, -1)).diag().diag()
+    else:
+        hess = torch.autograd.functional.hessian(log_prob, q, create_graph=True)
+        fish = -hess
     if nonfinite(fish):
         raise OracleLogProbError()
     if jitter is not None:
         n = fish.shape[0]
         fish += (torch.eye(n) * jit(n) * jitter).to(fish.device)
-    if metric == HESSIAN:
+    if metric in (HESSIAN, JACOBIAN_DIAG):
         return fish, None
     lam, vec = torch.linalg.eigh(fish, UPLO='L')
     abs_lam = (1. / torch.tanh(alpha * lam)) * lam
@@ -168,7 +177,7 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
     burn_prev = params_init.clone()
     kept = [params_init.clone()]
     accepted, ham_old, ham_new, diverged = [], [], [], []
-    state_in, proposal, jitter_draws, nan_retries = [], [], [], []          # diagnostics for the teacher-forced parity tests
+    state_in, proposal, jitter_draws, nan_retries, gibbs_done = [], [], [], [], []          # diagnostics for the teacher-forced parity tests
     rejected = 0
     for n in range(num_samples):
         jit = JitterSource(None if uniforms is None else uniforms[n])
@@ -176,6 +185,7 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
         h0 = h1 = float('nan')
         state_in.append(q.detach().clone())
         prop = torch.full_like(params_init, float('nan'))
+        got_p = False
         try:
             G = fisher(q, log_prob, jitter, softabs_const, metric, jit)[0]                    # gibbs :183-184
             if normals is None:
@@ -183,6 +193,7 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
             else:
                 p = torch.mv(torch.linalg.cholesky(G.detach()), normals[n])
             p = p.detach()
+            got_p = True
             H0 = rm_hamiltonian(q, p, *args)                                                  # :971 (explicit: 2H, /2)
             if integrator == EXPLICIT:
                 H0 = 2 * H0
@@ -228,6 +239,7 @@ def sample_rmhmc(log_prob, params_init, num_samples=10, num_steps_per_sample=10,
         proposal.append(prop)
         jitter_draws.append(jit.i)
         nan_retries.append(jit.retries)
+        gibbs_done.append(got_p)
     return dict(samples=[t.detach() for t in kept], accepted=accepted, ham_old=ham_old, ham_new=ham_new,
                 num_rejected=rejected, diverged=diverged, state_in=state_in, proposal=proposal,
-                jitter_draws=jitter_draws, nan_retries=nan_retries)
+                jitter_draws=jitter_draws, nan_retries=nan_retries, gibbs_done=gibbs_done)

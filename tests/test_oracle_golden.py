@@ -109,7 +109,7 @@ def test_rmhmc_oracle_reproduces_reference_fixture(name):
     kw = dict(num_samples=case['num_samples'], num_steps_per_sample=case['num_steps_per_sample'],
               step_size=case['step_size'], burn=case['burn'], jitter=case['jitter'], softabs_const=case['softabs_const'],
               integrator=R.EXPLICIT if explicit else R.IMPLICIT,
-              metric=R.SOFTABS if case['metric'] == 'SOFTABS' else R.HESSIAN)
+              metric={'SOFTABS': R.SOFTABS, 'HESSIAN': R.HESSIAN, 'JACOBIAN_DIAG': R.JACOBIAN_DIAG}[case['metric']])
     if explicit:
         kw['explicit_binding_const'] = case['explicit_binding_const']
     else:

@@ -36,7 +36,8 @@ def test_golden_chain_parity(name):
                            explicit_binding_const=case.get('explicit_binding_const', 100),
                            fixed_point_threshold=case.get('fixed_point_threshold', 1e-5),
                            fixed_point_max_iterations=case.get('fixed_point_max_iterations', 1000),
-                           explicit=explicit, softabs=case['metric'] == 'SOFTABS', normals=z, log_uniforms=logu,
+                           explicit=explicit, softabs=case['metric'] == 'SOFTABS', jacdiag=case['metric'] == 'JACOBIAN_DIAG',
+                           normals=z, log_uniforms=logu,
                            uniforms=uni if case['jitter'] is not None else None, record_ham=True)
     torch.cuda.synchronize()
     for c in range(nC):
@@ -46,10 +47,14 @@ def test_golden_chain_parity(name):
         # a large energy error (-> reject) the kernel may overflow to a non-finite H (-> "diverged", also a reject).
         # That is the only place a diverged flag is tolerated.
         dH_ref = d['ham_new_%d' % c] - d['ham_old_%d' % c]
-        assert not np.any(div & ~(dH_ref > 1.0)), 'kernel diverged where the reference integrated fine'
+        rdiv = d['diverged_%d' % c].astype(bool) if 'diverged_%d' % c in d.files else np.zeros(S, bool)
+        # the reference's LogProbError iterations (newer fixtures record them) are rejects here too; elsewhere the kernel
+        # may only flag an iteration the reference ended with a large energy error
+        assert not np.any(div & ~rdiv & ~(dH_ref > 1.0)), 'kernel diverged where the reference integrated fine'
+        assert not np.any(res.accepted[c].cpu().numpy().astype(bool) & rdiv)
         if explicit:
-            assert not div.any()
-        ok = ~div
+            assert not (div & ~rdiv).any()
+        ok = ~div & ~rdiv
         np.testing.assert_allclose(ham[ok, 0], d['ham_old_%d' % c][ok], rtol=RM_RTOL, atol=RM_RTOL)
         np.testing.assert_allclose(ham[ok, 1], d['ham_new_%d' % c][ok], rtol=RM_RTOL, atol=RM_RTOL)
         m = parity.first_decision_mismatch(res.accepted[c].cpu().numpy(), d['accepted_%d' % c])
