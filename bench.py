@@ -13,6 +13,7 @@ Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import signal
@@ -556,24 +557,37 @@ def run_b200_arm(args, rank, world, local_rank):
     barrier()
 
     # ---- device-timed region: EXACTLY K steps, inputs resident in HBM ----
-    # The stream is first given ~25 ms of head start (a spin kernel) so that the host has queued all K launches before
-    # the first timed event executes: the events then bracket K kernels running back to back on the device and a host
-    # hiccup (allocator, GC, a CFS throttle of the container's CPU quota -- one 20 ms stall in one of 20 steps was seen
-    # on a 2-GPU box) cannot leak into a device-side timestamp.
+    # The stream is first given ~25 ms of head start -- 16 more UNTIMED steps queued right after the barrier -- so that
+    # the host has queued all K timed launches before the first timed event executes: the events then bracket K kernels
+    # running back to back on the device, and a host hiccup (allocator, GC, a CFS throttle of the container's CPU quota)
+    # cannot leak into a device-side timestamp.  Real steps, not a spin kernel: the GPU must not see an idle gap between
+    # the warm-up and the timed region (after ~25 ms of near-idle spinning single steps of 20 - 40 ms were measured: the
+    # power state drops although NVML keeps reporting the maximum SM clock).
     def head_start():
-        torch.cuda._sleep(int(25e-3 * 1.9e9))
+        for i in range(16):
+            step(5000 + i)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     for e_ in ev:                                  # create the CUDA events now, not lazily inside the timed region
         e_.record()
+    # Python's cyclic garbage collector is parked for the timed regions: a generation-2 pass over the heap torch leaves
+    # behind takes 20 - 400 ms, lands at an allocation count (deterministically in the SECOND timed step of this script:
+    # measured 19.6, 41.5 and 436 ms against 1.51 ms for every other step) and starves the launch queue.
+    gc.collect()
+    gc.disable()
     barrier()
     head_start()
     ev[0].record()
+    res = None
     for k in range(args.steps):
         ev[1 + 2 * k].record()
         res = step(100 + k)
         ev[2 + 2 * k].record()
         keep_stats(k, res)
+        # drop the result before the next call allocates its (small) output tensors: with two result sets alive the
+        # caching allocator has to cudaMalloc a new segment inside the timed region, and cudaMalloc behind a full launch
+        # queue was measured at 7 - 436 ms (always in the second timed step) against 1.51 ms for every other step
+        res = None
     gather_stats()
     ev[-1].record()
     barrier()
@@ -683,6 +697,7 @@ def run_b200_arm(args, rank, world, local_rank):
     t_stream_ms = s0.elapsed_time(s1) / n_s
     del qs, ps, qo, po
     clk = clocks.stop() if rank == 0 else None        # sampled across all timed regions above (all under load)
+    gc.enable()
 
     # ---- BASELINE configs 3 / 4 / 5 with this rank's share of their chains ----
     others = None
@@ -731,7 +746,7 @@ def run_b200_arm(args, rank, world, local_rank):
                           'extra_untimed_warmup_steps': extra_warmup, 'warmup_gpu_busy_ms': busy_ms,
                           'warmup_step_ms_trace': warm_trace,
                           'timed_step_ms': {'min': sorted_ms[0], 'median': sorted_ms[len(sorted_ms) // 2],
-                                            'max': sorted_ms[-1]},
+                                            'max': sorted_ms[-1], 'all': [round(x, 4) for x in step_ms]},
                           'numa': numa,
                           'parity': 'config 2: samples bit-exact vs the reference (tests/test_hmc_gpu.py); config 5 (NUTS): '
                                     'bit-exact under the reference step-size schedule (teacher forcing); configs 3/4: see '

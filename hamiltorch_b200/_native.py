@@ -98,6 +98,12 @@ _PROTOS = {
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    'hmcx_rmhmc_leapfrog': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(RmhmcStruct), C.POINTER(RngStruct), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'hmcx_rmhmc_hamiltonian': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(RmhmcStruct), C.POINTER(RngStruct),
+                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     'hmcx_rmhmc_dense_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
     'hmcx_rmhmc_dense_run': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(RmhmcStruct), C.POINTER(ConstMetricStruct),
                                        C.POINTER(RngStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

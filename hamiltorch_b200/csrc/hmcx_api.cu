@@ -33,6 +33,9 @@ int dense_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, c
                   cudaStream_t);
 int rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
               int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
+int rmhmc_cta_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
+                  int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, const float*, float*, float*,
+                  float*, float*, int, float*, cudaStream_t);
 }  // namespace hmcx
 
 static inline bool is_elem(const hmcx_target_t* t) {
@@ -144,8 +147,29 @@ int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const h
                    float* q_cur, const float* eps, int32_t C, int32_t ld, int32_t L, int32_t num_samples,
                    int32_t burn, int32_t iter_begin, int32_t iter_end, float* samples_out, uint8_t* accept_out,
                    uint8_t* diverged_out, float* ham_out, int32_t* num_rejected, void* stream) {
+    if (target && target->dim > 16)      // metric / eigenvectors in shared memory, one CTA per chain (hmcx_rmhmc_cta.cu)
+        return hmcx::rmhmc_cta_run(target, cfg, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin, iter_end,
+                                   samples_out, accept_out, diverged_out, ham_out, num_rejected, nullptr, nullptr, nullptr,
+                                   nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
     return hmcx::rmhmc_run(target, cfg, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin, iter_end,
                            samples_out, accept_out, diverged_out, ham_out, num_rejected, (cudaStream_t)stream);
+}
+
+int hmcx_rmhmc_leapfrog(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng, const float* q_in,
+                        const float* p_in, const float* eps, int32_t C, int32_t ld, int32_t L, float* q_traj,
+                        float* p_traj, float* q_copy_out, float* p_copy_out, uint8_t* flags_out, void* stream) {
+    if (!q_in || !p_in || !q_traj || !p_traj) return HMCX_ERR_INVALID_ARG;
+    // one "iteration" with the momentum given and no MH
+    return hmcx::rmhmc_cta_run(target, cfg, rng, q_in, nullptr, eps, C, ld, L, 1, 0, 0, 1, nullptr, nullptr, flags_out,
+                               nullptr, nullptr, p_in, q_traj, p_traj, q_copy_out, p_copy_out, 0, nullptr,
+                               (cudaStream_t)stream);
+}
+
+int hmcx_rmhmc_hamiltonian(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng, const float* q,
+                           const float* p, int32_t C, int32_t ld, float* H_out, uint8_t* flags_out, void* stream) {
+    if (!q || !p || !H_out) return HMCX_ERR_INVALID_ARG;
+    return hmcx::rmhmc_cta_run(target, cfg, rng, q, nullptr, nullptr, C, ld, 1, 1, 0, 0, 1, nullptr, nullptr, flags_out,
+                               nullptr, nullptr, p, nullptr, nullptr, nullptr, nullptr, 1, H_out, (cudaStream_t)stream);
 }
 
 size_t hmcx_rmhmc_dense_workspace_bytes(int32_t C, int32_t D) {

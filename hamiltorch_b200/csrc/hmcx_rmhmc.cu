@@ -18,16 +18,9 @@
 // evaluation is thread-private, so 512 chains need no synchronisation at all; the arithmetic is latency/SFU bound
 // (exp, tanh, sinh, sqrt, divisions), not a tensor-core or HBM problem at these sizes.
 #include "hmcx_common.cuh"
+#include "hmcx_rm.cuh"
 
 namespace hmcx {
-
-struct RmTarget {
-    int kind, D;
-    float log_norm, inv_var_v;
-    const float* mean;
-    const float* ivar;
-    const float* prec;        // GAUSS_FULL: [D,D] row-major
-};
 
 // DM is the capacity of the per-thread arrays.  The DM == 2 instantiation is launched only for D == 2 (BASELINE
 // config 3), so there the dimension is a compile-time constant: every loop unrolls and the 2x2 metric algebra lives
@@ -167,13 +160,6 @@ struct Metric {
     float lam[DM];        // eigenvalues of G (+ jitter)
     float lt[DM];         // lam~ = softabs(lam) (or lam for the HESSIAN metric)
     float dlt[DM];        // d lam~ / d lam
-};
-
-struct RmCfg {
-    int softabs;          // Metric.SOFTABS (1) or Metric.HESSIAN (0)
-    int jacdiag;          // Metric.JACOBIAN_DIAG (:100-106): G = diag((d log p / d theta_i)^2), no eigen-decomposition
-    float alpha, jitter;  // softabs_const, jitter scale (jitter < 0: none)
-    float pi_term;        // D*log(2*pi) in fp32 as samplers.py:712
 };
 
 // fisher(): G = -Hess (+ diag(u*jitter)), eigh, softabs.  false <=> the reference raises LogProbError (:110-112, :717)

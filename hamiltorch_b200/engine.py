@@ -504,9 +504,10 @@ def const_metric(target, softabs, softabs_const):
 
 
 def _rmhmc_is_dense(target, jitter, jacdiag=False):
-    """Gaussian targets without jitter have a constant metric: the tensor-core path (any D).  GaussianIso / GaussianDiag
-    at D <= 16 stay on the thread-per-chain kernel (which also handles jitter).  Metric.JACOBIAN_DIAG depends on the
-    gradient, i.e. on the position, for every target: never constant."""
+    """Gaussian targets without jitter have a constant metric: the tensor-core path (GaussianFull at any D; GaussianIso /
+    GaussianDiag above D = 16, below they stay on the thread-per-chain kernel).  Everything else -- Funnel, jitter,
+    Metric.JACOBIAN_DIAG (depends on the gradient, i.e. on the position) -- assembles and factorises its metric inside
+    the kernel: hmcx_rmhmc_run (D <= 16 one thread per chain, D <= 64 one CTA per chain)."""
     if jitter is not None or jacdiag:
         return False
     if isinstance(target, T.GaussianFull):
@@ -543,18 +544,8 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
     if softabs and softabs_const is None:
         raise RuntimeError('Metric.SOFTABS needs softabs_const')
 
-    cfg = N.RmhmcStruct()
-    cfg.integrator = 1 if explicit else 2
-    cfg.metric = 3 if jacdiag else (2 if softabs else 1)          # Metric enum values (samplers.py:28-31)
-    cfg.softabs_const = float(softabs_const) if softabs_const is not None else 0.0
-    cfg.jitter = float(jitter) if jitter is not None else -1.0
-    cfg.pi_term = float(D * torch.log(2. * torch.tensor(math.pi)))                              # samplers.py:711-712
-    eps0 = float(step_size) if not torch.is_tensor(step_size) else float(step_size.reshape(-1)[0])
-    cfg.cos_2we = float(torch.cos(torch.FloatTensor([2 * explicit_binding_const * eps0])))    # :435
-    cfg.sin_2we = float(torch.sin(torch.FloatTensor([2 * explicit_binding_const * eps0])))    # :436
-    cfg.fixed_point_threshold = float(fixed_point_threshold)
-    cfg.fixed_point_max_iterations = int(fixed_point_max_iterations)
-    cfg.jitter_max_tries = int(jitter_max_tries)
+    cfg = _rmhmc_cfg(D, step_size, jitter, softabs_const, explicit_binding_const, fixed_point_threshold,
+                     fixed_point_max_iterations, jitter_max_tries, explicit, softabs, jacdiag)
 
     rng = N.RngStruct()
     keep_alive = []
@@ -605,6 +596,95 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
     res.final_state = q_cur[:, :D]
     res._keep_alive = keep_alive
     return res
+
+
+def _rmhmc_cfg(D, step_size, jitter, softabs_const, explicit_binding_const, fixed_point_threshold,
+               fixed_point_max_iterations, jitter_max_tries, explicit, softabs, jacdiag):
+    cfg = N.RmhmcStruct()
+    cfg.integrator = 1 if explicit else 2
+    cfg.metric = 3 if jacdiag else (2 if softabs else 1)
+    cfg.softabs_const = float(softabs_const) if softabs_const is not None else 0.0
+    cfg.jitter = float(jitter) if jitter is not None else -1.0
+    cfg.pi_term = float(D * torch.log(2. * torch.tensor(math.pi)))                              # samplers.py:711-712
+    eps0 = float(step_size) if not torch.is_tensor(step_size) else float(step_size.reshape(-1)[0])
+    cfg.cos_2we = float(torch.cos(torch.FloatTensor([2 * explicit_binding_const * eps0])))    # :435
+    cfg.sin_2we = float(torch.sin(torch.FloatTensor([2 * explicit_binding_const * eps0])))    # :436
+    cfg.fixed_point_threshold = float(fixed_point_threshold)
+    cfg.fixed_point_max_iterations = int(fixed_point_max_iterations)
+    cfg.jitter_max_tries = int(jitter_max_tries)
+    return cfg
+
+
+def _standalone_rng(jitter, uniforms, seed, Cn, D, ld, device, keep):
+    """Jitter draws of a stand-alone RMHMC call: injected ``uniforms`` (C, J, D) / (J, D) in fisher() call order, else
+    Philox keyed by ``seed``."""
+    rng = N.RngStruct()
+    if jitter is not None and uniforms is not None:
+        u = uniforms.detach().to(device=device, dtype=torch.float32)
+        if u.dim() == 2:
+            u = u.unsqueeze(0)
+        if u.dim() != 3 or u.shape[0] != Cn or u.shape[2] != D:
+            raise RuntimeError('uniforms must be (C, J, D) = (%d, J, %d), got %s' % (Cn, D, tuple(u.shape)))
+        u = N.pad_rows(u.contiguous(), ld)
+        rng.mode, rng.uniforms, rng.uniforms_per_iter = N.RNG_INJECTED, u.data_ptr(), u.shape[1]
+        keep.append(u)
+    else:
+        rng.mode, rng.seed = N.RNG_PHILOX, int(seed)
+    return rng
+
+
+def rmhmc_leapfrog(target, q, p, steps, step_size, jitter=None, softabs_const=None, explicit_binding_const=100,
+                   fixed_point_threshold=1e-20, fixed_point_max_iterations=6, jitter_max_tries=10, explicit=True,
+                   softabs=False, jacdiag=False, uniforms=None, seed=0, device=None):
+    """Batched samplers.leapfrog with sampler=RMHMC (explicit :389-462 / implicit :305-387), D <= 64.  q, p: (C, D) or
+    (D,).  Returns (q_traj (L, C, D), p_traj (L, C, D), q_copy (C, D), p_copy (C, D), failed (C,) uint8)."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
+    Cn, L = qd.shape[0], int(steps)
+    eps = _eps_vector(step_size, Cn, device)
+    cfg = _rmhmc_cfg(D, step_size, jitter, softabs_const, explicit_binding_const, fixed_point_threshold,
+                     fixed_point_max_iterations, jitter_max_tries, explicit, softabs, jacdiag)
+    keep = []
+    rng = _standalone_rng(jitter, uniforms, seed, Cn, D, ld, device, keep)
+    q_traj = torch.zeros((L, Cn, ld), dtype=torch.float32, device=device)
+    p_traj = torch.zeros_like(q_traj)
+    q_copy = torch.zeros((Cn, ld), dtype=torch.float32, device=device)
+    p_copy = torch.zeros_like(q_copy)
+    failed = torch.zeros(Cn, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_rmhmc_leapfrog(nt.ref(), C.byref(cfg), C.byref(rng), N.ptr(qd), N.ptr(pd), N.ptr(eps), Cn, ld, L,
+                                     N.ptr(q_traj), N.ptr(p_traj), N.ptr(q_copy), N.ptr(p_copy), N.ptr(failed),
+                                     N.stream_ptr(device))
+    N.check(rc, 'hmcx_rmhmc_leapfrog')
+    torch.cuda.current_stream(device).synchronize()          # `keep` / the structs may go out of scope now
+    return q_traj[..., :D], p_traj[..., :D], q_copy[:, :D], p_copy[:, :D], failed
+
+
+def rmhmc_hamiltonian(target, q, p, jitter=None, softabs_const=None, softabs=False, jacdiag=False, uniforms=None, seed=0,
+                      device=None):
+    """Batched rm_hamiltonian (samplers.py:677-736): (H (C,), failed (C,) uint8)."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
+    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
+    Cn = qd.shape[0]
+    cfg = _rmhmc_cfg(D, 0.0, jitter, softabs_const, 100, 1e-5, 1, 10, True, softabs, jacdiag)
+    keep = []
+    rng = _standalone_rng(jitter, uniforms, seed, Cn, D, ld, device, keep)
+    H = torch.zeros(Cn, dtype=torch.float32, device=device)
+    failed = torch.zeros(Cn, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_rmhmc_hamiltonian(nt.ref(), C.byref(cfg), C.byref(rng), N.ptr(qd), N.ptr(pd), Cn, ld, N.ptr(H),
+                                        N.ptr(failed), N.stream_ptr(device))
+    N.check(rc, 'hmcx_rmhmc_hamiltonian')
+    torch.cuda.current_stream(device).synchronize()
+    return H, failed
 
 
 def gemm_nt(A, B):

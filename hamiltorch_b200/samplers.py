@@ -110,7 +110,8 @@ def gibbs(params, sampler=Sampler.HMC, log_prob_func=None, jitter=None, normaliz
 def leapfrog(params, momentum, log_prob_func, steps=10, step_size=0.1, jitter=0.01, normalizing_const=1.,
              softabs_const=1e6, explicit_binding_const=100, fixed_point_threshold=1e-20,
              fixed_point_max_iterations=6, jitter_max_tries=10, inv_mass=None, ham_func=None, sampler=Sampler.HMC,
-             integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, store_on_GPU=True, debug=False, pass_grad=None):
+             integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, store_on_GPU=True, debug=False, pass_grad=None,
+             *, rng_uniforms=None):
     """samplers.py:205-606.  Plain HMC branch on the GPU; returns ``(ret_params, ret_momenta)``: two lists of
     ``steps`` tensors, the last momentum carrying the half-step correction (:302).  ``params`` may be (D,) as in
     the reference or (C, D) for C chains at once."""
@@ -133,16 +134,61 @@ def leapfrog(params, momentum, log_prob_func, steps=10, step_size=0.1, jitter=0.
     if sampler == Sampler.RMHMC:
         if pass_grad is not None:
             raise RuntimeError('Passing user-determined gradients not implemented for RMHMC')  # :310, :390-391
-        raise NotImplementedError('stand-alone RMHMC leapfrog: use sample(sampler=Sampler.RMHMC)')
+        if integrator not in (Integrator.EXPLICIT, Integrator.IMPLICIT):
+            raise NotImplementedError()                                                         # S3: :606
+        _check_rmhmc_target(log_prob_func, metric)
+        if jitter is not None and rng_uniforms is None and not torch.is_tensor(jitter):
+            # the reference draws torch.rand(D) inside every fisher() call (:115): a data-dependent number of draws for
+            # the implicit integrator and for NaN retries, so they are drawn on the fly inside the kernel (Philox keyed
+            # by a seed taken from torch's generator) unless the caller injects them
+            pass
+        explicit = integrator == Integrator.EXPLICIT
+        seed = int(torch.randint(0, 2 ** 62, (1,)))
+        qt, ptj, qcopy, pcopy, failed = engine.rmhmc_leapfrog(
+            log_prob_func, params, momentum, steps, step_size, jitter=jitter, softabs_const=softabs_const,
+            explicit_binding_const=explicit_binding_const, fixed_point_threshold=fixed_point_threshold,
+            fixed_point_max_iterations=fixed_point_max_iterations, jitter_max_tries=jitter_max_tries, explicit=explicit,
+            softabs=(metric == Metric.SOFTABS), jacdiag=(metric == Metric.JACOBIAN_DIAG), uniforms=rng_uniforms, seed=seed)
+        if int(failed.sum()) > 0:
+            raise util.LogProbError()                                                           # :110-112, :717, :733
+        dev = params.device
+        single = params.dim() == 1
+        ret_params = [(t[0] if single else t).to(dev) for t in qt.unbind(0)]
+        ret_momenta = [(t[0] if single else t).to(dev) for t in ptj.unbind(0)]
+        if explicit:                                                                            # :462
+            return [ret_params, (qcopy[0] if single else qcopy).to(dev)], \
+                   [ret_momenta, (pcopy[0] if single else pcopy).to(dev)]
+        return ret_params, ret_momenta
     raise NotImplementedError()
+
+
+def _check_rmhmc_target(log_prob_func, metric):
+    if isinstance(log_prob_func, list) or not isinstance(log_prob_func, (T.Funnel, T.GaussianIso, T.GaussianDiag,
+                                                                         T.GaussianFull)):
+        raise NotImplementedError('RMHMC needs closed-form third derivatives: Funnel / Gaussian descriptors')
+    if metric not in (Metric.HESSIAN, Metric.SOFTABS, Metric.JACOBIAN_DIAG):
+        raise NotImplementedError()
+    if log_prob_func.dim > 64:
+        raise NotImplementedError('stand-alone RMHMC leapfrog / hamiltonian: D <= 64 (metric in shared memory)')
 
 
 def hamiltonian(params, momentum, log_prob_func, jitter=0.01, normalizing_const=1., softabs_const=1e6,
                 explicit_binding_const=100, inv_mass=None, ham_func=None, sampler=Sampler.HMC,
-                integrator=Integrator.EXPLICIT, metric=Metric.HESSIAN):
-    """samplers.py:738-846, sampler=HMC branch.  Raises util.LogProbError on a non-finite log-prob like the
+                integrator=Integrator.EXPLICIT, metric=Metric.HESSIAN, *, rng_uniforms=None):
+    """samplers.py:738-846: sampler=HMC (:779-815) and sampler=RMHMC (:817-829 -> rm_hamiltonian).  Raises util.LogProbError on a non-finite log-prob like the
     reference (:783-785).  (D,) -> tensor of shape (); (C, D) -> (C,)."""
     _require_target(log_prob_func)
+    if sampler == Sampler.RMHMC:                                                                # :817-829
+        _check_rmhmc_target(log_prob_func, metric)
+        H, flags = engine.rmhmc_hamiltonian(log_prob_func, params, momentum, jitter=jitter, softabs_const=softabs_const,
+                                            softabs=(metric == Metric.SOFTABS), jacdiag=(metric == Metric.JACOBIAN_DIAG),
+                                            uniforms=rng_uniforms, seed=int(torch.randint(0, 2 ** 62, (1,))))
+        if int(flags.sum()) > 0:
+            raise util.LogProbError()
+        if integrator == Integrator.EXPLICIT:
+            H = 2 * H                                                                           # :822
+        H = H.to(params.device)
+        return H[0].reshape(1, 1) if params.dim() == 1 else H       # the reference returns a (1, 1) tensor (:731)
     if sampler != Sampler.HMC or isinstance(log_prob_func, list):
         raise NotImplementedError()
     H, flags = engine.hamiltonian(log_prob_func, params, momentum, inv_mass=inv_mass)
@@ -364,13 +410,13 @@ def _run_chains(log_prob_func, q0, num_samples, L, step_size, burn, jitter, inv_
         jacdiag = metric == Metric.JACOBIAN_DIAG
         if metric not in (Metric.HESSIAN, Metric.SOFTABS, Metric.JACOBIAN_DIAG):
             raise NotImplementedError()
-        small = log_prob_func.dim <= 16
-        if isinstance(log_prob_func, T.GaussianFull) and not small and (jitter is not None or jacdiag):
-            raise NotImplementedError('GaussianFull under RMHMC at D > 16 runs on the constant-metric tensor-core path: '
-                                      'jitter=None, HESSIAN / SOFTABS')
-        if not isinstance(log_prob_func, T.GaussianFull) and not small and \
-                (isinstance(log_prob_func, T.Funnel) or jitter is not None or jacdiag):
-            raise NotImplementedError('RMHMC at D > 16: Gaussian targets with jitter=None (constant metric, tensor cores)')
+        Dd = log_prob_func.dim
+        const_metric = jitter is None and not jacdiag and isinstance(log_prob_func, (T.GaussianIso, T.GaussianDiag,
+                                                                                     T.GaussianFull))
+        if Dd > 64 and not const_metric:
+            raise NotImplementedError('RMHMC with a position-dependent or jittered metric: D <= 64 (metric, eigenvectors '
+                                      'and one work matrix in shared memory); Gaussian targets with jitter=None run on '
+                                      'the constant-metric tensor-core path at any D')
         if inv_mass is not None:
             pass                                            # the reference ignores inv_mass for RMHMC (:989 comment)
         D = log_prob_func.dim

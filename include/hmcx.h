@@ -248,9 +248,12 @@ int hmcx_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const h
 
 /*
  * hmcx_rmhmc_run == the sample() loop for sampler=RMHMC (samplers.py:965-1067 with gibbs :183-184, rm_hamiltonian
- * :677-736, fisher :69-127, explicit :389-462 / implicit :305-387 leapfrog).  Targets: FUNNEL, GAUSS_ISO, GAUSS_DIAG
- * with dim <= 16 (closed-form Hessian and third-derivative contraction).  One thread per chain.  Arguments as
- * hmcx_hmc_run (eps is read-only: the reference never adapts the step size of RMHMC).
+ * :677-736, fisher :69-127, explicit :389-462 / implicit :305-387 leapfrog).  Targets: FUNNEL, GAUSS_ISO, GAUSS_DIAG,
+ * GAUSS_FULL (closed-form Hessian and third-derivative contraction), any jitter, metrics HESSIAN / SOFTABS /
+ * JACOBIAN_DIAG.  dim <= 16: one thread per chain (dim == 2 with the explicit integrator -- BASELINE config 3 -- a
+ * pair of warps per 32 chains that evaluates dH/dtheta and dH/dp concurrently); 16 < dim <= 64: one CTA per chain, the
+ * metric assembled, eigen-decomposed (parallel-order Jacobi) and solved in shared memory.  Arguments as hmcx_hmc_run
+ * (eps is read-only: the reference never adapts the step size of RMHMC).
  */
 int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng,
                    const float* q_init, float* q_cur, const float* eps,
@@ -258,6 +261,31 @@ int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const h
                    int32_t iter_begin, int32_t iter_end,
                    float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
                    int32_t* num_rejected, void* stream);
+
+/*
+ * hmcx_rmhmc_leapfrog == samplers.leapfrog with sampler=RMHMC called on its own (explicit :389-462, implicit :305-387):
+ * L steps from (q_in, p_in), same targets / metrics as hmcx_rmhmc_run, dim <= 64.
+ *   q_traj, p_traj   [L, C, ld]  theta and p after every step (the reference's ret_params / ret_momenta lists)
+ *   q_copy_out, p_copy_out  optional [C, ld]: the explicit integrator's params_copy / momentum_copy after the last step
+ *                    (second elements of the pairs it returns, :462)
+ *   flags_out        [C] (uint8) 1 where the reference raises LogProbError inside the trajectory (outputs of that chain
+ *                    from the failing step on are unspecified)
+ * rng: jitter draws of the fisher() calls in call order from row 0 (INJECTED: uniforms [1, C, J, ld]) or Philox with
+ * iteration index 0; normals / log_uniforms are not read.
+ */
+int hmcx_rmhmc_leapfrog(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng,
+                        const float* q_in, const float* p_in, const float* eps, int32_t C, int32_t ld, int32_t L,
+                        float* q_traj, float* p_traj, float* q_copy_out, float* p_copy_out, uint8_t* flags_out,
+                        void* stream);
+
+/*
+ * hmcx_rmhmc_hamiltonian == samplers.hamiltonian with sampler=RMHMC (:817-829) == rm_hamiltonian (:677-736):
+ * H_out[c] = -log p + 0.5 D log 2pi + 0.5 log det G + 0.5 p.G^-1 p (the caller doubles it for the explicit integrator's
+ * augmented form, :822); flags_out [C] = 1 where the reference raises LogProbError.  One jitter row (row 0).
+ */
+int hmcx_rmhmc_hamiltonian(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng,
+                           const float* q, const float* p, int32_t C, int32_t ld, float* H_out, uint8_t* flags_out,
+                           void* stream);
 
 /*
  * hmcx_grad_log_prob == collect_gradients(log_prob_func(params), params) (samplers.py:33-66, :270-278) for C

@@ -54,7 +54,7 @@ def test_golden_chain_parity(name):
         assert not np.any(res.accepted[c].cpu().numpy().astype(bool) & rdiv)
         if explicit:
             assert not (div & ~rdiv).any()
-        ok = ~div & ~rdiv
+        ok = ~div & ~rdiv & ~(dH_ref > 50.0)      # a blown-up trajectory (reject on both sides) has no meaningful H
         np.testing.assert_allclose(ham[ok, 0], d['ham_old_%d' % c][ok], rtol=RM_RTOL, atol=RM_RTOL)
         np.testing.assert_allclose(ham[ok, 1], d['ham_new_%d' % c][ok], rtol=RM_RTOL, atol=RM_RTOL)
         m = parity.first_decision_mismatch(res.accepted[c].cpu().numpy(), d['accepted_%d' % c])
