@@ -1,4 +1,5 @@
 // hmcx_api.cu -- the extern "C" surface declared in include/hmcx.h; validates and dispatches on target kind.
+#include <cstdlib>
 #include "hmcx_common.cuh"
 
 namespace hmcx {
@@ -147,7 +148,10 @@ int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const h
                    float* q_cur, const float* eps, int32_t C, int32_t ld, int32_t L, int32_t num_samples,
                    int32_t burn, int32_t iter_begin, int32_t iter_end, float* samples_out, uint8_t* accept_out,
                    uint8_t* diverged_out, float* ham_out, int32_t* num_rejected, void* stream) {
-    if (target && target->dim > 16)      // metric / eigenvectors in shared memory, one CTA per chain (hmcx_rmhmc_cta.cu)
+    // metric / eigenvectors in shared memory, one CTA per chain (hmcx_rmhmc_cta.cu); HMCX_RMHMC_FORCE_CTA=1 sends the small
+    // problems there too (tests run every golden chain through both kernels)
+    const char* force = getenv("HMCX_RMHMC_FORCE_CTA");
+    if (target && (target->dim > 16 || (force && force[0] == '1')))
         return hmcx::rmhmc_cta_run(target, cfg, rng, q_init, q_cur, eps, C, ld, L, num_samples, burn, iter_begin, iter_end,
                                    samples_out, accept_out, diverged_out, ham_out, num_rejected, nullptr, nullptr, nullptr,
                                    nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);

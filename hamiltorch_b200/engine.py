@@ -4,6 +4,7 @@ Everything here is plumbing -- device buffers, padding to the (C, ld) layout, th
 the random-stream modes.  The arithmetic of the hot path lives in csrc/*.cu.
 """
 import ctypes as C
+import os
 import math
 
 import torch
@@ -508,7 +509,7 @@ def _rmhmc_is_dense(target, jitter, jacdiag=False):
     GaussianDiag above D = 16, below they stay on the thread-per-chain kernel).  Everything else -- Funnel, jitter,
     Metric.JACOBIAN_DIAG (depends on the gradient, i.e. on the position) -- assembles and factorises its metric inside
     the kernel: hmcx_rmhmc_run (D <= 16 one thread per chain, D <= 64 one CTA per chain)."""
-    if jitter is not None or jacdiag:
+    if jitter is not None or jacdiag or os.environ.get('HMCX_RMHMC_FORCE_CTA') == '1':
         return False
     if isinstance(target, T.GaussianFull):
         return True

@@ -221,6 +221,30 @@ def rmhmc_cases():
                                                num_steps_per_sample=3, step_size=0.2, burn=1,
                                                explicit_binding_const=10, metric='SOFTABS', jitter=1e-2,
                                                softabs_const=1e3, seeds=[14]),
+        # ---- one-CTA-per-chain kernel (hmcx_rmhmc_cta.cu): metric assembled / eigen-decomposed in shared memory, 16 < D <= 64
+        # position-dependent metric beyond the register kernel: the funnel at D = 32
+        'rmhmc_exp_funnel32': dict(target=T.Funnel(32), init=[0.] + [0.5 * (((i * 5) % 7) - 3) / 3 for i in range(31)],
+                                   integrator='EXPLICIT', num_samples=7, num_steps_per_sample=3, step_size=0.03, burn=1,
+                                   explicit_binding_const=10, seeds=[21, 22], **funnel_kw),
+        # dense precision with the reference's jitter: a per-call random metric at D = 48
+        'rmhmc_exp_softabs_full48_jitter': dict(target=T.GaussianFull(torch.linspace(-0.5, 0.5, 48), cov=_spd64(48, 75)),
+                                                init=[0.1 * ((i * 7) % 5 - 2) for i in range(48)], integrator='EXPLICIT',
+                                                num_samples=6, num_steps_per_sample=3, step_size=0.3, burn=1,
+                                                explicit_binding_const=10, metric='SOFTABS', jitter=1e-3,
+                                                softabs_const=1e3, seeds=[23]),
+        # implicit integrator with a position-dependent metric beyond D = 16 (the funnel's Hessian has an eigenvalue of
+        # multiplicity D-2, so without jitter the reference's eigh backward is NaN: JACOBIAN_DIAG on a Gaussian instead)
+        'rmhmc_imp_jacdiag_diag24': dict(target=T.GaussianDiag(torch.linspace(-1, 1, 24), _rand_var(24, 77)),
+                                         init=[1.5 + 0.2 * ((i * 3) % 7) for i in range(24)], integrator='IMPLICIT',
+                                         num_samples=6, num_steps_per_sample=3, step_size=0.05, burn=1,
+                                         metric='JACOBIAN_DIAG', jitter=None, softabs_const=None,
+                                         fixed_point_threshold=1e-5, fixed_point_max_iterations=1000, seeds=[24, 26]),
+        # HESSIAN metric + jitter on a diagonal Gaussian at D = 64 (the kernel's largest size)
+        'rmhmc_exp_hess_diag64_jitter': dict(target=T.GaussianDiag(torch.linspace(-1, 1, 64), _rand_var(64, 76)),
+                                             init=[0.2 * ((i * 3) % 7 - 3) for i in range(64)], integrator='EXPLICIT',
+                                             num_samples=5, num_steps_per_sample=2, step_size=0.2, burn=0,
+                                             explicit_binding_const=10, metric='HESSIAN', jitter=1e-3,
+                                             softabs_const=None, seeds=[25]),
         'rmhmc_imp_softabs_diag20': dict(target=T.GaussianDiag(torch.linspace(-1, 1, 20), _rand_var(20, 72)),
                                          init=[0.2 * ((i * 3) % 7 - 3) for i in range(20)], integrator='IMPLICIT',
                                          num_samples=6, num_steps_per_sample=3, step_size=0.5, burn=1,
@@ -228,3 +252,20 @@ def rmhmc_cases():
                                          fixed_point_max_iterations=1000, seeds=[9]),
     }
     return cases
+
+
+def standalone_rm_cases():
+    """Stand-alone samplers.leapfrog / samplers.hamiltonian with sampler=RMHMC (:305-462, :817-829) -- name -> kwargs."""
+    return {
+        'exp_funnel5': dict(target=T.Funnel(5), q=[0.3, 1., -1., 0.5, 0.8], integrator='EXPLICIT', metric='SOFTABS',
+                            steps=3, step_size=0.05, jitter=1e-3, softabs_const=1e6, explicit_binding_const=10, seed=31),
+        'exp_funnel32': dict(target=T.Funnel(32), q=[0.2] + [0.5 * (((i * 5) % 7) - 3) / 3 for i in range(31)],
+                             integrator='EXPLICIT', metric='SOFTABS', steps=2, step_size=0.03, jitter=1e-3,
+                             softabs_const=1e6, explicit_binding_const=10, seed=32),
+        'imp_jacdiag_gauss3': dict(target=T.GaussianDiag(torch.tensor([0., 1., -1.]), torch.tensor([.5, 1., 2.]) ** 2),
+                                   q=[0.6, 0.2, -2.5], integrator='IMPLICIT', metric='JACOBIAN_DIAG', steps=3,
+                                   step_size=0.05, jitter=None, softabs_const=None, seed=33),
+        'imp_hess_full24': dict(target=T.GaussianFull(torch.linspace(-0.5, 0.5, 24), cov=_spd64(24, 71)),
+                                q=[0.1 * ((i * 7) % 5 - 2) for i in range(24)], integrator='IMPLICIT', metric='HESSIAN',
+                                steps=3, step_size=0.3, jitter=None, softabs_const=None, seed=34),
+    }

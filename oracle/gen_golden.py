@@ -267,6 +267,45 @@ def run_rmhmc_case(ref, name, case):
           'LogProbError', [int(out['diverged_%d' % c].sum()) for c in range(len(case['seeds']))])
 
 
+def run_rm_standalone(ref):
+    """Reference outputs of leapfrog(sampler=RMHMC) -- (ret_params, ret_momenta[, params_copy, momentum_copy]) -- and of
+    hamiltonian(sampler=RMHMC) at the start point; the jitter stream torch.rand(D) of the call is recorded."""
+    out = {}
+    for name, c in cases.standalone_rm_cases().items():
+        tgt, D = c['target'], c['target'].dim
+        q = torch.tensor(c['q'])
+        torch.manual_seed(c['seed'])
+        p = torch.randn(D)
+        explicit = c['integrator'] == 'EXPLICIT'
+        kw = dict(jitter=c['jitter'], softabs_const=c['softabs_const'], sampler=ref.Sampler.RMHMC,
+                  integrator=getattr(ref.Integrator, c['integrator']), metric=getattr(ref.Metric, c['metric']))
+        st = torch.get_rng_state()
+        H = ref.samplers.hamiltonian(q.clone().requires_grad_(), p, tgt, explicit_binding_const=c.get('explicit_binding_const', 100),
+                            **kw)
+        torch.set_rng_state(st)
+        out[name + '.uni_h'] = torch.rand(1, D).numpy()
+        st = torch.get_rng_state()
+        lk = dict(kw, steps=c['steps'], step_size=c['step_size'])
+        if explicit:
+            lk['explicit_binding_const'] = c['explicit_binding_const']
+        ret_q, ret_p = ref.samplers.leapfrog(q.clone().requires_grad_(), p, tgt, **lk)
+        torch.set_rng_state(st)
+        J = 8 * c['steps'] if (explicit and c['jitter'] is not None) else 1
+        out[name + '.uni_l'] = torch.rand(J, D).numpy()
+        if explicit:
+            (qs, qc), (ps, pc) = ret_q, ret_p
+            out[name + '.q_copy'] = qc.detach().numpy()
+            out[name + '.p_copy'] = pc.detach().numpy()
+        else:
+            qs, ps = ret_q, ret_p
+        out[name + '.p0'] = p.numpy()
+        out[name + '.H'] = H.detach().numpy().reshape(-1)
+        out[name + '.q_traj'] = torch.stack([t.detach() for t in qs]).numpy()
+        out[name + '.p_traj'] = torch.stack([t.detach() for t in ps]).numpy()
+        print('standalone', name, 'H', float(H), 'q_L', out[name + '.q_traj'][-1][:3])
+    np.savez_compressed(os.path.join(OUT, 'rmhmc_standalone.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -288,6 +327,8 @@ def main():
         for name, case in cases.rmhmc_cases().items():
             if not only or name in only:
                 run_rmhmc_case(ref, name, case)
+        if not only or 'rmhmc_standalone' in only:
+            run_rm_standalone(ref)
 
 
 if __name__ == '__main__':

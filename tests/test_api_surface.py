@@ -91,17 +91,17 @@ def test_nuts_table_matches_python_doubles():
 
 def test_sink_and_rmhmc_routing_errors_are_raised_on_the_host():
     """Argument checks that must fire before any CUDA work (so they are testable without a GPU): the sample sink is only
-    wired into the element-wise persistent kernel; RMHMC at D > 16 needs a constant metric."""
+    wired into the element-wise persistent kernel; RMHMC at D > 64 needs a constant metric."""
     import pytest
     import torch
     import hamiltorch_b200 as hb
     from hamiltorch_b200 import targets as T
-    D = 24
+    D = 80
     full = T.GaussianFull(torch.zeros(D), cov=torch.eye(D, dtype=torch.float64) * 2)
     for kw in (dict(thin=2), dict(moments=True), dict(keep_samples=False), dict(store_on_GPU=False)):
         with pytest.raises(NotImplementedError):
             hb.sample_chains(full, torch.zeros(2, D), num_samples=5, **kw)
-    with pytest.raises(NotImplementedError):                       # position-dependent metric at D > 16
+    with pytest.raises(NotImplementedError):                       # position-dependent metric at D > 64
         hb.sample_chains(T.Funnel(D), torch.zeros(2, D), num_samples=5, sampler=hb.Sampler.RMHMC,
                          integrator=hb.Integrator.EXPLICIT)
     with pytest.raises(NotImplementedError):                       # jitter makes the metric a per-call random matrix

@@ -20,6 +20,25 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 RM_RTOL = 2e-3
 
 
+@pytest.fixture
+def force_cta(monkeypatch):
+    monkeypatch.setenv('HMCX_RMHMC_FORCE_CTA', '1')
+
+
+@pytest.mark.parametrize('name', sorted(n for n, c in cases.rmhmc_cases().items() if c['target'].dim <= 16
+                                        or not (c['jitter'] is None and c['metric'] != 'JACOBIAN_DIAG')))
+def test_golden_chain_parity_cta_kernel(name, force_cta):
+    """Every golden chain that normally runs on the thread-per-chain kernel (D <= 16) or the constant-metric tensor-core
+    path also goes through the one-CTA-per-chain kernel (hmcx_rmhmc_cta.cu): same bounds."""
+    test_golden_chain_parity(name)
+
+
+@pytest.mark.parametrize('name', sorted(n for n, c in cases.rmhmc_cases().items() if c['target'].dim > 16 and
+                                        c['jitter'] is None and c['metric'] != 'JACOBIAN_DIAG'))
+def test_golden_chain_parity_const_metric_on_cta_kernel(name, force_cta):
+    test_golden_chain_parity(name)
+
+
 @pytest.mark.parametrize('name', sorted(cases.rmhmc_cases()))
 def test_golden_chain_parity(name):
     case = cases.rmhmc_cases()[name]
@@ -30,7 +49,9 @@ def test_golden_chain_parity(name):
     init = torch.tensor(case['init']).repeat(nC, 1)
     z = torch.stack([torch.from_numpy(d['z_%d' % c]) for c in range(nC)], 1)
     logu = torch.stack([torch.from_numpy(d['logu_%d' % c]) for c in range(nC)], 1)
-    uni = torch.stack([torch.from_numpy(d['uniforms_%d' % c]) for c in range(nC)], 1)      # (S, C, J, D)
+    unis = [torch.from_numpy(d['uniforms_%d' % c]) for c in range(nC)]                      # (S, J_c, D) each
+    J = max(u.shape[1] for u in unis)            # a chain with NaN-gradient retries (:402-410) consumed more draws
+    uni = torch.stack([torch.nn.functional.pad(u, (0, 0, 0, J - u.shape[1])) for u in unis], 1)     # (S, C, J, D)
     res = engine.rmhmc_run(case['target'], init, S, L, case['step_size'], burn=case['burn'], jitter=case['jitter'],
                            softabs_const=case['softabs_const'],
                            explicit_binding_const=case.get('explicit_binding_const', 100),
@@ -91,3 +112,47 @@ def test_config3_philox_funnel_statistics():
     v = res.samples[:, S // 2:, 0].cpu()
     assert abs(v.mean().item()) < 0.5
     assert 1.5 < v.std().item() < 4.0
+
+
+# ----------------------------------------------------------------------------------------------------------
+# stand-alone samplers.leapfrog / samplers.hamiltonian with sampler=RMHMC (samplers.py:305-462, :817-829)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', sorted(cases.standalone_rm_cases()))
+def test_standalone_rmhmc_leapfrog_and_hamiltonian_match_the_reference(name):
+    c = cases.standalone_rm_cases()[name]
+    d = np.load(os.path.join(GOLD, 'rmhmc_standalone.npz'))
+    q, p = torch.tensor(c['q']), torch.from_numpy(d[name + '.p0'])
+    explicit = c['integrator'] == 'EXPLICIT'
+    kw = dict(jitter=c['jitter'], softabs_const=c['softabs_const'], sampler=hb.Sampler.RMHMC,
+              integrator=getattr(hb.Integrator, c['integrator']), metric=getattr(hb.Metric, c['metric']))
+    H = hb.hamiltonian(q, p, c['target'], explicit_binding_const=c.get('explicit_binding_const', 100),
+                       rng_uniforms=torch.from_numpy(d[name + '.uni_h']) if c['jitter'] is not None else None, **kw)
+    assert tuple(H.shape) == (1, 1)                                           # :731
+    np.testing.assert_allclose(H.cpu().numpy().reshape(-1), d[name + '.H'], rtol=RM_RTOL)
+    lk = dict(kw, steps=c['steps'], step_size=c['step_size'])
+    if explicit:
+        lk['explicit_binding_const'] = c['explicit_binding_const']
+    ret_q, ret_p = hb.leapfrog(q, p, c['target'],
+                               rng_uniforms=torch.from_numpy(d[name + '.uni_l']) if c['jitter'] is not None else None, **lk)
+    if explicit:                                                              # :462
+        (qs, qc), (ps, pc) = ret_q, ret_p
+        np.testing.assert_allclose(qc.cpu().numpy(), d[name + '.q_copy'], rtol=RM_RTOL, atol=RM_RTOL)
+        np.testing.assert_allclose(pc.cpu().numpy(), d[name + '.p_copy'], rtol=RM_RTOL, atol=RM_RTOL)
+    else:
+        qs, ps = ret_q, ret_p
+    assert len(qs) == len(ps) == c['steps']
+    np.testing.assert_allclose(torch.stack(qs).cpu().numpy(), d[name + '.q_traj'], rtol=RM_RTOL, atol=RM_RTOL)
+    np.testing.assert_allclose(torch.stack(ps).cpu().numpy(), d[name + '.p_traj'], rtol=RM_RTOL, atol=RM_RTOL)
+    # batched form: C identical chains give C identical rows
+    qb, pb = q.repeat(3, 1), p.repeat(3, 1)
+    Hb = hb.hamiltonian(qb, pb, c['target'], explicit_binding_const=c.get('explicit_binding_const', 100),
+                        rng_uniforms=torch.from_numpy(d[name + '.uni_h']).repeat(3, 1, 1) if c['jitter'] is not None else None,
+                        **kw)
+    assert tuple(Hb.shape) == (3,) and float((Hb - Hb[0]).abs().max()) == 0.0
+    np.testing.assert_allclose(Hb.cpu().numpy()[:1], d[name + '.H'], rtol=RM_RTOL)
+
+
+def test_standalone_rmhmc_hamiltonian_raises_logproberror_on_nonfinite():
+    with pytest.raises(hb.util.LogProbError):
+        hb.hamiltonian(torch.tensor([200., 1., 1.]), torch.ones(3), T.Funnel(3), jitter=None, softabs_const=1e6,
+                       sampler=hb.Sampler.RMHMC, integrator=hb.Integrator.EXPLICIT, metric=hb.Metric.SOFTABS)
