@@ -37,6 +37,32 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 enum { STREAM_MOMENTUM = 0, STREAM_ACCEPT = 1, STREAM_JITTER = 2, STREAM_PERM = 3 };
 
+// The key schedule k_r = k_0 + r*(W0, W1) depends on (seed, chain) only: a persistent kernel that owns one chain computes it
+// once and keeps the 20 words in registers (the asm makes them opaque, otherwise the compiler re-derives each with an
+// IADD3 per round and iteration: 20 of the ~60 instructions of a Philox call).
+struct PhiloxKeys { uint32_t x[10], y[10]; };
+__device__ __forceinline__ void philox_make_keys(uint64_t seed, uint64_t chain, PhiloxKeys& K) {
+    uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32) ^ (uint32_t)(chain >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        K.x[r] = kx; K.y[r] = ky;
+        asm volatile("" : "+r"(K.x[r]), "+r"(K.y[r]));
+        kx += 0x9E3779B9u; ky += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ uint4 philox_draw(const PhiloxKeys& K, uint64_t chain, uint64_t iter, uint32_t vec,
+                                             uint32_t stream) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint4 c = make_uint4(vec, (uint32_t)iter, (uint32_t)(iter >> 32) | (stream << 24), (uint32_t)chain);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ K.x[r], lo1, hi0 ^ c.w ^ K.y[r], lo0);
+    }
+    return c;
+}
+
 __device__ __forceinline__ uint4 philox_draw(uint64_t seed, uint64_t chain, uint64_t iter, uint32_t vec,
                                              uint32_t stream) {
     uint4 c = make_uint4(vec, (uint32_t)iter, (uint32_t)(iter >> 32) | (stream << 24), (uint32_t)chain);
@@ -76,6 +102,19 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t chain, ui
     if (pair & 1) box_muller(r.z, r.w, z[0], z[1]);
     else box_muller(r.x, r.y, z[0], z[1]);
 }
+// the same streams from a precomputed key schedule
+template <int E> __device__ __forceinline__ void philox_normals(const PhiloxKeys& K, uint64_t chain, uint64_t iter,
+                                                                uint32_t grp, float* z) {
+    const uint4 r = philox_draw(K, chain, iter, E == 4 ? grp : grp >> 1, STREAM_MOMENTUM);
+    if (E == 4) {
+        box_muller(r.x, r.y, z[0], z[1]);
+        box_muller(r.z, r.w, z[2], z[3]);
+    } else if (grp & 1) {
+        box_muller(r.z, r.w, z[0], z[1]);
+    } else {
+        box_muller(r.x, r.y, z[0], z[1]);
+    }
+}
 template <int E> __device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t chain, uint64_t iter,
                                                                 uint32_t grp, float* z);
 template <> __device__ __forceinline__ void philox_normals<4>(uint64_t seed, uint64_t chain, uint64_t iter,
@@ -87,6 +126,10 @@ template <> __device__ __forceinline__ void philox_normals<2>(uint64_t seed, uin
     philox_normal2(seed, chain, iter, grp, z);
 }
 
+__device__ __forceinline__ float philox_log_uniform(const PhiloxKeys& K, uint64_t chain, uint64_t iter) {
+    const uint4 r = philox_draw(K, chain, iter, 0xFFFFFFFFu, STREAM_ACCEPT);
+    return logf(u01(r.x));
+}
 __device__ __forceinline__ float philox_log_uniform(uint64_t seed, uint64_t chain, uint64_t iter) {
     const uint4 r = philox_draw(seed, chain, iter, 0xFFFFFFFFu, STREAM_ACCEPT);
     return logf(u01(r.x));

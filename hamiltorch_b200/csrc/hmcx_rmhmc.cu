@@ -590,6 +590,10 @@ __device__ __forceinline__ const float* rm2_jitter_row(const RmRunArgs& a, int c
     return buf;
 }
 
+// Code layout: the iteration is ONE loop over its 4L+3 metric evaluations (gibbs, H_old, the 4L flows A B B A ..., H_new)
+// around a SINGLE inlined copy of eval_metric / rm_hamiltonian / grad_params / grad_momentum (~2k instructions).  The
+// first form of this kernel inlined a copy per call site -- 14.5k instructions, 11k of them in the iteration loop = 180 KB of
+// code streamed through the instruction cache once per iteration by two warps -- and ran at the instruction-fetch rate.
 __global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
     __shared__ PairMail mailQ[2][32], mailP[2][32];
     const int lane = threadIdx.x & 31;
@@ -614,116 +618,107 @@ __global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
     const bool jit_on = a.cfg.jitter >= 0.0f;
     int phase = 0;
     Metric<2> M;
+    const int nsteps = 4 * a.L + 3;
+    q[0] = q[1] = p[0] = p[1] = qt[0] = qt[1] = pt[0] = pt[1] = 0.0f;
 
     for (int n = a.it0; n < a.it1; ++n) {
         int idx = 0;                                          // jitter rows consumed so far in this iteration
         bool ok = true;
         float h_old = nanf(""), h_new = nanf("");
-        // one dH/dtheta with the reference's NaN-retry loop; returns the number of extra rows it consumed
-        auto dHdq = [&](const float* th, const float* pp, int first_row, float* out, bool& good) -> int {
-            int tries = 0;
-            for (;; ++tries) {
-                if (!eval_metric<2>(t, a.cfg, th, rm2_jitter_row(a, cc, n, chain_id, first_row + tries, ub), M)) { good = false; break; }
-                bool okh = true;
-                rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
-                if (!okh) { good = false; break; }
-                if (a.cfg.jacdiag) grad_params_jacdiag<2>(t, th, M, pp, out); else grad_params<2>(t, th, M, pp, out);
-                if (finite_f(out[0]) && finite_f(out[1])) break;
-                if (tries + 1 > a.jitter_max_tries) { good = false; break; }
-            }
-            return tries;
-        };
-        auto dHdp = [&](const float* th, const float* pp, int rowi, float* out, bool& good) {
-            if (!eval_metric<2>(t, a.cfg, th, rm2_jitter_row(a, cc, n, chain_id, rowi, ub), M)) { good = false; return; }
-            bool okh = true;
-            rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
-            if (!okh) { good = false; return; }
-            grad_momentum<2>(t, M, pp, out);
-        };
-        // One flow: warp 0 evaluates dH/dtheta(th, pp), warp 1 dH/dp(th, pp).  q_first: the reference calls dH/dtheta
-        // first (A flows) -- else dH/dp first (B flows).  On return gq / gp hold both gradients in BOTH threads.
-        auto flow = [&](const float* th, const float* pp, bool q_first, float* gq, float* gp) {
+        q[0] = qc[0]; q[1] = qc[1];
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
+            // s = 0 gibbs (:969 -> :183-184) | s = 1 H(theta, p) (:971) | flows A B [C] B A per step (:423-461) | last: H_new (:989)
+            const bool is_flow = s >= 2 && s + 1 < nsteps;
+            const int ph = (s - 2) & 3;
+            const bool isA = ph == 0 || ph == 3;              // A: (theta, p~); B: (theta~, p)
+            const bool useB = is_flow && !isA, useA = is_flow && isA;
+            float th[2], pp[2];
+            th[0] = useB ? qt[0] : q[0]; th[1] = useB ? qt[1] : q[1];
+            pp[0] = useA ? pt[0] : p[0]; pp[1] = useA ? pt[1] : p[1];
+            // One flow: warp 0 evaluates dH/dtheta(th, pp), warp 1 dH/dp(th, pp), concurrently.  The reference calls
+            // dH/dtheta first in A flows, dH/dp first in B flows: that fixes which jitter row each one consumes.
+            int myrow = idx;
+            if (is_flow) myrow = roleP ? (isA ? idx + 1 : idx) : (isA ? idx : idx + 1);
             const int b = phase & 1;
-            ++phase;
-            const int rowQ = q_first ? idx : idx + 1, rowP = q_first ? idx + 1 : idx;
+            if (is_flow) ++phase;
+            PairMail mq = PairMail{0.0f, 0.0f, 1, 0}, mp = mq;
+            float H = nanf("");
             bool good = true;
-            if (ok) {
-                if (!roleP) {
-                    const int r = dHdq(th, pp, rowQ, g, good);
-                    mailQ[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, r};
-                } else {
-                    dHdp(th, pp, rowP, g, good);
-                    mailP[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, 0};
-                }
-            }
-            __syncthreads();
-            PairMail mq = mailQ[b][lane], mp = mailP[b][lane];
-            if (jit_on && q_first) {                          // retries of dH/dtheta shift the row of the dH/dp after it
-                const bool redo = ok && mq.ok && mq.retries > 0;
-                if (__syncthreads_or(redo)) {
-                    if (redo && roleP) {
-                        good = true;
-                        dHdp(th, pp, rowP + mq.retries, g, good);
-                        mailP[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, 0};
+            for (int pass = 0;; ++pass) {
+                const bool redo = pass == 1 && ok && mq.ok && mq.retries > 0;
+                if (ok && (pass == 0 || (redo && roleP))) {
+                    const int first_row = myrow + (pass == 1 ? mq.retries : 0);
+                    good = true;
+                    int tries = 0;
+                    for (;; ++tries) {                        // the NaN-retry loop of dH/dtheta (:402-410); one trip otherwise
+                        if (!eval_metric<2>(t, a.cfg, th, rm2_jitter_row(a, cc, n, chain_id, first_row + tries, ub), M)) { good = false; break; }
+                        if (s == 0) break;
+                        bool okh = true;
+                        H = rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
+                        if (!okh) { good = false; break; }
+                        if (!is_flow) break;
+                        if (roleP) { grad_momentum<2>(t, M, pp, g); break; }
+                        if (a.cfg.jacdiag) grad_params_jacdiag<2>(t, th, M, pp, g); else grad_params<2>(t, th, M, pp, g);
+                        if (finite_f(g[0]) && finite_f(g[1])) break;
+                        if (tries + 1 > a.jitter_max_tries) { good = false; break; }
                     }
-                    __syncthreads();
-                    mp = mailP[b][lane];
+                    if (is_flow) {
+                        if (!roleP) mailQ[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, tries};
+                        else mailP[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, 0};
+                    }
                 }
+                if (!is_flow) break;
+                __syncthreads();
+                mq = mailQ[b][lane]; mp = mailP[b][lane];
+                // retries of dH/dtheta shift the row of the dH/dp that follows it in an A flow: warp 1 re-runs those chains
+                if (pass == 1 || !(jit_on && isA)) break;
+                if (!__syncthreads_or(ok && mq.ok && mq.retries > 0)) break;
             }
-            if (ok) {
+            if (s == 0) {
+                ++idx;
+                ok = good;
+                float z[2];
+                if (a.rng_mode == HMCX_RNG_INJECTED) {
+                    const float* zp = a.normals + ((size_t)(n - a.it0) * a.C + cc) * a.ld;
+                    z[0] = zp[0]; z[1] = zp[1];
+                } else {
+                    float z4[4];
+                    philox_normal4(a.seed, chain_id, (uint64_t)n, 0u, z4);
+                    z[0] = z4[0]; z[1] = z4[1];
+                }
+                if (ok) ok = gibbs_rm<2>(t, M, z, p);         // both threads of the pair (identical bits)
+            } else if (!is_flow) {
+                if (ok) {
+                    ++idx;
+                    if (s == 1) h_old = H; else h_new = H;    // NaN when the metric itself failed
+                    ok = good;
+                }
+                if (s == 1) { qt[0] = q[0]; qt[1] = q[1]; pt[0] = p[0]; pt[1] = p[1]; }
+            } else if (ok) {
                 // reference order: the first call's LogProbError aborts before the second call is made
                 ok = mq.ok && mp.ok;
-                gq[0] = mq.g0; gq[1] = mq.g1; gp[0] = mp.g0; gp[1] = mp.g1;
                 idx += 2 + mq.retries;
-            }
-        };
-
-        // ---- gibbs (:969 -> :183-184); both threads of the pair do it (identical bits) ----
-        ok = eval_metric<2>(t, a.cfg, qc, rm2_jitter_row(a, cc, n, chain_id, idx++, ub), M);
-        {
-            float z[2];
-            if (a.rng_mode == HMCX_RNG_INJECTED) {
-                const float* zp = a.normals + ((size_t)(n - a.it0) * a.C + cc) * a.ld;
-                z[0] = zp[0]; z[1] = zp[1];
-            } else {
-                float z4[4];
-                philox_normal4(a.seed, chain_id, (uint64_t)n, 0u, z4);
-                z[0] = z4[0]; z[1] = z4[1];
-            }
-            if (ok) ok = gibbs_rm<2>(t, M, z, p);
-        }
-        q[0] = qc[0]; q[1] = qc[1];
-        // ---- H(theta, p) (:971) ----
-        if (ok && eval_metric<2>(t, a.cfg, q, rm2_jitter_row(a, cc, n, chain_id, idx++, ub), M))
-            h_old = rm_hamiltonian<2>(t, a.cfg, q, p, M, w, ok);
-        else ok = false;
-        // ---- explicit trajectory (:423-461): every thread of the CTA runs all L steps' barriers ----
-        qt[0] = q[0]; qt[1] = q[1]; pt[0] = p[0]; pt[1] = p[1];
-        float gq[2], gp[2];
-        for (int l = 0; l < a.L; ++l) {
-            flow(q, pt, true, gq, gp);                                                                  // A
-            if (ok) for (int i = 0; i < 2; ++i) { p[i] = sub(p[i], mul(half, gq[i])); qt[i] = add(qt[i], mul(half, gp[i])); }
-            flow(qt, p, false, gq, gp);                                                                 // B
-            if (ok) {
-                for (int i = 0; i < 2; ++i) { q[i] = add(q[i], mul(half, gp[i])); pt[i] = sub(pt[i], mul(half, gq[i])); }
-                for (int i = 0; i < 2; ++i) {                                                           // C, sequential
-                    const float cw = a.cosw, sw = a.sinw;
-                    const float qn = mul(0.5f, add(add(add(q[i], qt[i]), mul(cw, sub(q[i], qt[i]))), mul(sw, sub(p[i], pt[i]))));
-                    const float pn = mul(0.5f, add(sub(add(p[i], pt[i]), mul(sw, sub(qn, qt[i]))), mul(cw, sub(p[i], pt[i]))));
-                    const float qtn = mul(0.5f, sub(sub(add(qn, qt[i]), mul(cw, sub(qn, qt[i]))), mul(sw, sub(pn, pt[i]))));
-                    const float ptn = mul(0.5f, sub(add(add(pn, pt[i]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[i]))));
-                    q[i] = qn; p[i] = pn; qt[i] = qtn; pt[i] = ptn;
+                if (ok) {
+                    const float gq[2] = {mq.g0, mq.g1}, gp[2] = {mp.g0, mp.g1};
+                    if (isA) {
+                        for (int i = 0; i < 2; ++i) { p[i] = sub(p[i], mul(half, gq[i])); qt[i] = add(qt[i], mul(half, gp[i])); }
+                    } else {
+                        for (int i = 0; i < 2; ++i) { q[i] = add(q[i], mul(half, gp[i])); pt[i] = sub(pt[i], mul(half, gq[i])); }
+                        if (ph == 1) {
+                            for (int i = 0; i < 2; ++i) {                                               // C, sequential
+                                const float cw = a.cosw, sw = a.sinw;
+                                const float qn = mul(0.5f, add(add(add(q[i], qt[i]), mul(cw, sub(q[i], qt[i]))), mul(sw, sub(p[i], pt[i]))));
+                                const float pn = mul(0.5f, add(sub(add(p[i], pt[i]), mul(sw, sub(qn, qt[i]))), mul(cw, sub(p[i], pt[i]))));
+                                const float qtn = mul(0.5f, sub(sub(add(qn, qt[i]), mul(cw, sub(qn, qt[i]))), mul(sw, sub(pn, pt[i]))));
+                                const float ptn = mul(0.5f, sub(add(add(pn, pt[i]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[i]))));
+                                q[i] = qn; p[i] = pn; qt[i] = qtn; pt[i] = ptn;
+                            }
+                        }
+                    }
                 }
             }
-            flow(qt, p, false, gq, gp);                                                                 // B
-            if (ok) for (int i = 0; i < 2; ++i) { q[i] = add(q[i], mul(half, gp[i])); pt[i] = sub(pt[i], mul(half, gq[i])); }
-            flow(q, pt, true, gq, gp);                                                                  // A
-            if (ok) for (int i = 0; i < 2; ++i) { p[i] = sub(p[i], mul(half, gq[i])); qt[i] = add(qt[i], mul(half, gp[i])); }
         }
-        // ---- H(theta_L, p_L) on the un-augmented Hamiltonian (:989) ----
-        if (ok && eval_metric<2>(t, a.cfg, q, rm2_jitter_row(a, cc, n, chain_id, idx++, ub), M))
-            h_new = rm_hamiltonian<2>(t, a.cfg, q, p, M, w, ok);
-        else ok = false;
         // ---- MH + bookkeeping (both threads decide identically; warp 0 stores) ----
         const float x = add(-h_new, h_old);
         const float rho = (x < 0.0f) ? x : 0.0f;
