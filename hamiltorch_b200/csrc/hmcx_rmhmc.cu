@@ -405,6 +405,36 @@ struct JitterSrc {                // the jitter uniforms of fisher() (:115), one
     }
 };
 
+// Every metric evaluation of the thread-per-chain kernel goes through this ONE out-of-line function.  The first form
+// inlined eval_metric / rm_hamiltonian / grad_* at each of the 15 call sites of an iteration (gibbs, 2 x H, 8 explicit +
+// 4 implicit flows): 100k instructions (1.6 MB of code) for DM = 6 / 16, executed at the instruction-fetch rate.
+//   RM_EVAL_METRIC  fisher() only (gibbs)                 RM_EVAL_H     + rm_hamiltonian -> *H_out (NaN if the metric failed)
+//   RM_EVAL_DHDQ    dH/dtheta with the NaN-retry loop     RM_EVAL_DHDP  dH/dp
+// Returns false <=> the reference raises LogProbError.
+enum { RM_EVAL_METRIC = 0, RM_EVAL_H = 1, RM_EVAL_DHDQ = 2, RM_EVAL_DHDP = 3 };
+
+template <int DM>
+__device__ __noinline__ bool rm_eval(JitterSrc<DM>& jit, int kind, const float* th, const float* pp, Metric<DM>& M,
+                                     float* w, float* ub, float* out, float* H_out) {
+    const RmRunArgs& a = jit.a;
+    const RmTarget& t = a.t;
+    const int d = rm_dim<DM>(t);
+    for (int tries = 0;; ++tries) {
+        if (!eval_metric<DM>(t, a.cfg, th, jit.next(ub), M)) return false;
+        if (kind == RM_EVAL_METRIC) return true;
+        bool okh = true;
+        const float H = rm_hamiltonian<DM>(t, a.cfg, th, pp, M, w, okh);
+        if (kind == RM_EVAL_H) { *H_out = H; return okh; }
+        if (!okh) return false;
+        if (kind == RM_EVAL_DHDP) { grad_momentum<DM>(t, M, pp, out); return true; }
+        if (a.cfg.jacdiag) grad_params_jacdiag<DM>(t, th, M, pp, out); else grad_params<DM>(t, th, M, pp, out);
+        bool fin = true;
+        for (int i = 0; i < d; ++i) fin = fin && finite_f(out[i]);
+        if (fin) return true;
+        if (tries + 1 > a.jitter_max_tries) return false;
+    }
+}
+
 template <int DM>
 __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,31 +459,16 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
         JitterSrc<DM> jit(a, c, n);
         bool ok = true;
         float h_old = nanf(""), h_new = nanf("");
-        // dH/dtheta with the reference's NaN-retry loop (:402-410); dH/dp (:415-422)
+        // dH/dtheta with the reference's NaN-retry loop (:402-410); dH/dp (:415-422): calls of the ONE out-of-line copy
         auto dHdq = [&](const float* th, const float* pp, float* out) {
-            for (int tries = 0; ok; ++tries) {
-                if (!eval_metric<DM>(t, a.cfg, th, jit.next(ub), M)) { ok = false; break; }
-                bool okh = true;
-                rm_hamiltonian<DM>(t, a.cfg, th, pp, M, w, okh);
-                if (!okh) { ok = false; break; }
-                if (a.cfg.jacdiag) grad_params_jacdiag<DM>(t, th, M, pp, out); else grad_params<DM>(t, th, M, pp, out);
-                bool fin = true;
-                for (int i = 0; i < d; ++i) fin = fin && finite_f(out[i]);
-                if (fin) break;
-                if (tries + 1 > a.jitter_max_tries) { ok = false; break; }
-            }
+            if (ok) ok = rm_eval<DM>(jit, RM_EVAL_DHDQ, th, pp, M, w, ub, out, nullptr);
         };
         auto dHdp = [&](const float* th, const float* pp, float* out) {
-            if (!ok) return;
-            if (!eval_metric<DM>(t, a.cfg, th, jit.next(ub), M)) { ok = false; return; }
-            bool okh = true;
-            rm_hamiltonian<DM>(t, a.cfg, th, pp, M, w, okh);
-            if (!okh) { ok = false; return; }
-            grad_momentum<DM>(t, M, pp, out);
+            if (ok) ok = rm_eval<DM>(jit, RM_EVAL_DHDP, th, pp, M, w, ub, out, nullptr);
         };
 
         // ---- gibbs (:969 -> :183-184) ----
-        ok = eval_metric<DM>(t, a.cfg, qc, jit.next(ub), M);
+        ok = rm_eval<DM>(jit, RM_EVAL_METRIC, qc, nullptr, M, w, ub, nullptr, nullptr);
         {
             float z[DM];
             if (a.rng_mode == HMCX_RNG_INJECTED) {
@@ -469,8 +484,7 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
         }
         for (int i = 0; i < d; ++i) q[i] = qc[i];
         // ---- H(theta, p) (:971; the explicit branch's 2*H ... /2 is exact) ----
-        if (ok && eval_metric<DM>(t, a.cfg, q, jit.next(ub), M)) h_old = rm_hamiltonian<DM>(t, a.cfg, q, p, M, w, ok);
-        else ok = false;
+        if (ok) ok = rm_eval<DM>(jit, RM_EVAL_H, q, p, M, w, ub, nullptr, &h_old);
         // ---- trajectory ----
         if (ok && a.integrator == 1) {                                              // explicit (:423-461)
             for (int i = 0; i < d; ++i) { qt[i] = q[i]; pt[i] = p[i]; }
@@ -530,8 +544,7 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
             }
         }
         // ---- H(theta_L, p_L) on the un-augmented Hamiltonian (:989) ----
-        if (ok && eval_metric<DM>(t, a.cfg, q, jit.next(ub), M)) h_new = rm_hamiltonian<DM>(t, a.cfg, q, p, M, w, ok);
-        else ok = false;
+        if (ok) ok = rm_eval<DM>(jit, RM_EVAL_H, q, p, M, w, ub, nullptr, &h_new);
         // ---- MH + bookkeeping ----
         const float x = add(-h_new, h_old);
         const float rho = (x < 0.0f) ? x : 0.0f;

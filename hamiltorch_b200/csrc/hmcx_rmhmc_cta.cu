@@ -85,6 +85,9 @@ __device__ __forceinline__ float rc_block_sum(const Rc& c, float v) {
     return s;                                          // same bits in every thread
 }
 
+// Code size: rc_eval_metric / rc_hamiltonian / rc_grad_* are OUT-OF-LINE (one copy each).  Inlined at the iteration's 15 call
+// sites the kernel was 91k instructions (1.4 MB) and ran at the instruction-fetch rate; all threads of the CTA call them
+// convergently (they contain barriers).
 // ---- targets (same closed forms as hmcx_rmhmc.cu, vectorised over the CTA) ------------------------------------------
 // sum of x_i^2 over i >= 1 (Funnel) -- every thread gets the value
 __device__ __forceinline__ float rc_funnel_s(const Rc& c, const float* th) {
@@ -236,7 +239,7 @@ __device__ void rc_jacobi(const Rc& c) {
 
 // fisher(): false <=> the reference raises LogProbError (:110-112, :717).  Leaves Q, lam, lt, dlt.  urow = this call's
 // jitter uniforms (shared, D) or NULL.
-__device__ bool rc_eval_metric(const Rc& c, const RmTarget& t, const RmCfg& cfg, const float* th, const float* urow) {
+__device__ __noinline__ bool rc_eval_metric(const Rc& c, const RmTarget& t, const RmCfg& cfg, const float* th, const float* urow) {
     const int d = c.D, DP = c.DP, tid = c.tid;
     int bad = 0;
     if (cfg.jacdiag) {                                 // G = diag(g_i^2 (+ jitter)): already diagonal
@@ -282,7 +285,7 @@ __device__ bool rc_eval_metric(const Rc& c, const RmTarget& t, const RmCfg& cfg,
 }
 
 // rm_hamiltonian (:710-736) given the metric; leaves w = Q^T p (shared).  ok=false <=> LogProbError.
-__device__ float rc_hamiltonian(const Rc& c, const RmTarget& t, const RmCfg& cfg, const float* th, const float* p, bool& ok) {
+__device__ __noinline__ float rc_hamiltonian(const Rc& c, const RmTarget& t, const RmCfg& cfg, const float* th, const float* p, bool& ok) {
     const int d = c.D, DP = c.DP, tid = c.tid;
     const float lp = rc_log_prob(c, t, th);
     float ld_part = 0.0f, q_part = 0.0f;
@@ -305,7 +308,7 @@ __device__ float rc_hamiltonian(const Rc& c, const RmTarget& t, const RmCfg& cfg
 }
 
 // dH/dp = G~^-1 p -> out (shared); needs w from rc_hamiltonian.  Callers barrier before reading out.
-__device__ void rc_grad_momentum(const Rc& c, float* out) {
+__device__ __noinline__ void rc_grad_momentum(const Rc& c, float* out) {
     const int d = c.D, DP = c.DP, tid = c.tid;
     for (int i = tid; i < d; i += RC_T) c.u[i] = c.w[i] / c.lt[i];
     __syncthreads();
@@ -317,7 +320,7 @@ __device__ void rc_grad_momentum(const Rc& c, float* out) {
 }
 
 // dH/dtheta -> out (shared); needs w.  Returns false when a component is non-finite (the NaN-retry test, :402).
-__device__ bool rc_grad_params(const Rc& c, const RmTarget& t, const RmCfg& cfg, const float* th, const float* p, float* out) {
+__device__ __noinline__ bool rc_grad_params(const Rc& c, const RmTarget& t, const RmCfg& cfg, const float* th, const float* p, float* out) {
     const int d = c.D, DP = c.DP, tid = c.tid;
     rc_grad_log_prob(c, t, th, c.glp);
     __syncthreads();
@@ -377,7 +380,7 @@ __device__ bool rc_grad_params(const Rc& c, const RmTarget& t, const RmCfg& cfg,
 }
 
 // gibbs (:183-184): p = chol(G~) z,  G~ = Q diag(lam~) Q^T  (MultivariateNormal's scale_tril)
-__device__ bool rc_gibbs(const Rc& c, const float* z, float* p) {
+__device__ __noinline__ bool rc_gibbs(const Rc& c, const float* z, float* p) {
     const int d = c.D, DP = c.DP, tid = c.tid;
     for (int e = tid; e < d * d; e += RC_T) {
         const int a = e / d, b = e - a * d;
