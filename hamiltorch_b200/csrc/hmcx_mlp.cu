@@ -1088,46 +1088,43 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         }
         __syncthreads();
         const float kin0 = kinetic();
-        // ---- trajectory ----
-        if (a.scheme == HMCX_SCHEME_PLAIN) {                              // samplers.py:281-302
-            mlp_grad_split<CS>(m, q, g, tile, -1, cc, tc);
-            kick(half);
-            for (int l = 0; l < a.L; ++l) {
-                drift(eps);
-                mlp_grad_split<CS>(m, q, g, tile, -1, cc, tc);
-                kick(eps);
-            }
-            kick(-half);                                                  // p - half*g == p + (-half)*g exactly
-        } else if (a.scheme == HMCX_SCHEME_SPLIT_SYM) {                   // :499-540
-            const float cd = (float)(eps_double(eps) / (double)((M - 1) * 2));
-            for (int l = 0; l < a.L; ++l) {
-                for (int s = 0; s < M; ++s) {
-                    mlp_grad_split<CS>(m, q, g, tile, s, cc, tc);
-                    kick(half);
-                    if (s < M - 1) drift(cd);
+        // ---- trajectory: every integrator schedule is a sequence of steps [drift] grad(split) kick [drift] ----
+        // ONE loop around ONE inlined copy of the gradient evaluation (nine call sites, one per schedule position, made
+        // each instantiation of this kernel ~100k instructions = 1.6 MB of code and minutes of ptxas; an out-of-line copy
+        // was measured 1.6x slower: the model descriptor then lives behind a pointer instead of in the constant bank).
+        //   PLAIN (:281-302)      t = 0: grad, kick(eps/2); t = 1..L: drift(eps), grad, kick(eps); finally kick(-eps/2)
+        //   SPLITTING (:499-540)  per step j = 0..2M-1: s = j < M ? j : 2M-1-j; grad(s), kick(eps/2), drift(eps/(2(M-1))) unless
+        //                         the sweep's last split
+        //   SPLITTING_RAND (:551-568)  per step, split s = perm[j/2]: grad, kick(eps/2), drift(eps/M) | grad, kick(eps/2)
+        //   SPLITTING_KMID (:579-598)  M kicks up, drift(eps), M kicks down
+        {
+            const int twoM = 2 * M;
+            const bool plain = a.scheme == HMCX_SCHEME_PLAIN;
+            const int T = plain ? a.L + 1 : a.L * twoM;
+            float cd = 0.0f;
+            if (a.scheme == HMCX_SCHEME_SPLIT_SYM) cd = (float)(eps_double(eps) / (double)((M - 1) * 2));
+            else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) cd = (float)(eps_double(eps) / (double)M);
+            else if (a.scheme == HMCX_SCHEME_SPLIT_KMID) cd = eps;
+            int jj = 0;
+#pragma unroll 1
+            for (int t = 0; t < T; ++t) {
+                int sp = -1;
+                float kc = half;
+                bool post = false;
+                if (plain) {
+                    if (t > 0) { drift(eps); kc = eps; }
+                } else {
+                    const int up = jj < M ? jj : twoM - 1 - jj;
+                    if (a.scheme == HMCX_SCHEME_SPLIT_SYM) { sp = up; post = jj < M ? (up < M - 1) : (up > 0); }
+                    else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) { sp = s_perm[jj >> 1]; post = (jj & 1) == 0; }
+                    else { sp = up; post = jj == M - 1; }
+                    if (++jj == twoM) jj = 0;
                 }
-                for (int s = M - 1; s >= 0; --s) {
-                    mlp_grad_split<CS>(m, q, g, tile, s, cc, tc);
-                    kick(half);
-                    if (s > 0) drift(cd);
-                }
+                mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc);
+                kick(kc);
+                if (post) drift(cd);
             }
-        } else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) {                  // :551-568
-            const float cd = (float)(eps_double(eps) / (double)M);
-            for (int l = 0; l < a.L; ++l)
-                for (int s = 0; s < M; ++s) {
-                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc, tc);
-                    kick(half);
-                    drift(cd);
-                    mlp_grad_split<CS>(m, q, g, tile, s_perm[s], cc, tc);
-                    kick(half);
-                }
-        } else {                                                          // KMID :579-598
-            for (int l = 0; l < a.L; ++l) {
-                for (int s = 0; s < M; ++s) { mlp_grad_split<CS>(m, q, g, tile, s, cc, tc); kick(half); }
-                drift(eps);
-                for (int s = M - 1; s >= 0; --s) { mlp_grad_split<CS>(m, q, g, tile, s, cc, tc); kick(half); }
-            }
+            if (plain) kick(-half);                                       // p - half*g == p + (-half)*g exactly
         }
         // ---- Hamiltonians + MH ----
         const float lp_new = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
