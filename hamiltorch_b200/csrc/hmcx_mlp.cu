@@ -448,7 +448,8 @@ __device__ __forceinline__ float cluster_sum_scalar(float x, float* slot) {
 constexpr int TC_TR = 64;                 // data rows per tile (MMA N forward, MMA K backward)
 constexpr int TC_H = 128;                 // hidden units = MMA M = TMEM lanes
 constexpr int TC_NLMAX = 4;               // outputs handled by the register head
-constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COLS = 256;   // TMEM columns: H hh / dH hi | H hl / dH lo | dW1 hh | dW1 hl
+// TMEM columns: H hh / dH hi | H hl / dH lo | dW1 hh | dW1 hl | W1 hi | W1 lo (the forward A operand, written once per evaluation)
+constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COL_W1HI = 256, TC_COL_W1LO = 320, TC_COLS = 512;
 
 static_assert(TC_TR / 4 == MLP_THREADS / 32 && TC_TR == 64, "staging / epilogue thread maps assume 16 warps and 64-row tiles");
 
@@ -499,23 +500,46 @@ __device__ __forceinline__ void tc_split4(const float4 v, float4& h, float4& l) 
     l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
 }
 
-// q's W1 (flat, row-major 128 x n0) -> A operand, canonical K-major / no-swizzle core matrices, tf32 hi and lo.
-// The chunk index is rotated per lane so that both the strided reads and the packed writes are conflict-free.
-__device__ __forceinline__ void tc_pack_w1(const MlpDev& m, const float* q, float* tile) {
-    const int n0 = m.n[0], nch = n0 >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* W = q + m.woff[0];
-    float* hi = tile + m.tc_w1hi;
-    float* lo = tile + m.tc_w1lo;
-    const int u = 32 * (warp & 3) + lane, rot = lane % nch;
-    for (int j = warp >> 2; j < nch; j += MLP_THREADS / 128) {
-        int c = j + rot;                                          // rotate the chunk index per lane
-        c -= (c >= nch) ? nch : 0;
-        float4 h, l;
-        tc_split4(*reinterpret_cast<const float4*>(W + u * n0 + 4 * c), h, l);
-        const int off = (c * (TC_H >> 3) + (u >> 3)) * 32 + (u & 7) * 4;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
+// q's W1 (flat, row-major 128 x n0) -> the forward A operand IN TENSOR MEMORY (lane = hidden unit, one 32-bit column per
+// input k), tf32 hi and lo: thread (unit u, column group cq) owns 16 consecutive k of row u.  The four float4 chunks are
+// read in a per-lane rotated order (2-way instead of 8-way bank conflicts on the stride-n0 rows) and rotated back in
+// registers.  Keeping W1 out of shared memory frees 64 KB for the X operand pipeline.
+__device__ __forceinline__ void tc_pack_w1(const MlpDev& m, const float* q, const TcCtx& tc) {
+    const int n0 = m.n[0], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lq = warp & 3, cq = warp >> 2, u = 32 * lq + lane;
+    if (16 * cq < n0) {
+        const float* W = q + m.woff[0] + u * n0 + 16 * cq;
+        float4 t[4], a[4], o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = *reinterpret_cast<const float4*>(W + 4 * ((j + lane) & 3));
+        // t[j] holds chunk (j + lane) & 3, i.e. chunk c sits in t[(c - lane) & 3]: rotate right by lane & 3
+        const bool r1 = lane & 1, r2 = lane & 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            a[c].x = r1 ? t[(c + 3) & 3].x : t[c].x; a[c].y = r1 ? t[(c + 3) & 3].y : t[c].y;
+            a[c].z = r1 ? t[(c + 3) & 3].z : t[c].z; a[c].w = r1 ? t[(c + 3) & 3].w : t[c].w;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            o[c].x = r2 ? a[(c + 2) & 3].x : a[c].x; o[c].y = r2 ? a[(c + 2) & 3].y : a[c].y;
+            o[c].z = r2 ? a[(c + 2) & 3].z : a[c].z; o[c].w = r2 ? a[(c + 2) & 3].w : a[c].w;
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float4 h, l;
+            tc_split4(o[c], h, l);
+            hi[4 * c] = __float_as_uint(h.x); hi[4 * c + 1] = __float_as_uint(h.y);
+            hi[4 * c + 2] = __float_as_uint(h.z); hi[4 * c + 3] = __float_as_uint(h.w);
+            lo[4 * c] = __float_as_uint(l.x); lo[4 * c + 1] = __float_as_uint(l.y);
+            lo[4 * c + 2] = __float_as_uint(l.z); lo[4 * c + 3] = __float_as_uint(l.w);
+        }
+        const uint32_t tl = tc.tmem + ((uint32_t)(32 * lq) << 16) + 16 * cq;
+        tmem_st16(tl + TC_COL_W1HI, hi);
+        tmem_st16(tl + TC_COL_W1LO, lo);
     }
+    tmem_st_wait();
+    tc_fence_before();                                        // the caller's __syncthreads orders it before the UMMAs
 }
 
 // Prefetch the raw rows [r0, r0 + cnt) of X -- contiguous in global memory -- with ONE bulk TMA copy (thread 0, completion
@@ -582,23 +606,22 @@ __device__ __forceinline__ void tc_stage_x_bwd(const MlpDev& m, float* tile) {
     }
 }
 
-// H^T = W1 . X^T  (one elected thread; completion -> barH).  Two UMMAs per k-step: W1_hi . [X_hi | X_lo]^T (N = 128, the
-// two products land in columns [0,64) and [64,128)) and W1_lo . X_hi^T (N = 64, accumulated onto [0,64)); the epilogue
-// adds the two column blocks.  The descriptors differ only in the start-address field (bits 0-13, 16-byte units), so
-// a k-step is an integer add.
+// H^T = W1 . X^T  (one elected thread; completion -> barH).  A = W1 from TENSOR MEMORY (8 columns per k-step).  Two UMMAs per
+// k-step: W1_hi . [X_hi | X_lo]^T (N = 128, the two products land in columns [0,64) and [64,128)) and W1_lo . X_hi^T
+// (N = 64, accumulated onto [0,64)); the epilogue adds the two column blocks.  The B descriptors differ only in the
+// start-address field (bits 0-13, 16-byte units), so a k-step is an integer add.
 __device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, float* tile) {
     const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * TC_TR), idesc1 = make_idesc_tf32(TC_H, TC_TR);
-    constexpr uint32_t A_LBO = (TC_H / 8) * 128, B_LBO = (2 * TC_TR / 8) * 128;
-    uint64_t ah = make_kmajor_desc(smem_u32(tile + m.tc_w1hi), A_LBO, 128);
-    uint64_t al = make_kmajor_desc(smem_u32(tile + m.tc_w1lo), A_LBO, 128);
+    constexpr uint32_t B_LBO = (2 * TC_TR / 8) * 128;
     uint64_t b = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
     const int ksteps = m.n[0] >> 3;
     const uint32_t d = tc.tmem + TC_COL_H;
+    uint32_t a_hi = tc.tmem + TC_COL_W1HI, a_lo = tc.tmem + TC_COL_W1LO;
     tc_fence_after();
     for (int k = 0; k < ksteps; ++k) {
-        umma_tf32(d, ah, b, idesc2, k != 0);
-        umma_tf32(d, al, b, idesc1, true);
-        ah += (2 * A_LBO) >> 4; al += (2 * A_LBO) >> 4; b += (2 * B_LBO) >> 4;
+        umma_tf32_ta(d, a_hi, b, idesc2, k != 0);
+        umma_tf32_ta(d, a_lo, b, idesc1, true);
+        a_hi += 8; a_lo += 8; b += (2 * B_LBO) >> 4;
     }
     umma_commit(tc.barH);
 }
@@ -890,7 +913,7 @@ __device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, 
     TC_MARK(1);
     if (cc.rank == 0) mlp_prior_grad(m, q, g);                 // the prior part enters the rank-ordered sum once
     else for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) g[i] = 0.0f;
-    if (m.tc) tc_pack_w1(m, q, tile);
+    if (m.tc) tc_pack_w1(m, q, tc);
     __syncthreads();
     TC_MARK(2);
     if (m.has_data) {
@@ -931,7 +954,7 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
     if (!m.has_data) return prior_term;
     TcEpi te;
     if (m.tc) {
-        tc_pack_w1(m, q, tile);
+        tc_pack_w1(m, q, tc);
         tc_epi_begin(m, q, te);
     }
     float lp = 0.0f;
@@ -1266,12 +1289,12 @@ static bool mlp_layout_tc(MlpDev& m, int state_vectors) {
         return false;
     const int n0 = m.n[0];
     int off = 0;
-    m.tc_w1hi = off; off += TC_H * n0;
-    m.tc_w1lo = off; off += TC_H * n0;          // adjacent to w1hi: together they stage dW1 (pitch n0 + 4)
     m.tc_xhi = off; off += TC_TR * n0;
     m.tc_xlo = off; off += TC_TR * n0;
+    m.tc_raw = off; off += TC_TR * n0;          // xhi | xlo | raw are adjacent: together they stage dW1 (128 rows, pitch n0 + 4)
+    m.tc_w1hi = m.tc_xhi; m.tc_w1lo = m.tc_xlo; // (W1 itself lives in tensor memory)
+    if (off < TC_H * (n0 + 4)) off = TC_H * (n0 + 4);
     m.tc_part = off; off += 4 * TC_H * (1 + TC_NLMAX);
-    m.tc_raw = off; off += TC_TR * n0;
     m.tc_yraw = off; off += TC_TR * TC_NLMAX;
     m.aoff[0] = m.aoff[1] = 0;
     m.aoff[2] = off; off += TC_TR * TC_NLMAX;
