@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libhmcx.so')
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 MASS_NONE, MASS_DIAG, MASS_FULL = 0, 1, 2
 RNG_INJECTED, RNG_PHILOX = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class NativeError(RuntimeError):
@@ -33,7 +33,7 @@ class MlpStruct(C.Structure):
                 ('prior_log_scale', C.c_float * (2 * MLP_MAX_LAYERS)),
                 ('prior_grad_coef', C.c_float * (2 * MLP_MAX_LAYERS)), ('x', C.c_void_p), ('y', C.c_void_p),
                 ('num_rows', C.c_int32), ('num_splits', C.c_int32), ('split_begin', C.c_int32 * (MLP_MAX_SPLITS + 1)),
-                ('cluster_size', C.c_int32), ('tensor_cores', C.c_int32)]
+                ('cluster_size', C.c_int32), ('tensor_cores', C.c_int32), ('x_packed', C.c_void_p)]
 
 
 class TargetStruct(C.Structure):
@@ -119,6 +119,8 @@ _PROTOS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     'hmcx_mlp_predict': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'hmcx_mlp_packed_x_bytes': (C.c_size_t, [C.POINTER(TargetStruct)]),
+    'hmcx_mlp_pack_x': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -34,6 +34,8 @@ int dense_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, c
                   cudaStream_t);
 int rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
               int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
+size_t mlp_packed_x_floats(const hmcx_target_t*);
+int mlp_pack_x(const hmcx_target_t*, float*, cudaStream_t);
 int rmhmc_cta_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_rng_t*, const float*, float*, const float*, int,
                   int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, const float*, float*, float*,
                   float*, float*, int, float*, cudaStream_t);
@@ -207,6 +209,17 @@ int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t 
     if (!target) return HMCX_ERR_INVALID_ARG;
     if (target->kind != HMCX_TARGET_MLP) return HMCX_ERR_UNSUPPORTED;
     return hmcx::mlp_predict(target, samples, S, ld, pred_out, log_prob_out, (cudaStream_t)stream);
+}
+
+size_t hmcx_mlp_packed_x_bytes(const hmcx_target_t* target) {
+    if (!target || target->kind != HMCX_TARGET_MLP) return 0;
+    return hmcx::mlp_packed_x_floats(target) * sizeof(float);
+}
+
+int hmcx_mlp_pack_x(const hmcx_target_t* target, float* packed_out, void* stream) {
+    if (!target) return HMCX_ERR_INVALID_ARG;
+    if (target->kind != HMCX_TARGET_MLP) return HMCX_ERR_UNSUPPORTED;
+    return hmcx::mlp_pack_x(target, packed_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

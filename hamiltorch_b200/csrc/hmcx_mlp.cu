@@ -38,8 +38,11 @@ struct MlpDev {
     int tile_base;                        // float offset of the tile area in dynamic shared memory (after the state vectors)
     int T;                                // rows per tile (multiple of 4)
     int tc;                               // 1: the first layer's GEMMs run on tcgen05 (layout below), 0: SIMT tiles
-    int tc_w1hi, tc_w1lo, tc_xhi, tc_xlo, tc_part;   // tile-area offsets (floats) of the tensor-core staging buffers
-    int tc_raw, tc_yraw;                  // cp.async landing buffers: the next tile's raw X rows and targets
+    int tc_f0, tc_f1, tc_b, tc_part;      // tile-area offsets (floats): two forward X operand buffers, the backward one, partials
+    int tc_yraw;                          // cp.async landing buffer of the tile's targets
+    const float* xp;                      // packed X operands (hmcx_mlp_pack_x): per tile [fwd hi|lo (128 n0) | bwd hi|lo (128 n0)]
+    int tb[HMCX_MLP_MAX_SPLITS + 1];      // first packed tile of split s (tiles of a split start at its first row)
+    int flat_base;                        // first packed tile of the all-rows tiling (rows 0, 64, ...)
     float tau_out, prior_scale, c_ll;     // c_ll = fp32(-0.5*tau_out) (regression, :1184) or fp32(-tau_out) (:1172-1180)
     float two_var[2 * HMCX_MLP_MAX_LAYERS], log_scale[2 * HMCX_MLP_MAX_LAYERS], gcoef[2 * HMCX_MLP_MAX_LAYERS];
     const float* x;
@@ -453,21 +456,19 @@ constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COL_W1HI = 256, T
 
 static_assert(TC_TR / 4 == MLP_THREADS / 32 && TC_TR == 64, "staging / epilogue thread maps assume 16 warps and 64-row tiles");
 
-struct TcCtx { uint32_t tmem, barH, barW, barX, parH, parW, parX; };
+struct TcCtx { uint32_t tmem, barH, barW, barF[2], barB, parH, parW, parF[2], parB; };
 
 #ifdef HMCX_TC_PROF
-__device__ long long g_tc_prof[64];
+__device__ long long g_tc_prof[512];
 __device__ int g_tc_prof_n;
-#define TC_MARK(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { int k_ = g_tc_prof_n; if (k_ < 62) { g_tc_prof[k_] = ((long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFll); g_tc_prof_n = k_ + 1; } } } while (0)
+#define TC_MARK(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { int k_ = g_tc_prof_n; if (k_ < 510) { g_tc_prof[k_] = ((long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFll); g_tc_prof_n = k_ + 1; } } } while (0)
 #else
 #define TC_MARK(id) do {} while (0)
 #endif
 
 __device__ __forceinline__ void tc_init(TcCtx& tc, uint64_t* bars, uint32_t* slot) {
     if (threadIdx.x == 0) {
-        mbar_init(smem_u32(&bars[0]), 1);
-        mbar_init(smem_u32(&bars[1]), 1);
-        mbar_init(smem_u32(&bars[2]), 1);
+        for (int b = 0; b < 5; ++b) mbar_init(smem_u32(&bars[b]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -480,8 +481,8 @@ __device__ __forceinline__ void tc_init(TcCtx& tc, uint64_t* bars, uint32_t* slo
     tc.tmem = *slot;
     tc.barH = smem_u32(&bars[0]);
     tc.barW = smem_u32(&bars[1]);
-    tc.barX = smem_u32(&bars[2]);
-    tc.parH = tc.parW = tc.parX = 0;
+    tc.barF[0] = smem_u32(&bars[2]); tc.barF[1] = smem_u32(&bars[3]); tc.barB = smem_u32(&bars[4]);
+    tc.parH = tc.parW = tc.parF[0] = tc.parF[1] = tc.parB = 0;
 }
 __device__ __forceinline__ void tc_fini(const TcCtx& tc) {
     tc_fence_before();
@@ -542,19 +543,66 @@ __device__ __forceinline__ void tc_pack_w1(const MlpDev& m, const float* q, cons
     tc_fence_before();                                        // the caller's __syncthreads orders it before the UMMAs
 }
 
-// Prefetch the raw rows [r0, r0 + cnt) of X -- contiguous in global memory -- with ONE bulk TMA copy (thread 0, completion
-// on barX) and their targets with 4-byte cp.async (warp 1), into the landing buffers; a ragged last tile zero-fills
-// the missing rows.  The staging passes then read shared memory instead of waiting on L2.
-__device__ __forceinline__ void tc_prefetch(const MlpDev& m, float* tile, const TcCtx& tc, int r0, int cnt) {
-    const int n0 = m.n[0];
-    float* raw = tile + m.tc_raw;
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)(cnt * n0) * 4u;
-        mbar_expect_tx(tc.barX, bytes);
-        bulk_g2s(smem_u32(raw), m.x + (size_t)r0 * n0, bytes, tc.barX);
+// X never changes during a run, so its tf32 hi / lo split and both operand layouts are built ONCE (hmcx_mlp_pack_x ->
+// mlp_pack_x_kernel) and a tile's operands arrive ready-made by one bulk TMA copy each -- no staging pass, no landing
+// buffer (the first form re-split and re-laid-out every tile twice per evaluation: ~2.4k of its ~9.9k cycles):
+//   forward B operand  [64 rows hi | 64 rows lo (N = 128)] x [n0 (K)], K-major core matrices (8 rows x 16 B); stacking
+//       hi|lo along N lets ONE UMMA produce W1_hi X_hi^T and W1_hi X_lo^T side by side;
+//   backward B operand [n0 hi | n0 lo (N = 2 n0)] x [64 rows (K)], K-major (4 consecutive ROWS of one input column per 16 B).
+// Rows past the end of a ragged last tile are zero in the packed copy.
+__device__ __forceinline__ int tc_pack_off_fwd(int r, int c) { return (c * (2 * TC_TR >> 3) + (r >> 3)) * 32 + (r & 7) * 4; }
+__device__ __forceinline__ int tc_pack_off_bwd(int a, int n, int n0) { return (a * (2 * n0 >> 3) + (n >> 3)) * 32 + (n & 7) * 4; }
+
+__global__ void __launch_bounds__(256) mlp_pack_x_kernel(const MlpDev m, float* __restrict__ out) {
+    const int n0 = m.n[0], nch = n0 >> 2, tile_id = blockIdx.x;
+    int r0, r_end;
+    if (tile_id >= m.flat_base && m.flat_base >= m.tb[m.M]) {        // the all-rows tiling (only packed when it differs)
+        r0 = TC_TR * (tile_id - m.flat_base); r_end = m.N;
+    } else {
+        int sp = 0;
+        while (sp + 1 < m.M && tile_id >= m.tb[sp + 1]) ++sp;
+        r0 = m.sb[sp] + TC_TR * (tile_id - m.tb[sp]); r_end = m.sb[sp + 1];
     }
-    if (cnt < TC_TR)
-        for (int i = cnt * n0 + threadIdx.x; i < TC_TR * n0; i += MLP_THREADS) raw[i] = 0.0f;
+    const int cnt = min(TC_TR, r_end - r0);
+    float* fwd = out + (size_t)tile_id * (2 * 2 * TC_TR * n0);
+    float* bwd = fwd + 2 * TC_TR * n0;
+    for (int i = threadIdx.x; i < TC_TR * nch; i += blockDim.x) {
+        const int r = i / nch, c = i - r * nch;
+        const float4 v = r < cnt ? *reinterpret_cast<const float4*>(m.x + (size_t)(r0 + r) * n0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 h, l;
+        tc_split4(v, h, l);
+        *reinterpret_cast<float4*>(fwd + tc_pack_off_fwd(r, c)) = h;
+        *reinterpret_cast<float4*>(fwd + tc_pack_off_fwd(r, c) + (TC_TR >> 3) * 32) = l;
+    }
+    for (int i = threadIdx.x; i < (TC_TR / 4) * n0; i += blockDim.x) {
+        const int a = i / n0, n = i - a * n0;
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = (4 * a + k) < cnt ? m.x[(size_t)(r0 + 4 * a + k) * n0 + n] : 0.0f;
+        float4 h, l;
+        tc_split4(make_float4(e[0], e[1], e[2], e[3]), h, l);
+        *reinterpret_cast<float4*>(bwd + tc_pack_off_bwd(a, n, n0)) = h;
+        *reinterpret_cast<float4*>(bwd + tc_pack_off_bwd(a, n, n0) + (n0 >> 3) * 32) = l;
+    }
+}
+
+// one bulk TMA copy per operand (thread 0; completion on the buffer's mbarrier)
+__device__ __forceinline__ void tc_prefetch_fwd(const MlpDev& m, float* tile, const TcCtx& tc, int tile_id, int buf) {
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(2 * TC_TR * m.n[0]) * 4u;
+        mbar_expect_tx(tc.barF[buf], bytes);
+        bulk_g2s(smem_u32(tile + (buf ? m.tc_f1 : m.tc_f0)), m.xp + (size_t)tile_id * (4 * TC_TR * m.n[0]), bytes, tc.barF[buf]);
+    }
+}
+__device__ __forceinline__ void tc_prefetch_bwd(const MlpDev& m, float* tile, const TcCtx& tc, int tile_id) {
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(2 * TC_TR * m.n[0]) * 4u;
+        mbar_expect_tx(tc.barB, bytes);
+        bulk_g2s(smem_u32(tile + m.tc_b), m.xp + (size_t)tile_id * (4 * TC_TR * m.n[0]) + 2 * TC_TR * m.n[0], bytes, tc.barB);
+    }
+}
+// the tile's targets: 4-byte cp.async by warp 1 (waited for by the same warp at the top of tc_forward_tile)
+__device__ __forceinline__ void tc_prefetch_y(const MlpDev& m, float* tile, int r0, int cnt) {
     if (threadIdx.x >= 32 && threadIdx.x < 64) {
         const int ycols = (m.loss == HMCX_LOSS_REGRESSION || m.loss == HMCX_LOSS_BINARY) ? m.n[2] : 1;
         const uint32_t yraw = smem_u32(tile + m.tc_yraw);
@@ -563,57 +611,15 @@ __device__ __forceinline__ void tc_prefetch(const MlpDev& m, float* tile, const 
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 }
-__device__ __forceinline__ void tc_prefetch_wait(TcCtx& tc) {
-    if (threadIdx.x >= 32 && threadIdx.x < 64) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    mbar_wait(tc.barX, tc.parX);
-    tc.parX ^= 1;
-    __syncthreads();
-}
-
-// forward B operand: X tile as [64 rows hi | 64 rows lo (N = 128)] x [n0 (K)], K-major, from the landing buffer (row and
-// chunk index both vary over an 8-lane phase: conflict-free reads and writes).  Stacking hi|lo along N lets ONE UMMA
-// produce W1_hi X_hi^T and W1_hi X_lo^T side by side (the A tile is fetched once for both).
-__device__ __forceinline__ void tc_stage_x_fwd(const MlpDev& m, float* tile) {
-    const int n0 = m.n[0], nch = n0 >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* raw = tile + m.tc_raw;
-    float* xb = tile + m.tc_xhi;
-    const int r = 8 * (warp & 7) + (lane & 7);
-    for (int c0 = (lane >> 3) + 4 * (warp >> 3); c0 < nch; c0 += 8) {
-        int c = c0 + (lane & 7);
-        c -= (c >= nch) ? nch : 0;
-        c -= (c >= nch) ? nch : 0;                                // nch >= 4: two conditional subtractions are a modulo
-        float4 h, l;
-        tc_split4(*reinterpret_cast<const float4*>(raw + r * n0 + 4 * c), h, l);
-        const int off = (c * (2 * TC_TR >> 3) + (r >> 3)) * 32 + (r & 7) * 4;      // hi|lo stacked along N: 128 "rows"
-        *reinterpret_cast<float4*>(xb + off) = h;
-        *reinterpret_cast<float4*>(xb + off + (TC_TR >> 3) * 32) = l;
-    }
-}
-
-// backward B operand: X tile as [n0 (N)] x [64 rows (K)], K-major (4 consecutive ROWS of one input column per 16 bytes)
-__device__ __forceinline__ void tc_stage_x_bwd(const MlpDev& m, float* tile) {
-    const int n0 = m.n[0];
-    const float* raw = tile + m.tc_raw;
-    float* xb = tile + m.tc_xhi;
-    const int a = threadIdx.x >> 5;                               // 16 warps <-> the 16 four-row groups of the tile
-    for (int n = threadIdx.x & 31; n < n0; n += 32) {
-        const float* src = raw + 4 * a * n0 + n;
-        float4 h, l;
-        tc_split4(make_float4(src[0], src[n0], src[2 * n0], src[3 * n0]), h, l);
-        const int off = (a * (2 * n0 >> 3) + (n >> 3)) * 32 + (n & 7) * 4;         // hi|lo stacked along N: 2*n0 "rows"
-        *reinterpret_cast<float4*>(xb + off) = h;
-        *reinterpret_cast<float4*>(xb + off + (n0 >> 3) * 32) = l;
-    }
-}
 
 // H^T = W1 . X^T  (one elected thread; completion -> barH).  A = W1 from TENSOR MEMORY (8 columns per k-step).  Two UMMAs per
 // k-step: W1_hi . [X_hi | X_lo]^T (N = 128, the two products land in columns [0,64) and [64,128)) and W1_lo . X_hi^T
 // (N = 64, accumulated onto [0,64)); the epilogue adds the two column blocks.  The B descriptors differ only in the
 // start-address field (bits 0-13, 16-byte units), so a k-step is an integer add.
-__device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, float* tile) {
+__device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, const float* xop) {
     const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * TC_TR), idesc1 = make_idesc_tf32(TC_H, TC_TR);
     constexpr uint32_t B_LBO = (2 * TC_TR / 8) * 128;
-    uint64_t b = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
+    uint64_t b = make_kmajor_desc(smem_u32(xop), B_LBO, 128);
     const int ksteps = m.n[0] >> 3;
     const uint32_t d = tc.tmem + TC_COL_H;
     uint32_t a_hi = tc.tmem + TC_COL_W1HI, a_lo = tc.tmem + TC_COL_W1LO;
@@ -627,11 +633,11 @@ __device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, f
 }
 
 // dW1 (+)= dH^T . X   (A from tensor memory; completion -> barW): dH_hi . [X_hi | X_lo] (N = 2 n0) and dH_lo . X_hi (N = n0)
-__device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, float* tile, bool accumulate) {
+__device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, const float* xop, bool accumulate) {
     const int n0 = m.n[0];
     const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * n0), idesc1 = make_idesc_tf32(TC_H, n0);
     const uint32_t B_LBO = (uint32_t)(2 * n0 / 8) * 128;
-    uint64_t b = make_kmajor_desc(smem_u32(tile + m.tc_xhi), B_LBO, 128);
+    uint64_t b = make_kmajor_desc(smem_u32(xop), B_LBO, 128);
     const uint32_t d = tc.tmem + TC_COL_W;
     uint32_t a_hi = tc.tmem + TC_COL_H, a_lo = tc.tmem + TC_COL_LO;
     tc_fence_after();
@@ -706,14 +712,15 @@ __device__ __forceinline__ void tc_epi_begin(const MlpDev& m, const float* q, Tc
 // forward of one (prefetched) tile up to the network outputs: out[r * nL + j] (the loss stage's layout); the hidden
 // activations of this thread's (unit, 16 rows) block stay in `act`.  Ends with every thread past a __syncthreads.
 __device__ __forceinline__ void tc_forward_tile(const MlpDev& m, const float* q, float* tile, TcCtx& tc, const TcEpi& e,
-                                                float (&act)[16]) {
+                                                float (&act)[16], int buf) {
     const int nL = m.n[2], lane = threadIdx.x & 31;
-    tc_prefetch_wait(tc);                                         // this tile's raw rows have landed
-    tc_stage_x_fwd(m, tile);
-    fence_async_smem();
-    __syncthreads();
-    TC_MARK(3);
-    if (threadIdx.x == 0) tc_issue_fwd(m, tc, tile);
+    if (threadIdx.x >= 32 && threadIdx.x < 64) asm volatile("cp.async.wait_group 0;" ::: "memory");    // the targets
+    if (threadIdx.x == 0) {
+        mbar_wait(tc.barF[buf], tc.parF[buf]);                    // this tile's forward operand has landed
+        TC_MARK(3);
+        tc_issue_fwd(m, tc, tile + (buf ? m.tc_f1 : m.tc_f0));
+    }
+    tc.parF[buf] ^= 1;
     TC_MARK(4);
     mbar_wait(tc.barH, tc.parH);
     tc.parH ^= 1;
@@ -751,7 +758,7 @@ __device__ __forceinline__ void tc_forward_tile(const MlpDev& m, const float* q,
 
 // g += d ll_split / dq over this rank's 64-row tiles of [r_begin, r_end)
 __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, TcCtx& tc,
-                                                 int r_begin, int r_end, ClusterCtx cc) {
+                                                 int r_begin, int r_end, int tile0, ClusterCtx cc) {
     const int nL = m.n[2], n0 = m.n[0];
     TcEpi e;
     tc_epi_begin(m, q, e);
@@ -761,17 +768,22 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
     const int stride = TC_TR * cc.size;
     int done = 0;
     int r0 = r_begin + TC_TR * cc.rank;                           // this rank's tiles: rank, rank + size, ...
-    if (r0 < r_end) tc_prefetch(m, tile, tc, r0, min(TC_TR, r_end - r0));
-    for (; r0 < r_end; r0 += stride) {
-        const int cnt = min(TC_TR, r_end - r0);
+    int id = tile0 + cc.rank;                                     // ... and their packed operands
+    if (r0 < r_end) {
+        tc_prefetch_fwd(m, tile, tc, id, 0);
+        tc_prefetch_bwd(m, tile, tc, id);
+        tc_prefetch_y(m, tile, r0, min(TC_TR, r_end - r0));
+    }
+    for (; r0 < r_end; r0 += stride, id += cc.size) {
+        const int cnt = min(TC_TR, r_end - r0), buf = done & 1;
+        const bool has_next = r0 + stride < r_end;
+        if (has_next) tc_prefetch_fwd(m, tile, tc, id + cc.size, buf ^ 1);   // last read by the forward MMA of tile t-1: complete
         float act[16];
-        tc_forward_tile(m, q, tile, tc, e, act);                  // the forward MMA has completed: the X buffers are free
-        tc_stage_x_bwd(m, tile);
-        fence_async_smem();
+        tc_forward_tile(m, q, tile, tc, e, act, buf);
         mlp_loss_tile(m, out, dz, r0, cnt, r_end - r_begin, false, ytile);
         __syncthreads();
         TC_MARK(8);
-        if (r0 + stride < r_end) tc_prefetch(m, tile, tc, r0 + stride, min(TC_TR, r_end - r0 - stride));   // landing buffers are free
+        if (has_next) tc_prefetch_y(m, tile, r0 + stride, min(TC_TR, r_end - r0 - stride));   // the target buffer is free
         if (threadIdx.x < TC_TR * nL) e.db2 += dz[threadIdx.x];   // element (r, j) of every tile; reduced over r at the end
         float dact[16];
         tc_dact16(act, dact, m.act[0]);
@@ -802,17 +814,22 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
         TC_MARK(9);
         __syncthreads();
         TC_MARK(10);
-        if (threadIdx.x == 0) tc_issue_bwd(m, tc, tile, done != 0);
+        if (threadIdx.x == 0) {
+            mbar_wait(tc.barB, tc.parB);                          // the backward operand has landed (long ago)
+            tc_issue_bwd(m, tc, tile + m.tc_b, done != 0);
+        }
+        tc.parB ^= 1;
         ++done;
         TC_MARK(11);
-        mbar_wait(tc.barW, tc.parW);                              // X buffers and the dH columns are free again
+        mbar_wait(tc.barW, tc.parW);                              // the backward operand buffer and the dH columns are free again
         tc.parW ^= 1;
+        if (has_next) tc_prefetch_bwd(m, tile, tc, id + cc.size);
         TC_MARK(12);
     }
     if (done == 0) return;                                        // (uniform over the CTA)
     tc_fence_after();
     // ---- dW1: TMEM -> padded staging (the W1 operand area is idle now) -> g, conflict-free both ways
-    float* stg = tile + m.tc_w1hi;
+    float* stg = tile + m.tc_f0;                 // the two forward operand buffers are idle now (no prefetch pending)
     const int pitch = n0 + 4;
     if (16 * e.cq < n0) {
         uint32_t v[16], w[16];
@@ -909,18 +926,23 @@ __device__ __forceinline__ void mlp_prior_grad(const MlpDev& m, const float* q, 
 // g = d log p_split / dq for split s (s < 0: all rows as one potential)
 template <int CS>
 __device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, float* g, float* tile, int s,
-                                               ClusterCtx cc, TcCtx& tc) {
+                                               ClusterCtx cc, TcCtx& tc, bool leave_partials = false) {
     TC_MARK(1);
     if (cc.rank == 0) mlp_prior_grad(m, q, g);                 // the prior part enters the rank-ordered sum once
     else for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) g[i] = 0.0f;
-    if (m.tc) tc_pack_w1(m, q, tc);
+    if (m.tc) { tc_pack_w1(m, q, tc); fence_async_smem(); }    // (generic accesses of the operand buffers precede the TMA writes)
     __syncthreads();
     TC_MARK(2);
     if (m.has_data) {
         const int rb = s < 0 ? 0 : m.sb[s], re = s < 0 ? m.N : m.sb[s + 1];
-        if (m.tc) tc_backprop_rows(m, q, g, tile, tc, rb, re, cc);
+        if (m.tc) tc_backprop_rows(m, q, g, tile, tc, rb, re, s < 0 ? m.flat_base : m.tb[s], cc);
         else mlp_backprop_rows(m, q, g, tile, rb, re, cc);
-        cluster_sum_vector<CS>(g, m.D);
+        TC_MARK(14);
+        // leave_partials: the caller's kick adds the ranks' partial gradients itself (one DSMEM pass instead of reduce +
+        // write back + kick); all it needs here is that every rank's partial is complete
+        if (!leave_partials) cluster_sum_vector<CS>(g, m.D);
+        else if (CS > 1) cg::this_cluster().sync();
+        TC_MARK(15);
     }
 }
 
@@ -956,6 +978,8 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
     if (m.tc) {
         tc_pack_w1(m, q, tc);
         tc_epi_begin(m, q, te);
+        fence_async_smem();
+        __syncthreads();
     }
     float lp = 0.0f;
     const int s0 = s < 0 ? 0 : s, s1 = s < 0 ? m.M : s + 1;
@@ -967,8 +991,9 @@ __device__ __forceinline__ float mlp_log_prob(const MlpDev& m, const float* q, f
             const int cnt = min(m.T, m.sb[sp + 1] - r0);
             if (m.tc) {
                 float act[16];
-                tc_prefetch(m, tile, tc, r0, cnt);
-                tc_forward_tile(m, q, tile, tc, te, act);
+                tc_prefetch_fwd(m, tile, tc, m.tb[sp] + ti, 0);
+                tc_prefetch_y(m, tile, r0, cnt);
+                tc_forward_tile(m, q, tile, tc, te, act, 0);
             } else {
                 mlp_forward_tile(m, q, tile, r0, cnt);
             }
@@ -1031,7 +1056,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
     __shared__ float s_bcast[4];
     __shared__ float s_xchg;
     __shared__ int s_perm[HMCX_MLP_MAX_SPLITS];
-    __shared__ __align__(8) uint64_t s_bars[3];
+    __shared__ __align__(8) uint64_t s_bars[5];
     __shared__ uint32_t s_tmem;
 
     const MlpDev& m = a.m;
@@ -1073,6 +1098,32 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         for (int i = tid; i < D; i += MLP_THREADS) p[i] = add(p[i], mul(coef, g[i]));
         __syncthreads();
     };
+    // momentum += coef * (g_rank0 + g_rank1 + ...): the cluster reduction of the split gradient FUSED into the kick -- every
+    // rank reads all partials through distributed shared memory (16-byte loads), adds them in rank order (the same bits as
+    // reduce-then-kick) and updates its replica of p.  The peers may overwrite their g only after everybody has read it:
+    // barrier.cluster arrive here, wait after the drift that follows (its latency hides behind the drift).
+    auto kick_partials = [&](float coef) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const float4* gr[CS];
+#pragma unroll
+        for (int r = 0; r < CS; ++r) gr[r] = reinterpret_cast<const float4*>(r == cc.rank ? g : cluster.map_shared_rank(g, r));
+        float4* p4 = reinterpret_cast<float4*>(p);
+        for (int i = tid; i < (m.Dp >> 2); i += MLP_THREADS) {
+            float4 sg = gr[0][i];
+#pragma unroll
+            for (int r = 1; r < CS; ++r) {
+                const float4 x = gr[r][i];
+                sg.x = add(sg.x, x.x); sg.y = add(sg.y, x.y); sg.z = add(sg.z, x.z); sg.w = add(sg.w, x.w);
+            }
+            float4 pv = p4[i];
+            pv.x = add(pv.x, mul(coef, sg.x)); pv.y = add(pv.y, mul(coef, sg.y));
+            pv.z = add(pv.z, mul(coef, sg.z)); pv.w = add(pv.w, mul(coef, sg.w));
+            p4[i] = pv;
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        __syncthreads();
+    };
+    const bool fused_kick = CS > 1 && m.has_data;
     auto drift = [&](float coef) {                             // params += coef * M^-1 momentum
         for (int i = tid; i < D; i += MLP_THREADS)
             q[i] = add(q[i], a.mk == HMCX_MASS_DIAG ? mul(mul(coef, a.im[i]), p[i]) : mul(coef, p[i]));
@@ -1143,11 +1194,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                     else { sp = up; post = jj == M - 1; }
                     if (++jj == twoM) jj = 0;
                 }
-                mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc);
-                kick(kc);
+                mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc, fused_kick);
+                if (fused_kick) kick_partials(kc); else kick(kc);
+                TC_MARK(16);
                 if (post) drift(cd);
+                if (fused_kick) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                TC_MARK(17);
             }
-            if (plain) kick(-half);                                       // p - half*g == p + (-half)*g exactly
+            if (plain) {                                                  // p - half*g == p + (-half)*g exactly
+                if (fused_kick) { kick_partials(-half); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+                else kick(-half);
+            }
         }
         // ---- Hamiltonians + MH ----
         const float lp_new = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
@@ -1224,7 +1281,7 @@ mlp_grad_kernel(const MlpDev m, const float* __restrict__ qin, int ld, int split
                 float* __restrict__ lpout) {
     extern __shared__ __align__(128) float sm[];
     __shared__ float sred[64];
-    __shared__ __align__(8) uint64_t s_bars[3];
+    __shared__ __align__(8) uint64_t s_bars[5];
     __shared__ uint32_t s_tmem;
     float* q = sm;
     float* g = q + m.Dp;
@@ -1252,7 +1309,7 @@ mlp_predict_kernel(const MlpDev m, const float* __restrict__ samples, int ld, fl
                    float* __restrict__ lpout) {
     extern __shared__ __align__(128) float sm[];
     __shared__ float sred[64];
-    __shared__ __align__(8) uint64_t s_bars[3];
+    __shared__ __align__(8) uint64_t s_bars[5];
     __shared__ uint32_t s_tmem;
     float* q = sm;
     float* tile = sm + m.tile_base;
@@ -1283,17 +1340,18 @@ static void mlp_layout_tiles(MlpDev& m, int T) {
     m.T = T;
 }
 
+static bool mlp_tc_shape(const MlpDev& m) {
+    return m.L == 2 && m.n[1] == TC_H && m.n[0] >= 16 && m.n[0] <= 64 && (m.n[0] & 15) == 0 && m.n[2] <= TC_NLMAX && m.has_data;
+}
+
 // tensor-core layout of the tile area (one-hidden-layer stacks n0 -> 128 -> nL, see the tcgen05 section above)
 static bool mlp_layout_tc(MlpDev& m, int state_vectors) {
-    if (m.L != 2 || m.n[1] != TC_H || m.n[0] < 16 || m.n[0] > 64 || (m.n[0] & 15) || m.n[2] > TC_NLMAX || !m.has_data)
-        return false;
+    if (!mlp_tc_shape(m) || !m.xp) return false;
     const int n0 = m.n[0];
     int off = 0;
-    m.tc_xhi = off; off += TC_TR * n0;
-    m.tc_xlo = off; off += TC_TR * n0;
-    m.tc_raw = off; off += TC_TR * n0;          // xhi | xlo | raw are adjacent: together they stage dW1 (128 rows, pitch n0 + 4)
-    m.tc_w1hi = m.tc_xhi; m.tc_w1lo = m.tc_xlo; // (W1 itself lives in tensor memory)
-    if (off < TC_H * (n0 + 4)) off = TC_H * (n0 + 4);
+    m.tc_f0 = off; off += 2 * TC_TR * n0;       // forward X operand (hi|lo), double-buffered; f0 | f1 also stage dW1
+    m.tc_f1 = off; off += 2 * TC_TR * n0;       //   (128 rows, pitch n0 + 4) at the end of an evaluation
+    m.tc_b = off; off += 2 * TC_TR * n0;        // backward X operand (hi|lo)
     m.tc_part = off; off += 4 * TC_H * (1 + TC_NLMAX);
     m.tc_yraw = off; off += TC_TR * TC_NLMAX;
     m.aoff[0] = m.aoff[1] = 0;
@@ -1316,6 +1374,22 @@ static bool mlp_pick_tile(MlpDev& m, int state_vectors, bool allow_tc = false) {
         if ((size_t)(state_vectors * m.Dp + m.tile_floats) * sizeof(float) <= 227 * 1024 - 4096) return true;
     }
     return false;
+}
+
+// packed-operand tile numbering (see mlp_pack_x_kernel): the tiles of every split, then -- only when some interior split
+// boundary is not a multiple of the tile height -- the tiles of the all-rows tiling; returns the number of tiles
+static int mlp_packed_tiles(MlpDev& m) {
+    int t = 0;
+    bool aligned = true;
+    for (int s = 0; s < m.M; ++s) {
+        m.tb[s] = t;
+        t += (m.sb[s + 1] - m.sb[s] + TC_TR - 1) / TC_TR;
+        if (s > 0 && (m.sb[s] % TC_TR) != 0) aligned = false;
+    }
+    m.tb[m.M] = t;
+    if (aligned) { m.flat_base = 0; return t; }
+    m.flat_base = t;
+    return t + (m.N + TC_TR - 1) / TC_TR;
 }
 
 static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
@@ -1361,6 +1435,8 @@ static int fill_mlp(const hmcx_target_t* target, MlpDev& m) {
     } else {
         for (int s = 0; s <= m.M; ++s) m.sb[s] = 0;
     }
+    mlp_packed_tiles(m);
+    m.xp = h.x_packed;
     return HMCX_OK;
 }
 
@@ -1474,12 +1550,29 @@ int mlp_predict(const hmcx_target_t* target, const float* samples, int S, int ld
     return cuda_status();
 }
 
+// packed X operands of the tensor-core path (hmcx_mlp_t.x_packed): size in floats (0: the stack does not use it) / build
+size_t mlp_packed_x_floats(const hmcx_target_t* target) {
+    MlpDev m = {};
+    if (fill_mlp(target, m) != HMCX_OK || !mlp_tc_shape(m)) return 0;
+    return (size_t)mlp_packed_tiles(m) * 4 * TC_TR * m.n[0];
+}
+
+int mlp_pack_x(const hmcx_target_t* target, float* out, cudaStream_t st) {
+    MlpDev m = {};
+    const int rc = fill_mlp(target, m);
+    if (rc != HMCX_OK) return rc;
+    if (!out) return HMCX_ERR_INVALID_ARG;
+    if (!mlp_tc_shape(m)) return HMCX_ERR_UNSUPPORTED;
+    mlp_pack_x_kernel<<<mlp_packed_tiles(m), 256, 0, st>>>(m, out);
+    return cuda_status();
+}
+
 #ifdef HMCX_TC_PROF
 extern "C" int hmcx_debug_tc_prof(long long* out) {           // developer build only (scripts/prof_tc_phases.py)
     int n = 0;
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(&n, g_tc_prof_n, sizeof(int));
-    cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(long long) * 64);
+    cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(long long) * 512);
     int zero = 0;
     cudaMemcpyToSymbol(g_tc_prof_n, &zero, sizeof(int));
     return n;

@@ -105,6 +105,16 @@ class NativeTarget:
         s.kind, s.dim = T.KIND_MLP, first.dim
         s.mlp = C.pointer(m)
         self.struct = s
+        if x is not None and m.tensor_cores == 0 and self.device.type == 'cuda':
+            # tensor-core form: x as ready-made tcgen05 operands (tf32 hi | lo, both GEMM layouts), built once per target
+            lib = N.load_library()
+            nbytes = int(lib.hmcx_mlp_packed_x_bytes(C.byref(s)))
+            if nbytes:
+                xp = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+                with torch.cuda.device(self.device):
+                    N.check(lib.hmcx_mlp_pack_x(C.byref(s), N.ptr(xp), N.stream_ptr(self.device)), 'hmcx_mlp_pack_x')
+                self._keep['x_packed'] = xp
+                m.x_packed = xp.data_ptr()
 
     def ref(self):
         return C.byref(self.struct)

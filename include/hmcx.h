@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HMCX_ABI_VERSION 5
+#define HMCX_ABI_VERSION 6
 
 #define HMCX_MLP_TC_AUTO 0
 #define HMCX_MLP_TC_OFF  1
@@ -95,6 +95,9 @@ typedef struct hmcx_mlp {
     int32_t tensor_cores;                          /* HMCX_MLP_TC_AUTO: first-layer GEMMs on tcgen05 (3xTF32, fp32-level
                                                       accuracy) when the stack is n0 -> 128 -> nL with n0 in
                                                       {16,32,48,64}, nL <= 4; HMCX_MLP_TC_OFF: fp32 SIMT tiles  */
+    const float* x_packed;                         /* device buffer of hmcx_mlp_packed_x_bytes() filled by hmcx_mlp_pack_x():
+                                                      x as ready-made tcgen05 operands (tf32 hi | lo, both GEMM layouts),
+                                                      one bulk TMA copy per tile.  NULL: fp32 SIMT tiles               */
 } hmcx_mlp_t;
 
 typedef struct hmcx_target {
@@ -301,6 +304,16 @@ int hmcx_grad_log_prob(const hmcx_target_t* target, const float* q, int32_t C, i
  */
 int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t S, int32_t ld,
                      float* pred_out, float* log_prob_out, void* stream);
+
+/*
+ * Packed X operands of the BNN tensor-core path (hmcx_mlp_t.x_packed).  The data matrix of define_model_log_prob
+ * (samplers.py:1093-1201) never changes during a run, so its tf32 hi / lo split and the two tcgen05 operand layouts
+ * (forward: rows x inputs, backward: inputs x rows) are built once per target:
+ *   hmcx_mlp_packed_x_bytes   size of the buffer (0: this stack has no tensor-core form -- leave x_packed NULL)
+ *   hmcx_mlp_pack_x           fills it from target->mlp->x on `stream` (x_packed itself is not read)
+ */
+size_t hmcx_mlp_packed_x_bytes(const hmcx_target_t* target);
+int hmcx_mlp_pack_x(const hmcx_target_t* target, float* packed_out, void* stream);
 
 /*
  * hmcx_gemm_nt_tf32x3: D[M,N] = A[M,K] . B[N,K]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32 with
