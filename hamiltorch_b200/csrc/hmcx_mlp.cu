@@ -456,7 +456,7 @@ constexpr int TC_COL_H = 0, TC_COL_LO = 64, TC_COL_W = 128, TC_COL_W1HI = 256, T
 
 static_assert(TC_TR / 4 == MLP_THREADS / 32 && TC_TR == 64, "staging / epilogue thread maps assume 16 warps and 64-row tiles");
 
-struct TcCtx { uint32_t tmem, barH, barW, barF[2], barB, parH, parW, parF[2], parB; };
+struct TcCtx { uint32_t tmem, barH, barW, barF[2], barB, parH, parW, parF[2], parB; int pre_id; };   // pre_id: tile whose operands an earlier evaluation already prefetched (-1: none)
 
 #ifdef HMCX_TC_PROF
 __device__ long long g_tc_prof[512];
@@ -483,6 +483,7 @@ __device__ __forceinline__ void tc_init(TcCtx& tc, uint64_t* bars, uint32_t* slo
     tc.barW = smem_u32(&bars[1]);
     tc.barF[0] = smem_u32(&bars[2]); tc.barF[1] = smem_u32(&bars[3]); tc.barB = smem_u32(&bars[4]);
     tc.parH = tc.parW = tc.parF[0] = tc.parF[1] = tc.parB = 0;
+    tc.pre_id = -1;
 }
 __device__ __forceinline__ void tc_fini(const TcCtx& tc) {
     tc_fence_before();
@@ -758,7 +759,7 @@ __device__ __forceinline__ void tc_forward_tile(const MlpDev& m, const float* q,
 
 // g += d ll_split / dq over this rank's 64-row tiles of [r_begin, r_end)
 __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q, float* g, float* tile, TcCtx& tc,
-                                                 int r_begin, int r_end, int tile0, ClusterCtx cc) {
+                                                 int r_begin, int r_end, int tile0, ClusterCtx cc, int next_s = -2) {
     const int nL = m.n[2], n0 = m.n[0];
     TcEpi e;
     tc_epi_begin(m, q, e);
@@ -769,11 +770,12 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
     int done = 0;
     int r0 = r_begin + TC_TR * cc.rank;                           // this rank's tiles: rank, rank + size, ...
     int id = tile0 + cc.rank;                                     // ... and their packed operands
-    if (r0 < r_end) {
+    if (r0 < r_end && tc.pre_id != id) {                          // (else: the previous evaluation already fetched them)
         tc_prefetch_fwd(m, tile, tc, id, 0);
         tc_prefetch_bwd(m, tile, tc, id);
         tc_prefetch_y(m, tile, r0, min(TC_TR, r_end - r0));
     }
+    tc.pre_id = -1;
     for (; r0 < r_end; r0 += stride, id += cc.size) {
         const int cnt = min(TC_TR, r_end - r0), buf = done & 1;
         const bool has_next = r0 + stride < r_end;
@@ -827,9 +829,22 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
         TC_MARK(12);
     }
     if (done == 0) return;                                        // (uniform over the CTA)
+    // The first tile of the NEXT evaluation (the schedule knows its split): its operands do not depend on q, so they are
+    // requested now and land while this evaluation finishes (dW1 read-out, reductions, cluster sum, kick, drift) -- an
+    // evaluation used to start with ~2.3k cycles of exposed TMA latency.
+    int nid = -1;
+    if (next_s > -2) {
+        const int nb = next_s < 0 ? 0 : m.sb[next_s], ne = next_s < 0 ? m.N : m.sb[next_s + 1];
+        const int nr0 = nb + TC_TR * cc.rank;
+        if (nr0 < ne) {
+            nid = (next_s < 0 ? m.flat_base : m.tb[next_s]) + cc.rank;
+            tc_prefetch_fwd(m, tile, tc, nid, 0);                 // every forward MMA of this evaluation has completed
+            tc_prefetch_y(m, tile, nr0, min(TC_TR, ne - nr0));    // the last loss stage is over
+        }
+    }
     tc_fence_after();
-    // ---- dW1: TMEM -> padded staging (the W1 operand area is idle now) -> g, conflict-free both ways
-    float* stg = tile + m.tc_f0;                 // the two forward operand buffers are idle now (no prefetch pending)
+    // ---- dW1: TMEM -> padded staging -> g, conflict-free both ways
+    float* stg = tile + m.tc_f1;                 // forward buffer 1 | backward buffer (adjacent, both idle now)
     const int pitch = n0 + 4;
     if (16 * e.cq < n0) {
         uint32_t v[16], w[16];
@@ -857,7 +872,9 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
     red[(e.cq * TC_H + e.u) * (1 + TC_NLMAX)] = e.db1;
 #pragma unroll
     for (int j = 0; j < TC_NLMAX; ++j) red[(e.cq * TC_H + e.u) * (1 + TC_NLMAX) + 1 + j] = e.dw2[j];
+    fence_async_smem();                                           // the staging reads above precede the TMA write below
     __syncthreads();
+    if (nid >= 0) { tc_prefetch_bwd(m, tile, tc, nid); tc.pre_id = nid; }
     if (threadIdx.x < TC_H) {
         const int u = threadIdx.x;
         auto tot = [&](int f) {
@@ -926,7 +943,7 @@ __device__ __forceinline__ void mlp_prior_grad(const MlpDev& m, const float* q, 
 // g = d log p_split / dq for split s (s < 0: all rows as one potential)
 template <int CS>
 __device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, float* g, float* tile, int s,
-                                               ClusterCtx cc, TcCtx& tc, bool leave_partials = false) {
+                                               ClusterCtx cc, TcCtx& tc, bool leave_partials = false, int next_s = -2) {
     TC_MARK(1);
     if (cc.rank == 0) mlp_prior_grad(m, q, g);                 // the prior part enters the rank-ordered sum once
     else for (int i = threadIdx.x; i < m.Dp; i += MLP_THREADS) g[i] = 0.0f;
@@ -935,7 +952,7 @@ __device__ __forceinline__ void mlp_grad_split(const MlpDev& m, const float* q, 
     TC_MARK(2);
     if (m.has_data) {
         const int rb = s < 0 ? 0 : m.sb[s], re = s < 0 ? m.N : m.sb[s + 1];
-        if (m.tc) tc_backprop_rows(m, q, g, tile, tc, rb, re, s < 0 ? m.flat_base : m.tb[s], cc);
+        if (m.tc) tc_backprop_rows(m, q, g, tile, tc, rb, re, s < 0 ? m.flat_base : m.tb[s], cc, next_s);
         else mlp_backprop_rows(m, q, g, tile, rb, re, cc);
         TC_MARK(14);
         // leave_partials: the caller's kick adds the ranks' partial gradients itself (one DSMEM pass instead of reduce +
@@ -1094,8 +1111,32 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         __syncthreads();
         return s[0];
     };
+    // element-wise passes over the state: 16-byte accesses, VPT independent vectors per thread in flight (the inverse-mass
+    // read of a drift comes from L2 and the partial gradients of a fused kick from a peer SM: latency-bound otherwise).
+    // The padding lanes [D, Dp) of q / p / g are zero and stay zero (inv_mass lanes past D are read as 0).
+    constexpr int VPT = 5;                                     // Dp/4 <= 512 * 5 vectors covers D <= 10240 in one round
+    const int nvec = m.Dp >> 2;
+    const bool im_aligned = (reinterpret_cast<size_t>(a.im) & 15) == 0;
+    auto ld_im4 = [&](int v) {
+        const int i = 4 * v;
+        if (i + 3 < D && im_aligned) return __ldg(reinterpret_cast<const float4*>(a.im) + v);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < D) r.x = a.im[i];
+        if (i + 1 < D) r.y = a.im[i + 1];
+        if (i + 2 < D) r.z = a.im[i + 2];
+        if (i + 3 < D) r.w = a.im[i + 3];
+        return r;
+    };
     auto kick = [&](float coef) {                              // momentum += coef * grad
-        for (int i = tid; i < D; i += MLP_THREADS) p[i] = add(p[i], mul(coef, g[i]));
+        float4* p4 = reinterpret_cast<float4*>(p);
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (int v = tid; v < nvec; v += MLP_THREADS) {
+            float4 pv = p4[v];
+            const float4 gv = g4[v];
+            pv.x = add(pv.x, mul(coef, gv.x)); pv.y = add(pv.y, mul(coef, gv.y));
+            pv.z = add(pv.z, mul(coef, gv.z)); pv.w = add(pv.w, mul(coef, gv.w));
+            p4[v] = pv;
+        }
         __syncthreads();
     };
     // momentum += coef * (g_rank0 + g_rank1 + ...): the cluster reduction of the split gradient FUSED into the kick -- every
@@ -1108,25 +1149,68 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
 #pragma unroll
         for (int r = 0; r < CS; ++r) gr[r] = reinterpret_cast<const float4*>(r == cc.rank ? g : cluster.map_shared_rank(g, r));
         float4* p4 = reinterpret_cast<float4*>(p);
-        for (int i = tid; i < (m.Dp >> 2); i += MLP_THREADS) {
-            float4 sg = gr[0][i];
+        constexpr int KV = CS >= 4 ? 2 : VPT;                  // (register budget: KV * CS vectors live)
+        for (int v0 = tid; v0 < nvec; v0 += MLP_THREADS * KV) {
+            float4 part[KV][CS];
 #pragma unroll
-            for (int r = 1; r < CS; ++r) {
-                const float4 x = gr[r][i];
-                sg.x = add(sg.x, x.x); sg.y = add(sg.y, x.y); sg.z = add(sg.z, x.z); sg.w = add(sg.w, x.w);
+            for (int k = 0; k < KV; ++k) {                     // all remote loads of the round in flight together
+                const int v = v0 + k * MLP_THREADS;
+#pragma unroll
+                for (int r = 0; r < CS; ++r) part[k][r] = v < nvec ? gr[r][v] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float4 pv = p4[i];
-            pv.x = add(pv.x, mul(coef, sg.x)); pv.y = add(pv.y, mul(coef, sg.y));
-            pv.z = add(pv.z, mul(coef, sg.z)); pv.w = add(pv.w, mul(coef, sg.w));
-            p4[i] = pv;
+#pragma unroll
+            for (int k = 0; k < KV; ++k) {
+                const int v = v0 + k * MLP_THREADS;
+                if (v < nvec) {
+                    float4 sg = part[k][0];
+#pragma unroll
+                    for (int r = 1; r < CS; ++r) {
+                        sg.x = add(sg.x, part[k][r].x); sg.y = add(sg.y, part[k][r].y);
+                        sg.z = add(sg.z, part[k][r].z); sg.w = add(sg.w, part[k][r].w);
+                    }
+                    float4 pv = p4[v];
+                    pv.x = add(pv.x, mul(coef, sg.x)); pv.y = add(pv.y, mul(coef, sg.y));
+                    pv.z = add(pv.z, mul(coef, sg.z)); pv.w = add(pv.w, mul(coef, sg.w));
+                    p4[v] = pv;
+                }
+            }
         }
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         __syncthreads();
     };
     const bool fused_kick = CS > 1 && m.has_data;
     auto drift = [&](float coef) {                             // params += coef * M^-1 momentum
-        for (int i = tid; i < D; i += MLP_THREADS)
-            q[i] = add(q[i], a.mk == HMCX_MASS_DIAG ? mul(mul(coef, a.im[i]), p[i]) : mul(coef, p[i]));
+        float4* q4 = reinterpret_cast<float4*>(q);
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        if (a.mk == HMCX_MASS_DIAG) {
+            for (int v0 = tid; v0 < nvec; v0 += MLP_THREADS * VPT) {
+                float4 im[VPT];
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {                // the L2 reads of the round in flight together
+                    const int v = v0 + k * MLP_THREADS;
+                    im[k] = v < nvec ? ld_im4(v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const int v = v0 + k * MLP_THREADS;
+                    if (v < nvec) {
+                        float4 qv = q4[v];
+                        const float4 pv = p4[v];
+                        qv.x = add(qv.x, mul(mul(coef, im[k].x), pv.x)); qv.y = add(qv.y, mul(mul(coef, im[k].y), pv.y));
+                        qv.z = add(qv.z, mul(mul(coef, im[k].z), pv.z)); qv.w = add(qv.w, mul(mul(coef, im[k].w), pv.w));
+                        q4[v] = qv;
+                    }
+                }
+            }
+        } else {
+            for (int v = tid; v < nvec; v += MLP_THREADS) {
+                float4 qv = q4[v];
+                const float4 pv = p4[v];
+                qv.x = add(qv.x, mul(coef, pv.x)); qv.y = add(qv.y, mul(coef, pv.y));
+                qv.z = add(qv.z, mul(coef, pv.z)); qv.w = add(qv.w, mul(coef, pv.w));
+                q4[v] = qv;
+            }
+        }
         __syncthreads();
     };
 
@@ -1180,21 +1264,28 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) cd = (float)(eps_double(eps) / (double)M);
             else if (a.scheme == HMCX_SCHEME_SPLIT_KMID) cd = eps;
             int jj = 0;
+            auto split_at = [&](int j) {                                  // the data split of schedule position j
+                const int up = j < M ? j : twoM - 1 - j;
+                return a.scheme == HMCX_SCHEME_SPLIT_RAND ? s_perm[j >> 1] : up;
+            };
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
-                int sp = -1;
+                int sp = -1, sp_next = -1;
                 float kc = half;
                 bool post = false;
                 if (plain) {
                     if (t > 0) { drift(eps); kc = eps; }
                 } else {
                     const int up = jj < M ? jj : twoM - 1 - jj;
-                    if (a.scheme == HMCX_SCHEME_SPLIT_SYM) { sp = up; post = jj < M ? (up < M - 1) : (up > 0); }
-                    else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) { sp = s_perm[jj >> 1]; post = (jj & 1) == 0; }
-                    else { sp = up; post = jj == M - 1; }
+                    sp = split_at(jj);
+                    if (a.scheme == HMCX_SCHEME_SPLIT_SYM) post = jj < M ? (up < M - 1) : (up > 0);
+                    else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) post = (jj & 1) == 0;
+                    else post = jj == M - 1;
                     if (++jj == twoM) jj = 0;
+                    sp_next = split_at(jj);
                 }
-                mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc, fused_kick);
+                if (t + 1 == T) sp_next = -2;                             // the Hamiltonian evaluation follows: nothing to prefetch
+                mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc, fused_kick, sp_next);
                 if (fused_kick) kick_partials(kc); else kick(kc);
                 TC_MARK(16);
                 if (post) drift(cd);
