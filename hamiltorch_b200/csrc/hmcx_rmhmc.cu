@@ -573,18 +573,27 @@ __global__ void __launch_bounds__(128) rmhmc_run_kernel(const RmRunArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // BASELINE config 3 form: D == 2, explicit integrator.  A chain is a serial recurrence of 8L+3 metric evaluations per
-// iteration, ~1e3 dependent instructions each, so the run time is the LATENCY of that recurrence, not throughput.  The
-// two evaluations of every A / B flow of the explicit step (samplers.py:429-430, :432-433, :454-455, :457-458) take the
-// SAME arguments and differ only in the jitter row and in what is differentiated (dH/dtheta vs dH/dp): they are
-// independent.  So a chain is owned by a PAIR of threads in two different warps (= two schedulers of the SM): warp 0
-// evaluates every dH/dtheta, warp 1 every dH/dp, at the same time; results cross through a double-buffered shared
-// mailbox with one barrier per flow, and both threads apply both updates to their replica of (theta, p, theta~, p~)
-// with the reference's roundings, so they stay bit-identical and every scalar decision is taken twice, identically.
-// Critical path per iteration: 4L+3 evaluations instead of 8L+3.  32 chains per CTA -> 512 chains = 16 CTAs on 16 SMs.
+// iteration, ~600 dependent instructions each, so the run time is the LATENCY of that recurrence, not throughput.
+// Independent evaluations are therefore run CONCURRENTLY by different warps (= different schedulers of the SM); a chain
+// is owned by one lane of each of the CTA's 4 warps:
+//   * the two evaluations of every A / B flow of the explicit step (samplers.py:429-430, :432-433, :454-455, :457-458) take
+//     the SAME arguments and differ only in the jitter row and in what is differentiated: warp 0 dH/dtheta, warp 1 dH/dp;
+//   * the LAST A flow of step l and the FIRST A flow of step l+1 both act on (theta, p~) and update only (p, theta~): their
+//     four evaluations are independent -> one stage of 4 warps ("AA");
+//   * H(theta, p) before the trajectory (:971) and the first A flow see the same (theta, p~ = p): one stage (warp 2 takes H).
+// Results cross through a double-buffered shared mailbox with one barrier per stage, and every warp applies all updates
+// to its replica of (theta, p, theta~, p~) with the reference's roundings, so the replicas stay bit-identical and every
+// scalar decision is taken four times, identically.  Serial stages per iteration: 3L+3 instead of 8L+3 evaluations
+// (4L+3 for the two-warp form of this kernel).  32 chains per CTA -> 512 chains = 16 CTAs.
 //
-// Jitter rows (fisher's torch.rand(D), :115) are consumed in the reference's order.  In an A flow dH/dtheta comes first
-// and its NaN-retry loop (:402-410) may take extra rows, shifting the row of the dH/dp that follows: warp 1 assumes no
-// retry and is re-run for the (rare) chains where warp 0 reports some.
+// Jitter rows (fisher's torch.rand(D), :115) are consumed in the reference's order.  The NaN-retry loop of a dH/dtheta
+// (:402-410) may take extra rows, which shifts the rows of every later evaluation of the stage: each warp first assumes
+// no retries and is re-run (rare) when the retry counts that precede it turn out non-zero.
+//
+// Code layout: the iteration is ONE loop over its stages around a SINGLE inlined copy of eval_metric / rm_hamiltonian /
+// grad_params / grad_momentum (~2k instructions).  The first form of this kernel inlined a copy per call site -- 14.5k
+// instructions, 11k of them in the iteration loop = 180 KB of code streamed through the instruction cache once per
+// iteration -- and ran at the instruction-fetch rate (ncu: no_instruction was the top stall reason).
 // ---------------------------------------------------------------------------------------------------------
 struct PairMail { float g0, g1; int ok, retries; };
 
@@ -603,21 +612,19 @@ __device__ __forceinline__ const float* rm2_jitter_row(const RmRunArgs& a, int c
     return buf;
 }
 
-// Code layout: the iteration is ONE loop over its 4L+3 metric evaluations (gibbs, H_old, the 4L flows A B B A ..., H_new)
-// around a SINGLE inlined copy of eval_metric / rm_hamiltonian / grad_params / grad_momentum (~2k instructions).  The
-// first form of this kernel inlined a copy per call site -- 14.5k instructions, 11k of them in the iteration loop = 180 KB of
-// code streamed through the instruction cache once per iteration by two warps -- and ran at the instruction-fetch rate.
-__global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
-    __shared__ PairMail mailQ[2][32], mailP[2][32];
-    const int lane = threadIdx.x & 31;
-    const bool roleP = threadIdx.x >= 32;                     // warp 1: dH/dp evaluations; warp 0: dH/dtheta + all stores
+enum { RQ_GIBBS = 0, RQ_HOLD_A = 1, RQ_B = 2, RQ_AA = 3, RQ_A = 4, RQ_HNEW = 5 };     // stage kinds
+enum { RQ_EV_METRIC = 0, RQ_EV_H = 1, RQ_EV_DHDQ = 2, RQ_EV_DHDP = 3 };
+
+__global__ void __launch_bounds__(128) rmhmc2_quad_kernel(const RmRunArgs a) {
+    __shared__ PairMail mail[2][4][32];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     const bool live = c < a.C;
     const int cc = live ? c : a.C - 1;                        // idle lanes shadow the last chain (no stores)
     const RmTarget& t = a.t;
     const size_t row = (size_t)cc * a.ld;
     const uint64_t chain_id = a.chain_offset + (uint64_t)cc;
-    const bool writer = live && !roleP;
+    const bool writer = live && role == 0;
 
     float qc[2], q[2], p[2], qt[2], pt[2], g[2], w[2], ub[2];
     qc[0] = a.q_cur[row]; qc[1] = a.q_cur[row + 1];
@@ -631,8 +638,8 @@ __global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
     const bool jit_on = a.cfg.jitter >= 0.0f;
     int phase = 0;
     Metric<2> M;
-    const int nsteps = 4 * a.L + 3;
-    q[0] = q[1] = p[0] = p[1] = qt[0] = qt[1] = pt[0] = pt[1] = 0.0f;
+    const int nst = 3 * a.L + 3;
+    q[0] = q[1] = p[0] = p[1] = qt[0] = qt[1] = pt[0] = pt[1] = g[0] = g[1] = 0.0f;
 
     for (int n = a.it0; n < a.it1; ++n) {
         int idx = 0;                                          // jitter rows consumed so far in this iteration
@@ -640,55 +647,84 @@ __global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
         float h_old = nanf(""), h_new = nanf("");
         q[0] = qc[0]; q[1] = qc[1];
 #pragma unroll 1
-        for (int s = 0; s < nsteps; ++s) {
-            // s = 0 gibbs (:969 -> :183-184) | s = 1 H(theta, p) (:971) | flows A B [C] B A per step (:423-461) | last: H_new (:989)
-            const bool is_flow = s >= 2 && s + 1 < nsteps;
-            const int ph = (s - 2) & 3;
-            const bool isA = ph == 0 || ph == 3;              // A: (theta, p~); B: (theta~, p)
-            const bool useB = is_flow && !isA, useA = is_flow && isA;
+        for (int st = 0; st < nst; ++st) {
+            // ---- what this stage is, and what this warp evaluates in it ----
+            int kind;
+            bool first_b = false;
+            if (st == 0) kind = RQ_GIBBS;
+            else if (st == 1) kind = RQ_HOLD_A;
+            else if (st == nst - 1) kind = RQ_HNEW;
+            else {
+                const int l = (st - 2) / 3, k = (st - 2) - 3 * l;
+                kind = k < 2 ? RQ_B : (l == a.L - 1 ? RQ_A : RQ_AA);
+                first_b = k == 0;
+            }
+            if (kind == RQ_HOLD_A) { qt[0] = q[0]; qt[1] = q[1]; pt[0] = p[0]; pt[1] = p[1]; }    // :423-424
+            const bool mailed = kind != RQ_GIBBS && kind != RQ_HNEW;
+            int ev, off;                                      // evaluation kind, jitter-row offset before retry shifts
+            bool active = true;
+            if (kind == RQ_GIBBS) { ev = RQ_EV_METRIC; off = 0; }
+            else if (kind == RQ_HNEW) { ev = RQ_EV_H; off = 0; }
+            else if (kind == RQ_HOLD_A) {                     // H(theta, p) row 0 | first A flow: dH/dtheta row 1, dH/dp row 2
+                ev = role == 0 ? RQ_EV_DHDQ : (role == 1 ? RQ_EV_DHDP : RQ_EV_H);
+                off = role == 0 ? 1 : (role == 1 ? 2 : 0);
+                active = role < 3;
+            } else if (kind == RQ_B) {                        // the reference calls dH/dp first in B flows
+                ev = role == 0 ? RQ_EV_DHDQ : RQ_EV_DHDP;
+                off = role == 0 ? 1 : 0;
+                active = role < 2;
+            } else {                                          // A / AA: dH/dtheta first
+                ev = (role & 1) ? RQ_EV_DHDP : RQ_EV_DHDQ;
+                off = role;
+                active = kind == RQ_AA || role < 2;
+            }
+            const bool useB = kind == RQ_B, useA = kind == RQ_AA || kind == RQ_A;     // B: (theta~, p); A: (theta, p~)
             float th[2], pp[2];
             th[0] = useB ? qt[0] : q[0]; th[1] = useB ? qt[1] : q[1];
             pp[0] = useA ? pt[0] : p[0]; pp[1] = useA ? pt[1] : p[1];
-            // One flow: warp 0 evaluates dH/dtheta(th, pp), warp 1 dH/dp(th, pp), concurrently.  The reference calls
-            // dH/dtheta first in A flows, dH/dp first in B flows: that fixes which jitter row each one consumes.
-            int myrow = idx;
-            if (is_flow) myrow = roleP ? (isA ? idx + 1 : idx) : (isA ? idx : idx + 1);
             const int b = phase & 1;
-            if (is_flow) ++phase;
-            PairMail mq = PairMail{0.0f, 0.0f, 1, 0}, mp = mq;
+            if (mailed) ++phase;
+            PairMail m0 = PairMail{0.0f, 0.0f, 1, 0}, m1 = m0, m2 = m0, m3 = m0;
             float H = nanf("");
             bool good = true;
+            int used_shift = 0;
             for (int pass = 0;; ++pass) {
-                const bool redo = pass == 1 && ok && mq.ok && mq.retries > 0;
-                if (ok && (pass == 0 || (redo && roleP))) {
-                    const int first_row = myrow + (pass == 1 ? mq.retries : 0);
+                // retries of the dH/dtheta evaluations that precede this warp's in the reference's order shift its row
+                int shift = 0;
+                if (pass > 0) {
+                    if (kind == RQ_AA) shift = role == 0 ? 0 : (role == 3 ? m0.retries + m2.retries : m0.retries);
+                    else if (kind != RQ_B) shift = role == 1 ? m0.retries : 0;
+                }
+                if (ok && active && (pass == 0 || shift != used_shift)) {
+                    used_shift = shift;
+                    const int first_row = idx + off + shift;
                     good = true;
                     int tries = 0;
                     for (;; ++tries) {                        // the NaN-retry loop of dH/dtheta (:402-410); one trip otherwise
                         if (!eval_metric<2>(t, a.cfg, th, rm2_jitter_row(a, cc, n, chain_id, first_row + tries, ub), M)) { good = false; break; }
-                        if (s == 0) break;
+                        if (ev == RQ_EV_METRIC) break;
                         bool okh = true;
                         H = rm_hamiltonian<2>(t, a.cfg, th, pp, M, w, okh);
                         if (!okh) { good = false; break; }
-                        if (!is_flow) break;
-                        if (roleP) { grad_momentum<2>(t, M, pp, g); break; }
+                        if (ev == RQ_EV_H) break;
+                        if (ev == RQ_EV_DHDP) { grad_momentum<2>(t, M, pp, g); break; }
                         if (a.cfg.jacdiag) grad_params_jacdiag<2>(t, th, M, pp, g); else grad_params<2>(t, th, M, pp, g);
                         if (finite_f(g[0]) && finite_f(g[1])) break;
                         if (tries + 1 > a.jitter_max_tries) { good = false; break; }
                     }
-                    if (is_flow) {
-                        if (!roleP) mailQ[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, tries};
-                        else mailP[b][lane] = PairMail{g[0], g[1], good ? 1 : 0, 0};
-                    }
+                    if (mailed) mail[b][role][lane] = PairMail{ev == RQ_EV_H ? H : g[0], g[1], good ? 1 : 0, ev == RQ_EV_DHDQ ? tries : 0};
                 }
-                if (!is_flow) break;
+                if (!mailed) break;
                 __syncthreads();
-                mq = mailQ[b][lane]; mp = mailP[b][lane];
-                // retries of dH/dtheta shift the row of the dH/dp that follows it in an A flow: warp 1 re-runs those chains
-                if (pass == 1 || !(jit_on && isA)) break;
-                if (!__syncthreads_or(ok && mq.ok && mq.retries > 0)) break;
+                m0 = mail[b][0][lane]; m1 = mail[b][1][lane]; m2 = mail[b][2][lane]; m3 = mail[b][3][lane];
+                if (!jit_on || kind == RQ_B || pass == 2) break;
+                int want = 0;
+                if (kind == RQ_AA) want = role == 0 ? 0 : (role == 3 ? m0.retries + m2.retries : m0.retries);
+                else want = role == 1 ? m0.retries : 0;
+                if (!__syncthreads_or(ok && active && want != used_shift)) break;
             }
-            if (s == 0) {
+            // ---- apply the stage (every warp, identically) ----
+            if (kind == RQ_GIBBS) {
                 ++idx;
                 ok = good;
                 float z[2];
@@ -700,39 +736,54 @@ __global__ void __launch_bounds__(64) rmhmc2_pair_kernel(const RmRunArgs a) {
                     philox_normal4(a.seed, chain_id, (uint64_t)n, 0u, z4);
                     z[0] = z4[0]; z[1] = z4[1];
                 }
-                if (ok) ok = gibbs_rm<2>(t, M, z, p);         // both threads of the pair (identical bits)
-            } else if (!is_flow) {
-                if (ok) {
-                    ++idx;
-                    if (s == 1) h_old = H; else h_new = H;    // NaN when the metric itself failed
-                    ok = good;
-                }
-                if (s == 1) { qt[0] = q[0]; qt[1] = q[1]; pt[0] = p[0]; pt[1] = p[1]; }
+                if (ok) ok = gibbs_rm<2>(t, M, z, p);
+            } else if (kind == RQ_HNEW) {
+                if (ok) { ++idx; h_new = H; ok = good; }       // NaN when the metric itself failed
             } else if (ok) {
-                // reference order: the first call's LogProbError aborts before the second call is made
-                ok = mq.ok && mp.ok;
-                idx += 2 + mq.retries;
+                auto flow_a = [&](const PairMail& mq, const PairMail& mp) {
+                    for (int i = 0; i < 2; ++i) {
+                        const float gq = i ? mq.g1 : mq.g0, gp = i ? mp.g1 : mp.g0;
+                        p[i] = sub(p[i], mul(half, gq)); qt[i] = add(qt[i], mul(half, gp));
+                    }
+                };
+                if (kind == RQ_HOLD_A) {                       // reference order: H_old, then the flow (:971, :429-430)
+                    ++idx;
+                    h_old = m2.g0;
+                    ok = m2.ok != 0;
+                }
                 if (ok) {
-                    const float gq[2] = {mq.g0, mq.g1}, gp[2] = {mp.g0, mp.g1};
-                    if (isA) {
-                        for (int i = 0; i < 2; ++i) { p[i] = sub(p[i], mul(half, gq[i])); qt[i] = add(qt[i], mul(half, gp[i])); }
-                    } else {
-                        for (int i = 0; i < 2; ++i) { q[i] = add(q[i], mul(half, gp[i])); pt[i] = sub(pt[i], mul(half, gq[i])); }
-                        if (ph == 1) {
-                            for (int i = 0; i < 2; ++i) {                                               // C, sequential
-                                const float cw = a.cosw, sw = a.sinw;
-                                const float qn = mul(0.5f, add(add(add(q[i], qt[i]), mul(cw, sub(q[i], qt[i]))), mul(sw, sub(p[i], pt[i]))));
-                                const float pn = mul(0.5f, add(sub(add(p[i], pt[i]), mul(sw, sub(qn, qt[i]))), mul(cw, sub(p[i], pt[i]))));
-                                const float qtn = mul(0.5f, sub(sub(add(qn, qt[i]), mul(cw, sub(qn, qt[i]))), mul(sw, sub(pn, pt[i]))));
-                                const float ptn = mul(0.5f, sub(add(add(pn, pt[i]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[i]))));
-                                q[i] = qn; p[i] = pn; qt[i] = qtn; pt[i] = ptn;
+                    // the first call's LogProbError aborts before the second call is made
+                    ok = m0.ok && m1.ok;
+                    idx += 2 + m0.retries;
+                    if (ok) {
+                        if (kind != RQ_B) {
+                            flow_a(m0, m1);
+                            if (kind == RQ_AA) {               // the next step's first A flow: same arguments, next rows
+                                ok = m2.ok && m3.ok;
+                                idx += 2 + m2.retries;
+                                if (ok) flow_a(m2, m3);
+                            }
+                        } else {
+                            for (int i = 0; i < 2; ++i) {
+                                const float gq = i ? m0.g1 : m0.g0, gp = i ? m1.g1 : m1.g0;
+                                q[i] = add(q[i], mul(half, gp)); pt[i] = sub(pt[i], mul(half, gq));
+                            }
+                            if (first_b) {
+                                for (int i = 0; i < 2; ++i) {                                           // C, sequential
+                                    const float cw = a.cosw, sw = a.sinw;
+                                    const float qn = mul(0.5f, add(add(add(q[i], qt[i]), mul(cw, sub(q[i], qt[i]))), mul(sw, sub(p[i], pt[i]))));
+                                    const float pn = mul(0.5f, add(sub(add(p[i], pt[i]), mul(sw, sub(qn, qt[i]))), mul(cw, sub(p[i], pt[i]))));
+                                    const float qtn = mul(0.5f, sub(sub(add(qn, qt[i]), mul(cw, sub(qn, qt[i]))), mul(sw, sub(pn, pt[i]))));
+                                    const float ptn = mul(0.5f, sub(add(add(pn, pt[i]), mul(sw, sub(qn, qtn))), mul(cw, sub(pn, pt[i]))));
+                                    q[i] = qn; p[i] = pn; qt[i] = qtn; pt[i] = ptn;
+                                }
                             }
                         }
                     }
                 }
             }
         }
-        // ---- MH + bookkeeping (both threads decide identically; warp 0 stores) ----
+        // ---- MH + bookkeeping (all warps decide identically; warp 0 stores) ----
         const float x = add(-h_new, h_old);
         const float rho = (x < 0.0f) ? x : 0.0f;
         const float logu = (a.rng_mode == HMCX_RNG_INJECTED) ? a.logu[(size_t)(n - a.it0) * a.C + cc]
@@ -994,7 +1045,7 @@ int rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_r
     a.q_init = q_init; a.q_cur = q_cur; a.eps = eps; a.L = L; a.S = S; a.burn = burn; a.it0 = it0; a.it1 = it1;
     a.samples = samples; a.accept = accept; a.diverged = diverged; a.ham = ham; a.num_rejected = num_rejected;
     const int block = 128, grid = (C + block - 1) / block;
-    if (D == 2 && cfg->integrator == 1) rmhmc2_pair_kernel<<<(C + 31) / 32, 64, 0, st>>>(a);       // BASELINE config 3
+    if (D == 2 && cfg->integrator == 1) rmhmc2_quad_kernel<<<(C + 31) / 32, 128, 0, st>>>(a);       // BASELINE config 3
     else if (D == 2) rmhmc_run_kernel<2><<<grid, block, 0, st>>>(a);
     else if (D <= 6) rmhmc_run_kernel<6><<<grid, block, 0, st>>>(a);
     else rmhmc_run_kernel<16><<<grid, block, 0, st>>>(a);
