@@ -173,6 +173,30 @@ class NativeMass:
     def kind(self):
         return self.struct.kind
 
+
+# A full (2-D) or block-list inv_mass costs a host inversion + Cholesky factorisation (samplers.py:942-952 does it once per
+# sample() call).  Repeated calls with the SAME tensor object, unmodified (torch's version counter), reuse the device
+# operands: the entry holds a reference to the caller's tensor(s), so a recycled address can never alias it.
+_MASS_CACHE = []
+
+
+def native_mass(inv_mass, dim, device):
+    if isinstance(inv_mass, NativeMass):
+        return inv_mass
+    heavy = isinstance(inv_mass, list) or (torch.is_tensor(inv_mass) and inv_mass.dim() == 2)
+    if not heavy:
+        return NativeMass(inv_mass, dim, device)
+    parts = inv_mass if isinstance(inv_mass, list) else [inv_mass]
+    key = (tuple(id(t) for t in parts), tuple(t._version for t in parts), dim, str(torch.device(device)))
+    for k, refs, nm in _MASS_CACHE:
+        if k == key:
+            return nm
+    nm = NativeMass(inv_mass, dim, device)
+    _MASS_CACHE.append((key, list(parts), nm))
+    if len(_MASS_CACHE) > 4:
+        _MASS_CACHE.pop(0)
+    return nm
+
     def ref(self):
         return C.byref(self.struct)
 
@@ -219,7 +243,7 @@ def leapfrog(target, q, p, steps, step_size, inv_mass=None, return_trajectory=Fa
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
     nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
-    nm = NativeMass(inv_mass, D, device)
+    nm = native_mass(inv_mass, D, device)
     qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
     Cn = qd.shape[0]
     eps = _eps_vector(step_size, Cn, device)
@@ -244,7 +268,7 @@ def hamiltonian(target, q, p, inv_mass=None, device=None):
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
     nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
-    nm = NativeMass(inv_mass, D, device)
+    nm = native_mass(inv_mass, D, device)
     qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
     Cn = qd.shape[0]
     H = torch.empty(Cn, dtype=torch.float32, device=device)
@@ -262,7 +286,7 @@ def gibbs(dim, num_chains, seed, iteration=0, inv_mass=None, chain_offset=0, dev
     lib = N.load_library()
     device = torch.device(device)
     ld = N.padded_ld(dim)
-    nm = NativeMass(inv_mass, dim, device)
+    nm = native_mass(inv_mass, dim, device)
     rng = N.RngStruct()
     rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
     p = torch.empty((num_chains, ld), dtype=torch.float32, device=device)
@@ -326,7 +350,7 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     device = torch.device(device)
     nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
-    nm = inv_mass if isinstance(inv_mass, NativeMass) else NativeMass(inv_mass, D, device)
+    nm = native_mass(inv_mass, D, device)
     S, L, burn = int(num_samples), int(num_steps_per_sample), int(burn)
     q_init = _as_rows(params_init, ld, device)
     if q_init.shape[1] != ld or params_init.shape[-1] != D:

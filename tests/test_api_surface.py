@@ -123,3 +123,22 @@ def test_bench_clock_sampler_degrades_without_a_gpu():
     s.start()
     out = s.stop()
     assert set(out) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+
+
+def test_full_inv_mass_operands_are_cached_per_tensor_object_and_version():
+    """engine.native_mass: a 2-D / block-list inv_mass is inverted and factorised once per tensor OBJECT and version
+    (samplers.py:942-952 does it once per sample() call); an in-place update or another tensor builds new operands."""
+    import torch
+    from hamiltorch_b200 import engine
+    A = torch.eye(6) * 2.0
+    m1 = engine.native_mass(A, 6, 'cpu')
+    assert engine.native_mass(A, 6, 'cpu') is m1
+    A.mul_(2.0)                                              # version bump
+    m2 = engine.native_mass(A, 6, 'cpu')
+    assert m2 is not m1
+    assert torch.allclose(m2._keep['tril'], torch.eye(6) * 0.5)
+    assert engine.native_mass(A.clone(), 6, 'cpu') is not m2
+    blocks = [torch.eye(2), torch.eye(4) * 4.0]
+    b1 = engine.native_mass(blocks, 6, 'cpu')
+    assert engine.native_mass(blocks, 6, 'cpu') is b1
+    assert engine.native_mass(torch.ones(6), 6, 'cpu') is not engine.native_mass(torch.ones(6), 6, 'cpu')   # 1-D: cheap, uncached
