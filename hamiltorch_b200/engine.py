@@ -173,6 +173,9 @@ class NativeMass:
     def kind(self):
         return self.struct.kind
 
+    def ref(self):
+        return C.byref(self.struct)
+
 
 # A full (2-D) or block-list inv_mass costs a host inversion + Cholesky factorisation (samplers.py:942-952 does it once per
 # sample() call).  Repeated calls with the SAME tensor object, unmodified (torch's version counter), reuse the device
@@ -196,9 +199,6 @@ def native_mass(inv_mass, dim, device):
     if len(_MASS_CACHE) > 4:
         _MASS_CACHE.pop(0)
     return nm
-
-    def ref(self):
-        return C.byref(self.struct)
 
 
 def nuts_table(burn):

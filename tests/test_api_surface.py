@@ -133,6 +133,7 @@ def test_full_inv_mass_operands_are_cached_per_tensor_object_and_version():
     A = torch.eye(6) * 2.0
     m1 = engine.native_mass(A, 6, 'cpu')
     assert engine.native_mass(A, 6, 'cpu') is m1
+    assert m1.ref() is not None and m1.kind == 2
     A.mul_(2.0)                                              # version bump
     m2 = engine.native_mass(A, 6, 'cpu')
     assert m2 is not m1
