@@ -27,8 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, C_PER_GPU, S, L, EPS = 1024, 256, 1000, 10, 0.05
-WARP_INST_PER_LAUNCH = 1076063104          # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
-                                           # (profiles/r1i_prof_hmc_run.summary.txt)
+WARP_INST_PER_LAUNCH = 836294520           # config 2, E=4 K=1 geometry: ncu smsp__inst_executed.sum of one launch
+                                           # (profiles/r2_prof_hmc_run.summary.txt; 1076063104 before the packed fp32x2 leapfrog)
 METRIC = 'leapfrog-steps x chains / sec'
 UNIT = 'chain-steps/s'
 REFERENCE_ARM_BUDGET_S = 75.0              # wall-clock bound of `--impl reference` whatever --steps says
@@ -414,7 +414,7 @@ def other_configs(dev, rank, world):
         explicit_binding_const=10, sampler=hb.Sampler.RMHMC, integrator=hb.Integrator.EXPLICIT,
         metric=hb.Metric.SOFTABS, rng='philox', seed=2, chain_offset=rank * C3), reps=3)
     out['config3'] = {'workload': 'explicit RMHMC, 2-D funnel, softabs 1e6, omega=10, jitter 1e-3, 512 chains/GPU, '
-                                  'L=10, eps=0.05, S=200', 'kernel': 'rmhmc_run_kernel<2>', 'bound': 'latency/SFU',
+                                  'L=10, eps=0.05, S=200', 'kernel': 'rmhmc2_quad_kernel', 'bound': 'latency (serial recurrence of 3L+3 stages)',
                       'kernel_ms': ms, 'value': C3 * S3 * 10 / (ms * 1e-3), 'unit': UNIT,
                       'accept_rate': float(res.accepted.float().mean()),
                       'log_prob_error_rate': float(res.diverged.float().mean())}
@@ -754,13 +754,13 @@ def run_b200_arm(args, rank, world, local_rank):
             'roofline': {'bound': 'hbm', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1,PHILOX,NUTS=0>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
-                         # profiles/r1i_prof_hmc_run.summary.txt (1.14 MB read + 990.40 MB written)
-                         'traffic': 991.5e6, 'peak_source': peak_src,
+                         # profiles/r2_prof_hmc_run.summary.txt (1.20 MB read + 989.99 MB written)
+                         'traffic': 991.2e6, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'kernel_ms': t_kernel_ms,
                          'note': 'fused trajectory kernel: L=10 steps per 4*D bytes written, fp32-issue bound by design; '
                                  'see roofline_streaming for the HBM-bound form'},
             # what actually bounds the fused kernel: warp-instruction issue.  Instructions per launch are static for this
-            # geometry (ncu smsp__inst_executed.sum, profiles/r1i_prof_hmc_run.summary.txt); time is measured live.
+            # geometry (ncu smsp__inst_executed.sum, profiles/r2_prof_hmc_run.summary.txt); time is measured live.
             'roofline_issue': {'bound': 'issue', 'kernel': 'hmc_run_kernel<ISO,NONE,E=4,K=1>',
                                'warp_instructions_per_launch': WARP_INST_PER_LAUNCH,
                                'achieved': WARP_INST_PER_LAUNCH / (t_kernel_ms * 1e-3) / 1e9,
