@@ -119,6 +119,9 @@ _PROTOS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     'hmcx_mlp_predict': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'hmcx_split_leapfrog': (C.c_int, [C.POINTER(TargetStruct), C.POINTER(MassStruct), C.POINTER(RngStruct), C.c_int32,
+                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     'hmcx_mlp_packed_x_bytes': (C.c_size_t, [C.POINTER(TargetStruct)]),
     'hmcx_mlp_pack_x': (C.c_int, [C.POINTER(TargetStruct), C.c_void_p, C.c_void_p]),
 }

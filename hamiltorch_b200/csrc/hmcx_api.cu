@@ -21,7 +21,9 @@ int dense_rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_const_
                     float*, int32_t*, float*, cudaStream_t);
 int mlp_split_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, int, const float*,
                   float*, float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
-                  cudaStream_t);
+                  cudaStream_t, const float*, float*, float*);
+int mlp_leapfrog(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, int, double, const float*, const float*, float*,
+                 int, int, int, float*, float*, cudaStream_t);
 int mlp_grad_log_prob(const hmcx_target_t*, const float*, int, int, int, float*, float*, cudaStream_t);
 int mlp_predict(const hmcx_target_t*, const float*, int, int, float*, float*, cudaStream_t);
 int small_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*, float*,
@@ -130,7 +132,7 @@ int hmcx_hmc_run_sink(const hmcx_target_t* target, const hmcx_mass_t* mass, cons
     if (target->kind == HMCX_TARGET_MLP)      // un-split Bayesian NN == sample_model (samplers.py:1261)
         return hmcx::mlp_split_run(target, mass, rng, nuts, HMCX_SCHEME_PLAIN, q_init, q_cur, eps, C, ld, L,
                                    num_samples, burn, iter_begin, iter_end, samples_out, accept_out, diverged_out,
-                                   ham_out, num_rejected, (cudaStream_t)stream);
+                                   ham_out, num_rejected, (cudaStream_t)stream, nullptr, nullptr, nullptr);
     return HMCX_ERR_UNSUPPORTED;
 }
 
@@ -143,7 +145,16 @@ int hmcx_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const h
     if (target->kind != HMCX_TARGET_MLP) return HMCX_ERR_UNSUPPORTED;
     return hmcx::mlp_split_run(target, mass, rng, nuts, scheme, q_init, q_cur, eps, C, ld, L, num_samples, burn,
                                iter_begin, iter_end, samples_out, accept_out, diverged_out, ham_out, num_rejected,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+
+int hmcx_split_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t scheme,
+                        double step_size, const float* q_in, const float* p_in, float* eps, int32_t C, int32_t ld, int32_t L,
+                        float* q_traj, float* p_traj, void* stream) {
+    if (!target || !rng) return HMCX_ERR_INVALID_ARG;
+    if (target->kind != HMCX_TARGET_MLP) return HMCX_ERR_UNSUPPORTED;
+    return hmcx::mlp_leapfrog(target, mass, rng, scheme, step_size, q_in, p_in, eps, C, ld, L, q_traj, p_traj,
+                              (cudaStream_t)stream);
 }
 
 int hmcx_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_rng_t* rng, const float* q_init,

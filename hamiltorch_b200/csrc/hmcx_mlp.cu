@@ -1064,6 +1064,10 @@ struct MlpRunArgs {
     uint8_t* diverged;
     float* ham;
     int32_t* num_rejected;
+    // stand-alone samplers.leapfrog with a SPLITTING integrator (:494-603): the momentum is given, the trajectory recorded
+    const float* p_given;         // [C, ld] or NULL
+    float* q_traj;                // [L, C, ld]: params after every step (ret_params)
+    float* p_traj;                // [L, C, ld]: momentum after every step (ret_momenta)
 };
 
 template <int CS>
@@ -1092,7 +1096,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
 
     for (int i = tid; i < m.Dp; i += MLP_THREADS) { q[i] = i < D ? a.q_cur[row + i] : 0.0f; p[i] = 0.0f; g[i] = 0.0f; }
     __syncthreads();
-    float lp_cur = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
+    float lp_cur = a.p_given ? 0.0f : mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
 
     float eps = a.eps[c];
     double h_bar = 0.0, eps_bar = 1.0;
@@ -1221,8 +1225,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * a.C + c];
         const float half = mul(0.5f, eps);
-        // ---- gibbs ----
-        for (int v = tid; 4 * v < a.ld; v += MLP_THREADS) {
+        // ---- gibbs (or the caller's momentum) ----
+        if (a.p_given) for (int i = tid; i < D; i += MLP_THREADS) p[i] = a.p_given[row + i];
+        else for (int v = tid; 4 * v < a.ld; v += MLP_THREADS) {
             float z[4];
             if (a.rng_mode == HMCX_RNG_INJECTED) ld4_stream(a.normals + ((size_t)(n - a.it0) * a.C + c) * a.ld + 4 * v, z);
             else philox_normal4(a.seed, chain_id, (uint64_t)n, (uint32_t)v, z);
@@ -1245,7 +1250,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             }
         }
         __syncthreads();
-        const float kin0 = kinetic();
+        const float kin0 = a.p_given ? 0.0f : kinetic();
         // ---- trajectory: every integrator schedule is a sequence of steps [drift] grad(split) kick [drift] ----
         // ONE loop around ONE inlined copy of the gradient evaluation (nine call sites, one per schedule position, made
         // each instantiation of this kernel ~100k instructions = 1.6 MB of code and minutes of ptxas; an out-of-line copy
@@ -1291,12 +1296,20 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                 if (post) drift(cd);
                 if (fused_kick) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
                 TC_MARK(17);
+                if (a.q_traj && !plain && jj == 0 && lead) {              // a leapfrog step just ended (:546-547, :570-571, :600-601)
+                    const size_t o = ((size_t)(t / twoM) * a.C + c) * a.ld;
+                    for (int i = tid; i < a.ld; i += MLP_THREADS) {
+                        a.q_traj[o + i] = i < D ? q[i] : 0.0f;
+                        a.p_traj[o + i] = i < D ? p[i] : 0.0f;
+                    }
+                }
             }
             if (plain) {                                                  // p - half*g == p + (-half)*g exactly
                 if (fused_kick) { kick_partials(-half); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
                 else kick(-half);
             }
         }
+        if (a.p_given) break;                                             // stand-alone leapfrog: no Hamiltonian, no MH
         // ---- Hamiltonians + MH ----
         const float lp_new = mlp_log_prob<CS>(m, q, tile, sred, -1, nullptr, cc, &s_xchg, tc);
         const float kin1 = kinetic();
@@ -1358,7 +1371,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         }
         __syncthreads();
     }
-    if (tid == 0 && lead) {
+    if (tid == 0 && lead && !a.p_given) {
         a.eps[c] = eps;
         if (a.nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
         if (a.num_rejected) a.num_rejected[c] += rejected;
@@ -1546,8 +1559,9 @@ static int prepare_smem(Kern kern, size_t bytes) {
 int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, const hmcx_nuts_t* nuts,
                   int scheme, const float* q_init, float* q_cur, float* eps, int C, int ld, int L, int S, int burn,
                   int it0, int it1, float* samples, uint8_t* accept, uint8_t* diverged, float* ham,
-                  int32_t* num_rejected, cudaStream_t st) {
+                  int32_t* num_rejected, cudaStream_t st, const float* p_given, float* q_traj, float* p_traj) {
     MlpRunArgs a = {};
+    a.p_given = p_given; a.q_traj = q_traj; a.p_traj = p_traj;
     int rc = fill_mlp(target, a.m);
     if (rc != HMCX_OK) return rc;
     const int mk = mass ? mass->kind : HMCX_MASS_NONE;
@@ -1559,7 +1573,7 @@ int mlp_split_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     if (scheme < HMCX_SCHEME_PLAIN || scheme > HMCX_SCHEME_SPLIT_KMID) return HMCX_ERR_INVALID_ARG;
     if ((scheme == HMCX_SCHEME_SPLIT_SYM || scheme == HMCX_SCHEME_SPLIT_KMID) && a.m.M < 2) return HMCX_ERR_INVALID_ARG;  // :497-498
     if (rng->mode == HMCX_RNG_INJECTED) {
-        if (!rng->normals || !rng->log_uniforms) return HMCX_ERR_INVALID_ARG;
+        if (!p_given && (!rng->normals || !rng->log_uniforms)) return HMCX_ERR_INVALID_ARG;
         if (scheme == HMCX_SCHEME_SPLIT_RAND && !rng->perms) return HMCX_ERR_INVALID_ARG;
     } else if (rng->mode != HMCX_RNG_PHILOX) {
         return HMCX_ERR_INVALID_ARG;
@@ -1639,6 +1653,18 @@ int mlp_predict(const hmcx_target_t* target, const float* samples, int S, int ld
     if (rc != HMCX_OK) return rc;
     mlp_predict_kernel<<<S, MLP_THREADS, smem, st>>>(m, samples, ld, pred_out, log_prob_out);
     return cuda_status();
+}
+
+// stand-alone samplers.leapfrog with Integrator.SPLITTING / _RAND / _KMID (:494-603) over C chains: one "iteration" of the run
+// kernel with the momentum given, no Hamiltonian and no MH; q_traj / p_traj [L, C, ld] take the state after every step
+int mlp_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, int scheme, double step_size,
+                 const float* q_in, const float* p_in, float* eps, int C, int ld, int L, float* q_traj, float* p_traj,
+                 cudaStream_t st) {
+    if (!p_in || !q_traj || !p_traj || scheme == HMCX_SCHEME_PLAIN) return HMCX_ERR_INVALID_ARG;
+    hmcx_nuts_t no_nuts = {};
+    no_nuts.step_size_init = step_size;                        // the Python double the drifts divide (:513, :558)
+    return mlp_split_run(target, mass, rng, &no_nuts, scheme, q_in, const_cast<float*>(q_in), eps, C, ld, L, 1, 0, 0, 1,
+                         nullptr, nullptr, nullptr, nullptr, nullptr, st, p_in, q_traj, p_traj);
 }
 
 // packed X operands of the tensor-core path (hmcx_mlp_t.x_packed): size in floats (0: the stack does not use it) / build

@@ -261,6 +261,39 @@ def leapfrog(target, q, p, steps, step_size, inv_mass=None, return_trajectory=Fa
     return q_out[:, :D], p_out[:, :D]
 
 
+def split_leapfrog(targets, q, p, steps, step_size, scheme, inv_mass=None, perms=None, seed=0, device=None):
+    """Batched samplers.leapfrog with Integrator.SPLITTING / SPLITTING_RAND / SPLITTING_KMID (:494-603) on the list of
+    data-split closures ``targets``.  q, p: (C, D) or (D,).  Returns the (L, C, D) trajectories of params and momentum
+    (the state after every step).  SPLITTING_RAND: ``perms`` (C, M) injects the call's randperm(M) (:550), else Philox."""
+    N.require_cuda()
+    lib = N.load_library()
+    device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
+    nt = targets if isinstance(targets, NativeTarget) else NativeTarget(targets, device)
+    D, ld = nt.dim, N.padded_ld(nt.dim)
+    if isinstance(inv_mass, list) or (torch.is_tensor(inv_mass) and inv_mass.dim() != 1):
+        raise NotImplementedError('split leapfrog: inv_mass None or 1-D')
+    nm = native_mass(inv_mass, D, device)
+    qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
+    Cn, L = qd.shape[0], int(steps)
+    eps = _eps_vector(step_size, Cn, device)
+    rng = N.RngStruct()
+    keep = []
+    if perms is not None:
+        pm = perms.detach().to(device=device, dtype=torch.int32).reshape(Cn, nt.num_splits).contiguous()
+        rng.mode, rng.perms = N.RNG_INJECTED, pm.data_ptr()
+        keep.append(pm)
+    else:
+        rng.mode, rng.seed = N.RNG_PHILOX, int(seed)
+    q_traj = torch.zeros((L, Cn, ld), dtype=torch.float32, device=device)
+    p_traj = torch.zeros_like(q_traj)
+    with torch.cuda.device(device):
+        rc = lib.hmcx_split_leapfrog(nt.ref(), nm.ref(), C.byref(rng), int(scheme), float(step_size), N.ptr(qd), N.ptr(pd),
+                                     N.ptr(eps), Cn, ld, L, N.ptr(q_traj), N.ptr(p_traj), N.stream_ptr(device))
+    N.check(rc, 'hmcx_split_leapfrog')
+    torch.cuda.current_stream(device).synchronize()
+    return q_traj[..., :D], p_traj[..., :D]
+
+
 def hamiltonian(target, q, p, inv_mass=None, device=None):
     """Batched samplers.hamiltonian (sampler=HMC).  Returns (H (C,), nonfinite_flags (C,) uint8)."""
     N.require_cuda()

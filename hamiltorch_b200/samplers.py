@@ -111,10 +111,12 @@ def leapfrog(params, momentum, log_prob_func, steps=10, step_size=0.1, jitter=0.
              softabs_const=1e6, explicit_binding_const=100, fixed_point_threshold=1e-20,
              fixed_point_max_iterations=6, jitter_max_tries=10, inv_mass=None, ham_func=None, sampler=Sampler.HMC,
              integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, store_on_GPU=True, debug=False, pass_grad=None,
-             *, rng_uniforms=None):
-    """samplers.py:205-606.  Plain HMC branch on the GPU; returns ``(ret_params, ret_momenta)``: two lists of
-    ``steps`` tensors, the last momentum carrying the half-step correction (:302).  ``params`` may be (D,) as in
-    the reference or (C, D) for C chains at once."""
+             *, rng_uniforms=None, rng_perms=None):
+    """samplers.py:205-606: plain HMC (:269-304), the SPLITTING integrators on a list of data-split closures (:465-603)
+    and sampler=RMHMC (:305-462) on the GPU; returns ``(ret_params, ret_momenta)``: two lists of ``steps`` tensors (plain
+    HMC: the last momentum carries the half-step correction, :302).  ``params`` may be (D,) as in the reference or (C, D)
+    for C chains at once.  ``rng_uniforms`` / ``rng_perms`` inject the jitter draws (RMHMC) / the randperm of
+    SPLITTING_RAND instead of consuming torch's generator."""
     _require_target(log_prob_func)
     if sampler == Sampler.HMC and integrator not in _SPLIT_INTEGRATORS:
         if pass_grad is not None:
@@ -130,7 +132,27 @@ def leapfrog(params, momentum, log_prob_func, steps=10, step_size=0.1, jitter=0.
             raise RuntimeError('For splitting log_prob_func must be list of functions')       # :466-467
         if pass_grad is not None:
             raise RuntimeError('Passing user-determined gradients not implemented for splitting')
-        raise NotImplementedError('stand-alone split leapfrog: use sample_split_model')
+        M = len(log_prob_func)
+        if M == 1 and integrator in (Integrator.SPLITTING, Integrator.SPLITTING_KMID):
+            raise RuntimeError('For symmetric splitting log_prob_func must be list of functions greater than '
+                               'length 1')                                                      # :497-498, :577-578
+        if integrator not in (Integrator.SPLITTING, Integrator.SPLITTING_RAND, Integrator.SPLITTING_KMID):
+            raise NotImplementedError()
+        scheme = {Integrator.SPLITTING: N.SCHEME_SPLIT_SYM, Integrator.SPLITTING_RAND: N.SCHEME_SPLIT_RAND,
+                  Integrator.SPLITTING_KMID: N.SCHEME_SPLIT_KMID}[integrator]
+        perms = None
+        if integrator == Integrator.SPLITTING_RAND:
+            C_ = 1 if params.dim() == 1 else params.shape[0]
+            if rng_perms is not None:                           # (C, M) injected permutations
+                perms = rng_perms
+            else:                                               # the reference's draw: torch.randperm(M) per call (:550)
+                perms = torch.stack([torch.randperm(M) for _ in range(C_)])
+        q_traj, p_traj = engine.split_leapfrog(log_prob_func, params, momentum, steps, step_size, scheme,
+                                               inv_mass=inv_mass, perms=perms)
+        if params.dim() == 1:
+            q_traj, p_traj = q_traj[:, 0], p_traj[:, 0]
+        dev = params.device
+        return [t.to(dev) for t in q_traj.unbind(0)], [t.to(dev) for t in p_traj.unbind(0)]
     if sampler == Sampler.RMHMC:
         if pass_grad is not None:
             raise RuntimeError('Passing user-determined gradients not implemented for RMHMC')  # :310, :390-391

@@ -306,6 +306,17 @@ int hmcx_mlp_predict(const hmcx_target_t* target, const float* samples, int32_t 
                      float* pred_out, float* log_prob_out, void* stream);
 
 /*
+ * hmcx_split_leapfrog == samplers.leapfrog called directly with Integrator.SPLITTING / SPLITTING_RAND / SPLITTING_KMID on the
+ * list define_split_model_log_prob returns (samplers.py:494-603): L steps from (q_in, p_in) [C, ld]; q_traj / p_traj
+ * [L, C, ld] receive params and momentum after EVERY step (the reference's ret_params / ret_momenta lists).  eps [C] =
+ * (float)step_size per chain; step_size is the Python double the drifts divide before rounding (:513, :558).
+ * SPLITTING_RAND takes its one randperm(M) per call (:550) from rng->perms [C, M] (INJECTED) or from the Philox PERM stream.
+ */
+int hmcx_split_leapfrog(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t scheme,
+                        double step_size, const float* q_in, const float* p_in, float* eps, int32_t C, int32_t ld,
+                        int32_t L, float* q_traj, float* p_traj, void* stream);
+
+/*
  * Packed X operands of the BNN tensor-core path (hmcx_mlp_t.x_packed).  The data matrix of define_model_log_prob
  * (samplers.py:1093-1201) never changes during a run, so its tf32 hi / lo split and the two tcgen05 operand layouts
  * (forward: rows x inputs, backward: inputs x rows) are built once per target:

@@ -267,6 +267,35 @@ def run_rmhmc_case(ref, name, case):
           'LogProbError', [int(out['diverged_%d' % c].sum()) for c in range(len(case['seeds']))])
 
 
+def run_split_standalone(ref):
+    """Reference outputs of samplers.leapfrog called directly with a SPLITTING integrator (:494-603) on the descriptor list
+    of the split Bayesian-NN cases: ret_params / ret_momenta after every step; the randperm(M) of SPLITTING_RAND (:550) is
+    recorded."""
+    out = {}
+    for name in ('mlp_split_sym', 'mlp_split_rand', 'mlp_split_kmid', 'mlp_deep_tanh_mass'):
+        case = cases.mlp_cases()[name]
+        model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+        D = sum(p.numel() for p in model.parameters())
+        M = case['num_splits']
+        torch.manual_seed(41)
+        q = ref.util.flatten(model).detach().clone() + 0.05 * torch.randn(D)
+        p = torch.randn(D)
+        st = torch.get_rng_state()
+        qs, ps = ref.samplers.leapfrog(q.clone().requires_grad_(), p.clone(), descs, steps=3, step_size=case['step_size'],
+                                       inv_mass=inv_mass, sampler=ref.Sampler.HMC,
+                                       integrator=getattr(ref.Integrator, case['scheme']))
+        torch.set_rng_state(st)
+        perm = torch.randperm(M)
+        oq, op = O.leapfrog_split(descs, q, p, 3, case['step_size'], inv_mass, SCHEME_ID[case['scheme']],
+                                  perm if case['scheme'] == 'SPLITTING_RAND' else None)
+        assert torch.equal(torch.stack([t.detach() for t in qs]), torch.stack(oq)), name
+        out[name + '.q0'], out[name + '.p0'], out[name + '.perm'] = q.numpy(), p.numpy(), perm.numpy()
+        out[name + '.q_traj'] = torch.stack([t.detach() for t in qs]).numpy()
+        out[name + '.p_traj'] = torch.stack([t.detach() for t in ps]).numpy()
+        print('split standalone', name, out[name + '.q_traj'].shape)
+    np.savez_compressed(os.path.join(OUT, 'split_standalone.npz'), **out)
+
+
 def run_rm_standalone(ref):
     """Reference outputs of leapfrog(sampler=RMHMC) -- (ret_params, ret_momenta[, params_copy, momentum_copy]) -- and of
     hamiltonian(sampler=RMHMC) at the start point; the jitter stream torch.rand(D) of the call is recorded."""
@@ -329,6 +358,8 @@ def main():
                 run_rmhmc_case(ref, name, case)
         if not only or 'rmhmc_standalone' in only:
             run_rm_standalone(ref)
+    if 'mlp' in which and (not only or 'split_standalone' in only):
+        run_split_standalone(ref)
 
 
 if __name__ == '__main__':

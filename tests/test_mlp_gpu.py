@@ -208,3 +208,39 @@ def test_pinned_cluster_size_is_bit_reproducible_across_chain_counts():
     a, b = run(3), run(big)
     torch.cuda.synchronize()
     assert torch.equal(a.samples, b.samples[:3]) and torch.equal(a.accepted, b.accepted[:3])
+
+
+# ----------------------------------------------------------------------------------------------------------
+# stand-alone samplers.leapfrog with a SPLITTING integrator (samplers.py:494-603)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['mlp_split_sym', 'mlp_split_rand', 'mlp_split_kmid', 'mlp_deep_tanh_mass'])
+def test_standalone_split_leapfrog_matches_the_reference(name):
+    from oracle.gen_golden import build_mlp_case
+    case = cases.mlp_cases()[name]
+    d = np.load(os.path.join(GOLD, 'split_standalone.npz'))
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(case)
+    q, p = torch.from_numpy(d[name + '.q0']), torch.from_numpy(d[name + '.p0'])
+    integ = getattr(hb.Integrator, case['scheme'])
+    qs, ps = hb.leapfrog(q, p, descs, steps=3, step_size=case['step_size'], inv_mass=inv_mass, sampler=hb.Sampler.HMC,
+                         integrator=integ, rng_perms=torch.from_numpy(d[name + '.perm'])[None])
+    assert len(qs) == len(ps) == 3 and tuple(qs[0].shape) == (q.numel(),)
+    scale_q, scale_p = np.abs(d[name + '.q_traj']).max(), np.abs(d[name + '.p_traj']).max()
+    assert np.abs(torch.stack(qs).cpu().numpy() - d[name + '.q_traj']).max() <= MLP_RTOL * scale_q
+    assert np.abs(torch.stack(ps).cpu().numpy() - d[name + '.p_traj']).max() <= MLP_RTOL * scale_p
+    # batched: C chains at once, chain c == the single call
+    qb, pb = q.repeat(3, 1), p.repeat(3, 1)
+    qs3, ps3 = hb.leapfrog(qb, pb, descs, steps=3, step_size=case['step_size'], inv_mass=inv_mass, sampler=hb.Sampler.HMC,
+                           integrator=integ, rng_perms=torch.from_numpy(d[name + '.perm'])[None].repeat(3, 1))
+    assert tuple(qs3[0].shape) == (3, q.numel())
+    assert torch.equal(qs3[-1][1].cpu(), qs[-1].cpu()) and torch.equal(ps3[-1][2].cpu(), ps[-1].cpu())
+
+
+def test_standalone_split_leapfrog_argument_errors():
+    d = cases.mlp_cases()['mlp_split_sym']
+    from oracle.gen_golden import build_mlp_case
+    model, x, y, descs, inv_mass, tau_t = build_mlp_case(d)
+    q = hb.util.flatten(model).detach()
+    with pytest.raises(RuntimeError):                             # :466-467
+        hb.leapfrog(q, torch.zeros_like(q), descs[0], sampler=hb.Sampler.HMC, integrator=hb.Integrator.SPLITTING)
+    with pytest.raises(RuntimeError):                             # :497-498
+        hb.leapfrog(q, torch.zeros_like(q), descs[:1], sampler=hb.Sampler.HMC, integrator=hb.Integrator.SPLITTING)
