@@ -617,7 +617,7 @@ __device__ __forceinline__ void tc_prefetch_y(const MlpDev& m, float* tile, int 
 // k-step: W1_hi . [X_hi | X_lo]^T (N = 128, the two products land in columns [0,64) and [64,128)) and W1_lo . X_hi^T
 // (N = 64, accumulated onto [0,64)); the epilogue adds the two column blocks.  The B descriptors differ only in the
 // start-address field (bits 0-13, 16-byte units), so a k-step is an integer add.
-__device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, const float* xop) {
+__device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, const float* xop, uint32_t leader) {
     const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * TC_TR), idesc1 = make_idesc_tf32(TC_H, TC_TR);
     constexpr uint32_t B_LBO = (2 * TC_TR / 8) * 128;
     uint64_t b = make_kmajor_desc(smem_u32(xop), B_LBO, 128);
@@ -626,15 +626,15 @@ __device__ __forceinline__ void tc_issue_fwd(const MlpDev& m, const TcCtx& tc, c
     uint32_t a_hi = tc.tmem + TC_COL_W1HI, a_lo = tc.tmem + TC_COL_W1LO;
     tc_fence_after();
     for (int k = 0; k < ksteps; ++k) {
-        umma_tf32_ta(d, a_hi, b, idesc2, k != 0);
-        umma_tf32_ta(d, a_lo, b, idesc1, true);
+        umma_tf32_ta_p(d, a_hi, b, idesc2, k != 0, leader);
+        umma_tf32_ta_p(d, a_lo, b, idesc1, true, leader);
         a_hi += 8; a_lo += 8; b += (2 * B_LBO) >> 4;
     }
-    umma_commit(tc.barH);
+    umma_commit_p(tc.barH, leader);
 }
 
 // dW1 (+)= dH^T . X   (A from tensor memory; completion -> barW): dH_hi . [X_hi | X_lo] (N = 2 n0) and dH_lo . X_hi (N = n0)
-__device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, const float* xop, bool accumulate) {
+__device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, const float* xop, bool accumulate, uint32_t leader) {
     const int n0 = m.n[0];
     const uint32_t idesc2 = make_idesc_tf32(TC_H, 2 * n0), idesc1 = make_idesc_tf32(TC_H, n0);
     const uint32_t B_LBO = (uint32_t)(2 * n0 / 8) * 128;
@@ -644,11 +644,11 @@ __device__ __forceinline__ void tc_issue_bwd(const MlpDev& m, const TcCtx& tc, c
     tc_fence_after();
 #pragma unroll
     for (int k = 0; k < TC_TR / 8; ++k) {
-        umma_tf32_ta(d, a_hi, b, idesc2, accumulate || k != 0);
-        umma_tf32_ta(d, a_lo, b, idesc1, true);
+        umma_tf32_ta_p(d, a_hi, b, idesc2, accumulate || k != 0, leader);
+        umma_tf32_ta_p(d, a_lo, b, idesc1, true, leader);
         a_hi += 8; a_lo += 8; b += (2 * B_LBO) >> 4;
     }
-    umma_commit(tc.barW);
+    umma_commit_p(tc.barW, leader);
 }
 
 // v[i] = this lane's value for row i; returns the sum over the warp's 32 lanes for row (lane >> 1)
@@ -716,10 +716,10 @@ __device__ __forceinline__ void tc_forward_tile(const MlpDev& m, const float* q,
                                                 float (&act)[16], int buf) {
     const int nL = m.n[2], lane = threadIdx.x & 31;
     if (threadIdx.x >= 32 && threadIdx.x < 64) asm volatile("cp.async.wait_group 0;" ::: "memory");    // the targets
-    if (threadIdx.x == 0) {
-        mbar_wait(tc.barF[buf], tc.parF[buf]);                    // this tile's forward operand has landed
+    if (threadIdx.x < 32) {                                       // warp 0 issues, warp-uniformly (hmcx_umma.cuh): ~65 instead of
+        mbar_wait(tc.barF[buf], tc.parF[buf]);                    // ~115 cycles per MMA.  This tile's forward operand has landed
         TC_MARK(3);
-        tc_issue_fwd(m, tc, tile + (buf ? m.tc_f1 : m.tc_f0));
+        tc_issue_fwd(m, tc, tile + (buf ? m.tc_f1 : m.tc_f0), elect_one());
     }
     tc.parF[buf] ^= 1;
     TC_MARK(4);
@@ -816,9 +816,9 @@ __device__ __forceinline__ void tc_backprop_rows(const MlpDev& m, const float* q
         TC_MARK(9);
         __syncthreads();
         TC_MARK(10);
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
             mbar_wait(tc.barB, tc.parB);                          // the backward operand has landed (long ago)
-            tc_issue_bwd(m, tc, tile + m.tc_b, done != 0);
+            tc_issue_bwd(m, tc, tile + m.tc_b, done != 0, elect_one());
         }
         tc.parB ^= 1;
         ++done;

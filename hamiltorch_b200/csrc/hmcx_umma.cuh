@@ -76,6 +76,37 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, u
         :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 
+// ---- warp-uniform issue ------------------------------------------------------------------------------------------
+// tcgen05.mma takes its descriptors from UNIFORM registers.  Issued from `if (threadIdx.x == 0)` -- divergent control flow --
+// every operand of every instruction goes through an R2UR first, and the issue rate is ~112-120 cycles per MMA whatever
+// its size (scripts/bench_cuda/umma_rate.cu: N = 64, 128 and 256 all cost the same).  Issued by a WHOLE warp in warp-uniform
+// control flow with only the instruction predicated on the elected lane, the descriptor arithmetic stays in uniform
+// registers: 65 cycles per M=128 N=128 K=8 tf32 MMA (its floor is 64), 64 per MMA for the hi|lo N / N/2 pattern.
+__device__ __forceinline__ uint32_t elect_one() {            // 1 in exactly one lane of a converged warp
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.b32 %0, 1, 0, e;\n\t}\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate,
+                                            uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ta_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               bool accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t mbar, uint32_t leader) {     // by the lane that issued the MMAs
+    asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                 :: "r"(mbar), "r"(leader) : "memory");
+}
+
 // 32 lanes x 16 columns of 32-bit cells: thread (lane) <-> TMEM lane, register i <-> column i
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
