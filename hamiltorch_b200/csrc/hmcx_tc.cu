@@ -219,12 +219,34 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t 
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+// the 2 x 2 cluster form (multicast operands): grid.x and grid.y even
+template <typename... KArgs, typename... Args>
+static void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+static bool dense_cluster_ok(dim3 grid, int BN) {
+    // opt-in (HMCX_DENSE_CLUSTER=1): measured on B200, the multicast form does NOT beat one CTA per tile -- these GEMMs are
+    // bound by SHARED-MEMORY bandwidth (3xTF32: every MMA re-reads 8 KB of operands per 64 cycles = 128 B/clk, the SM's
+    // limit, plus the TMA writes), not by L2 -> SM traffic; see DESIGN.md 3.7
+    static const bool on = [] { const char* e = getenv("HMCX_DENSE_CLUSTER"); return e && e[0] == '1'; }();
+    return on && BN >= 64 && (grid.x % 2) == 0 && (grid.y % 2) == 0;
+}
 
 // Prologue shared by the dense kernels: mbarrier ring + accumulator columns in tensor memory (warp 0 allocates).
-template <int BN, int ST>
+template <int BN, int ST, bool CL = false>
 __device__ __forceinline__ uint32_t dense_prologue(uint64_t* s_full, uint64_t* s_empty, uint64_t* s_done, uint32_t* s_tmem) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+        // CL (2 x 2 cluster, multicast operands): a stage is written by this CTA, its row peer and its column peer, so it is
+        // free only when the MMA warps of all three have released it
+        for (int s = 0; s < ST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), CL ? 3 : 1); }
         mbar_init(smem_u32(s_done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -234,6 +256,7 @@ __device__ __forceinline__ uint32_t dense_prologue(uint64_t* s_full, uint64_t* s
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL) cluster_sync_all();                                // every CTA's barriers exist before a peer signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     return *s_tmem;
 }
@@ -241,23 +264,38 @@ __device__ __forceinline__ uint32_t dense_prologue(uint64_t* s_full, uint64_t* s
 // The warp-specialised main loop shared by the dense kernels: thread 0 = TMA producer (1-D bulk copies of the packed
 // hi|lo operand blocks into an ST-stage ring), thread 32 = MMA issuer (three tf32 UMMAs per 8-wide k-step: hi*hi +
 // hi*lo + lo*hi, fp32 accumulators in tensor memory), tcgen05.commit releasing stages / signalling `s_done`.
-template <int BN, int ST>
+// CL = true: launched as 2 x 2 thread-block clusters over (column tile, row tile).  The two CTAs of a cluster ROW share the
+// A block (same chains), the two of a cluster COLUMN share the B block (same columns of the matrix): every CTA fetches ONE
+// half (hi or lo) of its A block and of its B block and MULTICASTS it to both sharers, so each operand byte leaves L2 once
+// per cluster instead of once per CTA -- half the L2 -> SM traffic that bounded these kernels (512 MB per launch at
+// D = 2048 x 1024 chains = 8.4 TB/s).
+template <int BN, int ST, bool CL = false>
 __device__ __forceinline__ void dense_mainloop(float* smem, uint64_t* s_full, uint64_t* s_empty, uint64_t* s_done_p,
                                                uint32_t tmem, const float* __restrict__ QpIn,
                                                const float* __restrict__ Ppack, int tile_m, int tile_n, int kchunks) {
     constexpr int A_BLK = TC_M * TC_KC, B_BLK = BN * TC_KC;
     constexpr uint32_t STAGE_BYTES = (uint32_t)dense_stage_floats(BN) * 4u;
     uint64_t& s_done = *s_done_p;
+    const uint32_t cx = CL ? cluster_ctaid_x() : 0, cy = CL ? cluster_ctaid_y() : 0;       // cluster rank = cx + 2 cy
+    const uint16_t mask_row = (uint16_t)(0x3u << (2 * cy)), mask_col = (uint16_t)((1u << cx) | (1u << (cx + 2)));
     if (threadIdx.x == 0) {
-        // ===== TMA producer: 4 bulk copies per stage (A hi, A lo, B hi, B lo are adjacent pairs in global memory) =====
+        // ===== TMA producer: bulk copies per stage (A hi, A lo, B hi, B lo are adjacent pairs in global memory) =====
         for (int i = 0; i < kchunks; ++i) {
             const int s = i % ST;
             mbar_wait(smem_u32(&s_empty[s]), ((i / ST) & 1) ^ 1);
             const uint32_t full = smem_u32(&s_full[s]);
-            mbar_expect_tx(full, STAGE_BYTES);
+            mbar_expect_tx(full, STAGE_BYTES);                  // (a peer's multicast may complete bytes before this: fine)
             float* st = smem + (size_t)s * dense_stage_floats(BN);
-            bulk_g2s(smem_u32(st), QpIn + pack_block_base(tile_m, i, 0, kchunks, TC_M), 2 * A_BLK * 4, full);
-            bulk_g2s(smem_u32(st + 2 * A_BLK), Ppack + pack_block_base(tile_n, i, 0, kchunks, BN), 2 * B_BLK * 4, full);
+            if (CL) {
+                // my half of the A block (cx = 0: hi, 1: lo) to both CTAs of my row; my half of the B block (cy) to my column
+                bulk_g2s_multicast(smem_u32(st + cx * A_BLK), QpIn + pack_block_base(tile_m, i, (int)cx, kchunks, TC_M),
+                                   A_BLK * 4, full, mask_row);
+                bulk_g2s_multicast(smem_u32(st + 2 * A_BLK + cy * B_BLK), Ppack + pack_block_base(tile_n, i, (int)cy, kchunks, BN),
+                                   B_BLK * 4, full, mask_col);
+            } else {
+                bulk_g2s(smem_u32(st), QpIn + pack_block_base(tile_m, i, 0, kchunks, TC_M), 2 * A_BLK * 4, full);
+                bulk_g2s(smem_u32(st + 2 * A_BLK), Ppack + pack_block_base(tile_n, i, 0, kchunks, BN), 2 * B_BLK * 4, full);
+            }
         }
     } else if ((threadIdx.x >> 5) == 1) {
         // ===== MMA issuer: the WHOLE warp runs the loop (warp-uniform: descriptors in uniform registers), the elected lane's
@@ -281,17 +319,20 @@ __device__ __forceinline__ void dense_mainloop(float* smem, uint64_t* s_full, ui
                 umma_tf32_p(tmem, ah, bl, idesc, true, leader);
                 umma_tf32_p(tmem, al, bh, idesc, true, leader);
             }
-            umma_commit_p(smem_u32(&s_empty[s]), leader);       // frees the stage when these MMAs have read it
+            // frees the stage when these MMAs have read it -- in every CTA that writes into it
+            if (CL) umma_commit_multicast_p(smem_u32(&s_empty[s]), (uint16_t)(mask_row | mask_col), leader);
+            else umma_commit_p(smem_u32(&s_empty[s]), leader);
         }
         umma_commit_p(smem_u32(&s_done), leader);
     }
     __syncwarp();
     mbar_wait(smem_u32(&s_done), 0);
+    if (CL) cluster_sync_all();          // no CTA leaves while a peer's release may still arrive on its barriers
 }
 
 // One leapfrog step for all chains:  acc = (Q - mu) P  on tcgen05, then kick / drift in the epilogue.
 //   grid (Dp/BN, Cp/128), 128 threads: thread 0 = TMA producer, thread 32 = MMA issuer, all 4 warps = epilogue.
-template <int BN>
+template <int BN, bool CL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float* __restrict__ QpIn,
                   const float* __restrict__ Ppack, float* __restrict__ Qout, float* __restrict__ QpOut,
@@ -305,10 +346,10 @@ dense_step_kernel(const DenseArgs a, const float* __restrict__ Qin, const float*
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Dp = a.Dp, kchunks = Dp / TC_KC;
 
-    const uint32_t tmem = dense_prologue<BN, ST>(s_full, s_empty, &s_done, &s_tmem);
+    const uint32_t tmem = dense_prologue<BN, ST, CL>(s_full, s_empty, &s_done, &s_tmem);
 
     pdl_wait();               // everything above (barriers, TMEM) overlapped the previous launch's tail; its writes are visible now
-    dense_mainloop<BN, ST>(smem, s_full, s_empty, &s_done, tmem, QpIn, Ppack, tile_m, tile_n, kchunks);
+    dense_mainloop<BN, ST, CL>(smem, s_full, s_empty, &s_done, tmem, QpIn, Ppack, tile_m, tile_n, kchunks);
     // ===== epilogue: acc = ((Q-mu) P)[row, cols]; g = -acc; kick, optional drift (+ packed copy for the next GEMM) =====
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = tile_m * TC_M + warp * 32 + lane;
@@ -391,7 +432,7 @@ struct LinEpi {
     float sign;            // s = +1 / -1
 };
 
-template <int BN>
+template <int BN, bool CL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const float* __restrict__ Bpack, const LinEpi ep) {
     constexpr int ST = dense_stages(BN);
@@ -403,10 +444,10 @@ dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const f
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = Dp / TC_KC;
 
-    const uint32_t tmem = dense_prologue<BN, ST>(s_full, s_empty, &s_done, &s_tmem);
+    const uint32_t tmem = dense_prologue<BN, ST, CL>(s_full, s_empty, &s_done, &s_tmem);
 
     pdl_wait();
-    dense_mainloop<BN, ST>(smem, s_full, s_empty, &s_done, tmem, Apack, Bpack, tile_m, tile_n, kchunks);
+    dense_mainloop<BN, ST, CL>(smem, s_full, s_empty, &s_done, tmem, Apack, Bpack, tile_m, tile_n, kchunks);
 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = tile_m * TC_M + warp * 32 + lane;
@@ -464,7 +505,10 @@ dense_lin_kernel(int C, int Dp, int NT, const float* __restrict__ Apack, const f
 static bool lin_launch(int BN, dim3 grid, cudaStream_t st, int C, int Dp, int NT, const float* Apack, const float* Bpack,
                        const LinEpi& ep) {
     const size_t sm = (size_t)dense_stages(BN) * dense_stage_floats(BN) * sizeof(float);
-    if (BN == 128) launch_pdl(dense_lin_kernel<128>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
+    const bool cl = dense_cluster_ok(grid, BN);
+    if (BN == 128 && cl) launch_pdl_cluster(dense_lin_kernel<128, true>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
+    else if (BN == 64 && cl) launch_pdl_cluster(dense_lin_kernel<64, true>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
+    else if (BN == 128) launch_pdl(dense_lin_kernel<128>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
     else if (BN == 64) launch_pdl(dense_lin_kernel<64>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
     else launch_pdl(dense_lin_kernel<32>, grid, TC_THREADS, sm, st, C, Dp, NT, Apack, Bpack, ep);
     return true;
@@ -477,6 +521,10 @@ static bool lin_configure() {
                                     (int)((size_t)dense_stages(64) * dense_stage_floats(64) * 4)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(dense_lin_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)((size_t)dense_stages(32) * dense_stage_floats(32) * 4)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(dense_lin_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)dense_stages(128) * dense_stage_floats(128) * 4)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(dense_lin_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)dense_stages(64) * dense_stage_floats(64) * 4)) == cudaSuccess;
     if (!ok) cudaGetLastError();
     return ok;
 }
@@ -910,12 +958,15 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
 
     const dim3 ggrid(a.NT, mt);
     auto step = [&](const float* qin, const float* qpin, float* qout, float* qpout, int mode) -> bool {
+        const bool cl = dense_cluster_ok(ggrid, a.BN);
         if (a.BN == 128) {
             const size_t sm = (size_t)dense_stages(128) * dense_stage_floats(128) * sizeof(float);
-            launch_pdl(dense_step_kernel<128>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            if (cl) launch_pdl_cluster(dense_step_kernel<128, true>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            else launch_pdl(dense_step_kernel<128>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
         } else if (a.BN == 64) {
             const size_t sm = (size_t)dense_stages(64) * dense_stage_floats(64) * sizeof(float);
-            launch_pdl(dense_step_kernel<64>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            if (cl) launch_pdl_cluster(dense_step_kernel<64, true>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
+            else launch_pdl(dense_step_kernel<64>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
         } else {
             const size_t sm = (size_t)dense_stages(32) * dense_stage_floats(32) * sizeof(float);
             launch_pdl(dense_step_kernel<32>, ggrid, TC_THREADS, sm, st, a, qin, qpin, ppack, qout, qpout, P, eps, mode, upart);
@@ -930,6 +981,10 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
                                         (int)((size_t)dense_stages(64) * dense_stage_floats(64) * 4)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(dense_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)dense_stages(32) * dense_stage_floats(32) * 4)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(dense_step_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)dense_stages(128) * dense_stage_floats(128) * 4)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(dense_step_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)dense_stages(64) * dense_stage_floats(64) * 4)) == cudaSuccess;
         if (!ok) { cudaGetLastError(); return HMCX_ERR_CUDA; }
     }
     dense_pad_matrix_kernel<<<296, 256, 0, st>>>(target->prec, D, prec, a.Dp);

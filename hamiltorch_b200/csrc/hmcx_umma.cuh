@@ -107,6 +107,25 @@ __device__ __forceinline__ void umma_commit_p(uint32_t mbar, uint32_t leader) { 
                  :: "r"(mbar), "r"(leader) : "memory");
 }
 
+// ---- thread-block clusters: TMA multicast + multicast commit --------------------------------------------------------
+// One bulk copy lands at the SAME shared-memory offset of every CTA in `cta_mask` and completes `bytes` on the mbarrier at
+// the same offset in each of them.  A commit with a mask arrives on that barrier offset in every CTA of the mask.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast_p(uint32_t mbar, uint16_t cta_mask, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %2, 0;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n"
+                 :: "r"(mbar), "h"(cta_mask), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_ctaid_y() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(r)); return r; }
+
 // 32 lanes x 16 columns of 32-bit cells: thread (lane) <-> TMEM lane, register i <-> column i
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
