@@ -19,6 +19,14 @@
 
 namespace hmcx {
 
+// hmcx_flow.cu: the persistent small-D form of the flows below
+bool flow_small_ok(int D, int ld);
+int flow_small_hmc_run(const hmcx_target_t*, const hmcx_mass_t*, const hmcx_rng_t*, const hmcx_nuts_t*, const float*, float*,
+                       float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*, cudaStream_t);
+int flow_small_rmhmc_run(const hmcx_target_t*, const hmcx_rmhmc_t*, const hmcx_const_metric_t*, const hmcx_rng_t*, const float*,
+                         float*, const float*, int, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float*, int32_t*,
+                         float, float, cudaStream_t);
+
 // 32 lanes x 32 columns of the accumulator: thread (lane) <-> TMEM lane, register i <-> column i; waits for the data
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -917,6 +925,9 @@ int dense_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hm
     } else if (rng->mode != HMCX_RNG_PHILOX) {
         return HMCX_ERR_INVALID_ARG;
     }
+    if (flow_small_ok(D, ld))                    // D <= 128: the whole run in one persistent launch (hmcx_flow.cu)
+        return flow_small_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, S, burn, it0, it1, samples, accept,
+                                  diverged, ham, num_rejected, st);
     if (mk == HMCX_MASS_FULL)
         return dense_fullmass_hmc_run(target, mass, rng, nuts, q_init, q_cur, eps, C, ld, L, S, burn, it0, it1, samples,
                                       accept, diverged, ham, num_rejected, ws, st);
@@ -1079,6 +1090,9 @@ int dense_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const 
     } else if (rng->mode != HMCX_RNG_PHILOX) {
         return HMCX_ERR_INVALID_ARG;
     }
+    if (flow_small_ok(D, ld))                    // D <= 128: the whole run in one persistent launch (hmcx_flow.cu)
+        return flow_small_rmhmc_run(target, cfg, gm, rng, q_init, q_cur, eps, C, ld, L, S, burn, it0, it1, samples, accept,
+                                    diverged, ham, num_rejected, mul_host(0.5f, cfg->pi_term), mul_host(0.5f, gm->log_det), st);
     DenseRun r = {};
     DenseArgs& a = r.a;
     a.C = C; a.D = D; a.Cp = (C + 127) / 128 * 128;

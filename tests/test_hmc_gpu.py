@@ -68,6 +68,22 @@ def test_golden_chain_parity(name):
             assert float(res.step_size[c]) == np.float32(case['kw']['step_size'])
 
 
+def _is_small_dense(case):
+    """16 < D <= 128 with a dense precision or a 2-D / block-list inv_mass: runs on the persistent small-D kernel
+    (hmcx_flow.cu) by default and on the step-synchronous tcgen05 path when HMCX_FLOW_SMALL=0."""
+    import hamiltorch_b200.targets as T
+    tgt, im = case['target'], case['kw'].get('inv_mass')
+    full_mass = isinstance(im, list) or (torch.is_tensor(im) and im.dim() == 2)
+    return 16 < tgt.dim <= 128 and (isinstance(tgt, T.GaussianFull) or full_mass)
+
+
+@pytest.mark.parametrize('name', sorted(n for n, c in cases.plain_cases().items() if _is_small_dense(c)))
+def test_golden_chain_parity_tcgen05_path(name, monkeypatch):
+    """The golden chains of the small dense cases ALSO through the tcgen05 GEMM path (the default at D > 128)."""
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '0')
+    test_golden_chain_parity(name)
+
+
 @pytest.mark.parametrize('tuning', [1, 2, 4, 21, 22, 41, 42])
 def test_register_geometry_variants_agree(tuning):
     """The register geometry (float2 / float4 groups, 1-4 groups per thread; 41 / 42: the chain spread over a thread-block

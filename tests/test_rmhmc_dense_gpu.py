@@ -32,8 +32,12 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize('path', ['flow', 'tcgen05'])
 @pytest.mark.parametrize('name', sorted(CASES))
-def test_constant_metric_rmhmc_parity_vs_live_oracle(name):
+def test_constant_metric_rmhmc_parity_vs_live_oracle(name, path, monkeypatch):
+    # D <= 128: the persistent small-D kernel (hmcx_flow.cu, exact fp32 FMAs) by default; HMCX_FLOW_SMALL=0 keeps the
+    # step-synchronous tcgen05 GEMM path (the default above D = 128) under the same test
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '1' if path == 'flow' else '0')
     cs = CASES[name]
     D, S, burn, C = cs['D'], 6, 2, 3
     if cs['target'] == 'full':
@@ -87,7 +91,37 @@ def test_sample_dropin_rmhmc_gaussian_full():
     assert all(torch.isfinite(t).all() for t in out)
 
 
-def test_constant_metric_rmhmc_philox_statistics_d64():
+@pytest.mark.parametrize('integrator', ['EXPLICIT', 'IMPLICIT'])
+def test_flow_and_tcgen05_paths_agree_d64(integrator, monkeypatch):
+    """Same Philox streams, same element-wise operation order: the two forms of the constant-metric explicit integrator give
+    the same chains up to the summation order of the contractions (compared while the decisions agree)."""
+    D, C, S, L = 64, 70, 6, 4
+    tgt = _full_gaussian(D, 35)
+    init = tgt.mean[None] + 0.5 * torch.randn(C, D, generator=torch.Generator().manual_seed(9))
+    kw = dict(num_samples=S, num_steps_per_sample=L, step_size=0.2, explicit_binding_const=10, sampler=hb.Sampler.RMHMC,
+              integrator=getattr(hb.Integrator, integrator), metric=hb.Metric.HESSIAN,
+              rng='philox', seed=12, record_ham=True)
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '1')
+    a = hb.sample_chains(tgt, init, **kw)
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '0')
+    b = hb.sample_chains(tgt, init, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(a.accepted, b.accepted)
+    assert torch.allclose(a.ham, b.ham, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(a.samples, b.samples, rtol=2e-4, atol=2e-4)
+    assert 0 < int(a.accepted.sum())
+    # chains per warp (1 / 2 / 4, picked from the batch size) never change a chain's bits
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '1')
+    for r in ('1', '2', '4'):
+        monkeypatch.setenv('HMCX_FLOW_R', r)
+        c = hb.sample_chains(tgt, init, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(a.samples, c.samples) and torch.equal(a.ham, c.ham)
+
+
+@pytest.mark.parametrize('path', ['flow', 'tcgen05'])
+def test_constant_metric_rmhmc_philox_statistics_d64(path, monkeypatch):
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '1' if path == 'flow' else '0')
     """SURVEY 8d's 'D=64 Gaussian-Hessian variant' of config 3: 512 chains, explicit integrator, Hessian metric.  With
     G = P the dynamics are isotropic in the whitened space: high acceptance, second moment along a direction = cov."""
     D, C, S, L = 64, 512, 40, 6

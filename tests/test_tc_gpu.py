@@ -166,7 +166,9 @@ def test_full_inv_mass_philox_statistics_d512():
     assert abs(v - 1.0) < 0.1, v
 
 
-def test_dense_paths_edge_shapes():
+@pytest.mark.parametrize('path', ['flow', 'tcgen05'])
+def test_dense_paths_edge_shapes(path, monkeypatch):
+    monkeypatch.setenv('HMCX_FLOW_SMALL', '1' if path == 'flow' else '0')
     """Ragged shapes on the tensor-core paths: D = 17 (the smallest dense dimension, padded to one 32-wide K chunk),
     C = 130 chains (two 128-row tiles, the second almost empty), one iteration, and D = 33 (two chunks, last nearly empty):
     chain c of the big launch equals the same chain launched alone (rows never interact), decisions equal the oracle's."""
