@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
     constexpr int DP = NJ * 32;
     // partial sums per output element (independent FMA chains in flight).  A function of D only, never of R: a chain's
     // bits must not depend on how many chains share its warp (the launch picks R from the batch size)
-    constexpr int NACC = (NJ >= 4) ? 1 : (NJ >= 2 ? 2 : 4);
+    constexpr int NACC = (NJ >= 4) ? 1 : (NJ >= 3 ? 2 : 4);
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int D = a.D, K4 = (D + 3) & ~3, ld = a.ld;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) acc[t][r][jj] = 0.0f;
-#pragma unroll 2
+#pragma unroll(R <= 2 ? 4 : 2)
         for (int k = 0; k < K4; k += 4) {
             float4 xv[R];
 #pragma unroll
@@ -409,7 +409,7 @@ static int flow_threads_and_grid(int C, int D, int& R, int& threads, int& grid) 
     // shared-memory traffic per chain, fewer chains per warp = more warps (SMs) working on a small batch
     const char* fr = getenv("HMCX_FLOW_R");
     if (fr && (atoi(fr) == 1 || atoi(fr) == 2 || atoi(fr) == 4)) R = atoi(fr);
-    else R = (C <= 2 * sms) ? 1 : (C <= 8 * sms) ? 2 : 4;
+    else R = (C <= 4 * sms) ? 1 : (C <= 12 * sms) ? 2 : 4;        // measured: C = 512 -> 1, C >= 4096 -> 4 (profiles/r2_flow_small.txt)
     const int warps = (C + R - 1) / R;
     int w = (warps + sms - 1) / sms;
     if (w > 8) w = 8;

@@ -174,6 +174,9 @@ __device__ void rc_jacobi(const Rc& c) {
     const int np = m >> 1;
     for (int e = tid; e < d * d; e += RC_T) { const int a = e / d, b = e - a * d; c.Q[a * DP + b] = (a == b) ? 1.0f : 0.0f; }
     __syncthreads();
+    // e / np for e < 16384, np <= 64 as one multiply-shift (ncu: the two integer divisions of the update loops were 23 % of
+    // the kernel's instructions)
+    const unsigned magic = ((1u << 20) + (unsigned)np - 1u) / (unsigned)np;
     for (int sweep = 0; sweep < 14; ++sweep) {
         float off = 0.0f, dg = 0.0f;
         for (int e = tid; e < d * d; e += RC_T) {
@@ -188,26 +191,30 @@ __device__ void rc_jacobi(const Rc& c) {
             if (tid < np) {                            // pair k of round r (circle method, player m-1 fixed)
                 int p, q;
                 if (tid == 0) { p = m - 1; q = r; }
-                else { p = (r + tid) % (m - 1); q = (r - tid + (m - 1)) % (m - 1); }
+                else { p = r + tid; if (p >= m - 1) p -= m - 1; q = r - tid; if (q < 0) q += m - 1; }   // tid, r < m - 1
                 if (p > q) { const int x = p; p = q; q = x; }
                 float cc = 1.0f, ss = 0.0f;
                 if (q < d) {                           // (a pair with the dummy player of an odd D is skipped)
                     const float apq = c.A[p * DP + q];
                     if (fabsf(apq) >= 1e-30f) {
-                        const float theta = (c.A[q * DP + q] - c.A[p * DP + p]) / (2.0f * apq);
-                        const float tt = (theta >= 0.0f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+                        // (255 threads wait at the barrier below for these 16: MUFU forms; a rotation only has to be
+                        // orthogonal -- c^2 + s^2 = 1 to rsqrt accuracy -- and to shrink a_pq, the sweeps iterate to convergence)
+                        const float theta = __fdividef(c.A[q * DP + q] - c.A[p * DP + p], 2.0f * apq);
+                        const float tt = __fdividef(theta >= 0.0f ? 1.0f : -1.0f, fabsf(theta) + __fsqrt_rn(theta * theta + 1.0f));
                         cc = rsqrtf(tt * tt + 1.0f);
                         ss = tt * cc;
                     }
                 } else { q = -1; }
-                c.pr[2 * tid] = p; c.pr[2 * tid + 1] = q;
-                c.cs[2 * tid] = cc; c.cs[2 * tid + 1] = ss;
+                reinterpret_cast<int2*>(c.pr)[tid] = make_int2(p, q);          // (8-byte aligned: every carve-out before is even)
+                reinterpret_cast<float2*>(c.cs)[tid] = make_float2(cc, ss);
             }
             __syncthreads();
             for (int e = tid; e < np * np; e += RC_T) {         // A[P_i, P_j] <- J_i^T A[P_i, P_j] J_j
-                const int i = e / np, j = e - i * np;
-                const int p1 = c.pr[2 * i], q1 = c.pr[2 * i + 1], p2 = c.pr[2 * j], q2 = c.pr[2 * j + 1];
-                const float c1 = c.cs[2 * i], s1 = c.cs[2 * i + 1], c2 = c.cs[2 * j], s2 = c.cs[2 * j + 1];
+                const int i = (int)(((unsigned)e * magic) >> 20), j = e - i * np;
+                const int2 pi = reinterpret_cast<const int2*>(c.pr)[i], pj = reinterpret_cast<const int2*>(c.pr)[j];
+                const float2 ri = reinterpret_cast<const float2*>(c.cs)[i], rj = reinterpret_cast<const float2*>(c.cs)[j];
+                const int p1 = pi.x, q1 = pi.y, p2 = pj.x, q2 = pj.y;
+                const float c1 = ri.x, s1 = ri.y, c2 = rj.x, s2 = rj.y;
                 if (q1 < 0 && q2 < 0) continue;
                 if (q1 < 0) {                          // row p1 (the dummy's partner) only sees the column rotation
                     const float a = c.A[p1 * DP + p2], b = c.A[p1 * DP + q2];
@@ -223,10 +230,12 @@ __device__ void rc_jacobi(const Rc& c) {
                 }
             }
             for (int e = tid; e < d * np; e += RC_T) {          // Q <- Q J
-                const int k = e / np, j = e - k * np;
-                const int p = c.pr[2 * j], q = c.pr[2 * j + 1];
+                const int k = (int)(((unsigned)e * magic) >> 20), j = e - k * np;
+                const int2 pj = reinterpret_cast<const int2*>(c.pr)[j];
+                const int p = pj.x, q = pj.y;
                 if (q < 0) continue;
-                const float cc = c.cs[2 * j], ss = c.cs[2 * j + 1];
+                const float2 rj = reinterpret_cast<const float2*>(c.cs)[j];
+                const float cc = rj.x, ss = rj.y;
                 const float a = c.Q[k * DP + p], b = c.Q[k * DP + q];
                 c.Q[k * DP + p] = cc * a - ss * b; c.Q[k * DP + q] = ss * a + cc * b;
             }
