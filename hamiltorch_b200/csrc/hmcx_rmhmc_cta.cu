@@ -197,10 +197,8 @@ __device__ void rc_jacobi(const Rc& c) {
                 if (q < d) {                           // (a pair with the dummy player of an odd D is skipped)
                     const float apq = c.A[p * DP + q];
                     if (fabsf(apq) >= 1e-30f) {
-                        // (255 threads wait at the barrier below for these 16: MUFU forms; a rotation only has to be
-                        // orthogonal -- c^2 + s^2 = 1 to rsqrt accuracy -- and to shrink a_pq, the sweeps iterate to convergence)
-                        const float theta = __fdividef(c.A[q * DP + q] - c.A[p * DP + p], 2.0f * apq);
-                        const float tt = __fdividef(theta >= 0.0f ? 1.0f : -1.0f, fabsf(theta) + __fsqrt_rn(theta * theta + 1.0f));
+                        const float theta = (c.A[q * DP + q] - c.A[p * DP + p]) / (2.0f * apq);
+                        const float tt = (theta >= 0.0f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
                         cc = rsqrtf(tt * tt + 1.0f);
                         ss = tt * cc;
                     }
