@@ -10,9 +10,61 @@ Tolerances (stated once, used everywhere):
     Hamiltonian summation noise may legitimately flip; the comparison stops at such an iteration and the test
     requires that it is rare (never in the committed fixtures).
 """
+import json
+import os
+
 import numpy as np
 
 H_TOL_REL = 2e-6
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tolerances of the NON-bit-exact comparisons (RMHMC: closed form + Jacobi vs autograd through eigh; coupled / dense /
+# Bayesian-NN contractions: summation order) are set from MEASUREMENT, not from a guess: tests/golden/measured_errors.json
+# holds, per compared quantity (tag), the error max |a - d| / (1 + |d|) observed on B200 (regenerate: run the GPU tests with
+# HMCX_PARITY_REPORT=<file>.jsonl, then scripts/collect_parity.py).  A comparison passes when its error is within
+# TOL_FACTOR x that measurement (floor TOL_FLOOR, so that a re-ordered reduction does not flip a test), and never above the
+# test's ceiling -- the old blanket bound (2e-3 RMHMC, 2e-4 contractions).  A tag without a measurement uses the ceiling.
+# ---------------------------------------------------------------------------------------------------------------------
+TOL_FACTOR = 8.0
+TOL_FLOOR = 1e-5
+_MEASURED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'measured_errors.json')
+try:
+    with open(_MEASURED_PATH) as _f:
+        MEASURED = json.load(_f)
+except (OSError, ValueError):
+    MEASURED = {}
+
+
+def tol_for(tag, ceiling):
+    m = MEASURED.get(tag)
+    if m is None:
+        return ceiling
+    return min(ceiling, max(TOL_FACTOR * m, TOL_FLOOR))
+
+
+def scaled_error(actual, desired):
+    """max |a - d| / (1 + |d|): the quantity np.testing.assert_allclose(rtol=T, atol=T) bounds by T."""
+    a, d = np.asarray(actual, dtype=np.float64), np.asarray(desired, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    e = np.abs(a - d) / (1.0 + np.abs(d))
+    return float(np.nanmax(e)) if np.isfinite(e).any() else float('inf')
+
+
+def assert_close(tag, actual, desired, ceiling):
+    a, d = np.asarray(actual), np.asarray(desired)
+    assert a.shape == d.shape, (tag, a.shape, d.shape)
+    assert np.array_equal(np.isfinite(a), np.isfinite(d)), tag + ': non-finite pattern differs'
+    fin = np.isfinite(d)
+    m = scaled_error(a[fin], d[fin])
+    rep = os.environ.get('HMCX_PARITY_REPORT')
+    if rep:
+        with open(rep, 'a') as f:
+            f.write(json.dumps({'tag': tag, 'error': m}) + '\n')
+    tol = tol_for(tag, ceiling)
+    assert m <= tol, '%s: error %.3g > tolerance %.3g (measured on B200: %s, ceiling %.3g)' % (
+        tag, m, tol, MEASURED.get(tag), ceiling)
+
 # dual averaging (samplers.py:629-674): fp32 exp/log (CUDA libm vs Sleef, <= 2 ulp) and the summation-order noise of
 # rho are amplified by sqrt(t)/(gamma*(t+t0)) <= ~2 into the proposed step size
 NUTS_EPS_RTOL = 2e-4
@@ -32,7 +84,7 @@ def first_decision_mismatch(acc_a, acc_b):
 
 
 def assert_chain_parity(samples, accepted, ham, ref_samples, ref_accepted, ref_ham_old, ref_ham_new, ref_logu,
-                        burn, exact=True, rtol=0.0):
+                        burn, exact=True, rtol=0.0, tag=None):
     """samples (S-burn, D) vs reference; accepted (S,); ham (S,2) or None."""
     samples, ref_samples = np.asarray(samples), np.asarray(ref_samples)
     S = len(ref_accepted)
@@ -54,5 +106,7 @@ def assert_chain_parity(samples, accepted, ham, ref_samples, ref_accepted, ref_h
     assert samples.shape == ref_samples.shape, (samples.shape, ref_samples.shape)
     if exact:
         assert np.array_equal(samples, ref_samples), 'samples differ (max abs %g)' % np.abs(samples - ref_samples).max()
+    elif tag is not None:
+        assert_close(tag + '/samples', samples, ref_samples, rtol)          # measured tolerance, `rtol` is the ceiling
     else:
         np.testing.assert_allclose(samples, ref_samples, rtol=rtol, atol=rtol)

@@ -53,7 +53,8 @@ def test_golden_chain_parity(name):
         parity.assert_chain_parity(
             res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(), res.ham[c].cpu().numpy(),
             d['samples_%d' % c], d['accepted_%d' % c], d['ham_old_%d' % c], d['ham_new_%d' % c],
-            d['logu_%d' % c], case['kw']['burn'], exact=exact, rtol=case.get('rtol', 0.0))
+            d['logu_%d' % c], case['kw']['burn'], exact=exact, rtol=case.get('rtol', 0.0),
+            tag=None if exact else 'hmc/%s/%s/c%d' % (name, 'tcgen05' if os.environ.get('HMCX_FLOW_SMALL') == '0' else 'default', c))
         assert int(res.num_rejected[c]) == int((d['accepted_%d' % c] == 0).sum())
         if nuts:
             # the kernel's own dual averaging, fed the same history, proposes the reference's step sizes

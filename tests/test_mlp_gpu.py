@@ -19,7 +19,7 @@ from tests import parity
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-MLP_RTOL = 2e-4
+MLP_RTOL = 2e-4           # CEILING; the golden chains pass within 8x their measured error (<= 2e-7 -> 1e-5 floor, tests/parity.py)
 SCHEME = {None: N.SCHEME_PLAIN, 'SPLITTING': N.SCHEME_SPLIT_SYM, 'SPLITTING_RAND': N.SCHEME_SPLIT_RAND,
           'SPLITTING_KMID': N.SCHEME_SPLIT_KMID}
 
@@ -89,7 +89,7 @@ def test_golden_chain_parity(name):
         parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
                                    res.ham[c].cpu().numpy(), d['samples_%d' % c], d['accepted_%d' % c],
                                    d['ham_old_%d' % c], d['ham_new_%d' % c], d['logu_%d' % c], burn, exact=False,
-                                   rtol=MLP_RTOL)
+                                   rtol=MLP_RTOL, tag='mlp/%s/c%d' % (name, c))
 
 
 def test_sample_split_model_dropin_and_predict_model():

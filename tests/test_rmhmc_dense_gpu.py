@@ -14,7 +14,7 @@ from oracle import hmc_oracle as O, rmhmc_oracle as R
 from tests import parity
 
 pytestmark = pytest.mark.gpu
-RM_RTOL = 2e-3
+RM_RTOL = 2e-3            # CEILING only: measured <= 8.6e-7 (flow kernel) / 2.1e-6 (tcgen05) -> tolerance 1e-5 .. 1.7e-5 (tests/parity.py)
 
 
 def _full_gaussian(D, seed):
@@ -68,12 +68,12 @@ def test_constant_metric_rmhmc_parity_vs_live_oracle(name, path, monkeypatch):
         o = os_[c]
         assert not any(o['diverged'])
         ham = res.ham[c].cpu().numpy().astype(np.float64)
-        np.testing.assert_allclose(ham[:, 0], np.array(o['ham_old']), rtol=RM_RTOL, atol=RM_RTOL)
-        np.testing.assert_allclose(ham[:, 1], np.array(o['ham_new']), rtol=RM_RTOL, atol=RM_RTOL)
+        tag = 'rmhmc_const/%s/%s/c%d' % (name, path, c)            # tolerance = 8 x the error measured on B200 (tests/parity.py)
+        parity.assert_close(tag + '/ham_old', ham[:, 0], np.array(o['ham_old']), RM_RTOL)
+        parity.assert_close(tag + '/ham_new', ham[:, 1], np.array(o['ham_new']), RM_RTOL)
         m = parity.first_decision_mismatch(res.accepted[c].cpu().numpy(), o['accepted'])
         assert m is None, 'accept decision differs at iteration %d' % m
-        np.testing.assert_allclose(res.samples[c].cpu().numpy(), torch.stack(o['samples']).numpy(), rtol=RM_RTOL,
-                                   atol=RM_RTOL)
+        parity.assert_close(tag + '/samples', res.samples[c].cpu().numpy(), torch.stack(o['samples']).numpy(), RM_RTOL)
         n_acc += sum(o['accepted'])
     assert n_acc > 0, 'fixture never accepts: it would not exercise the trajectory'
 
