@@ -458,6 +458,27 @@ def other_configs(dev, rank, world):
                       'value': C5 * S5 * 10 / (ms * 1e-3), 'unit': UNIT,
                       'median_adapted_step_size': float(res.step_size.median()),
                       'post_burn_accept_rate': float(res.accepted[:, B5 + 1:].float().mean())}
+    # ---- SURVEY 8d's "D=64 Gaussian-Hessian variant" of config 3: explicit RMHMC with the metric solve as a dense
+    #      contraction, 512 chains per GPU, dense-precision Gaussian, L=10, S=200 -- the persistent small-D flow kernel ----
+    C6, D6, S6 = 512, 64, 200
+    A6 = torch.randn(D6, D6, generator=g, dtype=torch.float64) / D6 ** 0.5
+    tgt6 = T.GaussianFull(torch.zeros(D6), cov=A6 @ A6.t() + 0.5 * torch.eye(D6, dtype=torch.float64))
+    init6 = (0.5 * torch.randn(C6, D6, generator=g)).to(dev)
+    ms, res = _event_timed(lambda: hb.sample_chains(
+        tgt6, init6, num_samples=S6, num_steps_per_sample=10, step_size=0.1, explicit_binding_const=10,
+        sampler=hb.Sampler.RMHMC, integrator=hb.Integrator.EXPLICIT, metric=hb.Metric.HESSIAN, rng='philox', seed=4,
+        chain_offset=rank * C6), reps=3)
+    sm_clk = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
+    smem_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128.0 * sm_clk / 1e9     # GB/s
+    mv_bytes = C6 * S6 * (6 * 10 + 4) * D6 * D6 * 4.0      # every warp-matvec streams the D x D matrix once (R = 1 chain per warp)
+    out['rmhmc_dense_metric_d64'] = {
+        'workload': 'explicit RMHMC, constant dense metric (Gaussian-Hessian variant of config 3, SURVEY 8d), D=64, '
+                    '512 chains/GPU, L=10, eps=0.1, S=200', 'kernel': 'flow_small_kernel<2,1> (one launch per run)',
+        'bound': 'shared-memory bandwidth (matrices resident in smem; 128 B/clk/SM)', 'kernel_ms': ms,
+        'note': 'kernel_ms is the whole public-API call (host metric factorisation + launch)',
+        'value': C6 * S6 * 10 / (ms * 1e-3), 'unit': UNIT, 'smem_gbs': mv_bytes / (ms * 1e-3) / 1e9,
+        'smem_peak_gbs': smem_peak, 'roofline_frac': mv_bytes / (ms * 1e-3) / 1e9 / smem_peak,
+        'accept_rate': float(res.accepted.float().mean())}
     return out
 
 
@@ -799,6 +820,9 @@ def run_b200_arm(args, rank, world, local_rank):
                 if 'algorithmic_tflops' in e:
                     e['algorithmic_tflops_per_gpu'] = e.pop('algorithmic_tflops') * others[k]['kernel_ms'] / e['kernel_ms']
                     e['roofline_frac'] = e['algorithmic_tflops_per_gpu'] / e['roofline_peak_tflops']
+                if 'smem_gbs' in e:
+                    e['smem_gbs'] = e['smem_gbs'] * others[k]['kernel_ms'] / e['kernel_ms']          # per GPU
+                    e['roofline_frac'] = e['smem_gbs'] / e['smem_peak_gbs']
                 e['n_gpus'] = world
                 oc[k] = e
             line['other_configs'] = oc

@@ -1273,24 +1273,42 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                 const int up = j < M ? j : twoM - 1 - j;
                 return a.scheme == HMCX_SCHEME_SPLIT_RAND ? s_perm[j >> 1] : up;
             };
+            auto post_at = [&](int j) {                                   // a drift follows the kick of schedule position j
+                const int up = j < M ? j : twoM - 1 - j;
+                if (a.scheme == HMCX_SCHEME_SPLIT_SYM) return j < M ? (up < M - 1) : (up > 0);
+                if (a.scheme == HMCX_SCHEME_SPLIT_RAND) return (j & 1) == 0;
+                return j == M - 1;
+            };
+            // Two consecutive schedule positions with the SAME split and NO drift between them differentiate the same function
+            // at the same parameters: the turning point of the symmetric sweep (m = M-1 up, then M-1 down, :501-:523) and the
+            // step boundary (m = 0 down, then m = 0 up of the next step); SPLITTING_KMID has the latter.  The reference calls
+            // autograd twice and gets the same tensor twice; here the second evaluation is skipped and g (per-rank partials
+            // included) is kicked again -- the same bits, 2 of the 2M evaluations of a symmetric step saved.
+            int prev_sp = -3;
+            bool prev_post = true;
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 int sp = -1, sp_next = -1;
                 float kc = half;
-                bool post = false;
+                bool post = false, reuse = false;
                 if (plain) {
                     if (t > 0) { drift(eps); kc = eps; }
                 } else {
-                    const int up = jj < M ? jj : twoM - 1 - jj;
                     sp = split_at(jj);
-                    if (a.scheme == HMCX_SCHEME_SPLIT_SYM) post = jj < M ? (up < M - 1) : (up > 0);
-                    else if (a.scheme == HMCX_SCHEME_SPLIT_RAND) post = (jj & 1) == 0;
-                    else post = jj == M - 1;
+                    post = post_at(jj);
+                    reuse = sp == prev_sp && !prev_post;
                     if (++jj == twoM) jj = 0;
                     sp_next = split_at(jj);
+                    int ahead = 1;
+                    if (sp_next == sp && !post) {                         // the next position re-uses this gradient: prefetch for
+                        sp_next = split_at(jj + 1 == twoM ? 0 : jj + 1);  // the one after it
+                        ahead = 2;
+                    }
+                    if (t + ahead >= T) sp_next = -2;
+                    prev_sp = sp; prev_post = post;
                 }
                 if (t + 1 == T) sp_next = -2;                             // the Hamiltonian evaluation follows: nothing to prefetch
-                mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc, fused_kick, sp_next);
+                if (!reuse) mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc, fused_kick, sp_next);
                 if (fused_kick) kick_partials(kc); else kick(kc);
                 TC_MARK(16);
                 if (post) drift(cd);
