@@ -65,7 +65,8 @@ def test_dense_gaussian_full_chain_parity_vs_live_oracle(variant):
         o = os_[c]
         parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
                                    res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
-                                   o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4)
+                                   o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4,
+                                   tag='dense_d200/%s/c%d' % (variant, c))
         if nuts:
             own = res.eps_trace[c].cpu().numpy().astype(np.float64)
             np.testing.assert_allclose(own[:S - 1], np.array(o['step_sizes'])[1:], rtol=2e-3)
@@ -138,7 +139,8 @@ def test_full_inv_mass_large_d_chain_parity_vs_live_oracle(variant):
         o = os_[c]
         parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
                                    res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
-                                   o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4)
+                                   o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4,
+                                   tag='fullmass_d150/%s/c%d' % (variant, c))
         if nuts:
             own = res.eps_trace[c].cpu().numpy().astype(np.float64)
             np.testing.assert_allclose(own[:S - 1], np.array(o['step_sizes'])[1:], rtol=2e-3)
