@@ -571,6 +571,26 @@ def const_metric(target, softabs, softabs_const):
     return ginv.contiguous(), lower.contiguous(), log_det
 
 
+# The constant metric costs an eigh / Cholesky / inverse on the host (the reference pays them at EVERY fisher() call).  Repeated
+# runs on the SAME target object, unmodified, reuse the device operands -- keyed like _MASS_CACHE; the entry holds the target.
+_METRIC_CACHE = []
+
+
+def const_metric_device(target, softabs, softabs_const, device):
+    tensors = [t for t in (getattr(target, 'prec', None), getattr(target, 'inv_var', None)) if torch.is_tensor(t)]
+    key = (id(target), tuple(id(t) for t in tensors), tuple(t._version for t in tensors), bool(softabs),
+           float(softabs_const) if softabs else None, str(torch.device(device)))
+    for k, _, val in _METRIC_CACHE:
+        if k == key:
+            return val
+    ginv, lower, log_det = const_metric(target, softabs, softabs_const)
+    val = (ginv.to(device), lower.to(device), log_det)
+    _METRIC_CACHE.append((key, target, val))
+    if len(_METRIC_CACHE) > 4:
+        _METRIC_CACHE.pop(0)
+    return val
+
+
 def _rmhmc_is_dense(target, jitter, jacdiag=False):
     """Gaussian targets without jitter have a constant metric: the tensor-core path (GaussianFull at any D; GaussianIso /
     GaussianDiag above D = 16, below they stay on the thread-per-chain kernel).  Everything else -- Funnel, jitter,
@@ -643,9 +663,8 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
         rng.mode, rng.seed, rng.chain_offset = N.RNG_PHILOX, int(seed), int(chain_offset)
     with torch.cuda.device(device):
         if _rmhmc_is_dense(nt.target, jitter, jacdiag):
-            ginv, lower, log_det = const_metric(nt.target, softabs, softabs_const)
+            ginv_d, lower_d, log_det = const_metric_device(nt.target, softabs, softabs_const, device)
             gm = N.ConstMetricStruct()
-            ginv_d, lower_d = ginv.to(device), lower.to(device)
             gm.metric_inv, gm.metric_chol, gm.log_det = ginv_d.data_ptr(), lower_d.data_ptr(), log_det
             ws = torch.empty(lib.hmcx_rmhmc_dense_workspace_bytes(Cn, D) // 4, dtype=torch.float32, device=device)
             keep_alive += [ginv_d, lower_d, ws]

@@ -94,3 +94,24 @@ def test_const_metric_matches_the_oracle_fisher():
                 assert torch.allclose(ginv @ fish, torch.eye(D), atol=2e-5)
                 ref_ld = float(lam.log().sum()) if softabs else float(torch.slogdet(fish)[1])
                 assert abs(log_det - ref_ld) <= 1e-5 * (1 + abs(ref_ld))
+
+
+def test_const_metric_device_operands_are_cached_per_target_object_and_version():
+    """Repeated RMHMC runs on the same (unmodified) Gaussian descriptor reuse the factorised metric; an in-place edit of the
+    precision (torch's version counter) or another softabs constant recomputes it."""
+    from hamiltorch_b200 import engine
+    D = 6
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn(D, D, generator=g, dtype=torch.float64)
+    tgt = T.GaussianFull(torch.zeros(D), cov=A @ A.t() + torch.eye(D, dtype=torch.float64))
+    a = engine.const_metric_device(tgt, True, 0.7, 'cpu')
+    b = engine.const_metric_device(tgt, True, 0.7, 'cpu')
+    assert a[0] is b[0] and a[1] is b[1]
+    c = engine.const_metric_device(tgt, True, 0.9, 'cpu')
+    assert c[0] is not a[0]
+    h = engine.const_metric_device(tgt, False, None, 'cpu')
+    tgt.prec.mul_(2.0)
+    d = engine.const_metric_device(tgt, True, 0.7, 'cpu')
+    assert d[0] is not a[0]
+    h2 = engine.const_metric_device(tgt, False, None, 'cpu')             # HESSIAN: G = P, so G^-1 halves
+    assert h2[0] is not h[0] and torch.allclose(h2[0], h[0] / 2, rtol=1e-4, atol=1e-6)
