@@ -355,6 +355,9 @@ size_t hmcx_rmhmc_dense_workspace_bytes(int32_t C, int32_t D);
  * hmcx_rmhmc_dense_run == the sample() loop for sampler=RMHMC (as hmcx_rmhmc_run) for targets GAUSS_ISO / GAUSS_DIAG /
  * GAUSS_FULL of ANY dimension with cfg->jitter < 0 (None): every flow is a tcgen05 GEMM over all chains (3xTF32,
  * operands packed for 1-D bulk TMA), 8 per explicit leapfrog step.  workspace: hmcx_rmhmc_dense_workspace_bytes().
+ * D <= 128 (and ld <= D rounded up to 32): the whole run is ONE persistent launch instead (hmcx_flow.cu: the matrices in
+ * shared memory, a warp owns 1-4 chains, exact fp32 FMAs; the workspace is then unused; environment HMCX_FLOW_SMALL=0
+ * keeps the GEMM path).  The same holds for hmcx_hmc_run with a dense precision or a 2-D inv_mass at 16 < D <= 128.
  */
 int hmcx_rmhmc_dense_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const hmcx_const_metric_t* metric,
                          const hmcx_rng_t* rng, const float* q_init, float* q_cur, const float* eps,
