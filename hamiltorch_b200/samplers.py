@@ -601,7 +601,19 @@ def predict_model(model, samples, x=None, y=None, test_loader=None, model_loss='
         else:
             raise RuntimeError('Val data not defined (i.e. arguments x, y, val_loader are all not defined)')
         dev = samples[0].device
-        pred, lp = engine.mlp_predict(target, torch.stack(list(samples)))
+        stacked = torch.stack(list(samples))
+        cap = N.MLP_MAX_SPLITS
+        if isinstance(target, list) and len(target) > cap:
+            # a loader with more batches than one launch takes splits (e.g. a 10k test set at batch_size 100): launches of
+            # `cap` batches each, predictions concatenated in batch order, log-probs added (the reference's loop :1532-:1537)
+            preds, lp = [], None
+            for i in range(0, len(target), cap):
+                pr, l = engine.mlp_predict(target[i:i + cap], stacked)
+                preds.append(pr)
+                lp = l if lp is None else lp + l
+            pred = torch.cat(preds, dim=1)
+        else:
+            pred, lp = engine.mlp_predict(target, stacked)
         pred, lp = pred.to(dev), lp.to(dev)
     shape = (1,) if model_loss == 'regression' else ()          # the reference's closure: (O,) vs 0-d
     return pred, [l.reshape(shape) for l in lp.unbind(0)]

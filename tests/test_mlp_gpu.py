@@ -244,3 +244,23 @@ def test_standalone_split_leapfrog_argument_errors():
         hb.leapfrog(q, torch.zeros_like(q), descs[0], sampler=hb.Sampler.HMC, integrator=hb.Integrator.SPLITTING)
     with pytest.raises(RuntimeError):                             # :497-498
         hb.leapfrog(q, torch.zeros_like(q), descs[:1], sampler=hb.Sampler.HMC, integrator=hb.Integrator.SPLITTING)
+
+
+def test_predict_model_loader_with_more_batches_than_one_launch_takes():
+    """A DataLoader with 70 batches (> the 64 splits of one launch): launches of 64 + 6 batches, predictions concatenated in
+    batch order, log-probs added -- against the oracle's restatement of the reference loop (samplers.py:1527-1540)."""
+    import torch.utils.data as tud
+    model, x, y = cases.mlp_problem(seed=3, n=140, n_in=5, hidden=16)
+    loader = tud.DataLoader(tud.TensorDataset(x, y), batch_size=2, shuffle=False)
+    D = hb.util.flatten(model).numel()
+    g = torch.Generator().manual_seed(1)
+    samples = [hb.util.flatten(model).detach() + 0.1 * torch.randn(D, generator=g) for _ in range(3)]
+    pred, lps = hb.predict_model(model, [s.cuda() for s in samples], test_loader=loader, model_loss='regression', tau_out=10.)
+    assert pred.shape == (3, 140, 1) and len(lps) == 3
+    # the reference's sum over the 70 batch closures, each with the prior divided by the number of batches (:1527)
+    for i, s in enumerate(samples):
+        lp_ref = float(sum(T.MLPRegression.from_model(model, x[2 * b:2 * b + 2], y[2 * b:2 * b + 2], None, 10., prior_scale=70)(s)
+                           for b in range(70)))
+        assert abs(float(lps[i]) - lp_ref) <= 5e-5 * (1 + abs(lp_ref))
+    whole, _ = hb.predict_model(model, [s.cuda() for s in samples], x=x.cuda(), y=y.cuda(), model_loss='regression', tau_out=10.)
+    assert torch.allclose(pred.cpu(), whole.cpu(), rtol=1e-5, atol=1e-6)
