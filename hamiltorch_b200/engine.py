@@ -120,6 +120,30 @@ class NativeTarget:
         return C.byref(self.struct)
 
 
+# Descriptor targets (Gaussian / Funnel) carry small host tensors; uploading them is a pageable host-to-device copy = a host
+# synchronisation per call.  The same descriptor object, unmodified, reuses its device operands (keyed like _MASS_CACHE; the
+# entry holds the descriptor).  Bayesian-NN targets (lists / MLPRegression: data + packed operands) are rebuilt per call.
+_TARGET_CACHE = []
+
+
+def native_target(target, device):
+    if isinstance(target, NativeTarget):
+        return target
+    if isinstance(target, list) or isinstance(target, T.MLPRegression) or not T.is_target(target):
+        return NativeTarget(target, device)
+    tensors = [t for t in (getattr(target, a, None) for a in ('mean', 'inv_var', 'prec')) if torch.is_tensor(t)]
+    key = (id(target), tuple(id(t) for t in tensors), tuple(t._version for t in tensors), str(torch.device(device)),
+           target.dim, float(getattr(target, 'log_norm', 0.0)), float(getattr(target, 'inv_var_v', 0.0)))
+    for k, _, nt in _TARGET_CACHE:
+        if k == key:
+            return nt
+    nt = NativeTarget(target, device)
+    _TARGET_CACHE.append((key, target, nt))
+    if len(_TARGET_CACHE) > 8:
+        _TARGET_CACHE.pop(0)
+    return nt
+
+
 class NativeMass:
     """inv_mass as the reference accepts it (None | (D,) | (D,D)); the mass used by gibbs is inverted ONCE with
     the same torch ops as samplers.py:942-952 so that sqrt(mass) is bit-identical."""
@@ -211,6 +235,22 @@ def nuts_table(burn):
     return torch.tensor(rows, dtype=torch.float64)
 
 
+_NUTS_TABLES = {}
+
+
+def nuts_table_device(burn, device):
+    """The constants of nuts_table() on the device, built and uploaded once per (burn, device): the upload is a pageable
+    host-to-device copy, i.e. a host synchronisation with everything queued on the stream -- per call it kept a sampler that
+    is called in a loop from ever running ahead of the GPU."""
+    key = (int(burn), str(torch.device(device)))
+    t = _NUTS_TABLES.get(key)
+    if t is None:
+        if len(_NUTS_TABLES) > 16:
+            _NUTS_TABLES.clear()
+        t = _NUTS_TABLES[key] = nuts_table(burn).to(device)
+    return t
+
+
 def nuts_mu(step_size_init):
     """samplers.py:664 -- fp32 log of fp32(10*eps0), returned as a Python float."""
     return float(torch.log(10 * torch.FloatTensor([step_size_init])))
@@ -241,7 +281,7 @@ def leapfrog(target, q, p, steps, step_size, inv_mass=None, return_trajectory=Fa
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     nm = native_mass(inv_mass, D, device)
     qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
@@ -268,7 +308,7 @@ def split_leapfrog(targets, q, p, steps, step_size, scheme, inv_mass=None, perms
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
-    nt = targets if isinstance(targets, NativeTarget) else NativeTarget(targets, device)
+    nt = native_target(targets, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     if isinstance(inv_mass, list) or (torch.is_tensor(inv_mass) and inv_mass.dim() != 1):
         raise NotImplementedError('split leapfrog: inv_mass None or 1-D')
@@ -299,7 +339,7 @@ def hamiltonian(target, q, p, inv_mass=None, device=None):
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     nm = native_mass(inv_mass, D, device)
     qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
@@ -381,7 +421,7 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     if device is None:
         device = params_init.device if params_init.is_cuda else torch.device('cuda', torch.cuda.current_device())
     device = torch.device(device)
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     nm = native_mass(inv_mass, D, device)
     S, L, burn = int(num_samples), int(num_steps_per_sample), int(burn)
@@ -447,7 +487,7 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     if not torch.is_tensor(step_size):
         nuts_s.step_size_init = float(step_size)           # the double the reference divides in its split drifts
     if nuts:
-        table = nuts_table(burn).to(device)
+        table = nuts_table_device(burn, device)
         h_bar = torch.zeros(Cn, dtype=torch.float64, device=device)
         eps_bar = torch.ones(Cn, dtype=torch.float64, device=device)
         nuts_s.enabled = 1
@@ -513,7 +553,7 @@ def grad_log_prob(target, q, split=-1, want_grad=True, want_log_prob=True, devic
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     qd = _as_rows(q, ld, device)
     Cn = qd.shape[0]
@@ -530,7 +570,7 @@ def mlp_predict(target, samples, device=None):
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (samples.device if samples.is_cuda else 'cuda'))
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     sd = _as_rows(samples, ld, device)
     S = sd.shape[0]
@@ -617,7 +657,7 @@ def rmhmc_run(target, params_init, num_samples, num_steps_per_sample, step_size,
     if device is None:
         device = params_init.device if params_init.is_cuda else torch.device('cuda', torch.cuda.current_device())
     device = torch.device(device)
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     S, L, burn = int(num_samples), int(num_steps_per_sample), int(burn)
     q_init = _as_rows(params_init, ld, device)
@@ -728,7 +768,7 @@ def rmhmc_leapfrog(target, q, p, steps, step_size, jitter=None, softabs_const=No
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
     Cn, L = qd.shape[0], int(steps)
@@ -757,7 +797,7 @@ def rmhmc_hamiltonian(target, q, p, jitter=None, softabs_const=None, softabs=Fal
     N.require_cuda()
     lib = N.load_library()
     device = torch.device(device if device is not None else (q.device if q.is_cuda else 'cuda'))
-    nt = target if isinstance(target, NativeTarget) else NativeTarget(target, device)
+    nt = native_target(target, device)
     D, ld = nt.dim, N.padded_ld(nt.dim)
     qd, pd = _as_rows(q, ld, device), _as_rows(p, ld, device)
     Cn = qd.shape[0]
