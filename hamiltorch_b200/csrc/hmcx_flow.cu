@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
     }
 }
 
-static int flow_threads_and_grid(int C, int D, int& R, int& threads, int& grid) {
+static int flow_threads_and_grid(int C, int D, size_t matrix_bytes, int& R, int& threads, int& grid) {
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -412,7 +412,10 @@ static int flow_threads_and_grid(int C, int D, int& R, int& threads, int& grid) 
     else R = (C <= 4 * sms) ? 1 : (C <= 12 * sms) ? 2 : 4;        // measured: C = 512 -> 1, C >= 4096 -> 4 (profiles/r2_flow_small.txt)
     const int warps = (C + R - 1) / R;
     int w = (warps + sms - 1) / sms;
-    if (w > 8) w = 8;
+    // big batches: when two CTAs' matrices fit one SM, CTAs of 4 warps (finer waves, the same warps per SM); D = 128 with
+    // three matrices fills the SM with one CTA of 8
+    const int wmax = (const char*)getenv("HMCX_FLOW_W") ? atoi(getenv("HMCX_FLOW_W")) : (matrix_bytes <= 100 * 1024 ? 4 : 8);
+    if (w > wmax) w = wmax;
     if (w < 1) w = 1;
     threads = 32 * w;
     grid = (warps + w - 1) / w;
@@ -438,8 +441,8 @@ static int flow_launch_nj(const FlowArgs& a, int R, int threads, int grid, size_
 static int flow_launch(const FlowArgs& a, cudaStream_t st) {
     const int NJ = (a.D + 31) / 32, DP = NJ * 32, K4 = (a.D + 3) & ~3;
     int R, threads, grid;
-    flow_threads_and_grid(a.C, a.D, R, threads, grid);
     const int nmat = (a.tk == HMCX_TARGET_GAUSS_FULL ? 1 : 0) + (a.mk == HMCX_MASS_FULL ? 2 : 0);
+    flow_threads_and_grid(a.C, a.D, (size_t)nmat * K4 * DP * sizeof(float), R, threads, grid);
     const size_t smem = ((size_t)nmat * K4 * DP + (size_t)(threads / 32) * R * DP) * sizeof(float);
     switch (NJ) {
         case 1: return flow_launch_nj<1>(a, R, threads, grid, smem, st);

@@ -1131,7 +1131,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
         if (i + 3 < D) r.w = a.im[i + 3];
         return r;
     };
-    auto kick = [&](float coef) {                              // momentum += coef * grad
+    // momentum += coef * grad; `twice`: the NEXT schedule position re-uses this gradient with no drift in between, its
+    // kick (a second, separately rounded `+= coef2 * grad`) is applied in the same pass
+    auto kick = [&](float coef, bool twice = false, float coef2 = 0.0f) {
         float4* p4 = reinterpret_cast<float4*>(p);
         const float4* g4 = reinterpret_cast<const float4*>(g);
         for (int v = tid; v < nvec; v += MLP_THREADS) {
@@ -1139,6 +1141,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             const float4 gv = g4[v];
             pv.x = add(pv.x, mul(coef, gv.x)); pv.y = add(pv.y, mul(coef, gv.y));
             pv.z = add(pv.z, mul(coef, gv.z)); pv.w = add(pv.w, mul(coef, gv.w));
+            if (twice) {
+                pv.x = add(pv.x, mul(coef2, gv.x)); pv.y = add(pv.y, mul(coef2, gv.y));
+                pv.z = add(pv.z, mul(coef2, gv.z)); pv.w = add(pv.w, mul(coef2, gv.w));
+            }
             p4[v] = pv;
         }
         __syncthreads();
@@ -1147,7 +1153,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
     // rank reads all partials through distributed shared memory (16-byte loads), adds them in rank order (the same bits as
     // reduce-then-kick) and updates its replica of p.  The peers may overwrite their g only after everybody has read it:
     // barrier.cluster arrive here, wait after the drift that follows (its latency hides behind the drift).
-    auto kick_partials = [&](float coef) {
+    auto kick_partials = [&](float coef, bool twice = false, float coef2 = 0.0f) {
         cg::cluster_group cluster = cg::this_cluster();
         const float4* gr[CS];
 #pragma unroll
@@ -1175,6 +1181,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                     float4 pv = p4[v];
                     pv.x = add(pv.x, mul(coef, sg.x)); pv.y = add(pv.y, mul(coef, sg.y));
                     pv.z = add(pv.z, mul(coef, sg.z)); pv.w = add(pv.w, mul(coef, sg.w));
+                    if (twice) {
+                        pv.x = add(pv.x, mul(coef2, sg.x)); pv.y = add(pv.y, mul(coef2, sg.y));
+                        pv.z = add(pv.z, mul(coef2, sg.z)); pv.w = add(pv.w, mul(coef2, sg.w));
+                    }
                     p4[v] = pv;
                 }
             }
@@ -1285,12 +1295,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             // autograd twice and gets the same tensor twice; here the second evaluation is skipped and g (per-rank partials
             // included) is kicked again -- the same bits, 2 of the 2M evaluations of a symmetric step saved.
             int prev_sp = -3;
-            bool prev_post = true;
+            bool prev_post = true, kicked_ahead = false;
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 int sp = -1, sp_next = -1;
                 float kc = half;
-                bool post = false, reuse = false;
+                bool post = false, reuse = false, kick_twice = false;
                 if (plain) {
                     if (t > 0) { drift(eps); kc = eps; }
                 } else {
@@ -1303,13 +1313,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                     if (sp_next == sp && !post) {                         // the next position re-uses this gradient: prefetch for
                         sp_next = split_at(jj + 1 == twoM ? 0 : jj + 1);  // the one after it
                         ahead = 2;
+                        // ... and its kick joins this one -- unless a trajectory is being recorded and a leapfrog step
+                        // ends between the two (the recorded momentum is the one after the first kick only)
+                        kick_twice = !reuse && t + 1 < T && !(a.q_traj && jj == 0);
                     }
                     if (t + ahead >= T) sp_next = -2;
                     prev_sp = sp; prev_post = post;
                 }
                 if (t + 1 == T) sp_next = -2;                             // the Hamiltonian evaluation follows: nothing to prefetch
                 if (!reuse) mlp_grad_split<CS>(m, q, g, tile, sp, cc, tc, fused_kick, sp_next);
-                if (fused_kick) kick_partials(kc); else kick(kc);
+                if (kicked_ahead) {                                       // this position's kick was applied with the previous one
+                    kicked_ahead = false;
+                    if (fused_kick) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                } else if (fused_kick) {
+                    kick_partials(kc, kick_twice, half);
+                } else {
+                    kick(kc, kick_twice, half);
+                }
+                kicked_ahead = kick_twice;
                 TC_MARK(16);
                 if (post) drift(cd);
                 if (fused_kick) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
