@@ -158,6 +158,38 @@ def bind_to_gpu_numa_node(local_rank):
     return info
 
 
+_HUGE_KEEP = []
+
+
+def pinned_host_block(shape):
+    """The page-locked host block the e2e legs copy / stream the samples into.  BENCH_HUGEPAGES=1: an anonymous mapping
+    advised to transparent huge pages (2 MiB), first-touched under the NUMA policy above and registered with
+    cudaHostRegister -- fewer IOMMU translations per byte of device-to-host DMA than 4 KiB pages when several GPUs write
+    into one socket's memory.  Falls back to torch's pin_memory().  Returns (tensor, description)."""
+    import math
+    n = int(math.prod(shape)) * 4
+    if os.environ.get('BENCH_HUGEPAGES', '0') == '1':
+        try:
+            import mmap
+            size = (n + (1 << 21) - 1) & ~((1 << 21) - 1)
+            mm = mmap.mmap(-1, size + (1 << 21), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+            base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+            off = (-base) & ((1 << 21) - 1)
+            libc = ctypes.CDLL(None, use_errno=True)
+            libc.madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+            rc = libc.madvise(ctypes.c_void_p(base + off), size, 14)                    # MADV_HUGEPAGE
+            t = torch.frombuffer(mm, dtype=torch.float32, count=n // 4, offset=off).view(shape)
+            t.zero_()                                                                   # first touch (NUMA policy applies)
+            err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n, 0)
+            if int(err) != 0 or not t.is_pinned():
+                raise RuntimeError('cudaHostRegister -> %s' % err)
+            _HUGE_KEEP.append(mm)
+            return t, 'mmap + MADV_HUGEPAGE (rc %d) + cudaHostRegister' % rc
+        except Exception as e:                                  # pragma: no cover
+            sys.stderr.write('BENCH_HUGEPAGES: falling back to pin_memory(): %s\n' % e)
+    return torch.empty(shape, dtype=torch.float32).pin_memory(), 'torch pin_memory() (cudaHostAlloc)'
+
+
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port: same Python loop + autograd as hamiltorch.sample) on host cores
 # ----------------------------------------------------------------------------------------------------------
@@ -523,7 +555,7 @@ def run_b200_arm(args, rank, world, local_rank):
     q0_host = init_of(rank).pin_memory()
     q0 = q0_host.to(dev)
     out = torch.empty((C, S, ld), dtype=torch.float32, device=dev)           # 1 GiB: 8x the 126 MB L2
-    host_out = torch.empty((C, S, ld), dtype=torch.float32).pin_memory()
+    host_out, host_out_pages = pinned_host_block((C, S, ld))
     stats_local = torch.zeros((max(args.steps, args.warmup, 1), C, 2), dtype=torch.float32, device=dev)
     stats = torch.empty((world,) + tuple(stats_local.shape), dtype=torch.float32, device=dev)
     gathered = torch.empty((world, C, S, ld), dtype=torch.float32, device=dev) if world > 1 else None
@@ -778,7 +810,7 @@ def run_b200_arm(args, rank, world, local_rank):
                           'warmup_step_ms_trace': warm_trace,
                           'timed_step_ms': {'min': sorted_ms[0], 'median': sorted_ms[len(sorted_ms) // 2],
                                             'max': sorted_ms[-1], 'all': [round(x, 4) for x in step_ms]},
-                          'numa': numa,
+                          'numa': numa, 'host_block': host_out_pages,
                           'parity': 'config 2: samples bit-exact vs the reference (tests/test_hmc_gpu.py); config 5 (NUTS): '
                                     'bit-exact under the reference step-size schedule (teacher forcing); configs 3/4: see '
                                     'DESIGN.md section 4 for the measured tolerances'},
