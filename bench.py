@@ -420,12 +420,16 @@ def _event_timed(fn, reps):
     """Device time per call of `fn` (a public-API call that enqueues its work and returns): CUDA events around `reps` calls
     enqueued BEHIND a spinning head-start kernel, so that the host's per-call overhead (0.5-1 ms of Python, more on a
     loaded box: config 5's launch is 0.5 ms) runs ahead of the GPU instead of showing up as idle time between the events."""
-    fn()
+    w1 = fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    fn()                                                     # host-side cost of one call (second call: allocator warm)
+    w2 = fn()                                                # host-side cost of one call
     host_s = time.perf_counter() - t0
     torch.cuda.synchronize()
+    # both warm-up results were alive at once: the caching allocator now holds TWO blocks of every size a call allocates, so
+    # the timed `r = fn()` sequence (previous result alive while the next call allocates) never reaches cudaMalloc -- which
+    # synchronises with the head-start kernel (measured: 31 ms per call instead of 0.4)
+    del w1, w2
     head_s = min(0.2, 1.5 * reps * host_s + 2e-3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda._sleep(int(head_s * 1.9e9))                   # ~head_s of SM-clock spinning on the stream
