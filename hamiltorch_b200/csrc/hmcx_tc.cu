@@ -744,7 +744,7 @@ size_t dense_workspace_floats(int C, int D, int full_mass) {
 // (slot 0 of the chain's partials; the other slots are zeroed so dense_log_prob's fixed-order sum is unchanged).
 __global__ void __launch_bounds__(256)
 dense_kick_elem_kernel(const DenseArgs a, const float* __restrict__ Q, float* __restrict__ P, float* __restrict__ Ppack,
-                       const float* __restrict__ eps, int k1m, int k2m, float* __restrict__ upart) {
+                       const float* __restrict__ eps, int k1m, int k2m, float* __restrict__ upart, int k2add = 0) {
     __shared__ float sred[32];
     const int c = blockIdx.x, Dp = a.Dp, D = a.D;
     const float e = eps[c], half = mul(0.5f, e);
@@ -766,7 +766,7 @@ dense_kick_elem_kernel(const DenseArgs a, const float* __restrict__ Q, float* __
             us[0] = add(us[0], u);
             if (k1m) {
                 pv[j] = add(pv[j], mul(k1, g));                               // :281 / :298
-                if (k2m) pv[j] = sub(pv[j], mul(k2, g));                      // :302
+                if (k2m) pv[j] = k2add ? add(pv[j], mul(k2, g)) : sub(pv[j], mul(k2, g));   // :302 | a second, separate kick
             }
         }
         if (k1m) {
@@ -1136,14 +1136,17 @@ int dense_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const 
 
     const dim3 ggrid(a.NT, a.Cp / 128);
     // p_ <- p_ - k*dH/dtheta(q_) = p_ + k*grad log p(q_)  (k = 0: U-terms of q_ only)
-    auto kick = [&](float* q_, float* qpack_, float* p_, float* ppack_, int k1, float* part) {
+    // `twice`: the same kick applied two times (two separately rounded updates, one contraction) -- the last A flow of an
+    // explicit step and the first A flow of the next act on the same (theta, p~)
+    auto kick = [&](float* q_, float* qpack_, float* p_, float* ppack_, int k1, float* part, bool twice = false) {
         if (gemm_target) {
             LinEpi ep = {};
             ep.X = k1 ? p_ : nullptr; ep.Xpack = k1 ? ppack_ : nullptr; ep.Y = part ? q_ : nullptr; ep.yshift = mean;
             ep.part = part; ep.eps = eps; ep.k1 = k1; ep.sign = -1.0f;
+            if (twice) { ep.k2 = k1; ep.k2add = 1; }
             lin_launch(a.BN, ggrid, st, C, a.Dp, a.NT, qpack_, precpack, ep);
         } else {
-            dense_kick_elem_kernel<<<C, 256, 0, st>>>(a, q_, p_, ppack_, eps, k1, 0, part);
+            dense_kick_elem_kernel<<<C, 256, 0, st>>>(a, q_, p_, ppack_, eps, k1, twice ? k1 : 0, part, twice ? 1 : 0);
         }
     };
     // q_ <- q_ + k*G^-1 p_  [+ k*G^-1 p_]
@@ -1184,17 +1187,21 @@ int dense_rmhmc_run(const hmcx_target_t* target, const hmcx_rmhmc_t* cfg, const 
         if (explicit_int) {
             cudaMemcpyAsync(Qc, Q, 2 * CD * sizeof(float), cudaMemcpyDeviceToDevice, st);          // theta~, p~ (:425-426)
             cudaMemcpyAsync(Qcpack, Qpack, 4 * CD * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            // The last A flow of step l (:457-458) and the first A flow of step l+1 (:429-430) act on the same (theta, p~):
+            // one contraction each for dH/dtheta and G^-1 p~, applied twice in the epilogue (6L+2 GEMMs per trajectory
+            // instead of 8L; the same bits -- the second application re-reads the identical accumulator)
+            kick(Q, Qpack, P, Ppack, LIN_K_HALF, nullptr);                                          // A (:429-430)
+            drift(Qc, Qcpack, Pcpack, false);
             for (int l = 0; l < L; ++l) {
-                kick(Q, Qpack, P, Ppack, LIN_K_HALF, nullptr);                                      // A (:429-430)
-                drift(Qc, Qcpack, Pcpack, false);
+                const bool last = l == L - 1;
                 drift(Q, Qpack, Ppack, false);                                                      // B (:432-433)
                 kick(Qc, Qcpack, Pc, Pcpack, LIN_K_HALF, nullptr);
                 dense_rm_bind_kernel<<<C, 256, 0, st>>>(a, cfg->cos_2we, cfg->sin_2we, Q, P, Qc, Pc,  // C (:435-450)
                                                       gemm_target ? Qpack : nullptr, Ppack, Qcpack, Pcpack);
                 drift(Q, Qpack, Ppack, false);                                                      // B (:454-455)
                 kick(Qc, Qcpack, Pc, Pcpack, LIN_K_HALF, nullptr);
-                kick(Q, Qpack, P, Ppack, LIN_K_HALF, upart);                                        // A (:457-458)
-                drift(Qc, Qcpack, Pcpack, false);
+                kick(Q, Qpack, P, Ppack, LIN_K_HALF, last ? upart : nullptr, !last);                // A (:457-458) [+ :429-430]
+                drift(Qc, Qcpack, Pcpack, !last);
             }
         } else {
             for (int l = 0; l < L; ++l) {
