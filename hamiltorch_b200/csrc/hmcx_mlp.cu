@@ -1232,6 +1232,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
     // double while the chain still uses it, the fp32 value once dual averaging produced one (:668)
     auto eps_double = [&](float e) { return (a.eps0 != 0.0 && e == (float)a.eps0) ? a.eps0 : (double)e; };
 
+    int g_last_sp = -3;
+    bool g_fresh = false;
     for (int n = a.it0; n < a.it1; ++n) {
         if (a.eps_schedule) eps = a.eps_schedule[(size_t)n * a.C + c];
         const float half = mul(0.5f, eps);
@@ -1294,8 +1296,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             // step boundary (m = 0 down, then m = 0 up of the next step); SPLITTING_KMID has the latter.  The reference calls
             // autograd twice and gets the same tensor twice; here the second evaluation is skipped and g (per-rank partials
             // included) is kicked again -- the same bits, 2 of the 2M evaluations of a symmetric step saved.
-            int prev_sp = -3;
-            bool prev_post = true, kicked_ahead = false;
+            // The same across iterations: a trajectory ends with an evaluation at its final parameters and no drift after it;
+            // when the proposal is accepted the next trajectory starts by differentiating the same split (the whole potential
+            // for PLAIN) at those parameters -- g_last_sp / g_fresh carry the gradient over (1 of L+1 evaluations of
+            // sample_model's plain leapfrog at high acceptance).
+            int prev_sp = g_fresh ? g_last_sp : -3;
+            bool prev_post = !g_fresh, kicked_ahead = false;
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 int sp = -1, sp_next = -1;
@@ -1303,6 +1309,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                 bool post = false, reuse = false, kick_twice = false;
                 if (plain) {
                     if (t > 0) { drift(eps); kc = eps; }
+                    else reuse = g_fresh && g_last_sp == -1;
                 } else {
                     sp = split_at(jj);
                     post = post_at(jj);
@@ -1347,6 +1354,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                 if (fused_kick) { kick_partials(-half); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
                 else kick(-half);
             }
+            // g now holds the gradient of the last schedule position's split at the proposal, unless a drift followed it
+            g_last_sp = plain ? -1 : prev_sp;
+            g_fresh = plain || !prev_post;
         }
         if (a.p_given) break;                                             // stand-alone leapfrog: no Hamiltonian, no MH
         // ---- Hamiltonians + MH ----
@@ -1368,6 +1378,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             if (lead) for (int i = tid; i < D; i += MLP_THREADS) a.q_cur[row + i] = q[i];
         } else {
             ++rejected;
+            g_fresh = false;                                              // q goes back: g belongs to the rejected proposal
             const float* src = (n == a.burn + 1) ? a.q_init : a.q_cur;    // the first-stored-iteration quirk (:1018)
             for (int i = tid; i < D; i += MLP_THREADS) q[i] = src[row + i];
             __syncthreads();
