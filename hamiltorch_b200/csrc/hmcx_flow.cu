@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
     float* mt_prec = smem;
     float* mt_minv = mt_prec + (full_t ? K4 * DP : 0);
     float* mt_chol = mt_minv + (full_m ? K4 * DP : 0);
-    float* xs = mt_chol + (full_m ? K4 * DP : 0) + warp * (R * DP);
+    float* xs = mt_chol + (full_m ? K4 * DP : 0) + warp * (2 * R * DP);           // two staging rows per chain (paired matvecs)
+    float* xs2 = xs + R * DP;
     {
         const float* src[3] = {full_t ? a.prec : nullptr, full_m ? a.minv : nullptr, full_m ? a.chol : nullptr};
         float* dst[3] = {mt_prec, mt_minv, mt_chol};
@@ -142,6 +143,75 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
             for (int jj = 0; jj < NJ; ++jj) t = add(t, mul(x[r][jj], y[r][jj]));
             s[r] = warp_sum(t);
         }
+    };
+    // Two INDEPENDENT matvecs in one pass (the explicit integrator's dH/dtheta and G^-1 p of a flow): twice the FFMA chains in
+    // flight for a warp that is alone on its scheduler.  Each product accumulates exactly as in matvec() -- the same bits.
+    constexpr bool PAIR = R <= 2;                                  // (register budget; large batches hide latency with warps)
+    auto stage2 = [&](const float (&x1)[R][NJ], const float (&x2)[R][NJ]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) { xs[r * DP + jj * 32 + lane] = x1[r][jj]; xs2[r * DP + jj * 32 + lane] = x2[r][jj]; }
+        __syncwarp();
+    };
+    auto matvec2 = [&](const float* __restrict__ MT1, const float* __restrict__ MT2, float (&y1)[R][NJ], float (&y2)[R][NJ]) {
+        float a1[NACC][R][NJ], a2[NACC][R][NJ];
+#pragma unroll
+        for (int t = 0; t < NACC; ++t)
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) { a1[t][r][jj] = 0.0f; a2[t][r][jj] = 0.0f; }
+#pragma unroll 2
+        for (int k = 0; k < K4; k += 4) {
+            float4 x1[R], x2[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                x1[r] = *reinterpret_cast<const float4*>(xs + r * DP + k);
+                x2[r] = *reinterpret_cast<const float4*>(xs2 + r * DP + k);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    const float m1 = MT1[(k + kk) * DP + jj * 32 + lane], m2 = MT2[(k + kk) * DP + jj * 32 + lane];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        a1[kk % NACC][r][jj] = fmaf(m1, f4c(x1[r], kk), a1[kk % NACC][r][jj]);
+                        a2[kk % NACC][r][jj] = fmaf(m2, f4c(x2[r], kk), a2[kk % NACC][r][jj]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                float s1 = a1[0][r][jj], s2 = a2[0][r][jj];
+                if (NACC == 2) { s1 = add(s1, a1[1 % NACC][r][jj]); s2 = add(s2, a2[1 % NACC][r][jj]); }
+                if (NACC == 4) {
+                    s1 = add(add(s1, a1[1 % NACC][r][jj]), add(a1[2 % NACC][r][jj], a1[3 % NACC][r][jj]));
+                    s2 = add(add(s2, a2[1 % NACC][r][jj]), add(a2[2 % NACC][r][jj], a2[3 % NACC][r][jj]));
+                }
+                y1[r][jj] = s1; y2[r][jj] = s2;
+            }
+        __syncwarp();
+    };
+    // (grad log p(x), G^-1 w) together: == grad(x, g, u, want_u); vel(w, vv)
+    auto grad_vel = [&](const float (&x)[R][NJ], float (&g)[R][NJ], float (&u)[R], bool want_u, const float (&w)[R][NJ],
+                        float (&vv)[R][NJ]) {
+        float y[R][NJ];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) y[r][jj] = sub(x[r][jj], meanv[jj]);
+        stage2(y, w);
+        matvec2(mt_prec, mt_minv, g, vv);
+        if (want_u) dot(y, g, u);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) g[r][jj] = -g[r][jj];
     };
     // g = grad log p(q); u = the U-terms of log p (log p = -0.5*u + log_norm) when want_u
     auto grad = [&](const float (&q)[R][NJ], float (&g)[R][NJ], float (&u)[R], bool want_u) {
@@ -304,10 +374,17 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
                 axpy(p, half, g);                                                   // A (:429-430): flows of H(theta, p~)
                 axpy(qc, half, vc);
                 for (int b = 0; b < 2; ++b) {                                       // B (:432-433), C (:435-450), B (:454-455)
-                    vel(p, v);
-                    axpy(q, half, v);
-                    grad(qc, v, u_new, false);
-                    axpy(pc, half, v);
+                    if (PAIR && full_t && full_m) {
+                        float gc[R][NJ];
+                        grad_vel(qc, gc, u_new, false, p, v);
+                        axpy(q, half, v);
+                        axpy(pc, half, gc);
+                    } else {
+                        vel(p, v);
+                        axpy(q, half, v);
+                        grad(qc, v, u_new, false);
+                        axpy(pc, half, v);
+                    }
                     if (b == 0) {
 #pragma unroll
                         for (int r = 0; r < R; ++r)
@@ -322,11 +399,17 @@ __global__ void __launch_bounds__(256, 1) flow_small_kernel(const FlowArgs a) {
                             }
                     }
                 }
-                grad(q, g, u_new, l == a.L - 1);                                    // A (:457-458); g and vc also serve the next step's A
-                axpy(p, half, g);
-                if (l < a.L - 1) {
-                    vel(pc, vc);
+                if (PAIR && full_t && full_m && l < a.L - 1) {                      // A (:457-458); g and vc also serve the next step's A
+                    grad_vel(q, g, u_new, false, pc, vc);
+                    axpy(p, half, g);
                     axpy(qc, half, vc);
+                } else {
+                    grad(q, g, u_new, l == a.L - 1);
+                    axpy(p, half, g);
+                    if (l < a.L - 1) {
+                        vel(pc, vc);
+                        axpy(qc, half, vc);
+                    }
                 }
             }
         }
@@ -443,7 +526,7 @@ static int flow_launch(const FlowArgs& a, cudaStream_t st) {
     int R, threads, grid;
     const int nmat = (a.tk == HMCX_TARGET_GAUSS_FULL ? 1 : 0) + (a.mk == HMCX_MASS_FULL ? 2 : 0);
     flow_threads_and_grid(a.C, a.D, (size_t)nmat * K4 * DP * sizeof(float), R, threads, grid);
-    const size_t smem = ((size_t)nmat * K4 * DP + (size_t)(threads / 32) * R * DP) * sizeof(float);
+    const size_t smem = ((size_t)nmat * K4 * DP + (size_t)(threads / 32) * 2 * R * DP) * sizeof(float);
     switch (NJ) {
         case 1: return flow_launch_nj<1>(a, R, threads, grid, smem, st);
         case 2: return flow_launch_nj<2>(a, R, threads, grid, smem, st);
