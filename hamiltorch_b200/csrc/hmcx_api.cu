@@ -233,4 +233,12 @@ int hmcx_mlp_pack_x(const hmcx_target_t* target, float* packed_out, void* stream
     return hmcx::mlp_pack_x(target, packed_out, (cudaStream_t)stream);
 }
 
+int hmcx_copy_rows_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                         void* stream) {
+    if (!dst || !src || width > dpitch || width > spitch) return HMCX_ERR_INVALID_ARG;
+    if (width == 0 || height == 0) return HMCX_OK;
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, (cudaStream_t)stream) == cudaSuccess
+               ? HMCX_OK : HMCX_ERR_CUDA;
+}
+
 }  // extern "C"

@@ -225,6 +225,16 @@ def native_mass(inv_mass, dim, device):
     return nm
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(torch.device(device))
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def nuts_table(burn):
     """The five Python-double constants of samplers.py:659-671 for t = 1..burn+1 (gamma=.05, t0=10, kappa=.75)."""
     rows = []
@@ -397,7 +407,7 @@ class HMCResult:
 def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, burn=0, inv_mass=None,
             nuts=False, desired_accept_rate=0.8, seed=0, chain_offset=0, normals=None, log_uniforms=None,
             record_ham=False, out=None, device=None, tuning=0, eps_schedule=None, record_eps=False, scheme=None,
-            perms=None, thin=1, moments=False, keep_samples=True, host_samples=False):
+            perms=None, thin=1, moments=False, keep_samples=True, host_samples=False, host_windows=0):
     """The reference's sample() loop for sampler in {HMC, HMC_NUTS} as one persistent kernel over C chains.
 
     params_init (C, D) | (D,).  Randomness: in-kernel Philox keyed by (seed, chain_offset+c, iteration), or -- when
@@ -434,10 +444,18 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     thin = int(thin)
     if thin < 1:
         raise RuntimeError('thin must be >= 1')
+    host_out = None
     if out is not None and not out.is_cuda:
         if not out.is_pinned():
             raise RuntimeError('a host `out` buffer must be pinned (page-locked) memory')
-        host_samples = True                        # caller-provided pinned sample block: the kernel streams into it
+        if int(host_windows) >= 2 and thin == 1 and not moments and keep_samples and scheme is None:
+            # windowed delivery: the run is cut into `host_windows` windows of iterations; each window's sample slots
+            # leave for the pinned block through the COPY ENGINE on a second stream while the next window computes
+            # (hmcx_copy_rows_async).  Costs a device staging block of the samples' size; delivers at the DMA rate
+            # (57 GB/s on B200/PCIe 5) where SM-issued stores to host memory reach ~52.5.
+            host_out, out = out, None
+        else:
+            host_samples = True                    # caller-provided pinned sample block: the kernel streams into it
     use_sink = thin > 1 or moments or not keep_samples or host_samples
     if use_sink and scheme is not None:
         raise NotImplementedError('the sample sink is implemented for element-wise targets')
@@ -521,6 +539,37 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
                                            N.ptr(accepted), N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected),
                                            int(tuning), N.ptr(ws), C.byref(sink), N.stream_ptr(device))
                 N.check(rc, 'hmcx_hmc_run_sink')
+            elif host_out is not None:
+                if tuple(host_out.shape) != (Cn, keep, ld) or host_out.dtype != torch.float32 or not host_out.is_contiguous():
+                    raise RuntimeError('out must be a contiguous fp32 (C, S-burn, ld) tensor')
+                if normals is not None:
+                    raise NotImplementedError('host_windows with an injected stream')   # (rng pointers are per window)
+                W = min(int(host_windows), S)
+                main = torch.cuda.current_stream(device)
+                side = _side_stream(device)
+                pitch, slot_bytes = keep * ld * 4, ld * 4
+                for w in range(W):
+                    a, b = (S * w) // W, (S * (w + 1)) // W
+                    rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
+                                          N.ptr(eps), Cn, ld, L, S, burn, a, b, N.ptr(samples), N.ptr(accepted),
+                                          N.ptr(diverged), N.ptr(ham), N.ptr(num_rejected), int(tuning), N.ptr(ws),
+                                          C.c_void_p(main.cuda_stream))
+                    N.check(rc, 'hmcx_hmc_run')
+                    lo = 0 if a == 0 else max(a - burn, 1)               # slots this window wrote: 0 = params_init (:959),
+                    hi = max(b - burn, 1 if a == 0 else lo)              # n - burn for every iteration n > burn
+                    if hi > lo:
+                        ev = torch.cuda.Event()
+                        ev.record(main)
+                        side.wait_event(ev)
+                        rc = lib.hmcx_copy_rows_async(C.c_void_p(host_out.data_ptr() + lo * slot_bytes), pitch,
+                                                      C.c_void_p(samples.data_ptr() + lo * slot_bytes), pitch,
+                                                      (hi - lo) * slot_bytes, Cn, C.c_void_p(side.cuda_stream))
+                        N.check(rc, 'hmcx_copy_rows_async')
+                done = torch.cuda.Event()
+                done.record(side)
+                main.wait_event(done)                       # the caller's stream sees the delivered block
+                keep_alive.append(samples)
+                samples = host_out
             else:
                 rc = lib.hmcx_hmc_run(nt.ref(), nm.ref(), C.byref(rng), C.byref(nuts_s), N.ptr(q_init), N.ptr(q_cur),
                                       N.ptr(eps), Cn, ld, L, S, burn, 0, S, N.ptr(samples), N.ptr(accepted),

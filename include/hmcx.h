@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HMCX_ABI_VERSION 6
+#define HMCX_ABI_VERSION 7
 
 #define HMCX_MLP_TC_AUTO 0
 #define HMCX_MLP_TC_OFF  1
@@ -400,6 +400,16 @@ int hmcx_hmc_run_sink(const hmcx_target_t* target, const hmcx_mass_t* mass, cons
                       int32_t iter_begin, int32_t iter_end,
                       float* samples_out, uint8_t* accept_out, uint8_t* diverged_out, float* ham_out,
                       int32_t* num_rejected, int32_t tuning, float* workspace, const hmcx_sink_t* sink, void* stream);
+
+/*
+ * hmcx_copy_rows_async: `height` rows of `width` bytes from `src` (row pitch `spitch`) to `dst` (row pitch `dpitch`), either
+ * side device or PINNED host memory, enqueued on `stream` (cudaMemcpy2DAsync, cudaMemcpyDefault).  The delivery half of a
+ * windowed run: hmcx_hmc_run over iterations [a, b) on one stream, then the window's sample slots -- the same columns of
+ * every chain's [num_samples-burn, ld] block -- leave for the host on a second stream through the copy engine while the next
+ * window computes (the reference's store_on_GPU=False, samplers.py:1008-1012, without stalling the chains on PCIe).
+ */
+int hmcx_copy_rows_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                         void* stream);
 
 #ifdef __cplusplus
 }

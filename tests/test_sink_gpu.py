@@ -117,3 +117,24 @@ def test_moments_of_a_long_run_far_from_zero():
     allx = x.reshape(-1, D)
     assert pn == C * n and torch.allclose(pm, allx.mean(0), rtol=1e-9)
     assert torch.allclose(pv, allx.var(0, unbiased=False), rtol=2e-6)
+
+
+@pytest.mark.parametrize('nuts,windows,burn', [(False, 4, 7), (True, 3, 20), (False, 50, 0), (False, 7, 48)])
+def test_windowed_delivery_into_a_pinned_host_block_equals_the_plain_run(nuts, windows, burn):
+    """out=<pinned host block>, host_windows=W: the run is cut into W windows of iterations (hmcx_hmc_run with iter_begin /
+    iter_end) and each window's sample slots are delivered by hmcx_copy_rows_async on a second stream while the next window
+    computes: the same bytes as one launch, the same flags / step sizes (windows chain through q_cur, eps, the NUTS state)."""
+    tgt, init, im = _setup()
+    kw = dict(KW, inv_mass=im, burn=burn, sampler=hb.Sampler.HMC_NUTS if nuts else hb.Sampler.HMC, record_ham=True)
+    if nuts and burn < 1:
+        pytest.skip('NUTS needs burn >= 1')
+    full = hb.sample_chains(tgt, init, **kw)
+    S, C = KW['num_samples'], init.shape[0]
+    ld = full.samples_padded.shape[-1]
+    host = torch.full((C, S - burn, ld), float('nan')).pin_memory()
+    win = hb.sample_chains(tgt, init, out=host, host_windows=windows, **kw)
+    torch.cuda.synchronize()
+    assert not win.samples_padded.is_cuda and win.samples_padded.data_ptr() == host.data_ptr()
+    assert torch.equal(host, full.samples_padded.cpu())
+    assert torch.equal(win.accepted, full.accepted) and torch.equal(win.ham, full.ham)
+    assert torch.equal(win.step_size, full.step_size) and torch.equal(win.num_rejected, full.num_rejected)
