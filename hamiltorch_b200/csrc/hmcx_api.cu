@@ -54,6 +54,7 @@ int hmcx_abi_version(void) { return HMCX_ABI_VERSION; }
 size_t hmcx_hmc_workspace_bytes(const hmcx_target_t* target, const hmcx_mass_t* mass, int32_t C, int32_t ld) {
     const bool full_mass = mass && mass->kind == HMCX_MASS_FULL;
     if (is_elem(target) && !full_mass && ld > 4096) return (size_t)C * (size_t)ld * sizeof(float);
+    if (is_elem(target) && !full_mass) return (size_t)C * sizeof(float);      // log p(q_cur) carried between windows of iterations
     if (target && target->dim > 16 &&
         (target->kind == HMCX_TARGET_GAUSS_FULL || (full_mass && is_elem(target))))
         return hmcx::dense_workspace_floats(C, target->dim, full_mass ? 1 : 0) * sizeof(float);

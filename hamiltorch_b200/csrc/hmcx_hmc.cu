@@ -220,6 +220,10 @@ struct RunArgs {
     float* msumsq;
     float* msum_lo;           // optional: the compensation terms of the running sums (true sum = hi + lo)
     float* msumsq_lo;
+    // windows of iterations: [C] log p(q_cur) left by the launch that ended at iter_begin (the loop carries it in a register
+    // and its fused 3-value reduction does not associate like the prologue's recomputation: without the carry a run cut into
+    // windows differs from a single launch in the last bit of H_old at every window start)
+    float* lp_carry;
 };
 
 // Neumaier's compensated accumulation: s + c carries the running sum to ~2^-46 relative whatever the number of terms
@@ -369,6 +373,7 @@ hmc_run_kernel(const RunArgs a) {
         lp_cur = log_prob_from_sum(r[0], t.log_norm);
         __syncthreads();
     }
+    if (a.lp_carry && a.it0 > 0) lp_cur = a.lp_carry[c];
 
     float eps = a.eps[c];
     double h_bar = 0.0, eps_bar = 1.0;
@@ -604,6 +609,7 @@ hmc_run_kernel(const RunArgs a) {
         a.eps[c] = eps;
         if (nuts) { a.h_bar[c] = h_bar; a.eps_bar[c] = eps_bar; }
         if (a.num_rejected) a.num_rejected[c] += rejected;
+        if (a.lp_carry) a.lp_carry[c] = lp_cur;
     }
 }
 
@@ -1016,6 +1022,7 @@ int elem_hmc_run(const hmcx_target_t* target, const hmcx_mass_t* mass, const hmc
         return cuda_status();
     }
     if (!pick_geometry(ld, tuning, E, K, G)) return tuning ? HMCX_ERR_INVALID_ARG : HMCX_ERR_UNSUPPORTED;
+    a.lp_carry = workspace;                                // [C] floats (hmcx_hmc_workspace_bytes) or NULL
     const bool philox = a.rng_mode == HMCX_RNG_PHILOX;
 #define CALL(TK, MK)                                                                                    \
     if (E == 2 && K == 1) hmc_run_kernel<TK, MK, 2, 1, 1024><<<C, G, 0, st>>>(a);                       \

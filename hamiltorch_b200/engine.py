@@ -448,7 +448,8 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
     if out is not None and not out.is_cuda:
         if not out.is_pinned():
             raise RuntimeError('a host `out` buffer must be pinned (page-locked) memory')
-        if int(host_windows) >= 2 and thin == 1 and not moments and keep_samples and scheme is None:
+        if (int(host_windows) >= 2 and thin == 1 and not moments and keep_samples and scheme is None and ld <= 4096 and
+                nt.struct.kind in (T.GaussianIso.kind, T.GaussianDiag.kind) and nm.kind != N.MASS_FULL and normals is None):
             # windowed delivery: the run is cut into `host_windows` windows of iterations; each window's sample slots
             # leave for the pinned block through the COPY ENGINE on a second stream while the next window computes
             # (hmcx_copy_rows_async).  Costs a device staging block of the samples' size; delivers at the DMA rate
@@ -542,8 +543,6 @@ def hmc_run(target, params_init, num_samples, num_steps_per_sample, step_size, b
             elif host_out is not None:
                 if tuple(host_out.shape) != (Cn, keep, ld) or host_out.dtype != torch.float32 or not host_out.is_contiguous():
                     raise RuntimeError('out must be a contiguous fp32 (C, S-burn, ld) tensor')
-                if normals is not None:
-                    raise NotImplementedError('host_windows with an injected stream')   # (rng pointers are per window)
                 W = min(int(host_windows), S)
                 main = torch.cuda.current_stream(device)
                 side = _side_stream(device)

@@ -198,7 +198,11 @@ int hmcx_gibbs(const hmcx_mass_t* mass, const hmcx_rng_t* rng, int32_t D, int32_
  *   samples_out [C, num_samples-burn, ld]  slot 0 = params_init (:959), slot n-burn = iteration n > burn
  *   accept_out / diverged_out  optional [C, num_samples] (uint8); ham_out optional [C, num_samples, 2] = (H_old, H_new)
  *   num_rejected optional [C] int32 in/out counter (:961, :1016, :1046)
- *   workspace    hmcx_hmc_workspace_bytes() bytes of device scratch (NULL when that is 0)
+ *   workspace    hmcx_hmc_workspace_bytes() bytes of device scratch (NULL when that is 0).  For element-wise targets with
+ *                ld <= 4096 these are C floats that carry log p(q_cur) from one window of iterations to the next: pass the
+ *                SAME buffer to the launches [0, a), [a, b), ... of a run and they reproduce the single launch [0, S) bit for
+ *                bit; with NULL a window recomputes log p(q_cur) (a reduction that associates differently from the loop's:
+ *                H_old of its first iteration may differ in the last bit)
  *   tuning       0 = automatic register geometry (one float4 per thread for D <= 2560, two above); 1 = one float4 per
  *                thread; 2 / 4 = that many float4 groups per thread; 21 / 22 = one / two float2 groups per thread
  *                (tests and tuning sweeps; element-wise state and the random stream never depend on it)
