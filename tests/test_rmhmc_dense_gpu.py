@@ -29,6 +29,9 @@ CASES = {
     'full24_hessian_implicit': dict(D=24, target='full', metric=R.HESSIAN, integrator=R.IMPLICIT, eps=0.6, L=3),
     'diag24_softabs_explicit': dict(D=24, target='diag', metric=R.SOFTABS, integrator=R.EXPLICIT, eps=1.2, L=3),
     'iso20_hessian_explicit': dict(D=20, target='iso', metric=R.HESSIAN, integrator=R.EXPLICIT, eps=0.8, L=3),
+    # 3 and 4 register slots per lane of the persistent small-D kernel (64 < D <= 96, 96 < D <= 128)
+    'full72_hessian_explicit': dict(D=72, target='full', metric=R.HESSIAN, integrator=R.EXPLICIT, eps=0.5, L=3),
+    'full100_softabs_implicit': dict(D=100, target='full', metric=R.SOFTABS, integrator=R.IMPLICIT, eps=0.5, L=2),
 }
 
 

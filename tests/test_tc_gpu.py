@@ -32,8 +32,9 @@ def _corr_gaussian(D, seed):
     return T.GaussianFull(torch.randn(D, generator=g), cov=cov)
 
 
+@pytest.mark.parametrize('D', [200, 96, 128])
 @pytest.mark.parametrize('variant', ['hmc', 'diag_mass', 'nuts'])
-def test_dense_gaussian_full_chain_parity_vs_live_oracle(variant):
+def test_dense_gaussian_full_chain_parity_vs_live_oracle(variant, D):
     """Full-covariance Gaussian at D=200 (> 16: the tcgen05 step-synchronous path, one GEMM over all chains per
     leapfrog step) against the oracle under the injected stream.  The gradient is a 3xTF32 tensor-core contraction
     (~1e-6 relative), the reference's an fp32 mv: states agree to 2e-4, decisions identical."""
@@ -42,7 +43,9 @@ def test_dense_gaussian_full_chain_parity_vs_live_oracle(variant):
     from hamiltorch_b200 import engine
     from oracle import hmc_oracle as O
     from tests import parity
-    D, C, S, L, burn = 200, 5, 12, 6, 3
+    # D = 200: the tcgen05 step-synchronous path; D = 96 / 128: the persistent small-D kernel (hmcx_flow.cu) with 3 / 4
+    # register slots per lane
+    C, S, L, burn = 5, 12, 6, 3
     tgt = _corr_gaussian(D, 1)
     im = None
     if variant == 'diag_mass':
@@ -66,7 +69,7 @@ def test_dense_gaussian_full_chain_parity_vs_live_oracle(variant):
         parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
                                    res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
                                    o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4,
-                                   tag='dense_d200/%s/c%d' % (variant, c))
+                                   tag='dense_d%d/%s/c%d' % (D, variant, c))
         if nuts:
             own = res.eps_trace[c].cpu().numpy().astype(np.float64)
             np.testing.assert_allclose(own[:S - 1], np.array(o['step_sizes'])[1:], rtol=2e-3)
@@ -99,8 +102,9 @@ def _spd(D, seed, scale=1.0):
     return (scale * (A @ A.t() + 0.7 * torch.eye(D, dtype=torch.float64))).float()
 
 
+@pytest.mark.parametrize('D', [150, 96, 128])
 @pytest.mark.parametrize('variant', ['full_target', 'diag_target', 'iso_target_nuts'])
-def test_full_inv_mass_large_d_chain_parity_vs_live_oracle(variant):
+def test_full_inv_mass_large_d_chain_parity_vs_live_oracle(variant, D):
     """2-D inv_mass at D > 16 (samplers.py:199 gibbs through the Cholesky factor of inverse(inv_mass), :294 drift
     q += eps*(M^-1 p), :812 kinetic): momentum refresh, every drift and both kinetic energies are tcgen05 GEMMs over
     all chains (dense_lin_kernel), the gradient one more GEMM (GaussianFull) or element-wise (GaussianIso / Diag).
@@ -109,7 +113,7 @@ def test_full_inv_mass_large_d_chain_parity_vs_live_oracle(variant):
     import hamiltorch_b200.targets as T
     from oracle import hmc_oracle as O
     from tests import parity
-    D, C, S, L, burn = 150, 4, 10, 5, 3
+    C, S, L, burn = 4, 10, 5, 3            # D = 150: tcgen05 GEMMs; D = 96 / 128: the persistent small-D kernel
     nuts = variant.endswith('nuts')
     if variant == 'full_target':
         tgt = _corr_gaussian(D, 11)
@@ -140,7 +144,7 @@ def test_full_inv_mass_large_d_chain_parity_vs_live_oracle(variant):
         parity.assert_chain_parity(res.samples[c].cpu().numpy(), res.accepted[c].cpu().numpy(),
                                    res.ham[c].cpu().numpy(), torch.stack(o['samples']).numpy(), o['accepted'],
                                    o['ham_old'], o['ham_new'], lus[c].numpy(), burn, exact=False, rtol=2e-4,
-                                   tag='fullmass_d150/%s/c%d' % (variant, c))
+                                   tag='fullmass_d%d/%s/c%d' % (D, variant, c))
         if nuts:
             own = res.eps_trace[c].cpu().numpy().astype(np.float64)
             np.testing.assert_allclose(own[:S - 1], np.array(o['step_sizes'])[1:], rtol=2e-3)
