@@ -28,3 +28,10 @@ if [ "${SAN_ONLY:-}" = "flow" ] || [ -z "${SAN_ONLY:-}" ]; then
 run memcheck flow 500 tests/test_rmhmc_dense_gpu.py tests/test_tc_gpu.py tests/test_hmc_gpu.py -k "flow or (golden_chain_parity and (full48 or full40 or iso40 or blockmass) and not tcgen05) or paths_agree"
 run racecheck flow 500 tests/test_rmhmc_dense_gpu.py tests/test_tc_gpu.py -k "(flow and not statistics) or paths_agree"
 fi
+# later in round 2: windowed delivery (two streams + hmcx_copy_rows_async) and the split schedule's gradient re-use (cluster
+# barrier arrive / wait pairing at the positions that skip their evaluation or their kick)
+if [ "${SAN_ONLY:-}" = "late" ] || [ -z "${SAN_ONLY:-}" ]; then
+run memcheck windows 300 tests/test_sink_gpu.py -k "windowed"
+run synccheck reuse 500 tests/test_mlp_gpu.py -k "cluster_split or split_sym or split_kmid"
+run memcheck reuse 500 tests/test_mlp_gpu.py -k "cluster_split or split_sym or split_kmid"
+fi
