@@ -1153,20 +1153,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
     // rank reads all partials through distributed shared memory (16-byte loads), adds them in rank order (the same bits as
     // reduce-then-kick) and updates its replica of p.  The peers may overwrite their g only after everybody has read it:
     // barrier.cluster arrive here, wait after the drift that follows (its latency hides behind the drift).
-    auto kick_partials = [&](float coef, bool twice = false, float coef2 = 0.0f) {
+    // `drift_cd` != 0: the drift that follows this kick (params += drift_cd * M^-1 momentum, the same operations as drift()
+    // below on the just-updated momentum) in the same pass -- one sweep over the state and one barrier less per position
+    auto kick_partials = [&](float coef, bool twice = false, float coef2 = 0.0f, float drift_cd = 0.0f) {
         cg::cluster_group cluster = cg::this_cluster();
         const float4* gr[CS];
 #pragma unroll
         for (int r = 0; r < CS; ++r) gr[r] = reinterpret_cast<const float4*>(r == cc.rank ? g : cluster.map_shared_rank(g, r));
         float4* p4 = reinterpret_cast<float4*>(p);
+        float4* q4 = reinterpret_cast<float4*>(q);
+        const bool with_drift = drift_cd != 0.0f, with_im = with_drift && a.mk == HMCX_MASS_DIAG;
         constexpr int KV = CS >= 4 ? 2 : VPT;                  // (register budget: KV * CS vectors live)
         for (int v0 = tid; v0 < nvec; v0 += MLP_THREADS * KV) {
-            float4 part[KV][CS];
+            float4 part[KV][CS], imv[KV];
 #pragma unroll
-            for (int k = 0; k < KV; ++k) {                     // all remote loads of the round in flight together
+            for (int k = 0; k < KV; ++k) {                     // all remote (and L2) loads of the round in flight together
                 const int v = v0 + k * MLP_THREADS;
 #pragma unroll
                 for (int r = 0; r < CS; ++r) part[k][r] = v < nvec ? gr[r][v] : make_float4(0.f, 0.f, 0.f, 0.f);
+                imv[k] = (with_im && v < nvec) ? ld_im4(v) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int k = 0; k < KV; ++k) {
@@ -1186,6 +1191,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                         pv.z = add(pv.z, mul(coef2, sg.z)); pv.w = add(pv.w, mul(coef2, sg.w));
                     }
                     p4[v] = pv;
+                    if (with_drift) {
+                        float4 qv = q4[v];
+                        if (with_im) {
+                            qv.x = add(qv.x, mul(mul(drift_cd, imv[k].x), pv.x)); qv.y = add(qv.y, mul(mul(drift_cd, imv[k].y), pv.y));
+                            qv.z = add(qv.z, mul(mul(drift_cd, imv[k].z), pv.z)); qv.w = add(qv.w, mul(mul(drift_cd, imv[k].w), pv.w));
+                        } else {
+                            qv.x = add(qv.x, mul(drift_cd, pv.x)); qv.y = add(qv.y, mul(drift_cd, pv.y));
+                            qv.z = add(qv.z, mul(drift_cd, pv.z)); qv.w = add(qv.w, mul(drift_cd, pv.w));
+                        }
+                        q4[v] = qv;
+                    }
                 }
             }
         }
@@ -1306,7 +1322,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
             for (int t = 0; t < T; ++t) {
                 int sp = -1, sp_next = -1;
                 float kc = half;
-                bool post = false, reuse = false, kick_twice = false;
+                bool post = false, reuse = false, kick_twice = false, drift_done = false;
                 if (plain) {
                     if (t > 0) { drift(eps); kc = eps; }
                     else reuse = g_fresh && g_last_sp == -1;
@@ -1333,13 +1349,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_run_kernel(const MlpRunArg
                     kicked_ahead = false;
                     if (fused_kick) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
                 } else if (fused_kick) {
-                    kick_partials(kc, kick_twice, half);
+                    // (plain: the drift belongs to the NEXT position and takes its own pass; a recorded trajectory keeps the
+                    // separate pass too -- nothing to gain there)
+                    drift_done = post && !plain && cd != 0.0f;
+                    kick_partials(kc, kick_twice, half, drift_done ? cd : 0.0f);
                 } else {
                     kick(kc, kick_twice, half);
                 }
                 kicked_ahead = kick_twice;
                 TC_MARK(16);
-                if (post) drift(cd);
+                if (post && !drift_done) drift(cd);
                 if (fused_kick) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
                 TC_MARK(17);
                 if (a.q_traj && !plain && jj == 0 && lead) {              // a leapfrog step just ended (:546-547, :570-571, :600-601)
